@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the KD-loss hot path (BASELINE.json metric: KD loss fwd+bwd tokens/s @ V=151,936).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode reference|per_row]
+
+One "step" = one LoCa logit-KD forward+backward (loss + bf16 gradient w.r.t. the student logits) over a
+batch of B*S = 16 384 synthetic token rows per GPU (BASELINE.json configs[1]: B=8, S=2048, V=151 936, T=2.0).
+N > 1 is launched by torchrun (one rank per GPU); tokens are sharded across ranks (weak scaling: 16 384 rows
+per rank) and, in the as-written "reference" mode, the 16-byte token records are all-gathered over NCCL
+between the two phases.  Rank 0 prints ONE JSON line.
+
+``--impl reference`` times the reference's own CPU path (the eager-PyTorch port in oracle/reference_port.py —
+the reference is a Python tree that cannot travel to the GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+V = 151_936
+ROWS_PER_GPU = 16_384          # B=8 x S=2048
+T_KD, ALPHA = 2.0, 0.8
+CPU_SAMPLE_ROWS = 512          # BASELINE.json configs[0]: B=1, S=512 on the host CPU
+METRIC = "KD loss fwd+bwd tokens/s @ V=151,936"
+
+
+def load_peaks() -> tuple[float, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of this rank's GPU during the timed region (pynvml)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self) -> dict:
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU reference arm / baseline (oracle port; the only place bench.py touches oracle/)
+# --------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(repeats: int, warmup: int) -> tuple[float, int]:
+    from oracle import reference_port as P
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import synthetic
+    import warnings
+    warnings.filterwarnings("ignore", message=".*reduction: 'mean' divides.*")
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    t, s, lab = synthetic.logit_batch(CPU_SAMPLE_ROWS, V, seed=1234, dtype=torch.float32)
+    t, s, lab = t.reshape(1, CPU_SAMPLE_ROWS, V), s.reshape(1, CPU_SAMPLE_ROWS, V), lab.reshape(1, CPU_SAMPLE_ROWS)
+    best = float("inf")
+    for i in range(warmup + repeats):
+        sv = s.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        loss = P.loca_loss_eager(t, sv, lab, T_KD, ALPHA)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            best = min(best, dt)
+    return best, threads
+
+
+def cpu_model_name() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:  # noqa: BLE001
+        pass
+    return "unknown"
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    times = []
+    from oracle import reference_port as P
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import synthetic
+    import warnings
+    warnings.filterwarnings("ignore", message=".*reduction: 'mean' divides.*")
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    t, s, lab = synthetic.logit_batch(CPU_SAMPLE_ROWS, V, seed=1234, dtype=torch.float32)
+    t, s, lab = t.reshape(1, CPU_SAMPLE_ROWS, V), s.reshape(1, CPU_SAMPLE_ROWS, V), lab.reshape(1, CPU_SAMPLE_ROWS)
+    for i in range(args.warmup + args.steps):
+        sv = s.clone().requires_grad_(True)
+        a = time.perf_counter()
+        P.loca_loss_eager(t, sv, lab, T_KD, ALPHA).backward()
+        if i >= args.warmup:
+            times.append(time.perf_counter() - a)
+    ms = 1e3 * sum(times) / len(times)
+    value = CPU_SAMPLE_ROWS / (ms / 1e3)
+    sample = (f"each step = B=1,S={CPU_SAMPLE_ROWS} fp32 rows of the workload (BASELINE configs[0]); the eager path needs "
+              f"~10 [N,V] fp32 temporaries so 16 384 rows do not fit; {threads} threads on {cpu_model_name()}")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LoCa logit-KD fwd+bwd, B=8,S=2048,V=151936,T=2.0 (CPU sample B=1,S=512)", "mode": "reference"},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }))
+
+
+# --------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="reference", choices=["reference", "per_row"])
+    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="token rows per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the per_row / KL / InfoNCE / MSE side measurements")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    import knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 as kd
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import _lib, sharded, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != max(args.gpus, 1) and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    peak_gbs, peak_src = load_peaks()
+    N = args.rows
+    mode = args.mode
+
+    teacher, student, labels = synthetic.logit_batch(N, V, seed=1234 + rank, device=dev)
+    student.requires_grad_(True)
+    n_total = N * world
+    phases = sharded.CudaPhases()
+
+    def step():
+        """The public call a user makes: forward + backward through the autograd Function(s)."""
+        student.grad = None
+        if world == 1:
+            loss = kd.loca_kl(teacher, student, labels, T_KD, alpha=ALPHA, mode=mode)
+            loss.backward()
+        elif mode == "reference":
+            loss, grad = sharded.loca_kl_token_sharded(teacher, student.detach(), labels, T_KD, ALPHA, phases=phases)
+            student.grad = grad
+        else:
+            loss = sharded.per_row_token_sharded(kd.loca_kl, teacher, student, labels, T_KD, alpha=ALPHA, mode="per_row")
+            loss.backward()
+        return loss
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        sync_all()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = ms_total.item() / args.steps
+    value = n_total / (ms_step / 1e3)
+    loss_value = float(loss.item())
+
+    # ---- dominant kernel (phase C / emit) timed alone with CUDA events on its launch stream ------------
+    roof = None
+    side = {}
+    if rank == 0:
+        esize = 2
+        if mode == "reference":
+            rec, lse2_t, _ = phases.teacher_stats(teacher, labels, T_KD, ALPHA, V)
+            table, consts = phases.build_table(rec, V)
+            inv_norm = 1.0 / (float(N) * V)
+
+            def emit():
+                return phases.emit(teacher, student.detach(), lse2_t, table, consts, T_KD, 1e-8, inv_norm, None)
+
+            def stats():
+                return phases.teacher_stats(teacher, labels, T_KD, ALPHA, V)
+            for _ in range(3):
+                emit(); stats()
+            torch.cuda.synchronize()
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            k = max(args.steps // 2, 5)
+            a.record()
+            for _ in range(k):
+                emit()
+            b.record()
+            for _ in range(k):
+                stats()
+            c.record()
+            torch.cuda.synchronize()
+            emit_ms, stats_ms = a.elapsed_time(b) / k, b.elapsed_time(c) / k
+            emit_bytes = 3 * esize * V * N            # read teacher + read student + write grad
+            achieved = emit_bytes / (emit_ms / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": "LoCa emit (phase C: q/Q_r/loss/grad)", "achieved": achieved, "peak": peak_gbs,
+                    "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_token": 3 * esize * V, "kernel_ms": emit_ms}
+            side["teacher_stats"] = {"kernel_ms": stats_ms, "achieved_gbs": esize * V * N / (stats_ms / 1e3) / 1e9,
+                                     "frac": esize * V * N / (stats_ms / 1e3) / 1e9 / peak_gbs,
+                                     "algorithmic_bytes_per_token": esize * V}
+            step_bytes = 4 * esize * V * N
+        else:
+            step_bytes = 3 * esize * V * N
+            achieved = step_bytes / (ms_step / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": "LoCa per-row fused emit", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                    "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_token": 3 * esize * V, "kernel_ms": ms_step}
+        side["whole_step"] = {"algorithmic_bytes_per_token": step_bytes // N,
+                              "achieved_gbs": step_bytes / (ms_step / 1e3) / 1e9,
+                              "frac": step_bytes / (ms_step / 1e3) / 1e9 / peak_gbs}
+
+    # ---- secondary paths (one GPU, rank 0): per_row LoCa, plain KL, InfoNCE, MSE -----------------------
+    if rank == 0 and not args.no_secondary:
+        def timeit(fn, k=10, w=3):
+            for _ in range(w):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(k):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / k
+
+        def fb(f):
+            def run():
+                student.grad = None
+                f().backward()
+            return run
+        other = "per_row" if mode == "reference" else "reference"
+        for name, f, byt in (
+            (f"loca_{other}", fb(lambda: kd.loca_kl(teacher, student, labels, T_KD, alpha=ALPHA, mode=other)), (6 if other == "per_row" else 8) * V * N),
+            ("kl_plain_T0.8", fb(lambda: kd.temperature_kl(teacher, student, 0.8)), 6 * V * N),
+        ):
+            ms = timeit(f, k=5, w=2)
+            side[name] = {"ms": ms, "tokens_per_s": N / (ms / 1e3), "achieved_gbs": byt / (ms / 1e3) / 1e9,
+                          "frac": byt / (ms / 1e3) / 1e9 / peak_gbs}
+        xs, xt = synthetic.vision_feature_batch(64, 729, 1152, device=dev)
+        xs.requires_grad_(True)
+
+        def nce():
+            xs.grad = None
+            kd.info_nce(xs, xt).backward()
+        ms = timeit(nce)
+        side["info_nce_64x729x1152"] = {"us": ms * 1e3, "achieved_gbs": 3 * xs.numel() * 2 / (ms / 1e3) / 1e9}
+        del xs, xt
+        ha = torch.randn(65_536, 3584, device=dev, dtype=torch.bfloat16).requires_grad_(True)
+        hb = torch.randn(65_536, 3584, device=dev, dtype=torch.bfloat16)
+
+        def mse():
+            ha.grad = None
+            kd.feature_mse(ha, hb).backward()
+        ms = timeit(mse)
+        side["feature_mse_65536x3584"] = {"ms": ms, "achieved_gbs": 6 * ha.numel() / (ms / 1e3) / 1e9,
+                                          "frac": 6 * ha.numel() / (ms / 1e3) / 1e9 / peak_gbs}
+        del ha, hb
+        torch.cuda.empty_cache()
+
+    # ---- end-to-end through the public API with HOST buffers ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ht = torch.empty((N, V), dtype=torch.bfloat16, pin_memory=True)
+        hs = torch.empty((N, V), dtype=torch.bfloat16, pin_memory=True)
+        hl = torch.empty((N,), dtype=torch.int64, pin_memory=True)
+        ht.copy_(teacher, non_blocking=True)
+        hs.copy_(student.detach(), non_blocking=True)
+        hl.copy_(labels, non_blocking=True)
+        torch.cuda.synchronize()
+        dt_, ds_, dl_ = torch.empty_like(teacher), torch.empty_like(teacher), torch.empty_like(labels)
+        ds_.requires_grad_(True)
+
+        def e2e_step():
+            dt_.copy_(ht, non_blocking=True)
+            ds_.data.copy_(hs, non_blocking=True)
+            dl_.copy_(hl, non_blocking=True)
+            ds_.grad = None
+            if world == 1 or mode != "reference":
+                l_ = kd.loca_kl(dt_, ds_, dl_, T_KD, alpha=ALPHA, mode=mode, n_total=n_total)
+                l_.backward()
+            else:
+                l_, g_ = sharded.loca_kl_token_sharded(dt_, ds_.detach(), dl_, T_KD, ALPHA, phases=phases)
+            return float(l_.item())          # device -> host read of the step's result
+
+        ke = max(2, min(args.steps, 5))
+        e2e_step()
+        sync_all()
+        e0.record()
+        for _ in range(ke):
+            e2e_step()
+        e1.record()
+        sync_all()
+        ms_e = torch.tensor([e0.elapsed_time(e1) / ke], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_total / (ms_e.item() / 1e3), "unit": "tokens/s", "ms_per_step": ms_e.item(),
+               "h2d_bytes_per_step": 2 * N * V * 2 + N * 8, "d2h_bytes_per_step": 4, "steps": ke,
+               "note": "pinned host logits + labels copied H2D every step, loss read back; per-GPU bytes"}
+        del ht, hs, hl, dt_, ds_, dl_
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            best, threads = cpu_reference_step_time(repeats=3, warmup=1)
+            cpu = {"value": CPU_SAMPLE_ROWS / best, "unit": "tokens/s", "cores": threads, "kind": "port",
+                   "sample": f"oracle/reference_port.py eager LoCa fwd+bwd, fp32, B=1,S={CPU_SAMPLE_ROWS},V={V} "
+                             f"(BASELINE configs[0]), best of 3 after 1 warm-up = {best:.3f} s on {cpu_model_name()}"}
+        launches_per_step = 9 if mode == "reference" else 4
+        out = {
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"LoCa logit-KD fwd+bwd, B=8,S=2048 ({N} rows/GPU), V={V}, T={T_KD}, alpha={ALPHA}",
+                       "mode": mode, "parallelism": f"token-sharded x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs (2 x 4.98 GB/GPU) exceed the 126 MB L2; no flush needed"},
+            "loss": loss_value, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks.summary(), "secondary": side,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,137 @@
+/*
+ * kd_b200.h — C ABI of the B200-native KD-loss library (libkd_b200.so).
+ *
+ * The reference (shayekh00/Knowledge_Distillation_for_Sensory_Substitution_in_Multimodal_Models) has no
+ * FFI layer: its boundary for this path is a set of Python methods on the KD LightningModule.  Each entry
+ * point below names the reference method it replaces (paths relative to the reference root; P1 =
+ * distillation/knowledge_distillation7b_double_trouble/phase1/OnlineKnowledgeDistillationLLavaOneVision.py,
+ * LG = distillation/knowledge_distillation7b_logit_based/..., FB = ..._feature_based/...,
+ * EV = evaluation/onevisionv3/...).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller unless stated;
+ *   - the library never allocates or frees device memory and never synchronises the device;
+ *   - every call takes the CUDA stream (a cudaStream_t passed as void*) and is graph-capture safe;
+ *   - return value 0 = success, otherwise a KD_ERR_* code; kd_last_error() gives a thread-local message;
+ *   - row-major 2-D tensors are described by (pointer, leading dimension in ELEMENTS).
+ */
+#ifndef KD_B200_H_
+#define KD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KD_B200_ABI_VERSION 1
+
+/* element types of logits / features (gradients are written in the same type as the student tensor) */
+enum { KD_DTYPE_BF16 = 0, KD_DTYPE_F16 = 1, KD_DTYPE_F32 = 2 };
+
+/* logit-KD variants */
+enum {
+    KD_LOCA_REFERENCE = 0, /* P1:141-194 as written: one override table shared by every row (P1:184-185)   */
+    KD_LOCA_PER_ROW   = 1, /* per-row calibration (the reference applied token by token and averaged)        */
+    KD_KL_PLAIN       = 2, /* F.kl_div(log_softmax(s/T), softmax(t/T)) * T^2 — P1:331-343, EV:261-273         */
+    KD_KL_LOG_TARGET  = 3  /* same call with log_target=True on a probability target — FB:206-219, LG:115-122 */
+};
+
+/* error codes */
+enum {
+    KD_OK = 0,
+    KD_ERR_INVALID_ARGUMENT = 1,
+    KD_ERR_UNSUPPORTED = 2,
+    KD_ERR_WORKSPACE_TOO_SMALL = 3,
+    KD_ERR_CUDA = 4
+};
+
+/* bits of the device status word written by the logit-KD kernels (kd_logit_kd_status_offset) */
+#define KD_STATUS_BAD_LABEL 1u /* a label outside [0, V): the reference raises (P1:166); loss/grad are NaN-poisoned */
+
+/* flags of kd_logit_kd_fwd_bwd / kd_loca_emit */
+#define KD_FLAG_NO_GRAD        1u /* forward only: do not write grad_student                                  */
+#define KD_FLAG_FORCE_STREAMING 2u /* use the general multi-sweep kernel even where the cluster kernel applies  */
+
+int kd_abi_version(void);
+const char* kd_last_error(void);
+
+/* Device properties the host side sizes its grids with (SM count, max active clusters ...). Host pointers. */
+int kd_device_info(int* sm_count, int* max_smem_per_block, int* cluster4_max_active, int* cluster8_max_active);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Logit KD — replaces compute_loca_loss (P1:141-194, LG:208-261; call sites P1:254, P1:258, LG:165), the KL
+ * term of compute_vision_loss (P1:331-343; call P1:251, EV:236) and of compute_loss (FB:206-219; call FB:165).
+ *
+ *   loss = T^2 * inv_norm * sum_{r,v} pointwise(q[r,v], sp[r,v])            (one float, *loss_out)
+ *   grad = upstream * T * inv_norm * (sp * Q_r - w)                          (written to grad_student)
+ *
+ * inv_norm = 1/(N*V) reproduces reduction='mean'; 1/B gives 'batchmean' (EV:130-136, P1:378-381).
+ * `upstream` (device scalar, may be NULL = 1) is the incoming grad_output folded into the same pass.
+ * teacher may have more columns than V (ld_t >= V) — the slice at P1:155 is a stride, not a copy.
+ * labels: int64 [n_rows], required for the LoCa variants, must lie in [0, V).
+ * loss_out: one float (rows are summed in double on the device before the final rounding); per-row sums
+ * are kept in the workspace (kd_logit_kd_rowaux_offset).
+ * ---------------------------------------------------------------------------------------------------- */
+int kd_logit_kd_workspace_bytes(int64_t n_rows, int64_t V, size_t* bytes);
+int kd_logit_kd_status_offset(int64_t n_rows, int64_t V, size_t* offset);   /* uint32 status word   */
+int kd_logit_kd_rowaux_offset(int64_t n_rows, int64_t V, size_t* offset);   /* float4[n_rows]: lse2_t, lse2_s, Q_r, row loss */
+
+int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s,
+                        const int64_t* labels, void* grad_student, int64_t ld_g, float* loss_out,
+                        void* workspace, size_t workspace_bytes, int64_t n_rows, int64_t V, int dtype,
+                        float T, float alpha, float eps, int variant, double inv_norm,
+                        const float* upstream, unsigned flags, void* stream);
+
+/* Phase-split entry points of the LoCa reference mode, for token-sharded execution (one exchange step):
+ *   A. kd_loca_teacher_stats : rows -> per-token records {label, v1, k, v2} (16 B each) + lse2_t
+ *   (caller all-gathers the records of every rank in global token order)
+ *   B. kd_loca_build_table   : all records -> the V-entry override table (last token wins; k pass after labels)
+ *   C. kd_loca_emit          : local rows + table -> loss partial (already scaled) + gradient
+ */
+typedef struct {
+    int32_t label;
+    float v1;      /* 1 - s * (sum tp - p_gt)   (P1:184 rhs) */
+    int32_t k;     /* runner-up class index      (P1:170-171) */
+    float v2;      /* s * p_k                    (P1:185 rhs) */
+} kd_token_record;
+
+int kd_loca_teacher_stats(const void* teacher, int64_t ld_t, const int64_t* labels, kd_token_record* records,
+                          float* lse2_t, uint32_t* status, int64_t n_rows, int64_t V, int dtype, float T,
+                          float alpha, void* stream);
+int kd_loca_table_workspace_bytes(int64_t V, size_t* bytes);
+int kd_loca_build_table(const kd_token_record* records_all, int64_t n_tokens_all, int64_t V, float* table,
+                        double* table_consts /* [2]: sum xlogy(ov,ov), sum ov */, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const float* lse2_t,
+                 const float* table, const double* table_consts, void* grad_student, int64_t ld_g,
+                 float* loss_out, void* rowaux /* float4[n_rows] */, int64_t n_rows, int64_t V, int dtype,
+                 float T, float eps, double inv_norm, const float* upstream, unsigned flags, void* stream);
+
+/* grad *= (*factor) in place, skipped on device when *factor == 1 (autograd backward with grad_output != 1). */
+int kd_scale_rows(void* grad, int64_t ld_g, int64_t n_rows, int64_t V, int dtype, const float* factor, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * InfoNCE — replaces the pooling at P1:243-248 plus contrastive_loss (P1:393-416; calls P1:345, FB:162).
+ *   pooled[m,:] = normalize(mean_p x[m,p,:])   (tokens == 1 treats x as already [M, D])
+ *   loss = mean_m( logsumexp_j(us[m].ut[j]/temp) - us[m].ut[m]/temp )
+ * ---------------------------------------------------------------------------------------------------- */
+int kd_info_nce_workspace_bytes(int64_t M, int64_t tokens, int64_t D, size_t* bytes);
+int kd_info_nce_fwd_bwd(const void* student, const void* teacher, void* grad_student, float* loss_out,
+                        void* workspace, size_t workspace_bytes, int64_t M, int64_t tokens, int64_t D,
+                        int dtype, float temperature, const float* upstream, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Feature MSE — replaces mse_loss (EV:160-165): mean((input.float() - target.float())^2) and
+ * grad_input = upstream * 2 (a - b) / numel, written in input's dtype.
+ * ---------------------------------------------------------------------------------------------------- */
+int kd_feature_mse_workspace_bytes(int64_t numel, size_t* bytes);
+int kd_feature_mse_fwd_bwd(const void* input, const void* target, void* grad_input, float* loss_out,
+                           void* workspace, size_t workspace_bytes, int64_t numel, int dtype,
+                           const float* upstream, unsigned flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KD_B200_H_ */

@@ -1,0 +1,114 @@
+// feature_mse.cu — feature-distillation MSE, replaces mse_loss (EV:160-165 of the reference):
+//   loss = mean((input.float() - target.float())^2),  grad_input = upstream * 2 (a - b) / numel.
+// One streaming pass: 2 reads + 1 write per element (6 B/element in bf16), HBM-bound.
+#include "kd_common.cuh"
+
+namespace kd {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 148 * 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+mse_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ g, int64_t numel, float gscale,
+           const float* upstream, bool want_grad, bool vec, double* __restrict__ partials) {
+    constexpr int P = Elem<T>::kPack;
+    __shared__ double sh[kThreads / 32];
+    const float gs = gscale * (upstream ? *upstream : 1.f);
+    float acc = 0.f;          // per-thread fp32 partial over <= a few thousand terms, then double
+    double dacc = 0.0;
+    const int64_t nvec = vec ? numel / P : 0;
+    const uint4* av = reinterpret_cast<const uint4*>(a);
+    const uint4* bv = reinterpret_cast<const uint4*>(b);
+    uint4* gv = reinterpret_cast<uint4*>(g);
+    int since = 0;
+    for (int64_t v = blockIdx.x * (int64_t)kThreads + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * kThreads) {
+        float x[P], y[P], o[P];
+        Elem<T>::unpack(ldg_stream(av + v), x);
+        Elem<T>::unpack(ldg_stream(bv + v), y);
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const float d = x[i] - y[i];
+            acc = fmaf(d, d, acc);
+            o[i] = gs * d;
+        }
+        if (want_grad) stg_stream(gv + v, Elem<T>::pack(o));
+        if (++since == 64) { dacc += acc; acc = 0.f; since = 0; }
+    }
+    for (int64_t c = nvec * P + blockIdx.x * (int64_t)kThreads + threadIdx.x; c < numel; c += (int64_t)gridDim.x * kThreads) {
+        const float d = Elem<T>::to_float(a[c]) - Elem<T>::to_float(b[c]);
+        acc = fmaf(d, d, acc);
+        if (want_grad) g[c] = Elem<T>::from_float(gs * d);
+    }
+    dacc += acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = dacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < kThreads / 32; ++i) t += sh[i];
+        partials[blockIdx.x] = t;
+    }
+}
+
+__global__ void mse_finalize_kernel(const double* __restrict__ partials, int n, double inv_numel, float* __restrict__ loss) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) a += partials[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (threadIdx.x == 0) *loss = static_cast<float>(a * inv_numel);
+}
+
+template <typename T>
+int launch(const void* a, const void* b, void* g, float* loss, double* partials, int64_t numel, const float* upstream,
+           unsigned flags, cudaStream_t st) {
+    constexpr int P = Elem<T>::kPack;
+    const bool want_grad = !(flags & KD_FLAG_NO_GRAD);
+    const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                       (want_grad ? reinterpret_cast<uintptr_t>(g) : 0)) & 15u) == 0;
+    int64_t blocks = (numel / P + kThreads - 1) / kThreads;
+    if (blocks < 1) blocks = 1;
+    if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+    mse_kernel<T><<<(int)blocks, kThreads, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b), static_cast<T*>(g),
+                                                    numel, static_cast<float>(2.0 / (double)numel), upstream, want_grad, vec,
+                                                    partials);
+    KD_CHECK_LAUNCH("mse_kernel");
+    mse_finalize_kernel<<<1, 32, 0, st>>>(partials, (int)blocks, 1.0 / (double)numel, loss);
+    KD_CHECK_LAUNCH("mse_finalize_kernel");
+    return KD_OK;
+}
+
+}  // namespace
+}  // namespace kd
+
+extern "C" {
+
+int kd_feature_mse_workspace_bytes(int64_t numel, size_t* bytes) {
+    KD_CHECK_ARG(bytes != nullptr && numel >= 0, "kd_feature_mse_workspace_bytes: bad arguments");
+    *bytes = sizeof(double) * kd::kMaxBlocks;
+    return KD_OK;
+}
+
+int kd_feature_mse_fwd_bwd(const void* input, const void* target, void* grad_input, float* loss_out, void* workspace,
+                           size_t workspace_bytes, int64_t numel, int dtype, const float* upstream, unsigned flags,
+                           void* stream) {
+    KD_CHECK_ARG(input && target && loss_out && workspace, "kd_feature_mse_fwd_bwd: null pointer");
+    KD_CHECK_ARG((flags & KD_FLAG_NO_GRAD) || grad_input, "kd_feature_mse_fwd_bwd: grad_input is null");
+    KD_CHECK_ARG(numel > 0, "kd_feature_mse_fwd_bwd: numel must be positive (mean of an empty tensor is undefined)");
+    KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
+    if (workspace_bytes < sizeof(double) * kd::kMaxBlocks) {
+        kd::set_error("kd_feature_mse_fwd_bwd: workspace %zu < %zu bytes", workspace_bytes, sizeof(double) * kd::kMaxBlocks);
+        return KD_ERR_WORKSPACE_TOO_SMALL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* partials = static_cast<double*>(workspace);
+    switch (dtype) {
+        case KD_DTYPE_BF16: return kd::launch<__nv_bfloat16>(input, target, grad_input, loss_out, partials, numel, upstream, flags, st);
+        case KD_DTYPE_F16: return kd::launch<__half>(input, target, grad_input, loss_out, partials, numel, upstream, flags, st);
+        default: return kd::launch<float>(input, target, grad_input, loss_out, partials, numel, upstream, flags, st);
+    }
+}
+
+}  // extern "C"

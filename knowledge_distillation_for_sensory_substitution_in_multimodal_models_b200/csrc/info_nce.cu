@@ -1,0 +1,277 @@
+// info_nce.cu — vision-level contrastive loss: replaces the pooling at P1:243-248 and contrastive_loss
+// (P1:393-416; copies LG:307-330, FB:288-311, EV:327-350) of the reference.
+//
+//   u_s[m] = normalize(mean_p x_s[m,p,:]), u_t likewise (eps 1e-12; normalising twice == once)
+//   L = u_s u_t^T / temp ; loss = mean_m( logsumexp_j L[m,j] - L[m,m] )
+//   G = (softmax(L) - I)/M ; du = G u_t / temp ; dmean = (du - (du.u_s) u_s)/|mean| ; dx[m,p,:] = dmean[m,:]/P
+//
+// Three launches: pool+normalise (HBM-bound, the only pass that touches the [M,P,D] tensors), one CTA per
+// similarity row for logits -> log-softmax -> gradient row, and the broadcast write of dx.
+#include "kd_common.cuh"
+
+namespace kd {
+namespace {
+
+constexpr int kPoolThreads = 512;
+constexpr int kRowThreads = 256;
+constexpr float kNormEps = 1e-12f;   // F.normalize default
+
+// ---- pool + normalise: one CTA per (image, tensor) ---------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+pool_normalize_kernel(const T* __restrict__ xs, const T* __restrict__ xt, float* __restrict__ us, float* __restrict__ ut,
+                      float* __restrict__ norm_s, int M, int P, int D, bool vec) {
+    extern __shared__ float sm[];        // [groups][D] partial sums, then the pooled vector in sm[0..D)
+    __shared__ float red[kPoolThreads / 32];
+    constexpr int E = Elem<T>::kPack;
+    const int m = blockIdx.x % M;
+    const bool is_teacher = blockIdx.x >= M;
+    const T* x = (is_teacher ? xt : xs) + (int64_t)m * P * D;
+    float* u = (is_teacher ? ut : us) + (int64_t)m * D;
+
+    const int ncol = vec ? D / E : D;                       // column slots (vector or scalar)
+    const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
+    const int groups = kPoolThreads / lanes;                // row groups working on disjoint token subsets
+    const int col0 = threadIdx.x % lanes, grp = threadIdx.x / lanes;
+    for (int i = threadIdx.x; i < groups * D; i += kPoolThreads) sm[i] = 0.f;
+    __syncthreads();
+    if (grp < groups) {
+        for (int c = col0; c < ncol; c += lanes) {
+            if (vec) {
+                float acc[E];
+#pragma unroll
+                for (int i = 0; i < E; ++i) acc[i] = 0.f;
+#pragma unroll 4
+                for (int p = grp; p < P; p += groups) {
+                    float v[E];
+                    Elem<T>::unpack(ldg_stream(reinterpret_cast<const uint4*>(x + (int64_t)p * D) + c), v);
+#pragma unroll
+                    for (int i = 0; i < E; ++i) acc[i] += v[i];
+                }
+#pragma unroll
+                for (int i = 0; i < E; ++i) sm[grp * D + c * E + i] = acc[i];
+            } else {
+                float acc = 0.f;
+                for (int p = grp; p < P; p += groups) acc += Elem<T>::to_float(x[(int64_t)p * D + c]);
+                sm[grp * D + c] = acc;
+            }
+        }
+    }
+    __syncthreads();
+    float ss = 0.f;
+    const float invP = 1.f / (float)P;
+    for (int d = threadIdx.x; d < D; d += kPoolThreads) {
+        float a = 0.f;
+        for (int gI = 0; gI < groups; ++gI) a += sm[gI * D + d];
+        a *= invP;
+        ss = fmaf(a, a, ss);
+        sm[d] = a;        // safe: every thread only rewrites the columns it just summed (group 0 slot)
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < kPoolThreads / 32; ++i) tot += red[i];
+    const float nrm = sqrtf(tot);
+    const float inv = 1.f / fmaxf(nrm, kNormEps);
+    for (int d = threadIdx.x; d < D; d += kPoolThreads) u[d] = sm[d] * inv;
+    if (!is_teacher && threadIdx.x == 0) norm_s[m] = nrm;
+}
+
+// ---- one similarity row per CTA: logits, log-softmax, gradient w.r.t. the pooled student vector -----
+__global__ void __launch_bounds__(kRowThreads)
+similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut, const float* __restrict__ norm_s,
+                      float* __restrict__ dmean, float* __restrict__ rowloss, int M, int D, float inv_temp,
+                      float inv_tokens /* 1/P */, const float* upstream, bool want_grad) {
+    extern __shared__ float sm[];   // [D] u_s row | [M] logits / G row
+    float* su = sm;
+    float* sl = sm + D;
+    __shared__ float red[kRowThreads / 32];
+    __shared__ float bc[2];
+    const int i = blockIdx.x;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    for (int d = threadIdx.x; d < D; d += kRowThreads) su[d] = us[(int64_t)i * D + d];
+    __syncthreads();
+    for (int j = w; j < M; j += kRowThreads / 32) {
+        const float* t = ut + (int64_t)j * D;
+        float acc = 0.f;
+        for (int d = l; d < D; d += 32) acc = fmaf(su[d], t[d], acc);
+        acc = warp_sum(acc);
+        if (l == 0) sl[j] = acc * inv_temp;
+    }
+    __syncthreads();
+    // log-sum-exp over the row
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < M; j += kRowThreads) mx = fmaxf(mx, sl[j]);
+    mx = warp_max(mx);
+    if (l == 0) red[w] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int k = 1; k < kRowThreads / 32; ++k) mx = fmaxf(mx, red[k]);
+    __syncthreads();
+    float se = 0.f;
+    for (int j = threadIdx.x; j < M; j += kRowThreads) se += __expf(sl[j] - mx);
+    se = warp_sum(se);
+    if (l == 0) red[w] = se;
+    __syncthreads();
+    se = 0.f;
+    for (int k = 0; k < kRowThreads / 32; ++k) se += red[k];
+    const float lse = mx + logf(se);
+    if (threadIdx.x == 0) rowloss[i] = lse - sl[i];
+    if (!want_grad) return;
+    __syncthreads();
+    // G row: (softmax - onehot)/M, folded with 1/temp
+    for (int j = threadIdx.x; j < M; j += kRowThreads) {
+        const float pj = __expf(sl[j] - lse);
+        sl[j] = (pj - (j == i ? 1.f : 0.f)) * inv_temp / (float)M;
+    }
+    __syncthreads();
+    // du[d] = sum_j G[j] * ut[j,d]  (coalesced over d; ut is L2 resident)
+    const float nrm = norm_s[i];
+    float dots = 0.f;
+    for (int d = threadIdx.x; d < D; d += kRowThreads) {
+        float acc = 0.f;
+        for (int j = 0; j < M; ++j) acc = fmaf(sl[j], ut[(int64_t)j * D + d], acc);
+        dots = fmaf(acc, su[d], dots);
+        dmean[(int64_t)i * D + d] = acc;
+    }
+    dots = warp_sum(dots);
+    if (l == 0) red[w] = dots;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < kRowThreads / 32; ++k) t += red[k];
+        bc[0] = t;
+    }
+    __syncthreads();
+    const float dot = (nrm > kNormEps) ? bc[0] : 0.f;      // below eps normalize() is a plain scaling
+    const float sc = inv_tokens * (upstream ? *upstream : 1.f) / fmaxf(nrm, kNormEps);
+    for (int d = threadIdx.x; d < D; d += kRowThreads) {
+        const float du = dmean[(int64_t)i * D + d];
+        dmean[(int64_t)i * D + d] = (du - dot * su[d]) * sc;
+    }
+}
+
+__global__ void nce_finalize_kernel(const float* __restrict__ rowloss, int M, float* __restrict__ loss) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < M; i += 32) a += (double)rowloss[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (threadIdx.x == 0) *loss = static_cast<float>(a / (double)M);
+}
+
+// ---- dx[m,p,:] = dmean[m,:] -----------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P, int D, bool vec) {
+    constexpr int E = Elem<T>::kPack;
+    const int m = blockIdx.y;
+    const float* src = dmean + (int64_t)m * D;
+    T* dst = dx + (int64_t)m * P * D;
+    if (vec) {
+        const int ncol = D / E;
+        const int64_t total = (int64_t)P * ncol;
+        for (int64_t idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+            const int c = (int)(idx % ncol);
+            float v[E];
+#pragma unroll
+            for (int i = 0; i < E; ++i) v[i] = src[c * E + i];
+            stg_stream(reinterpret_cast<uint4*>(dst) + idx, Elem<T>::pack(v));
+        }
+    } else {
+        const int64_t total = (int64_t)P * D;
+        for (int64_t idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256)
+            dst[idx] = Elem<T>::from_float(src[idx % D]);
+    }
+}
+
+struct NceWorkspace { size_t us, ut, norm_s, dmean, rowloss, total; };
+NceWorkspace nce_layout(int64_t M, int64_t D) {
+    NceWorkspace w{};
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
+    w.us = take(sizeof(float) * M * D);
+    w.ut = take(sizeof(float) * M * D);
+    w.norm_s = take(sizeof(float) * M);
+    w.dmean = take(sizeof(float) * M * D);
+    w.rowloss = take(sizeof(float) * M);
+    w.total = off;
+    return w;
+}
+
+template <typename T>
+int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const NceWorkspace& w, int M, int P, int D,
+        float temperature, const float* upstream, unsigned flags, cudaStream_t st) {
+    constexpr int E = Elem<T>::kPack;
+    const bool want_grad = !(flags & KD_FLAG_NO_GRAD);
+    float* us = reinterpret_cast<float*>(ws + w.us);
+    float* ut = reinterpret_cast<float*>(ws + w.ut);
+    float* norm_s = reinterpret_cast<float*>(ws + w.norm_s);
+    float* dmean = reinterpret_cast<float*>(ws + w.dmean);
+    float* rowloss = reinterpret_cast<float*>(ws + w.rowloss);
+    const bool vec_in = (D % E == 0) && ((reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(xt)) & 15u) == 0;
+    {
+        const int ncol = vec_in ? D / E : D;
+        const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
+        const size_t smem = sizeof(float) * (size_t)(kPoolThreads / lanes) * D;
+        KD_CHECK_ARG(smem <= 200 * 1024, "info_nce: feature dimension %d too large for the pooling kernel", D);
+        auto kfn = pool_normalize_kernel<T>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kfn<<<2 * M, kPoolThreads, smem, st>>>(static_cast<const T*>(xs), static_cast<const T*>(xt), us, ut, norm_s, M, P, D, vec_in);
+        KD_CHECK_LAUNCH("pool_normalize_kernel");
+    }
+    {
+        const size_t smem = sizeof(float) * ((size_t)D + M);
+        KD_CHECK_ARG(smem <= 220 * 1024, "info_nce: M + D = %d floats exceed shared memory (tensor-core path not built yet)", M + D);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(similarity_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        similarity_row_kernel<<<M, kRowThreads, smem, st>>>(us, ut, norm_s, dmean, rowloss, M, D, 1.f / temperature,
+                                                            1.f / (float)P, upstream, want_grad);
+        KD_CHECK_LAUNCH("similarity_row_kernel");
+    }
+    nce_finalize_kernel<<<1, 32, 0, st>>>(rowloss, M, loss);
+    KD_CHECK_LAUNCH("nce_finalize_kernel");
+    if (want_grad) {
+        const bool vec_out = (D % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
+        int bx = (int)(((int64_t)P * (D / (vec_out ? E : 1)) + 255) / 256);
+        if (bx > 64) bx = 64;
+        if (bx < 1) bx = 1;
+        broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out);
+        KD_CHECK_LAUNCH("broadcast_rows_kernel");
+    }
+    return KD_OK;
+}
+
+}  // namespace
+}  // namespace kd
+
+extern "C" {
+
+int kd_info_nce_workspace_bytes(int64_t M, int64_t tokens, int64_t D, size_t* bytes) {
+    KD_CHECK_ARG(bytes != nullptr && M >= 1 && tokens >= 1 && D >= 1, "kd_info_nce_workspace_bytes: bad arguments");
+    *bytes = kd::nce_layout(M, D).total;
+    return KD_OK;
+}
+
+int kd_info_nce_fwd_bwd(const void* student, const void* teacher, void* grad_student, float* loss_out, void* workspace,
+                        size_t workspace_bytes, int64_t M, int64_t tokens, int64_t D, int dtype, float temperature,
+                        const float* upstream, unsigned flags, void* stream) {
+    KD_CHECK_ARG(student && teacher && loss_out && workspace, "kd_info_nce_fwd_bwd: null pointer");
+    KD_CHECK_ARG((flags & KD_FLAG_NO_GRAD) || grad_student, "kd_info_nce_fwd_bwd: grad_student is null");
+    KD_CHECK_ARG(M >= 1 && tokens >= 1 && D >= 1 && M < (1 << 20) && D < (1 << 20) && tokens < (1 << 24), "kd_info_nce_fwd_bwd: bad shape");
+    KD_CHECK_ARG(temperature > 0.f, "temperature must be positive");
+    KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
+    const kd::NceWorkspace w = kd::nce_layout(M, D);
+    if (workspace_bytes < w.total) {
+        kd::set_error("kd_info_nce_fwd_bwd: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return KD_ERR_WORKSPACE_TOO_SMALL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    switch (dtype) {
+        case KD_DTYPE_BF16: return kd::run<__nv_bfloat16>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st);
+        case KD_DTYPE_F16: return kd::run<__half>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st);
+        default: return kd::run<float>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// kd_common.cuh — device helpers shared by the KD-loss kernels (sm_100a).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kd_b200.h"
+
+namespace kd {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kWarp = 32;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (host)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define KD_CHECK_ARG(cond, ...)                      \
+    do {                                             \
+        if (!(cond)) {                               \
+            ::kd::set_error(__VA_ARGS__);            \
+            return KD_ERR_INVALID_ARGUMENT;          \
+        }                                            \
+    } while (0)
+
+#define KD_CHECK_LAUNCH(what)                                         \
+    do {                                                              \
+        cudaError_t e__ = cudaGetLastError();                         \
+        if (e__ != cudaSuccess) return ::kd::cuda_fail(e__, what);    \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// fast math
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2(float x) {   // MUFU.EX2, flush-to-zero; ex2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// packed fp32x2 FMA (Blackwell FFMA2): halves the issue slots of the scale-and-shift step
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+    unsigned long long a, bb, cc, d;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(bb) : "f"(b), "f"(b));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(cc) : "f"(c), "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 16-byte vector access for the three element types: a "pack" is what one 128-bit access moves
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<__nv_bfloat16> {
+    static constexpr int kPack = 8;
+    static __device__ __forceinline__ void unpack(const uint4& v, float (&x)[8]) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            x[2 * i] = __uint_as_float(w[i] << 16);
+            x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&x)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    static __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct Elem<__half> {
+    static constexpr int kPack = 8;
+    static __device__ __forceinline__ void unpack(const uint4& v, float (&x)[8]) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            x[2 * i] = f.x;
+            x[2 * i + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&x)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    static __device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_float(float v) { return __float2half_rn(v); }
+};
+template <> struct Elem<float> {
+    static constexpr int kPack = 4;
+    static __device__ __forceinline__ void unpack(const uint4& v, float (&x)[4]) {
+        x[0] = __uint_as_float(v.x);
+        x[1] = __uint_as_float(v.y);
+        x[2] = __uint_as_float(v.z);
+        x[3] = __uint_as_float(v.w);
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&x)[4]) {
+        return make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+    }
+    static __device__ __forceinline__ float to_float(float v) { return v; }
+    static __device__ __forceinline__ float from_float(float v) { return v; }
+};
+
+// streaming 128-bit global accesses
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {          // read-once data: do not pollute L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_keep(const void* p) {            // data re-read shortly (L2 resident)
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {  // write-once data
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// running (max, sum of 2^((x-max)*k2)) pair in the raw-logit domain
+struct MaxSum {
+    float m, s;
+    __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
+    __device__ __forceinline__ void merge(float om, float os, float k2) {
+        float nm = fmaxf(m, om);
+        float a = (m == -INFINITY) ? 0.f : s * ex2((m - nm) * k2);
+        float b = (om == -INFINITY) ? 0.f : os * ex2((om - nm) * k2);
+        m = nm;
+        s = a + b;
+    }
+};
+__device__ __forceinline__ void warp_merge(MaxSum& v, float k2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float om = __shfl_xor_sync(0xffffffffu, v.m, o);
+        float os = __shfl_xor_sync(0xffffffffu, v.s, o);
+        v.merge(om, os, k2);
+    }
+}
+
+// best / runner-up with "largest value, lowest index" ordering (our topk tie rule)
+struct Top2 {
+    float a1, a2;
+    int i1, i2;
+    __device__ __forceinline__ void init() { a1 = a2 = -INFINITY; i1 = i2 = 0x7fffffff; }
+    static __device__ __forceinline__ bool before(float va, int ia, float vb, int ib) {
+        return va > vb || (va == vb && ia < ib);
+    }
+    __device__ __forceinline__ void push(float v, int i) {
+        if (before(v, i, a1, i1)) { a2 = a1; i2 = i1; a1 = v; i1 = i; }
+        else if (before(v, i, a2, i2)) { a2 = v; i2 = i; }
+    }
+    __device__ __forceinline__ void merge(const Top2& o) { push(o.a1, o.i1); push(o.a2, o.i2); }
+};
+__device__ __forceinline__ void warp_merge(Top2& t) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Top2 p;
+        p.a1 = __shfl_xor_sync(0xffffffffu, t.a1, o);
+        p.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
+        p.a2 = __shfl_xor_sync(0xffffffffu, t.a2, o);
+        p.i2 = __shfl_xor_sync(0xffffffffu, t.i2, o);
+        t.merge(p);
+    }
+}
+
+}  // namespace kd

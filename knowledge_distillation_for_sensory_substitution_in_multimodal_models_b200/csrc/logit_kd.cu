@@ -1,0 +1,675 @@
+// logit_kd.cu — logit-KD kernels, general streaming path, and the C ABI of the logit-KD family.
+//
+// Replaces compute_loca_loss (P1:141-194 / LG:208-261), the KL term of compute_vision_loss (P1:331-343)
+// and of compute_loss (FB:206-219) of the reference.  Layout: row-major [n_rows, V] logits (bf16 / f16 / f32),
+// one token row per CTA iteration.  Kernels in this file read their rows straight from global memory in three
+// sweeps (stats -> accumulate -> emit); logit_kd_cluster.cu keeps the row pair resident in the distributed
+// shared memory of a thread-block cluster so that HBM sees every byte once.
+#include <math.h>
+
+#include "logit_kd.cuh"
+
+namespace kd {
+
+namespace {
+
+constexpr int kStatsThreads = 256;
+constexpr int kEmitThreads = 512;
+constexpr int kMaxWarps = 32;
+
+template <typename T>
+__device__ __forceinline__ bool aligned16(const T* p) {
+    return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide merges (results valid in every thread)
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ MaxSum block_merge(MaxSum v, float k2, float* sm /* 2*kMaxWarps */) {
+    warp_merge(v, k2);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) { sm[w] = v.m; sm[kMaxWarps + w] = v.s; }
+    __syncthreads();
+    MaxSum r;
+    r.init();
+    if (l < NT / 32) { r.m = sm[l]; r.s = sm[kMaxWarps + l]; }
+    warp_merge(r, k2);
+    return r;
+}
+
+template <int NT>
+__device__ __forceinline__ Top2 block_merge(Top2 t, float* smf /* 2*kMaxWarps */, int* smi /* 2*kMaxWarps */) {
+    warp_merge(t);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) { smf[w] = t.a1; smf[kMaxWarps + w] = t.a2; smi[w] = t.i1; smi[kMaxWarps + w] = t.i2; }
+    __syncthreads();
+    Top2 r;
+    r.init();
+    if (l < NT / 32) { r.a1 = smf[l]; r.a2 = smf[kMaxWarps + l]; r.i1 = smi[l]; r.i2 = smi[kMaxWarps + l]; }
+    warp_merge(r);
+    return r;
+}
+
+template <int NT>
+__device__ __forceinline__ float2 block_sum2(float x, float y, float* sm /* 2*kMaxWarps */) {
+    x = warp_sum(x);
+    y = warp_sum(y);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) { sm[w] = x; sm[kMaxWarps + w] = y; }
+    __syncthreads();
+    float a = (l < NT / 32) ? sm[l] : 0.f;
+    float b = (l < NT / 32) ? sm[kMaxWarps + l] : 0.f;
+    return make_float2(warp_sum(a), warp_sum(b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-thread running statistics over a strided share of one row
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool VEC, int NT, bool WANT_TOP2>
+__device__ __forceinline__ void row_stats(const T* __restrict__ row, int V, float k2, MaxSum& ms, Top2& top) {
+    constexpr int P = Elem<T>::kPack;
+    ms.init();
+    if (WANT_TOP2) top.init();
+    float mk2 = -INFINITY;     // ms.m * k2
+    int done = 0;
+    if (VEC) {
+        const int nvec = V / P;
+        const uint4* rv = reinterpret_cast<const uint4*>(row);
+#pragma unroll 2
+        for (int v = threadIdx.x; v < nvec; v += NT) {
+            float x[P];
+            Elem<T>::unpack(ldg_stream(rv + v), x);
+            float vm = x[0];
+#pragma unroll
+            for (int i = 1; i < P; ++i) vm = fmaxf(vm, x[i]);
+            if (vm > ms.m) {
+                ms.s *= ex2((ms.m - vm) * k2);
+                ms.m = vm;
+                mk2 = vm * k2;
+            }
+#pragma unroll
+            for (int i = 0; i < P; ++i) ms.s += ex2(fmaf(x[i], k2, -mk2));
+            if (WANT_TOP2 && vm > top.a2) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) top.push(x[i], v * P + i);
+            }
+        }
+        done = nvec * P;
+    }
+    for (int c = done + threadIdx.x; c < V; c += NT) {
+        const float x = Elem<T>::to_float(row[c]);
+        if (x > ms.m) {
+            ms.s *= ex2((ms.m - x) * k2);
+            ms.m = x;
+            mk2 = x * k2;
+        }
+        ms.s += ex2(fmaf(x, k2, -mk2));
+        if (WANT_TOP2) top.push(x, c);
+    }
+}
+
+__device__ __forceinline__ float lse2_of(const MaxSum& ms, float k2) { return fmaf(ms.m, k2, log2f(ms.s)); }
+
+// ------------------------------------------------------------------------------------------------
+// Phase A of the LoCa reference mode: teacher row -> token record {label, v1, k, v2} and lse2_t
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kStatsThreads)
+teacher_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const int64_t* __restrict__ labels,
+                     kd_token_record* __restrict__ rec, float* __restrict__ lse2_t, uint32_t* status,
+                     int64_t n_rows, int V, float k2, float alpha) {
+    __shared__ float smf[2 * kMaxWarps];
+    __shared__ int smi[2 * kMaxWarps];
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const T* row = teacher + r * ld_t;
+        MaxSum ms;
+        Top2 top;
+        row_stats<T, VEC, kStatsThreads, true>(row, V, k2, ms, top);
+        ms = block_merge<kStatsThreads>(ms, k2, smf);
+        top = block_merge<kStatsThreads>(top, smf, smi);
+        if (threadIdx.x == 0) {
+            const float l2 = lse2_of(ms, k2);
+            const int64_t lab = labels[r];
+            kd_token_record out;
+            if (lab < 0 || lab >= V) {
+                atomicOr(status, KD_STATUS_BAD_LABEL);
+                out.label = -1;
+                out.v1 = __int_as_float(0x7fc00000);
+                out.k = top.i2;
+                out.v2 = __int_as_float(0x7fc00000);
+            } else {
+                float v1, v2;
+                loca_scalars(Elem<T>::to_float(row[lab]), top.a2, l2, k2, alpha, v1, v2);
+                out.label = static_cast<int>(lab);
+                out.v1 = v1;
+                out.k = (V > 1) ? top.i2 : 0;
+                out.v2 = v2;
+            }
+            rec[r] = out;
+            lse2_t[r] = l2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// override table (P1:184-185): last token in flattened order wins; the k pass runs after the label pass
+// ------------------------------------------------------------------------------------------------
+__global__ void owner_init_kernel(int* own, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) own[i] = -1;
+}
+
+__global__ void owner_scatter_kernel(const kd_token_record* __restrict__ rec, int64_t n, int* own_l, int* own_k, int V) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const kd_token_record t = rec[r];
+        if (t.label >= 0 && t.label < V) atomicMax(own_l + t.label, static_cast<int>(r));
+        if (t.k >= 0 && t.k < V) atomicMax(own_k + t.k, static_cast<int>(r));
+    }
+}
+
+constexpr int kTableThreads = 256;
+
+__global__ void __launch_bounds__(kTableThreads)
+table_fill_kernel(const kd_token_record* __restrict__ rec, const int* __restrict__ own_l, const int* __restrict__ own_k,
+                  int V, float* __restrict__ table, double* __restrict__ partials /* 2 * gridDim.x */) {
+    __shared__ double sh[2][kTableThreads / 32];
+    double xl = 0.0, sv = 0.0;
+    const int v = blockIdx.x * kTableThreads + threadIdx.x;
+    if (v < V) {
+        float ov = __int_as_float(0x7fc00000);
+        const int ok = own_k[v], ol = own_l[v];
+        if (ok >= 0) ov = rec[ok].v2;
+        else if (ol >= 0) ov = rec[ol].v1;
+        table[v] = ov;
+        if (ok >= 0 || ol >= 0) {
+            const double d = static_cast<double>(ov);
+            xl = (d == 0.0) ? 0.0 : d * log(d);
+            sv = d;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xl += __shfl_xor_sync(0xffffffffu, xl, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = xl; sh[1][threadIdx.x >> 5] = sv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < kTableThreads / 32; ++i) { a += sh[0][i]; b += sh[1][i]; }
+        partials[2 * blockIdx.x] = a;
+        partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
+__global__ void table_consts_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ consts) {
+    // one warp, fixed order -> deterministic
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 32) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (threadIdx.x == 0) { consts[0] = a; consts[1] = b; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// general streaming emit kernel: three sweeps over one row pair per CTA iteration
+// ------------------------------------------------------------------------------------------------
+template <int VARIANT, typename T, bool VEC>
+__global__ void __launch_bounds__(kEmitThreads)
+row_emit_stream_kernel(const EmitParams p) {
+    constexpr int P = Elem<T>::kPack;
+    constexpr int NT = kEmitThreads;
+    constexpr bool LOCA = (VARIANT == KD_LOCA_REFERENCE || VARIANT == KD_LOCA_PER_ROW);
+    __shared__ float smf[2 * kMaxWarps];
+    __shared__ int smi[2 * kMaxWarps];
+
+    const float NaN = __int_as_float(0x7fc00000);
+    const int V = p.V;
+    const float k2 = p.k2, thr2 = p.thr2;
+    const float up = p.upstream ? *p.upstream : 1.f;
+    const float g = p.gscale * up;
+    const bool want_grad = !(p.flags & KD_FLAG_NO_GRAD);
+    const int nvec = VEC ? V / P : 0;
+
+    for (int64_t r = blockIdx.x; r < p.n_rows; r += gridDim.x) {
+        const T* trow = static_cast<const T*>(p.teacher) + r * p.ld_t;
+        const T* srow = static_cast<const T*>(p.student) + r * p.ld_s;
+        T* grow = static_cast<T*>(p.grad) + r * p.ld_g;
+        const uint4* tv = reinterpret_cast<const uint4*>(trow);
+        const uint4* sv = reinterpret_cast<const uint4*>(srow);
+
+        // ---- sweep A: softmax statistics ------------------------------------------------------
+        MaxSum ms_s;
+        Top2 top;
+        row_stats<T, VEC, NT, false>(srow, V, k2, ms_s, top);
+        ms_s = block_merge<NT>(ms_s, k2, smf);
+        const float lse2_s = lse2_of(ms_s, k2);
+        float lse2_t;
+        int ov_label = -1, ov_k = -1;     // per-row override columns
+        float v1 = NaN, v2 = NaN;
+        if constexpr (VARIANT == KD_LOCA_REFERENCE) {
+            lse2_t = p.lse2_t_in[r];
+        } else {
+            MaxSum ms_t;
+            row_stats<T, VEC, NT, VARIANT == KD_LOCA_PER_ROW>(trow, V, k2, ms_t, top);
+            ms_t = block_merge<NT>(ms_t, k2, smf);
+            lse2_t = lse2_of(ms_t, k2);
+            if constexpr (VARIANT == KD_LOCA_PER_ROW) {
+                top = block_merge<NT>(top, smf, smi);
+                const int64_t lab = p.labels[r];
+                if (lab < 0 || lab >= V) {
+                    if (threadIdx.x == 0) atomicOr(p.status, KD_STATUS_BAD_LABEL);
+                } else {
+                    ov_label = static_cast<int>(lab);
+                    ov_k = (V > 1) ? top.i2 : 0;
+                    loca_scalars(Elem<T>::to_float(trow[lab]), top.a2, lse2_t, k2, p.alpha, v1, v2);
+                }
+            }
+        }
+
+        auto override_of = [&](int c) -> float {
+            if constexpr (VARIANT == KD_LOCA_REFERENCE) return __ldg(p.table + c);
+            if constexpr (VARIANT == KD_LOCA_PER_ROW) return (c == ov_k) ? v2 : ((c == ov_label) ? v1 : NaN);
+            return NaN;
+        };
+
+        // ---- sweep B: Q_r and the row sum ---------------------------------------------------------
+        float row = 0.f, Q = 0.f;
+        if (VEC) {
+#pragma unroll 2
+            for (int v = threadIdx.x; v < nvec; v += NT) {
+                float xt[P], xs[P];
+                Elem<T>::unpack(ldg_keep(tv + v), xt);
+                Elem<T>::unpack(ldg_keep(sv + v), xs);
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+                    PointTerm<VARIANT>::accum(xt[i], xs[i], LOCA ? override_of(v * P + i) : NaN, k2, lse2_t, lse2_s, thr2, row, Q);
+            }
+        }
+        for (int c = nvec * P + threadIdx.x; c < V; c += NT)
+            PointTerm<VARIANT>::accum(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]), LOCA ? override_of(c) : NaN,
+                                      k2, lse2_t, lse2_s, thr2, row, Q);
+        const float2 red = block_sum2<NT>(row, Q, smf);
+        row = red.x;
+        Q = red.y;
+        if constexpr (VARIANT == KD_LOCA_PER_ROW) {   // xlogy(v,v) of this row's own overridden cells, in log2 units
+            if (ov_label >= 0) {
+                if (ov_k != ov_label && v1 != 0.f) row += v1 * log2f(v1);
+                if (v2 != 0.f) row += v2 * log2f(v2);
+            } else {
+                row = NaN;
+            }
+        }
+        if (threadIdx.x == 0) p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row);
+        if (!want_grad) continue;
+
+        // ---- sweep C: gradient ----------------------------------------------------------------------
+        const float gQ = g * Q;
+        if (VEC) {
+            uint4* gv = reinterpret_cast<uint4*>(grow);
+#pragma unroll 2
+            for (int v = threadIdx.x; v < nvec; v += NT) {
+                float xt[P], xs[P], o[P];
+                Elem<T>::unpack(ldg_stream(tv + v), xt);
+                Elem<T>::unpack(ldg_stream(sv + v), xs);
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+                    o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? override_of(v * P + i) : NaN, k2, lse2_t, lse2_s, thr2, g, gQ);
+                stg_stream(gv + v, Elem<T>::pack(o));
+            }
+        }
+        for (int c = nvec * P + threadIdx.x; c < V; c += NT)
+            grow[c] = Elem<T>::from_float(PointTerm<VARIANT>::grad(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]),
+                                                                   LOCA ? override_of(c) : NaN, k2, lse2_t, lse2_s, thr2, g, gQ));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss finalisation: deterministic double sum of the per-row sums
+//   loss = T^2 * inv_norm * ( unit * sum_r row[r] + n_rows * table_const )
+// ------------------------------------------------------------------------------------------------
+constexpr int kFinalThreads = 1024;
+__global__ void __launch_bounds__(kFinalThreads)
+loss_finalize_kernel(const float4* __restrict__ rowaux, int64_t n_rows, double unit, double scale,
+                     const double* __restrict__ table_consts, const uint32_t* __restrict__ status, float* __restrict__ loss_out) {
+    __shared__ double sh[kFinalThreads / 32];
+    double acc = 0.0;
+    for (int64_t r = threadIdx.x; r < n_rows; r += kFinalThreads) acc += static_cast<double>(rowaux[r].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < kFinalThreads / 32; ++i) tot += sh[i];
+        tot *= unit;
+        if (table_consts) tot += static_cast<double>(n_rows) * table_consts[0];
+        float out = static_cast<float>(tot * scale);
+        if (status && (*status & KD_STATUS_BAD_LABEL)) out = __int_as_float(0x7fc00000);
+        *loss_out = out;
+    }
+}
+
+__global__ void status_clear_kernel(uint32_t* status) { *status = 0u; }
+
+// ------------------------------------------------------------------------------------------------
+// in-place scaling of a gradient (autograd backward with grad_output != 1)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) scale_rows_kernel(T* g, int64_t ld, int64_t n_rows, int64_t V, const float* factor) {
+    const float f = *factor;
+    if (f == 1.f) return;
+    constexpr int P = Elem<T>::kPack;
+    for (int64_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
+        T* row = g + r * ld;
+        const bool vec = aligned16(row);
+        const int64_t nvec = vec ? V / P : 0;
+        uint4* rv = reinterpret_cast<uint4*>(row);
+        for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < nvec; v += gridDim.x * 256ll) {
+            float x[P];
+            Elem<T>::unpack(rv[v], x);
+#pragma unroll
+            for (int i = 0; i < P; ++i) x[i] *= f;
+            rv[v] = Elem<T>::pack(x);
+        }
+        for (int64_t c = nvec * P + blockIdx.x * 256ll + threadIdx.x; c < V; c += gridDim.x * 256ll)
+            row[c] = Elem<T>::from_float(Elem<T>::to_float(row[c]) * f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Workspace {   // layout of the caller-provided logit-KD workspace
+    size_t rowaux, records, lse2_t, table_ws, table_ws_bytes, table, consts, status, total;
+};
+
+size_t table_workspace_bytes(int64_t V) {   // owner arrays (labels pass, k pass) + per-block partial sums
+    const size_t blocks = (V + kTableThreads - 1) / kTableThreads;
+    return align_up(sizeof(int) * V, 256) * 2 + align_up(sizeof(double) * 2 * blocks, 256);
+}
+
+Workspace workspace_layout(int64_t n_rows, int64_t V) {
+    Workspace w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    w.rowaux = take(sizeof(float4) * n_rows);
+    w.records = take(sizeof(kd_token_record) * n_rows);
+    w.lse2_t = take(sizeof(float) * n_rows);
+    w.table_ws_bytes = table_workspace_bytes(V);
+    w.table_ws = take(w.table_ws_bytes);
+    w.table = take(sizeof(float) * V);
+    w.consts = take(sizeof(double) * 2);
+    w.status = take(sizeof(uint32_t));
+    w.total = off;
+    return w;
+}
+
+template <typename T>
+bool rows_vectorizable(const void* base, int64_t ld) {
+    return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && (ld * sizeof(T)) % 16 == 0;
+}
+
+template <typename T>
+int launch_teacher_stats(const void* teacher, int64_t ld_t, const int64_t* labels, kd_token_record* rec, float* lse2_t,
+                         uint32_t* status, int64_t n_rows, int V, float k2, float alpha, cudaStream_t st) {
+    const int grid = static_cast<int>(n_rows < (int64_t)sm_count() * 8 ? n_rows : (int64_t)sm_count() * 8);
+    if (rows_vectorizable<T>(teacher, ld_t))
+        teacher_stats_kernel<T, true><<<grid, kStatsThreads, 0, st>>>(static_cast<const T*>(teacher), ld_t, labels, rec,
+                                                                      lse2_t, status, n_rows, V, k2, alpha);
+    else
+        teacher_stats_kernel<T, false><<<grid, kStatsThreads, 0, st>>>(static_cast<const T*>(teacher), ld_t, labels, rec,
+                                                                       lse2_t, status, n_rows, V, k2, alpha);
+    KD_CHECK_LAUNCH("teacher_stats_kernel");
+    return KD_OK;
+}
+
+template <int VARIANT, typename T>
+int launch_emit_stream_t(const EmitParams& p, cudaStream_t st) {
+    const bool vec = rows_vectorizable<T>(p.teacher, p.ld_t) && rows_vectorizable<T>(p.student, p.ld_s) &&
+                     ((p.flags & KD_FLAG_NO_GRAD) || rows_vectorizable<T>(p.grad, p.ld_g));
+    const int64_t cap = (int64_t)sm_count() * 2;
+    const int grid = static_cast<int>(p.n_rows < cap ? p.n_rows : cap);
+    if (vec)
+        row_emit_stream_kernel<VARIANT, T, true><<<grid, kEmitThreads, 0, st>>>(p);
+    else
+        row_emit_stream_kernel<VARIANT, T, false><<<grid, kEmitThreads, 0, st>>>(p);
+    KD_CHECK_LAUNCH("row_emit_stream_kernel");
+    return KD_OK;
+}
+
+template <typename T>
+int launch_emit_stream_v(const EmitParams& p, int variant, cudaStream_t st) {
+    switch (variant) {
+        case KD_LOCA_REFERENCE: return launch_emit_stream_t<KD_LOCA_REFERENCE, T>(p, st);
+        case KD_LOCA_PER_ROW: return launch_emit_stream_t<KD_LOCA_PER_ROW, T>(p, st);
+        case KD_KL_PLAIN: return launch_emit_stream_t<KD_KL_PLAIN, T>(p, st);
+        case KD_KL_LOG_TARGET: return launch_emit_stream_t<KD_KL_LOG_TARGET, T>(p, st);
+    }
+    set_error("unknown logit-KD variant %d", variant);
+    return KD_ERR_INVALID_ARGUMENT;
+}
+
+int launch_emit(const EmitParams& p, int variant, int dtype, cudaStream_t st) {
+    if (!(p.flags & KD_FLAG_FORCE_STREAMING)) {
+        const int rc = launch_emit_cluster(p, variant, dtype, st);
+        if (rc != KD_ERR_UNSUPPORTED) return rc;
+    }
+    switch (dtype) {
+        case KD_DTYPE_BF16: return launch_emit_stream_v<__nv_bfloat16>(p, variant, st);
+        case KD_DTYPE_F16: return launch_emit_stream_v<__half>(p, variant, st);
+        case KD_DTYPE_F32: return launch_emit_stream_v<float>(p, variant, st);
+    }
+    set_error("unknown dtype %d", dtype);
+    return KD_ERR_INVALID_ARGUMENT;
+}
+
+int check_common(int64_t n_rows, int64_t V, int dtype, float T) {
+    KD_CHECK_ARG(n_rows >= 0, "n_rows must be >= 0 (got %lld)", (long long)n_rows);
+    KD_CHECK_ARG(V >= 1 && V < (1ll << 30), "V must be in [1, 2^30) (got %lld)", (long long)V);
+    KD_CHECK_ARG(n_rows < (1ll << 31), "n_rows must be < 2^31 (got %lld)", (long long)n_rows);
+    KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
+    KD_CHECK_ARG(T > 0.f && isfinite(T), "temperature must be positive and finite (got %g)", (double)T);
+    return KD_OK;
+}
+
+}  // namespace
+
+}  // namespace kd
+
+using namespace kd;
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int kd_logit_kd_workspace_bytes(int64_t n_rows, int64_t V, size_t* bytes) {
+    KD_CHECK_ARG(bytes != nullptr && n_rows >= 0 && V >= 1, "kd_logit_kd_workspace_bytes: bad arguments");
+    *bytes = workspace_layout(n_rows, V).total;
+    return KD_OK;
+}
+
+int kd_logit_kd_status_offset(int64_t n_rows, int64_t V, size_t* offset) {
+    KD_CHECK_ARG(offset != nullptr && n_rows >= 0 && V >= 1, "kd_logit_kd_status_offset: bad arguments");
+    *offset = workspace_layout(n_rows, V).status;
+    return KD_OK;
+}
+
+int kd_logit_kd_rowaux_offset(int64_t n_rows, int64_t V, size_t* offset) {
+    KD_CHECK_ARG(offset != nullptr && n_rows >= 0 && V >= 1, "kd_logit_kd_rowaux_offset: bad arguments");
+    *offset = workspace_layout(n_rows, V).rowaux;
+    return KD_OK;
+}
+
+int kd_loca_teacher_stats(const void* teacher, int64_t ld_t, const int64_t* labels, kd_token_record* records,
+                          float* lse2_t, uint32_t* status, int64_t n_rows, int64_t V, int dtype, float T, float alpha,
+                          void* stream) {
+    if (int rc = check_common(n_rows, V, dtype, T)) return rc;
+    KD_CHECK_ARG(teacher && labels && records && lse2_t && status, "kd_loca_teacher_stats: null pointer");
+    KD_CHECK_ARG(ld_t >= V, "teacher leading dimension %lld < V %lld", (long long)ld_t, (long long)V);
+    if (n_rows == 0) return KD_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float k2 = kLog2e / T;
+    switch (dtype) {
+        case KD_DTYPE_BF16: return launch_teacher_stats<__nv_bfloat16>(teacher, ld_t, labels, records, lse2_t, status, n_rows, (int)V, k2, alpha, st);
+        case KD_DTYPE_F16: return launch_teacher_stats<__half>(teacher, ld_t, labels, records, lse2_t, status, n_rows, (int)V, k2, alpha, st);
+        default: return launch_teacher_stats<float>(teacher, ld_t, labels, records, lse2_t, status, n_rows, (int)V, k2, alpha, st);
+    }
+}
+
+int kd_loca_table_workspace_bytes(int64_t V, size_t* bytes) {
+    KD_CHECK_ARG(bytes != nullptr && V >= 1, "kd_loca_table_workspace_bytes: bad arguments");
+    *bytes = table_workspace_bytes(V);
+    return KD_OK;
+}
+
+int kd_loca_build_table(const kd_token_record* records_all, int64_t n_tokens_all, int64_t V, float* table,
+                        double* table_consts, void* workspace, size_t workspace_bytes, void* stream) {
+    KD_CHECK_ARG(records_all && table && table_consts && workspace, "kd_loca_build_table: null pointer");
+    KD_CHECK_ARG(n_tokens_all >= 0 && n_tokens_all < (1ll << 31), "n_tokens_all out of range");
+    KD_CHECK_ARG(V >= 1 && V < (1ll << 30), "V out of range");
+    size_t need = 0;
+    kd_loca_table_workspace_bytes(V, &need);
+    if (workspace_bytes < need) {
+        set_error("kd_loca_build_table: workspace %zu < %zu bytes", workspace_bytes, need);
+        return KD_ERR_WORKSPACE_TOO_SMALL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    int* own_l = reinterpret_cast<int*>(ws);
+    int* own_k = reinterpret_cast<int*>(ws + align_up(sizeof(int) * V, 256));
+    double* partials = reinterpret_cast<double*>(ws + 2 * align_up(sizeof(int) * V, 256));
+    const int blocks = static_cast<int>((V + kTableThreads - 1) / kTableThreads);
+    // own_l and own_k are adjacent up to padding: initialise the whole span in one launch
+    const int span = static_cast<int>((reinterpret_cast<char*>(own_k) - reinterpret_cast<char*>(own_l)) / sizeof(int) + V);
+    owner_init_kernel<<<sm_count() * 2, 256, 0, st>>>(own_l, span);
+    KD_CHECK_LAUNCH("owner_init_kernel");
+    if (n_tokens_all > 0) {
+        const int g = static_cast<int>((n_tokens_all + 255) / 256);
+        owner_scatter_kernel<<<g < 4096 ? g : 4096, 256, 0, st>>>(records_all, n_tokens_all, own_l, own_k, (int)V);
+        KD_CHECK_LAUNCH("owner_scatter_kernel");
+    }
+    table_fill_kernel<<<blocks, kTableThreads, 0, st>>>(records_all, own_l, own_k, (int)V, table, partials);
+    KD_CHECK_LAUNCH("table_fill_kernel");
+    table_consts_kernel<<<1, 32, 0, st>>>(partials, blocks, table_consts);
+    KD_CHECK_LAUNCH("table_consts_kernel");
+    return KD_OK;
+}
+
+int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const float* lse2_t,
+                 const float* table, const double* table_consts, void* grad_student, int64_t ld_g, float* loss_out,
+                 void* rowaux, int64_t n_rows, int64_t V, int dtype, float T, float eps, double inv_norm,
+                 const float* upstream, unsigned flags, void* stream) {
+    if (int rc = check_common(n_rows, V, dtype, T)) return rc;
+    KD_CHECK_ARG(teacher && student && lse2_t && table && table_consts && loss_out && rowaux, "kd_loca_emit: null pointer");
+    KD_CHECK_ARG((flags & KD_FLAG_NO_GRAD) || grad_student, "kd_loca_emit: grad_student is null");
+    KD_CHECK_ARG(ld_t >= V && ld_s >= V && ((flags & KD_FLAG_NO_GRAD) || ld_g >= V), "leading dimension < V");
+    KD_CHECK_ARG(eps > 0.f, "eps must be positive");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    EmitParams p{};
+    p.teacher = teacher; p.ld_t = ld_t; p.student = student; p.ld_s = ld_s;
+    p.lse2_t_in = lse2_t; p.table = table; p.grad = grad_student; p.ld_g = ld_g;
+    p.rowaux = static_cast<float4*>(rowaux); p.upstream = upstream; p.n_rows = n_rows; p.V = (int)V;
+    p.k2 = kLog2e / T; p.thr2 = log2f(eps); p.gscale = static_cast<float>(T * inv_norm); p.flags = flags;
+    if (n_rows > 0) {
+        if (int rc = launch_emit(p, KD_LOCA_REFERENCE, dtype, st)) return rc;
+    }
+    loss_finalize_kernel<<<1, kFinalThreads, 0, st>>>(p.rowaux, n_rows, (double)kLn2, (double)T * T * inv_norm, table_consts,
+                                                      nullptr, loss_out);
+    KD_CHECK_LAUNCH("loss_finalize_kernel");
+    return KD_OK;
+}
+
+int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* labels,
+                        void* grad_student, int64_t ld_g, float* loss_out, void* workspace, size_t workspace_bytes,
+                        int64_t n_rows, int64_t V, int dtype, float T, float alpha, float eps, int variant,
+                        double inv_norm, const float* upstream, unsigned flags, void* stream) {
+    if (int rc = check_common(n_rows, V, dtype, T)) return rc;
+    KD_CHECK_ARG(variant >= KD_LOCA_REFERENCE && variant <= KD_KL_LOG_TARGET, "unknown logit-KD variant %d", variant);
+    const bool loca = (variant == KD_LOCA_REFERENCE || variant == KD_LOCA_PER_ROW);
+    KD_CHECK_ARG(teacher && student && loss_out && workspace, "kd_logit_kd_fwd_bwd: null pointer");
+    KD_CHECK_ARG(!loca || labels, "kd_logit_kd_fwd_bwd: LoCa variants need labels");
+    KD_CHECK_ARG((flags & KD_FLAG_NO_GRAD) || grad_student, "kd_logit_kd_fwd_bwd: grad_student is null");
+    KD_CHECK_ARG(ld_t >= V && ld_s >= V && ((flags & KD_FLAG_NO_GRAD) || ld_g >= V), "leading dimension < V");
+    KD_CHECK_ARG(!loca || eps > 0.f, "eps must be positive");
+    const Workspace w = workspace_layout(n_rows, V);
+    if (workspace_bytes < w.total) {
+        set_error("kd_logit_kd_fwd_bwd: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return KD_ERR_WORKSPACE_TOO_SMALL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    uint32_t* status = reinterpret_cast<uint32_t*>(ws + w.status);
+    float4* rowaux = reinterpret_cast<float4*>(ws + w.rowaux);
+    double* consts = reinterpret_cast<double*>(ws + w.consts);
+    status_clear_kernel<<<1, 1, 0, st>>>(status);
+    KD_CHECK_LAUNCH("status_clear_kernel");
+
+    EmitParams p{};
+    p.teacher = teacher; p.ld_t = ld_t; p.student = student; p.ld_s = ld_s; p.labels = labels;
+    p.grad = grad_student; p.ld_g = ld_g; p.rowaux = rowaux; p.status = status; p.upstream = upstream;
+    p.n_rows = n_rows; p.V = (int)V; p.k2 = kLog2e / T; p.alpha = alpha; p.thr2 = loca ? log2f(eps) : -INFINITY;
+    p.gscale = static_cast<float>(T * inv_norm); p.flags = flags;
+
+    if (variant == KD_LOCA_REFERENCE) {
+        kd_token_record* rec = reinterpret_cast<kd_token_record*>(ws + w.records);
+        float* lse2_t = reinterpret_cast<float*>(ws + w.lse2_t);
+        float* table = reinterpret_cast<float*>(ws + w.table);
+        if (n_rows > 0) {
+            if (int rc = kd_loca_teacher_stats(teacher, ld_t, labels, rec, lse2_t, status, n_rows, V, dtype, T, alpha, stream)) return rc;
+        }
+        if (int rc = kd_loca_build_table(rec, n_rows, V, table, consts, ws + w.table_ws, w.table_ws_bytes, stream)) return rc;
+        p.lse2_t_in = lse2_t;
+        p.table = table;
+    }
+    if (n_rows > 0) {
+        if (int rc = launch_emit(p, variant, dtype, st)) return rc;
+    }
+    const double unit = (variant == KD_KL_LOG_TARGET) ? 1.0 : (double)kLn2;
+    loss_finalize_kernel<<<1, kFinalThreads, 0, st>>>(rowaux, n_rows, unit, (double)T * T * inv_norm,
+                                                      variant == KD_LOCA_REFERENCE ? consts : nullptr, status, loss_out);
+    KD_CHECK_LAUNCH("loss_finalize_kernel");
+    return KD_OK;
+}
+
+int kd_scale_rows(void* grad, int64_t ld_g, int64_t n_rows, int64_t V, int dtype, const float* factor, void* stream) {
+    KD_CHECK_ARG(grad && factor, "kd_scale_rows: null pointer");
+    KD_CHECK_ARG(n_rows >= 0 && V >= 1 && ld_g >= V, "kd_scale_rows: bad shape");
+    KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
+    if (n_rows == 0) return KD_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int64_t gx = (V / 8 + 255) / 256;
+    gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
+    int64_t gy = 8192 / gx;
+    gy = gy < 1 ? 1 : (gy > n_rows ? n_rows : gy);
+    dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
+    switch (dtype) {
+        case KD_DTYPE_BF16: scale_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<__nv_bfloat16*>(grad), ld_g, n_rows, V, factor); break;
+        case KD_DTYPE_F16: scale_rows_kernel<__half><<<grid, 256, 0, st>>>(static_cast<__half*>(grad), ld_g, n_rows, V, factor); break;
+        default: scale_rows_kernel<float><<<grid, 256, 0, st>>>(static_cast<float*>(grad), ld_g, n_rows, V, factor); break;
+    }
+    KD_CHECK_LAUNCH("scale_rows_kernel");
+    return KD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// logit_kd.cuh — shapes, parameters and per-element math shared by the streaming (logit_kd.cu) and the
+// cluster-resident (logit_kd_cluster.cu) logit-KD kernels.
+//
+// Math (restating P1:141-194 / P1:331-343 / FB:206-219 of the reference), all in the log2 domain:
+//   k2 = log2(e)/T,  a = xs*k2 - lse2_s = log2 sp,  b = xt*k2 - lse2_t = log2 tp,  thr2 = log2(eps)
+//   LoCa : q = override ? ov : 2^b ; keep = a >= thr2 ; row2 += q*(lq - max(a,thr2)) with lq = override ? 0 : b
+//          (the row-independent sum of xlogy(ov,ov) is added once per row at finalisation)
+//          Q += keep ? q : 0 ;  grad = g*(2^a * Q - (keep ? q : 0))
+//   KL   : q = 2^b ; row2 += q*(b - a) ; Q += q ; grad = g*(2^a * Q - q)
+//   KLLT : w = e^(2^b) ; rowNat += w*(2^b - a*ln2) ; Q += w ; grad = g*(2^a * Q - w)
+#pragma once
+
+#include "kd_common.cuh"
+
+namespace kd {
+
+struct EmitParams {
+    const void* teacher;
+    int64_t ld_t;
+    const void* student;
+    int64_t ld_s;
+    const int64_t* labels;      // per-row variants
+    const float* lse2_t_in;     // LoCa reference mode: from the teacher-stats pass
+    const float* table;         // LoCa reference mode: V-entry override table (NaN = not overridden)
+    void* grad;
+    int64_t ld_g;
+    float4* rowaux;             // per row: lse2_t, lse2_s, Q_r, row sum (log2 units; natural for KLLT)
+    uint32_t* status;
+    const float* upstream;      // device scalar or nullptr
+    int64_t n_rows;
+    int V;
+    float k2;                   // log2(e)/T
+    float alpha;
+    float thr2;                 // log2(eps)
+    float gscale;               // T * inv_norm
+    unsigned flags;
+};
+
+template <int VARIANT>
+struct PointTerm {
+    // one (teacher, student) cell in the accumulate sweep: returns the row-sum term and the Q term
+    static __device__ __forceinline__ void accum(float xt, float xs, float ov, float k2, float lse2_t, float lse2_s,
+                                                 float thr2, float& row, float& Q) {
+        const float a = fmaf(xs, k2, -lse2_s);
+        const float b = fmaf(xt, k2, -lse2_t);
+        if constexpr (VARIANT == KD_LOCA_REFERENCE || VARIANT == KD_LOCA_PER_ROW) {
+            const bool over = (ov == ov);           // not NaN
+            const float q = over ? ov : ex2(b);
+            const float lq = over ? 0.f : b;
+            const float ac = fmaxf(a, thr2);
+            row = fmaf(q, lq - ac, row);
+            Q += (a >= thr2) ? q : 0.f;
+        } else if constexpr (VARIANT == KD_KL_PLAIN) {
+            const float q = ex2(b);
+            row = fmaf(q, b - a, row);
+            Q += q;
+        } else {
+            const float tp = ex2(b);
+            const float w = ex2(tp * kLog2e);
+            row = fmaf(w, fmaf(-a, kLn2, tp), row);
+            Q += w;
+        }
+    }
+    // the same cell in the emit sweep: gradient value g*(sp*Q - w), with gQ = g*Q
+    static __device__ __forceinline__ float grad(float xt, float xs, float ov, float k2, float lse2_t, float lse2_s,
+                                                 float thr2, float g, float gQ) {
+        const float a = fmaf(xs, k2, -lse2_s);
+        const float sp = ex2(a);
+        const float b = fmaf(xt, k2, -lse2_t);
+        if constexpr (VARIANT == KD_LOCA_REFERENCE || VARIANT == KD_LOCA_PER_ROW) {
+            const bool over = (ov == ov);
+            float q = over ? ov : ex2(b);
+            q = (a >= thr2) ? q : 0.f;
+            return fmaf(gQ, sp, -g * q);
+        } else if constexpr (VARIANT == KD_KL_PLAIN) {
+            return fmaf(gQ, sp, -g * ex2(b));
+        } else {
+            return fmaf(gQ, sp, -g * ex2(ex2(b) * kLog2e));
+        }
+    }
+};
+
+// per-row LoCa calibration scalars from (lse2_t, label logit, runner-up logit) — P1:166-185
+__device__ __forceinline__ void loca_scalars(float x_label, float x_runner, float lse2_t, float k2, float alpha,
+                                             float& v1, float& v2) {
+    const float p_gt = ex2(fmaf(x_label, k2, -lse2_t));
+    const float p_k = ex2(fmaf(x_runner, k2, -lse2_t));
+    const float sc = alpha / (1.f - p_gt + p_k);
+    v1 = 1.f - sc * (1.f - p_gt);     // sum_v tp taken as 1
+    v2 = sc * p_k;
+}
+
+// host-side launchers implemented in logit_kd_cluster.cu; return KD_ERR_UNSUPPORTED when the shape does not fit
+int launch_emit_cluster(const EmitParams& p, int variant, int dtype, cudaStream_t stream);
+
+}  // namespace kd

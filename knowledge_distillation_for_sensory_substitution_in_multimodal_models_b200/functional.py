@@ -1,0 +1,253 @@
+"""torch.autograd.Function front-ends of the B200 KD-loss kernels.
+
+These are the drop-in replacements for the reference's loss *calls* (SURVEY.md §8(b)):
+
+* :func:`loca_kl`        — body of ``compute_loca_loss`` (P1:141-194, LG:208-261) minus ``+ student_loss``
+* :func:`temperature_kl` — KL term of ``compute_vision_loss`` (P1:331-343) / of ``compute_loss`` (FB:206-219)
+* :func:`info_nce`       — pooling (P1:243-248) + ``contrastive_loss`` (P1:393-416)
+* :func:`feature_mse`    — ``mse_loss`` (EV:160-165)
+
+Forward and backward are ONE fused device pass: the gradient w.r.t. the student tensor is produced in
+the forward launch (scaled by ``upstream`` if given) and ``backward`` only rescales it when the
+incoming ``grad_output`` differs from 1 (checked on the device, no host sync).  PyTorch is used for
+memory, streams and autograd plumbing only; all arithmetic runs in ``libkd_b200.so``.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16, torch.float32: _lib.DTYPE_F32}
+_VARIANTS = {"reference": _lib.LOCA_REFERENCE, "per_row": _lib.LOCA_PER_ROW}
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("KD-loss kernels are CUDA-only (sm_100a); got a CPU tensor — there is no CPU fallback")
+        if t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {t.device} vs {dev}")
+    return dev
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; use bfloat16, float16 or float32") from None
+
+
+def _rows(x: torch.Tensor) -> torch.Tensor:
+    """View as [N, V] without copying when the last dim is contiguous and rows are evenly strided."""
+    v = x.shape[-1]
+    if x.dim() == 2 and x.stride(1) == 1:
+        return x
+    if x.stride(-1) == 1:
+        try:
+            return x.view(-1, v) if x.is_contiguous() else x.reshape(-1, v)
+        except RuntimeError:
+            pass
+    return x.reshape(-1, v).contiguous()
+
+
+def _stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _backward_factor(grad_output, upstream, dev):
+    """grad_output relative to the scale already folded in at forward time (device scalar, no sync)."""
+    go = grad_output.detach().to(device=dev, dtype=torch.float32).reshape(())
+    if upstream is not None:
+        go = go / upstream
+    return go.contiguous()
+
+
+def _upstream_ptr(upstream, dev):
+    if upstream is None:
+        return None, None
+    t = torch.as_tensor(upstream, dtype=torch.float32, device=dev).reshape(())
+    return t, t.data_ptr()
+
+
+def _inv_norm(reduction: str, n_rows: int, vocab: int, batch: int, n_total) -> float:
+    n = int(n_total) if n_total is not None else n_rows
+    if reduction == "mean":          # F.kl_div(reduction='mean'): divide by every element (P1:188-192)
+        return 1.0 / (float(n) * float(vocab))
+    if reduction == "batchmean":     # EV:130-136 / P1:378-381: divide by size(0)
+        return 1.0 / float(batch)
+    if reduction == "sum":
+        return 1.0
+    raise ValueError(f"unknown reduction {reduction!r}")
+
+
+class _LogitKD(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, teacher, student, labels, T, alpha, eps, variant, reduction, upstream, n_total, flags):
+        dev = _require_cuda(teacher, student, labels)
+        if teacher.dtype != student.dtype:
+            raise TypeError(f"teacher ({teacher.dtype}) and student ({student.dtype}) must share a dtype")
+        if teacher.shape[:-1] != student.shape[:-1]:
+            raise ValueError(f"teacher {tuple(teacher.shape)} and student {tuple(student.shape)} disagree on token dims")
+        V = student.shape[-1]
+        if teacher.shape[-1] < V:
+            raise ValueError("teacher vocabulary is smaller than the student's (the reference slices the teacher, P1:155)")
+        t2, s2 = _rows(teacher.detach()), _rows(student.detach())
+        n_rows = s2.shape[0]
+        batch = student.shape[0] if student.dim() > 1 else 1
+        lab = None
+        if variant in (_lib.LOCA_REFERENCE, _lib.LOCA_PER_ROW):
+            if labels is None:
+                raise ValueError("LoCa needs labels")
+            if labels.numel() != n_rows:
+                raise ValueError(f"labels has {labels.numel()} entries for {n_rows} tokens")
+            lab = labels.detach().reshape(-1).to(torch.int64).contiguous()
+        need_grad = student.requires_grad and not (flags & _lib.FLAG_NO_GRAD)
+        if not need_grad:
+            flags |= _lib.FLAG_NO_GRAD
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            ws_bytes = _lib.size_query("kd_logit_kd_workspace_bytes", n_rows, V)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            grad = torch.empty((n_rows, V), dtype=student.dtype, device=dev) if need_grad else None
+            up_t, up_ptr = _upstream_ptr(upstream, dev)
+            _lib.check(lib.kd_logit_kd_fwd_bwd(
+                t2.data_ptr(), t2.stride(0), s2.data_ptr(), s2.stride(0),
+                lab.data_ptr() if lab is not None else None,
+                grad.data_ptr() if grad is not None else None, V, loss.data_ptr(),
+                ws.data_ptr(), ws_bytes, n_rows, V, _dtype_code(student), float(T), float(alpha), float(eps),
+                int(variant), _inv_norm(reduction, n_rows, V, batch, n_total), up_ptr, int(flags), _stream_ptr(dev)))
+        ctx.grad = grad
+        ctx.student_shape = student.shape
+        ctx.dev = dev
+        ctx.upstream = up_t
+        ctx.workspace = ws      # row statistics stay alive for inspection (kd_logit_kd_rowaux_offset)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad = ctx.grad
+        if grad is None:
+            return (None,) * 11
+        ctx.grad = None
+        go = _backward_factor(grad_output, ctx.upstream, ctx.dev)
+        with torch.cuda.device(ctx.dev):
+            _lib.check(_lib.load().kd_scale_rows(grad.data_ptr(), grad.stride(0), grad.shape[0], grad.shape[1],
+                                                 _dtype_code(grad), go.data_ptr(), _stream_ptr(ctx.dev)))
+        return (None, grad.view(ctx.student_shape), None, None, None, None, None, None, None, None, None)
+
+
+def loca_kl(teacher_logits, student_logits, labels, T: float, alpha: float = 0.8, eps: float = 1e-8,
+            mode: str = "reference", reduction: str = "mean", upstream=None, n_total=None, force_streaming=False):
+    """LoCa-calibrated logit KL (P1:141-194) without the trailing ``+ student_loss``.
+
+    ``mode="reference"`` reproduces the as-written global column override (P1:184-185);
+    ``mode="per_row"`` calibrates each token's own two cells.  ``upstream`` is an optional scalar
+    (python float or 0-d tensor) folded into the gradient in the forward launch, e.g. ``gamma`` of
+    phase 3 (P1:260) or an AMP loss scale: ``backward`` divides the incoming ``grad_output`` by it, so when
+    the caller really multiplies the loss by that scalar the rescale pass is skipped on the device.
+    """
+    flags = _lib.FLAG_FORCE_STREAMING if force_streaming else 0
+    return _LogitKD.apply(teacher_logits, student_logits, labels, T, alpha, eps, _VARIANTS[mode], reduction,
+                          upstream, n_total, flags)
+
+
+def temperature_kl(teacher_logits, student_logits, T: float, reduction: str = "mean", log_target_quirk: bool = False,
+                   upstream=None, n_total=None, force_streaming=False):
+    """``F.kl_div(log_softmax(s/T), softmax(t/T), reduction) * T**2`` (P1:331-343); ``log_target_quirk``
+    reproduces FB:206-219 where the probability target is flagged ``log_target=True``."""
+    variant = _lib.KL_LOG_TARGET if log_target_quirk else _lib.KL_PLAIN
+    flags = _lib.FLAG_FORCE_STREAMING if force_streaming else 0
+    return _LogitKD.apply(teacher_logits, student_logits, None, T, 0.0, 1e-8, variant, reduction, upstream, n_total, flags)
+
+
+class _InfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student, teacher, temperature, upstream):
+        dev = _require_cuda(student, teacher)
+        if student.shape != teacher.shape or student.dtype != teacher.dtype:
+            raise ValueError("student and teacher features must have the same shape and dtype")
+        if student.dim() == 2:
+            M, P, D = student.shape[0], 1, student.shape[1]
+        elif student.dim() == 3:
+            M, P, D = student.shape
+        else:
+            raise ValueError("features must be [M, D] or [M, tokens, D]")
+        xs, xt = student.detach().contiguous(), teacher.detach().contiguous()
+        need_grad = student.requires_grad
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            ws_bytes = _lib.size_query("kd_info_nce_workspace_bytes", M, P, D)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            grad = torch.empty_like(xs) if need_grad else None
+            up_t, up_ptr = _upstream_ptr(upstream, dev)
+            _lib.check(lib.kd_info_nce_fwd_bwd(xs.data_ptr(), xt.data_ptr(), grad.data_ptr() if need_grad else None,
+                                               loss.data_ptr(), ws.data_ptr(), ws_bytes, M, P, D, _dtype_code(xs),
+                                               float(temperature), up_ptr, 0 if need_grad else _lib.FLAG_NO_GRAD,
+                                               _stream_ptr(dev)))
+        ctx.grad, ctx.dev, ctx.upstream = grad, dev, up_t
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad = ctx.grad
+        if grad is None:
+            return None, None, None, None
+        ctx.grad = None
+        go = _backward_factor(grad_output, ctx.upstream, ctx.dev)
+        flat = grad.view(1, -1)
+        with torch.cuda.device(ctx.dev):
+            _lib.check(_lib.load().kd_scale_rows(flat.data_ptr(), flat.shape[1], 1, flat.shape[1], _dtype_code(grad),
+                                                 go.data_ptr(), _stream_ptr(ctx.dev)))
+        return grad, None, None, None
+
+
+def info_nce(student_feats, teacher_feats, temperature: float = 0.07, upstream=None):
+    """Mean-pool over tokens (3-D input), L2-normalise, student x teacher^T / temperature, cross-entropy
+    against the diagonal — P1:243-248 followed by ``contrastive_loss`` (P1:393-416)."""
+    return _InfoNCE.apply(student_feats, teacher_feats, temperature, upstream)
+
+
+class _FeatureMSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, target, upstream):
+        dev = _require_cuda(inp, target)
+        if inp.shape != target.shape or inp.dtype != target.dtype:
+            raise ValueError("input and target must have the same shape and dtype")
+        a, b = inp.detach().contiguous(), target.detach().contiguous()
+        need_grad = inp.requires_grad
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            ws_bytes = _lib.size_query("kd_feature_mse_workspace_bytes", a.numel())
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            grad = torch.empty_like(a) if need_grad else None
+            up_t, up_ptr = _upstream_ptr(upstream, dev)
+            _lib.check(lib.kd_feature_mse_fwd_bwd(a.data_ptr(), b.data_ptr(), grad.data_ptr() if need_grad else None,
+                                                  loss.data_ptr(), ws.data_ptr(), ws_bytes, a.numel(), _dtype_code(a),
+                                                  up_ptr, 0 if need_grad else _lib.FLAG_NO_GRAD, _stream_ptr(dev)))
+        ctx.grad, ctx.dev, ctx.upstream = grad, dev, up_t
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad = ctx.grad
+        if grad is None:
+            return None, None, None
+        ctx.grad = None
+        go = _backward_factor(grad_output, ctx.upstream, ctx.dev)
+        flat = grad.view(1, -1)
+        with torch.cuda.device(ctx.dev):
+            _lib.check(_lib.load().kd_scale_rows(flat.data_ptr(), flat.shape[1], 1, flat.shape[1], _dtype_code(grad),
+                                                 go.data_ptr(), _stream_ptr(ctx.dev)))
+        return grad, None, None
+
+
+def feature_mse(inp, target, upstream=None):
+    """``mean((input.float() - target.float())**2)`` (EV:160-165); gradient in ``input``'s dtype."""
+    return _FeatureMSE.apply(inp, target, upstream)

@@ -1,0 +1,79 @@
+"""GPU parity of InfoNCE and feature MSE against goldens / oracle (tolerances as in BASELINE.json)."""
+import pytest
+import torch
+
+from _util import goldens_of_kind, load_golden, rel_err
+from oracle import kd_oracle as O
+import knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 as kd
+from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", goldens_of_kind("info_nce"))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+def test_info_nce_goldens(name, dtype):
+    g = load_golden(name)
+    xs = torch.from_numpy(g["student"]).to("cuda", dtype).requires_grad_(True)
+    xt = torch.from_numpy(g["teacher"]).to("cuda", dtype)
+    loss = kd.info_nce(xs, xt, float(g["temperature"]))
+    loss.backward()
+    # losses near zero (well-separated diagonal) are compared absolutely at the scale of log-softmax rounding
+    assert abs(loss.item() - float(g["loss"])) <= max(1e-5 * abs(float(g["loss"])), 2e-7)
+    assert rel_err(xs.grad.float().cpu(), g["grad"]) <= (2e-3 if dtype == torch.bfloat16 else 1e-4)
+
+
+@pytest.mark.parametrize("M,P,D", [(64, 729, 1152), (16, 10, 1152), (8, 1, 896), (5, 3, 100)])
+def test_info_nce_against_oracle(M, P, D):
+    xs, xt = synthetic.vision_feature_batch(M, P, D, seed=M)
+    if M == 16:     # unrelated teacher: every softmax entry matters
+        xt = synthetic.vision_feature_batch(M, P, D, seed=999)[0]
+    ref = O.info_nce(xs, xt)
+    xd = xs.cuda().requires_grad_(True)
+    loss = kd.info_nce(xd, xt.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref.loss.item()) <= max(1e-5 * abs(ref.loss.item()), 2e-7)
+    assert rel_err(xd.grad.float().cpu(), ref.grad) <= 2e-3
+
+
+def test_info_nce_2d_features_as_the_reference_passes_them():
+    """contrastive_loss receives already pooled+normalised [B, 1152] features (P1:243-248 -> P1:345)."""
+    xs, xt = synthetic.vision_feature_batch(12, 4, 1152, seed=3)
+    fs = torch.nn.functional.normalize(xs.float().mean(1), dim=-1)
+    ft = torch.nn.functional.normalize(synthetic.vision_feature_batch(12, 4, 1152, seed=4)[0].float().mean(1), dim=-1)
+    ref = O.info_nce(fs, ft, pool=False)
+    fd = fs.cuda().requires_grad_(True)
+    loss = kd.info_nce(fd, ft.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref.loss.item()) <= 1e-5 * abs(ref.loss.item())
+    assert rel_err(fd.grad.cpu(), ref.grad) <= 1e-4
+
+
+def test_mse_golden_and_oracle():
+    g = load_golden("mse_small")
+    a = torch.from_numpy(g["input"]).to("cuda", torch.bfloat16).requires_grad_(True)
+    b = torch.from_numpy(g["target"]).to("cuda", torch.bfloat16)
+    loss = kd.feature_mse(a, b)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert rel_err(a.grad.float().cpu(), g["grad"]) <= 2e-3
+    hs, ht, w = synthetic.hidden_state_batch(4096, 896, 3584, seed=2)
+    proj = (hs.float() @ w.float()).to(torch.bfloat16)       # projection is the caller's GEMM (not in the reference)
+    ref = O.feature_mse(proj, ht)
+    pd = proj.cuda().requires_grad_(True)
+    loss = kd.feature_mse(pd, ht.cuda())
+    (loss * 3.0).backward()
+    assert abs(loss.item() - ref.loss.item()) <= 1e-5 * ref.loss.item()
+    assert rel_err(pd.grad.float().cpu() / 3.0, ref.grad) <= 2e-3
+
+
+def test_mse_odd_sizes_and_unaligned():
+    for n in (1, 7, 1025, 8191):
+        a = torch.randn(n + 1, device="cuda", dtype=torch.bfloat16)[1:]     # 2-byte offset: not 16-B aligned
+        b = torch.randn(n, device="cuda", dtype=torch.bfloat16)
+        ref = O.feature_mse(a.cpu(), b.cpu())
+        ad = a.clone().requires_grad_(True) if n % 2 else a.detach().requires_grad_(True)
+        loss = kd.feature_mse(ad, b)
+        loss.backward()
+        assert abs(loss.item() - ref.loss.item()) <= 1e-5 * ref.loss.item()
+        assert rel_err(ad.grad.float().cpu(), ref.grad) <= 2e-3

@@ -1,0 +1,197 @@
+"""GPU parity: the CUDA logit-KD path (through the C ABI) against the goldens and the CPU oracle.
+
+Tolerances are BASELINE.json's: loss within 1e-5 relative (fp32 accumulation), gradient within 2e-3
+relative (bf16 output rounding) — relative error measured on the L2 norm of the whole gradient.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import goldens_of_kind, load_golden, rel_err
+from oracle import kd_oracle as O
+import knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 as kd
+from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import _lib, synthetic
+
+pytestmark = pytest.mark.gpu
+LOSS_RTOL = 1e-5
+GRAD_RTOL_BF16 = 2e-3
+GRAD_RTOL_F32 = 2e-5
+PATHS = [pytest.param(True, id="streaming"), pytest.param(False, id="auto")]
+
+
+def run_loca(t, s, lab, T, alpha, mode, dtype, force_streaming=False, **kw):
+    td = t.to("cuda", dtype)
+    sd = s.to("cuda", dtype).requires_grad_(True)
+    loss = kd.loca_kl(td, sd, lab.cuda(), T, alpha=alpha, mode=mode, force_streaming=force_streaming, **kw)
+    loss.backward()
+    return loss.item(), sd.grad.float().cpu()
+
+
+@pytest.mark.parametrize("force_streaming", PATHS)
+@pytest.mark.parametrize("name", goldens_of_kind("loca_reference", "loca_per_row"))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+def test_loca_goldens(name, dtype, force_streaming):
+    g = load_golden(name)
+    mode = "per_row" if str(g["kind"]) == "loca_per_row" else "reference"
+    t, s, lab = torch.from_numpy(g["teacher"]), torch.from_numpy(g["student"]), torch.from_numpy(g["labels"])
+    loss, grad = run_loca(t, s, lab, float(g["T"]), float(g["alpha"]), mode, dtype, force_streaming)
+    assert abs(loss - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    assert rel_err(grad, g["grad"]) <= (GRAD_RTOL_BF16 if dtype == torch.bfloat16 else GRAD_RTOL_F32)
+
+
+@pytest.mark.parametrize("force_streaming", PATHS)
+@pytest.mark.parametrize("name", goldens_of_kind("kl_plain", "kl_log_target"))
+def test_temperature_kl_goldens(name, force_streaming):
+    g = load_golden(name)
+    quirk = str(g["kind"]) == "kl_log_target"
+    t = torch.from_numpy(g["teacher"]).to("cuda", torch.bfloat16)
+    s = torch.from_numpy(g["student"]).to("cuda", torch.bfloat16).requires_grad_(True)
+    loss = kd.temperature_kl(t, s, float(g["T"]), log_target_quirk=quirk, force_streaming=force_streaming)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    assert rel_err(s.grad.float().cpu(), g["grad"]) <= GRAD_RTOL_BF16
+
+
+@pytest.mark.parametrize("force_streaming", PATHS)
+@pytest.mark.parametrize("name", goldens_of_kind("loca_reference_fullvocab"))
+def test_loca_full_vocab_golden(name, force_streaming):
+    g = load_golden(name)
+    t, s, lab = synthetic.logit_batch(int(g["n_rows"]), synthetic.VOCAB, seed=int(g["seed"]), peaked=bool(g["peaked"]))
+    if not np.array_equal(lab.numpy(), g["labels"]):
+        pytest.skip("torch RNG stream differs from the golden's")
+    loss, grad = run_loca(t, s, lab, float(g["T"]), float(g["alpha"]), "reference", torch.bfloat16, force_streaming)
+    assert abs(loss - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    st = int(g["grad_stride"])
+    assert rel_err(grad[:, ::st], g["grad_sample"]) <= GRAD_RTOL_BF16
+    assert rel_err(grad[:, lab], g["grad_at_labels"]) <= GRAD_RTOL_BF16
+    assert abs(grad.double().norm().item() - float(g["grad_norm"])) <= GRAD_RTOL_BF16 * float(g["grad_norm"])
+
+
+@pytest.mark.parametrize("force_streaming", PATHS)
+@pytest.mark.parametrize("mode", ["reference", "per_row"])
+@pytest.mark.parametrize("N,V,T,peaked,boost", [
+    (64, 151936, 2.0, False, 1.0),      # BASELINE config shape, fewer rows
+    (48, 151936, 0.8, True, 4.0),       # phase-2 temperature, clamp region active
+    (33, 32000, 1.0, False, 1.0),       # LG: T = 1
+    (7, 1001, 2.0, False, 1.0),         # ragged: V not a multiple of the vector width
+    (1, 151936, 2.0, True, 1.0),        # single token
+])
+def test_loca_against_oracle(N, V, T, peaked, boost, mode, force_streaming):
+    t, s, lab = synthetic.logit_batch(N, V, seed=100 + N, peaked=peaked)
+    s = (s.float() * boost).to(torch.bfloat16)
+    ref = O.loca_kl(t, s, lab, T, 0.8, mode=mode, chunk_rows=8)
+    loss, grad = run_loca(t, s, lab, T, 0.8, mode, torch.bfloat16, force_streaming)
+    assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    assert rel_err(grad, ref.grad) <= GRAD_RTOL_BF16
+    # row-wise check too: no single row may hide behind the others
+    row_err = (grad.double() - ref.grad).norm(dim=1) / ref.grad.norm(dim=1)
+    assert row_err.max().item() <= 2 * GRAD_RTOL_BF16
+
+
+@pytest.mark.parametrize("force_streaming", PATHS)
+def test_teacher_wider_than_student_and_strided_rows(force_streaming):
+    """P1:155 slices the teacher to the student's vocabulary: we take a row stride instead of a copy."""
+    N, V, Vt = 19, 4096, 4352
+    t, s, lab = synthetic.logit_batch(N, V, seed=5, teacher_vocab=Vt)
+    ref = O.loca_kl(t, s, lab, 2.0, 0.8)
+    loss, grad = run_loca(t, s, lab, 2.0, 0.8, "reference", torch.bfloat16, force_streaming)
+    assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    assert rel_err(grad, ref.grad) <= GRAD_RTOL_BF16
+    # 3-D [B,S,V] inputs and [B,S] labels, as the reference passes them
+    loss3, grad3 = run_loca(t.reshape(1, N, Vt), s.reshape(1, N, V), lab.reshape(1, N), 2.0, 0.8, "reference",
+                            torch.bfloat16, force_streaming)
+    assert loss3 == loss and torch.equal(grad3.reshape(N, V), grad)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32], ids=["f16", "f32"])
+def test_other_dtypes(dtype):
+    t, s, lab = synthetic.logit_batch(12, 5000, seed=8, dtype=dtype)
+    ref = O.loca_kl(t, s, lab, 2.0, 0.8)
+    loss, grad = run_loca(t, s, lab, 2.0, 0.8, "reference", dtype)
+    assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    assert rel_err(grad, ref.grad) <= (1e-3 if dtype == torch.float16 else GRAD_RTOL_F32)
+
+
+def test_out_of_range_label_poisons_the_loss():
+    """The reference raises on labels outside [0, V) (P1:166, e.g. -100 pads); we must not accept them silently."""
+    t, s, lab = synthetic.logit_batch(6, 999, seed=2)
+    lab[3] = -100
+    for mode in ("reference", "per_row"):
+        loss = kd.loca_kl(t.cuda(), s.cuda(), lab.cuda(), 2.0, mode=mode)
+        assert torch.isnan(loss).item()
+
+
+def test_duplicate_labels_last_token_wins():
+    """P1:184 with duplicate columns: the last token in flattened order provides the value (CPU index_put_)."""
+    t, s, lab = synthetic.logit_batch(40, 300, seed=4)
+    lab[:] = lab[0]
+    lab[7::2] = lab[1]
+    ref = O.loca_kl(t, s, lab, 2.0, 0.8)
+    loss, grad = run_loca(t, s, lab, 2.0, 0.8, "reference", torch.bfloat16)
+    assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    assert rel_err(grad, ref.grad) <= GRAD_RTOL_BF16
+
+
+def test_grad_output_and_upstream_scaling():
+    t, s, lab = synthetic.logit_batch(9, 2048, seed=6)
+    ref = O.loca_kl(t, s, lab, 2.0, 0.8)
+    td, ld = t.cuda(), lab.cuda()
+    # (a) grad_output != 1 handled in backward
+    sd = s.cuda().requires_grad_(True)
+    (kd.loca_kl(td, sd, ld, 2.0) * 0.8 * 1024.0).backward()
+    assert rel_err(sd.grad.float().cpu() / (0.8 * 1024.0), ref.grad) <= GRAD_RTOL_BF16
+    # (b) the same scale folded into the forward launch: identical result, no rescale pass
+    sd2 = s.cuda().requires_grad_(True)
+    (kd.loca_kl(td, sd2, ld, 2.0, upstream=0.8 * 1024.0) * 0.8 * 1024.0).backward()
+    assert rel_err(sd2.grad.float().cpu() / (0.8 * 1024.0), ref.grad) <= GRAD_RTOL_BF16
+    # (c) no grad requested: forward only
+    loss = kd.loca_kl(td, s.cuda(), ld, 2.0)
+    assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+
+
+def test_batchmean_and_sum_reductions():
+    t, s, _ = synthetic.logit_batch(12, 700, seed=12)
+    t3, s3 = t.reshape(3, 4, 700), s.reshape(3, 4, 700)
+    ref = O.temperature_kl(t3, s3, 2.0, inv_norm=1.0 / 3)
+    sd = s3.cuda().requires_grad_(True)
+    loss = kd.temperature_kl(t3.cuda(), sd, 2.0, reduction="batchmean")
+    loss.backward()
+    assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    assert rel_err(sd.grad.float().cpu(), ref.grad) <= GRAD_RTOL_BF16
+
+
+def test_size_independent_properties_at_full_size():
+    """BASELINE config shape (V = 151 936) at 512 rows: properties that need no oracle.
+    (i) every gradient row sums to ~0 scaled by (Q_r - sum q m) = 0;  (ii) plain KL of a tensor with
+    itself is 0 with zero gradient; (iii) row permutation invariance of per-row mode."""
+    N, V = 512, synthetic.VOCAB
+    t, s, lab = synthetic.logit_batch(N, V, seed=21, device="cuda")
+    sd = s.clone().requires_grad_(True)
+    kd.loca_kl(t, sd, lab, 2.0, mode="per_row").backward()
+    g = sd.grad.float()
+    assert (g.sum(dim=1).abs() / g.abs().sum(dim=1)).max().item() < 2e-3
+    # (ii)
+    sd2 = t.clone().requires_grad_(True)
+    l2 = kd.temperature_kl(t, sd2, 2.0)
+    l2.backward()
+    assert abs(l2.item()) < 1e-9 and sd2.grad.float().abs().max().item() < 1e-12
+    # (iii)
+    perm = torch.randperm(N, device="cuda")
+    sd3 = s[perm].clone().requires_grad_(True)
+    l3 = kd.loca_kl(t[perm], sd3, lab[perm], 2.0, mode="per_row")
+    l1 = kd.loca_kl(t, s, lab, 2.0, mode="per_row")
+    l3.backward()
+    assert abs(l3.item() - l1.item()) <= 1e-6 * abs(l1.item())
+    assert torch.equal(sd3.grad, sd.grad[perm])
+
+
+def test_phase_split_entry_points_match_fused_call():
+    """kd_loca_teacher_stats -> kd_loca_build_table -> kd_loca_emit (token-sharded building blocks)."""
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import sharded
+    t, s, lab = synthetic.logit_batch(23, 3000, seed=31)
+    td, sd, ld = t.cuda(), s.cuda(), lab.cuda()
+    full = kd.loca_kl(td, sd.clone().requires_grad_(True), ld, 2.0)
+    loss, grad = sharded.loca_kl_token_sharded(td, sd, ld, 2.0, group=None)
+    assert abs(loss.item() - full.item()) <= 1e-6 * abs(full.item())
+    ref = O.loca_kl(t, s, lab, 2.0, 0.8)
+    assert rel_err(grad.float().cpu(), ref.grad) <= GRAD_RTOL_BF16
