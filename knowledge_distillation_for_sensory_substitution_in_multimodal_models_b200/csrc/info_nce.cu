@@ -109,22 +109,27 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
     mx = red[0];
     for (int k = 1; k < kRowThreads / 32; ++k) mx = fmaxf(mx, red[k]);
     __syncthreads();
+    // sum over the OFF-diagonal entries only: 1 - p_ii = r/(exp(L_ii - mx) + r) and lse - L_ii = log1p-style, so a
+    // well-separated diagonal (p_ii -> 1) does not lose the gradient to cancellation
+    const float lii = sl[i];
     float se = 0.f;
-    for (int j = threadIdx.x; j < M; j += kRowThreads) se += __expf(sl[j] - mx);
+    for (int j = threadIdx.x; j < M; j += kRowThreads) se += (j == i) ? 0.f : __expf(sl[j] - mx);
     se = warp_sum(se);
     if (l == 0) red[w] = se;
     __syncthreads();
-    se = 0.f;
-    for (int k = 0; k < kRowThreads / 32; ++k) se += red[k];
-    const float lse = mx + logf(se);
-    if (threadIdx.x == 0) rowloss[i] = lse - sl[i];
+    float r = 0.f;
+    for (int k = 0; k < kRowThreads / 32; ++k) r += red[k];
+    const float ed = __expf(lii - mx);                 // diagonal term relative to the max
+    const float denom = ed + r;
+    // loss_i = lse - L_ii = log(denom) - (L_ii - mx);  when the diagonal is the max (ed == 1) use log1p(r)
+    const float loss_i = (lii == mx) ? log1pf(r) : (logf(denom) - (lii - mx));
+    if (threadIdx.x == 0) rowloss[i] = loss_i;
     if (!want_grad) return;
     __syncthreads();
-    // G row: (softmax - onehot)/M, folded with 1/temp
-    for (int j = threadIdx.x; j < M; j += kRowThreads) {
-        const float pj = __expf(sl[j] - lse);
-        sl[j] = (pj - (j == i ? 1.f : 0.f)) * inv_temp / (float)M;
-    }
+    // G row: (softmax - onehot)/M, folded with 1/temp; diagonal = -(sum of the others)/denom
+    const float gsc = inv_temp / ((float)M * denom);
+    for (int j = threadIdx.x; j < M; j += kRowThreads)
+        sl[j] = (j == i) ? -r * gsc : __expf(sl[j] - mx) * gsc;
     __syncthreads();
     // du[d] = sum_j G[j] * ut[j,d]  (coalesced over d; ut is L2 resident)
     const float nrm = norm_s[i];

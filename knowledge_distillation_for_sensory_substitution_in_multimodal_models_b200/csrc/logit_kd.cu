@@ -75,14 +75,14 @@ __device__ __forceinline__ void row_stats(const T* __restrict__ row, int V, floa
     ms.init();
     if (WANT_TOP2) top.init();
     float mk2 = -INFINITY;     // ms.m * k2
+    float thr_top = -INFINITY; // lower bound of the row's runner-up value (warp-refreshed): smaller cells cannot matter
     int done = 0;
     if (VEC) {
         const int nvec = V / P;
         const uint4* rv = reinterpret_cast<const uint4*>(row);
-#pragma unroll 2
-        for (int v = threadIdx.x; v < nvec; v += NT) {
+        auto consume = [&](const uint4& raw, int v) {
             float x[P];
-            Elem<T>::unpack(ldg_stream(rv + v), x);
+            Elem<T>::unpack(raw, x);
             float vm = x[0];
 #pragma unroll
             for (int i = 1; i < P; ++i) vm = fmaxf(vm, x[i]);
@@ -93,11 +93,24 @@ __device__ __forceinline__ void row_stats(const T* __restrict__ row, int V, floa
             }
 #pragma unroll
             for (int i = 0; i < P; ++i) ms.s += ex2(fmaf(x[i], k2, -mk2));
-            if (WANT_TOP2 && vm > top.a2) {
+            if (WANT_TOP2 && vm >= thr_top) {
 #pragma unroll
                 for (int i = 0; i < P; ++i) top.push(x[i], v * P + i);
+                thr_top = fmaxf(thr_top, top.a2);
             }
+        };
+        constexpr int U = 4;      // independent 128-bit loads in flight per thread
+        int v = threadIdx.x;
+        const int last_lane = 31 - (threadIdx.x & 31);      // warp-uniform trip count: test the warp's last lane
+        for (; v + last_lane + (U - 1) * NT < nvec; v += U * NT) {
+            uint4 raw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) raw[u] = ldg_stream(rv + v + u * NT);
+#pragma unroll
+            for (int u = 0; u < U; ++u) consume(raw[u], v + u * NT);
+            if (WANT_TOP2) thr_top = warp_max(thr_top);    // share the best bound across the warp
         }
+        for (; v < nvec; v += NT) consume(ldg_stream(rv + v), v);
         done = nvec * P;
     }
     for (int c = done + threadIdx.x; c < V; c += NT) {
@@ -282,15 +295,24 @@ row_emit_stream_kernel(const EmitParams p) {
         // ---- sweep B: Q_r and the row sum ---------------------------------------------------------
         float row = 0.f, Q = 0.f;
         if (VEC) {
-#pragma unroll 2
-            for (int v = threadIdx.x; v < nvec; v += NT) {
+            auto consume = [&](const uint4& rt, const uint4& rs, int v) {
                 float xt[P], xs[P];
-                Elem<T>::unpack(ldg_keep(tv + v), xt);
-                Elem<T>::unpack(ldg_keep(sv + v), xs);
+                Elem<T>::unpack(rt, xt);
+                Elem<T>::unpack(rs, xs);
 #pragma unroll
                 for (int i = 0; i < P; ++i)
                     PointTerm<VARIANT>::accum(xt[i], xs[i], LOCA ? override_of(v * P + i) : NaN, k2, lse2_t, lse2_s, thr2, row, Q);
+            };
+            constexpr int U = 2;
+            int v = threadIdx.x;
+            for (; v + (U - 1) * NT < nvec; v += U * NT) {
+                uint4 rt[U], rs[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { rt[u] = ldg_keep(tv + v + u * NT); rs[u] = ldg_keep(sv + v + u * NT); }
+#pragma unroll
+                for (int u = 0; u < U; ++u) consume(rt[u], rs[u], v + u * NT);
             }
+            for (; v < nvec; v += NT) consume(ldg_keep(tv + v), ldg_keep(sv + v), v);
         }
         for (int c = nvec * P + threadIdx.x; c < V; c += NT)
             PointTerm<VARIANT>::accum(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]), LOCA ? override_of(c) : NaN,
@@ -313,16 +335,25 @@ row_emit_stream_kernel(const EmitParams p) {
         const float gQ = g * Q;
         if (VEC) {
             uint4* gv = reinterpret_cast<uint4*>(grow);
-#pragma unroll 2
-            for (int v = threadIdx.x; v < nvec; v += NT) {
+            auto consume = [&](const uint4& rt, const uint4& rs, int v) {
                 float xt[P], xs[P], o[P];
-                Elem<T>::unpack(ldg_stream(tv + v), xt);
-                Elem<T>::unpack(ldg_stream(sv + v), xs);
+                Elem<T>::unpack(rt, xt);
+                Elem<T>::unpack(rs, xs);
 #pragma unroll
                 for (int i = 0; i < P; ++i)
                     o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? override_of(v * P + i) : NaN, k2, lse2_t, lse2_s, thr2, g, gQ);
                 stg_stream(gv + v, Elem<T>::pack(o));
+            };
+            constexpr int U = 2;
+            int v = threadIdx.x;
+            for (; v + (U - 1) * NT < nvec; v += U * NT) {
+                uint4 rt[U], rs[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { rt[u] = ldg_stream(tv + v + u * NT); rs[u] = ldg_stream(sv + v + u * NT); }
+#pragma unroll
+                for (int u = 0; u < U; ++u) consume(rt[u], rs[u], v + u * NT);
             }
+            for (; v < nvec; v += NT) consume(ldg_stream(tv + v), ldg_stream(sv + v), v);
         }
         for (int c = nvec * P + threadIdx.x; c < V; c += NT)
             grow[c] = Elem<T>::from_float(PointTerm<VARIANT>::grad(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]),

@@ -1,0 +1,5 @@
+set -x
+python tools/profile_emit.py 4096 reference 2 > gpurun_out/plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:row_emit_cluster -s 1 -c 1 -o gpurun_out/emit_r1 python tools/profile_emit.py 4096 reference 2 > gpurun_out/ncu_emit.log 2>&1
+tail -3 gpurun_out/ncu_emit.log
+ls -la gpurun_out/
