@@ -109,7 +109,17 @@ int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t
                  float* loss_out, void* rowaux /* float4[n_rows] */, int64_t n_rows, int64_t V, int dtype,
                  float T, float eps, double inv_norm, const float* upstream, unsigned flags, void* stream);
 
-/* grad *= (*factor) in place, skipped on device when *factor == 1 (autograd backward with grad_output != 1). */
+/* Re-emission of the gradient for autograd's backward when the incoming grad_output differs from the scale that
+ * was folded into the forward launch: grad = (*upstream) * T * inv_norm * (sp * Q_r - w) recomputed from the row
+ * statistics the forward left in `workspace` (one streaming sweep, ONE rounding to the output type — rescaling the
+ * already-rounded gradient would round twice).  The kernel returns immediately when *skip_if_one == 1.0f (device
+ * scalar, may be NULL = never skip), so the common "grad_output is what forward assumed" case costs one empty launch. */
+int kd_logit_kd_regrad(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, void* grad_student,
+                       int64_t ld_g, const void* workspace, size_t workspace_bytes, int64_t n_rows, int64_t V,
+                       int dtype, float T, float eps, int variant, double inv_norm, const float* upstream,
+                       const float* skip_if_one, void* stream);
+
+/* grad *= (*factor) in place, skipped on device when *factor == 1 (kept for callers that accept double rounding). */
 int kd_scale_rows(void* grad, int64_t ld_g, int64_t n_rows, int64_t V, int dtype, const float* factor, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
@@ -121,6 +131,10 @@ int kd_info_nce_workspace_bytes(int64_t M, int64_t tokens, int64_t D, size_t* by
 int kd_info_nce_fwd_bwd(const void* student, const void* teacher, void* grad_student, float* loss_out,
                         void* workspace, size_t workspace_bytes, int64_t M, int64_t tokens, int64_t D,
                         int dtype, float temperature, const float* upstream, unsigned flags, void* stream);
+/* backward re-emission from the fp32 pooled gradient kept in `workspace`: grad = (*ratio) * d(mean)/tokens broadcast
+ * over tokens, skipped when *ratio == 1 (ratio = grad_output / the upstream folded in at forward time). */
+int kd_info_nce_regrad(const void* workspace, size_t workspace_bytes, void* grad_student, int64_t M, int64_t tokens,
+                       int64_t D, int dtype, const float* ratio, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Feature MSE — replaces mse_loss (EV:160-165): mean((input.float() - target.float())^2) and
@@ -130,6 +144,9 @@ int kd_feature_mse_workspace_bytes(int64_t numel, size_t* bytes);
 int kd_feature_mse_fwd_bwd(const void* input, const void* target, void* grad_input, float* loss_out,
                            void* workspace, size_t workspace_bytes, int64_t numel, int dtype,
                            const float* upstream, unsigned flags, void* stream);
+/* backward re-emission (see kd_logit_kd_regrad): grad = (*upstream) * 2 (a - b) / numel unless *skip_if_one == 1 */
+int kd_feature_mse_regrad(const void* input, const void* target, void* grad_input, int64_t numel, int dtype,
+                          const float* upstream, const float* skip_if_one, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,11 +36,14 @@ SIGNATURES = {
     "kd_loca_table_workspace_bytes": (_i, [_i64, C.POINTER(_sz)]),
     "kd_loca_build_table": (_i, [_p, _i64, _i64, _p, _p, _p, _sz, _p]),
     "kd_loca_emit": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i, _f, _f, _d, _p, _u, _p]),
+    "kd_logit_kd_regrad": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _sz, _i64, _i64, _i, _f, _f, _i, _d, _p, _p, _p]),
     "kd_scale_rows": (_i, [_p, _i64, _i64, _i64, _i, _p, _p]),
     "kd_info_nce_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "kd_info_nce_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i64, _i64, _i64, _i, _f, _p, _u, _p]),
+    "kd_info_nce_regrad": (_i, [_p, _sz, _p, _i64, _i64, _i64, _i, _p, _p]),
     "kd_feature_mse_workspace_bytes": (_i, [_i64, C.POINTER(_sz)]),
     "kd_feature_mse_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i64, _i, _p, _u, _p]),
+    "kd_feature_mse_regrad": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p]),
 }
 
 

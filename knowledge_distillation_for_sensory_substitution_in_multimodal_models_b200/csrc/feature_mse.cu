@@ -53,6 +53,38 @@ mse_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ g, 
     }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+mse_regrad_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ g, int64_t numel, float gscale,
+                  const float* upstream, const float* skip_if_one, bool vec) {
+    if (skip_if_one && *skip_if_one == 1.f) return;
+    constexpr int P = Elem<T>::kPack;
+    const float gs = gscale * (upstream ? *upstream : 1.f);
+    const int64_t nvec = vec ? numel / P : 0;
+    for (int64_t v = blockIdx.x * (int64_t)kThreads + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * kThreads) {
+        float x[P], y[P], o[P];
+        Elem<T>::unpack(ldg_stream(reinterpret_cast<const uint4*>(a) + v), x);
+        Elem<T>::unpack(ldg_stream(reinterpret_cast<const uint4*>(b) + v), y);
+#pragma unroll
+        for (int i = 0; i < P; ++i) o[i] = gs * (x[i] - y[i]);
+        stg_stream(reinterpret_cast<uint4*>(g) + v, Elem<T>::pack(o));
+    }
+    for (int64_t c = nvec * P + blockIdx.x * (int64_t)kThreads + threadIdx.x; c < numel; c += (int64_t)gridDim.x * kThreads)
+        g[c] = Elem<T>::from_float(gs * (Elem<T>::to_float(a[c]) - Elem<T>::to_float(b[c])));
+}
+
+template <typename T>
+int launch_regrad(const void* a, const void* b, void* g, int64_t numel, const float* upstream, const float* skip, cudaStream_t st) {
+    constexpr int P = Elem<T>::kPack;
+    const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(g)) & 15u) == 0;
+    int64_t blocks = (numel / P + kThreads - 1) / kThreads;
+    blocks = blocks < 1 ? 1 : (blocks > kMaxBlocks ? kMaxBlocks : blocks);
+    mse_regrad_kernel<T><<<(int)blocks, kThreads, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b), static_cast<T*>(g), numel,
+                                                           static_cast<float>(2.0 / (double)numel), upstream, skip, vec);
+    KD_CHECK_LAUNCH("mse_regrad_kernel");
+    return KD_OK;
+}
+
 __global__ void mse_finalize_kernel(const double* __restrict__ partials, int n, double inv_numel, float* __restrict__ loss) {
     double a = 0.0;
     for (int i = threadIdx.x; i < n; i += 32) a += partials[i];
@@ -108,6 +140,19 @@ int kd_feature_mse_fwd_bwd(const void* input, const void* target, void* grad_inp
         case KD_DTYPE_BF16: return kd::launch<__nv_bfloat16>(input, target, grad_input, loss_out, partials, numel, upstream, flags, st);
         case KD_DTYPE_F16: return kd::launch<__half>(input, target, grad_input, loss_out, partials, numel, upstream, flags, st);
         default: return kd::launch<float>(input, target, grad_input, loss_out, partials, numel, upstream, flags, st);
+    }
+}
+
+int kd_feature_mse_regrad(const void* input, const void* target, void* grad_input, int64_t numel, int dtype,
+                          const float* upstream, const float* skip_if_one, void* stream) {
+    KD_CHECK_ARG(input && target && grad_input, "kd_feature_mse_regrad: null pointer");
+    KD_CHECK_ARG(numel > 0, "kd_feature_mse_regrad: numel must be positive");
+    KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case KD_DTYPE_BF16: return kd::launch_regrad<__nv_bfloat16>(input, target, grad_input, numel, upstream, skip_if_one, st);
+        case KD_DTYPE_F16: return kd::launch_regrad<__half>(input, target, grad_input, numel, upstream, skip_if_one, st);
+        default: return kd::launch_regrad<float>(input, target, grad_input, numel, upstream, skip_if_one, st);
     }
 }
 

@@ -168,8 +168,13 @@ __global__ void nce_finalize_kernel(const float* __restrict__ rowloss, int M, fl
 // ---- dx[m,p,:] = dmean[m,:] -----------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P, int D, bool vec) {
+broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P, int D, bool vec, const float* ratio) {
     constexpr int E = Elem<T>::kPack;
+    float f = 1.f;
+    if (ratio) {            // backward re-emission: skip when grad_output is what forward assumed
+        f = *ratio;
+        if (f == 1.f) return;
+    }
     const int m = blockIdx.y;
     const float* src = dmean + (int64_t)m * D;
     T* dst = dx + (int64_t)m * P * D;
@@ -180,13 +185,13 @@ broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P
             const int c = (int)(idx % ncol);
             float v[E];
 #pragma unroll
-            for (int i = 0; i < E; ++i) v[i] = src[c * E + i];
+            for (int i = 0; i < E; ++i) v[i] = src[c * E + i] * f;
             stg_stream(reinterpret_cast<uint4*>(dst) + idx, Elem<T>::pack(v));
         }
     } else {
         const int64_t total = (int64_t)P * D;
         for (int64_t idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256)
-            dst[idx] = Elem<T>::from_float(src[idx % D]);
+            dst[idx] = Elem<T>::from_float(src[idx % D] * f);
     }
 }
 
@@ -240,9 +245,20 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
         int bx = (int)(((int64_t)P * (D / (vec_out ? E : 1)) + 255) / 256);
         if (bx > 64) bx = 64;
         if (bx < 1) bx = 1;
-        broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out);
+        broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, nullptr);
         KD_CHECK_LAUNCH("broadcast_rows_kernel");
     }
+    return KD_OK;
+}
+
+template <typename T>
+int run_regrad(const float* dmean, void* dx, int M, int P, int D, const float* ratio, cudaStream_t st) {
+    constexpr int E = Elem<T>::kPack;
+    const bool vec_out = (D % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
+    int bx = (int)(((int64_t)P * (D / (vec_out ? E : 1)) + 255) / 256);
+    bx = bx > 64 ? 64 : (bx < 1 ? 1 : bx);
+    broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, ratio);
+    KD_CHECK_LAUNCH("broadcast_rows_kernel");
     return KD_OK;
 }
 
@@ -276,6 +292,25 @@ int kd_info_nce_fwd_bwd(const void* student, const void* teacher, void* grad_stu
         case KD_DTYPE_BF16: return kd::run<__nv_bfloat16>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st);
         case KD_DTYPE_F16: return kd::run<__half>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st);
         default: return kd::run<float>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st);
+    }
+}
+
+int kd_info_nce_regrad(const void* workspace, size_t workspace_bytes, void* grad_student, int64_t M, int64_t tokens,
+                       int64_t D, int dtype, const float* ratio, void* stream) {
+    KD_CHECK_ARG(workspace && grad_student && ratio, "kd_info_nce_regrad: null pointer");
+    KD_CHECK_ARG(M >= 1 && tokens >= 1 && D >= 1, "kd_info_nce_regrad: bad shape");
+    KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
+    const kd::NceWorkspace w = kd::nce_layout(M, D);
+    if (workspace_bytes < w.total) {
+        kd::set_error("kd_info_nce_regrad: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return KD_ERR_WORKSPACE_TOO_SMALL;
+    }
+    const float* dmean = reinterpret_cast<const float*>(static_cast<const char*>(workspace) + w.dmean);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case KD_DTYPE_BF16: return kd::run_regrad<__nv_bfloat16>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, st);
+        case KD_DTYPE_F16: return kd::run_regrad<__half>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, st);
+        default: return kd::run_regrad<float>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, st);
     }
 }
 

@@ -328,7 +328,16 @@ row_emit_stream_kernel(const EmitParams p) {
                 row = NaN;
             }
         }
-        if (threadIdx.x == 0) p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row);
+        if (threadIdx.x == 0) {
+            p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row);
+            if constexpr (VARIANT == KD_LOCA_PER_ROW) {
+                if (p.records) {
+                    kd_token_record rec;
+                    rec.label = ov_label; rec.v1 = v1; rec.k = ov_k; rec.v2 = v2;
+                    p.records[r] = rec;
+                }
+            }
+        }
         if (!want_grad) continue;
 
         // ---- sweep C: gradient ----------------------------------------------------------------------
@@ -358,6 +367,58 @@ row_emit_stream_kernel(const EmitParams p) {
         for (int c = nvec * P + threadIdx.x; c < V; c += NT)
             grow[c] = Elem<T>::from_float(PointTerm<VARIANT>::grad(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]),
                                                                    LOCA ? override_of(c) : NaN, k2, lse2_t, lse2_s, thr2, g, gQ));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward re-emission: one streaming sweep that recomputes the gradient from saved row statistics
+// ------------------------------------------------------------------------------------------------
+template <int VARIANT, typename T, bool VEC>
+__global__ void __launch_bounds__(256)
+regrad_kernel(const EmitParams p, const float* skip_if_one) {
+    if (skip_if_one && *skip_if_one == 1.f) return;
+    constexpr int P = Elem<T>::kPack;
+    constexpr bool LOCA = (VARIANT == KD_LOCA_REFERENCE || VARIANT == KD_LOCA_PER_ROW);
+    const float NaN = __int_as_float(0x7fc00000);
+    const int V = p.V;
+    const float g = p.gscale * (p.upstream ? *p.upstream : 1.f);
+    const int nvec = VEC ? V / P : 0;
+    for (int64_t r = blockIdx.y; r < p.n_rows; r += gridDim.y) {
+        const float4 aux = p.rowaux[r];
+        const float lse2_t = aux.x, lse2_s = aux.y, gQ = g * aux.z;
+        int ov_label = -1, ov_k = -1;
+        float v1 = NaN, v2 = NaN;
+        if constexpr (VARIANT == KD_LOCA_PER_ROW) {
+            const kd_token_record rec = p.records[r];
+            ov_label = rec.label; v1 = rec.v1; ov_k = rec.k; v2 = rec.v2;
+        }
+        auto override_of = [&](int c) -> float {
+            if constexpr (VARIANT == KD_LOCA_REFERENCE) return __ldg(p.table + c);
+            if constexpr (VARIANT == KD_LOCA_PER_ROW) return (c == ov_k) ? v2 : ((c == ov_label) ? v1 : NaN);
+            return NaN;
+        };
+        const T* trow = static_cast<const T*>(p.teacher) + r * p.ld_t;
+        const T* srow = static_cast<const T*>(p.student) + r * p.ld_s;
+        T* grow = static_cast<T*>(p.grad) + r * p.ld_g;
+        const int t0 = blockIdx.x * 256 + threadIdx.x, stride = gridDim.x * 256;
+        if (VEC) {
+            const uint4* tv = reinterpret_cast<const uint4*>(trow);
+            const uint4* sv = reinterpret_cast<const uint4*>(srow);
+            uint4* gv = reinterpret_cast<uint4*>(grow);
+#pragma unroll 2
+            for (int v = t0; v < nvec; v += stride) {
+                float xt[P], xs[P], o[P];
+                Elem<T>::unpack(ldg_stream(tv + v), xt);
+                Elem<T>::unpack(ldg_stream(sv + v), xs);
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+                    o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? override_of(v * P + i) : NaN, p.k2, lse2_t, lse2_s, p.thr2, g, gQ);
+                stg_stream(gv + v, Elem<T>::pack(o));
+            }
+        }
+        for (int c = nvec * P + t0; c < V; c += stride)
+            grow[c] = Elem<T>::from_float(PointTerm<VARIANT>::grad(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]),
+                                                                   LOCA ? override_of(c) : NaN, p.k2, lse2_t, lse2_s, p.thr2, g, gQ));
     }
 }
 
@@ -514,6 +575,33 @@ int launch_emit(const EmitParams& p, int variant, int dtype, cudaStream_t st) {
     return KD_ERR_INVALID_ARGUMENT;
 }
 
+template <int VARIANT, typename T>
+int launch_regrad_t(const EmitParams& p, const float* skip, cudaStream_t st) {
+    const bool vec = rows_vectorizable<T>(p.teacher, p.ld_t) && rows_vectorizable<T>(p.student, p.ld_s) &&
+                     rows_vectorizable<T>(p.grad, p.ld_g);
+    int64_t gx = (p.V / Elem<T>::kPack + 255) / 256;
+    gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
+    int64_t gy = (int64_t)sm_count() * 16 / gx;
+    gy = gy < 1 ? 1 : (gy > p.n_rows ? p.n_rows : gy);
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (vec) regrad_kernel<VARIANT, T, true><<<grid, 256, 0, st>>>(p, skip);
+    else regrad_kernel<VARIANT, T, false><<<grid, 256, 0, st>>>(p, skip);
+    KD_CHECK_LAUNCH("regrad_kernel");
+    return KD_OK;
+}
+
+template <typename T>
+int launch_regrad_v(const EmitParams& p, int variant, const float* skip, cudaStream_t st) {
+    switch (variant) {
+        case KD_LOCA_REFERENCE: return launch_regrad_t<KD_LOCA_REFERENCE, T>(p, skip, st);
+        case KD_LOCA_PER_ROW: return launch_regrad_t<KD_LOCA_PER_ROW, T>(p, skip, st);
+        case KD_KL_PLAIN: return launch_regrad_t<KD_KL_PLAIN, T>(p, skip, st);
+        case KD_KL_LOG_TARGET: return launch_regrad_t<KD_KL_LOG_TARGET, T>(p, skip, st);
+    }
+    set_error("unknown logit-KD variant %d", variant);
+    return KD_ERR_INVALID_ARGUMENT;
+}
+
 int check_common(int64_t n_rows, int64_t V, int dtype, float T) {
     KD_CHECK_ARG(n_rows >= 0, "n_rows must be >= 0 (got %lld)", (long long)n_rows);
     KD_CHECK_ARG(V >= 1 && V < (1ll << 30), "V must be in [1, 2^30) (got %lld)", (long long)V);
@@ -661,6 +749,7 @@ int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, 
     p.grad = grad_student; p.ld_g = ld_g; p.rowaux = rowaux; p.status = status; p.upstream = upstream;
     p.n_rows = n_rows; p.V = (int)V; p.k2 = kLog2e / T; p.alpha = alpha; p.thr2 = loca ? log2f(eps) : -INFINITY;
     p.gscale = static_cast<float>(T * inv_norm); p.flags = flags;
+    p.records = reinterpret_cast<kd_token_record*>(ws + w.records);
 
     if (variant == KD_LOCA_REFERENCE) {
         kd_token_record* rec = reinterpret_cast<kd_token_record*>(ws + w.records);
@@ -681,6 +770,37 @@ int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, 
                                                       variant == KD_LOCA_REFERENCE ? consts : nullptr, status, loss_out);
     KD_CHECK_LAUNCH("loss_finalize_kernel");
     return KD_OK;
+}
+
+int kd_logit_kd_regrad(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, void* grad_student,
+                       int64_t ld_g, const void* workspace, size_t workspace_bytes, int64_t n_rows, int64_t V, int dtype,
+                       float T, float eps, int variant, double inv_norm, const float* upstream, const float* skip_if_one,
+                       void* stream) {
+    if (int rc = check_common(n_rows, V, dtype, T)) return rc;
+    KD_CHECK_ARG(variant >= KD_LOCA_REFERENCE && variant <= KD_KL_LOG_TARGET, "unknown logit-KD variant %d", variant);
+    KD_CHECK_ARG(teacher && student && grad_student && workspace, "kd_logit_kd_regrad: null pointer");
+    KD_CHECK_ARG(ld_t >= V && ld_s >= V && ld_g >= V, "leading dimension < V");
+    const Workspace w = workspace_layout(n_rows, V);
+    if (workspace_bytes < w.total) {
+        set_error("kd_logit_kd_regrad: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return KD_ERR_WORKSPACE_TOO_SMALL;
+    }
+    if (n_rows == 0) return KD_OK;
+    const bool loca = (variant == KD_LOCA_REFERENCE || variant == KD_LOCA_PER_ROW);
+    char* ws = const_cast<char*>(static_cast<const char*>(workspace));
+    EmitParams p{};
+    p.teacher = teacher; p.ld_t = ld_t; p.student = student; p.ld_s = ld_s; p.grad = grad_student; p.ld_g = ld_g;
+    p.rowaux = reinterpret_cast<float4*>(ws + w.rowaux);
+    p.records = reinterpret_cast<kd_token_record*>(ws + w.records);
+    p.table = reinterpret_cast<const float*>(ws + w.table);
+    p.upstream = upstream; p.n_rows = n_rows; p.V = (int)V; p.k2 = kLog2e / T;
+    p.thr2 = loca ? log2f(eps) : -INFINITY; p.gscale = static_cast<float>(T * inv_norm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case KD_DTYPE_BF16: return launch_regrad_v<__nv_bfloat16>(p, variant, skip_if_one, st);
+        case KD_DTYPE_F16: return launch_regrad_v<__half>(p, variant, skip_if_one, st);
+        default: return launch_regrad_v<float>(p, variant, skip_if_one, st);
+    }
 }
 
 int kd_scale_rows(void* grad, int64_t ld_g, int64_t n_rows, int64_t V, int dtype, const float* factor, void* stream) {

@@ -25,6 +25,7 @@ struct EmitParams {
     void* grad;
     int64_t ld_g;
     float4* rowaux;             // per row: lse2_t, lse2_s, Q_r, row sum (log2 units; natural for KLLT)
+    kd_token_record* records;   // per-row LoCa: {label, v1, k, v2} written for the backward re-emission (may be null)
     uint32_t* status;
     const float* upstream;      // device scalar or nullptr
     int64_t n_rows;

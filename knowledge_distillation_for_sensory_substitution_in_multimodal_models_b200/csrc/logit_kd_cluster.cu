@@ -609,6 +609,13 @@ row_emit_cluster_kernel(const ClusterParams cp) {
                 }
             }
             p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row);
+            if constexpr (VARIANT == KD_LOCA_PER_ROW) {
+                if (p.records) {
+                    kd_token_record rec;
+                    rec.label = lab; rec.v1 = v1; rec.k = ov_k; rec.v2 = v2;
+                    p.records[r] = rec;
+                }
+            }
         }
 
         // ================= sweep C: gradient, written straight to HBM ===================================

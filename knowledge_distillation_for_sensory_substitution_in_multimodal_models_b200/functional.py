@@ -8,8 +8,10 @@ These are the drop-in replacements for the reference's loss *calls* (SURVEY.md Â
 * :func:`feature_mse`    â€” ``mse_loss`` (EV:160-165)
 
 Forward and backward are ONE fused device pass: the gradient w.r.t. the student tensor is produced in
-the forward launch (scaled by ``upstream`` if given) and ``backward`` only rescales it when the
-incoming ``grad_output`` differs from 1 (checked on the device, no host sync).  PyTorch is used for
+the forward launch (scaled by ``upstream`` if given).  ``backward`` launches a re-emission kernel that
+exits immediately when the incoming ``grad_output`` equals that scale (checked on the device, no host
+sync) and otherwise recomputes the gradient from the saved row statistics in one streaming sweep, so the
+result is rounded to the output dtype exactly once either way.  PyTorch is used for
 memory, streams and autograd plumbing only; all arithmetic runs in ``libkd_b200.so``.
 """
 from __future__ import annotations
@@ -58,12 +60,11 @@ def _stream_ptr(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-def _backward_factor(grad_output, upstream, dev):
-    """grad_output relative to the scale already folded in at forward time (device scalar, no sync)."""
-    go = grad_output.detach().to(device=dev, dtype=torch.float32).reshape(())
-    if upstream is not None:
-        go = go / upstream
-    return go.contiguous()
+def _backward_scalars(grad_output, upstream, dev):
+    """(grad_output, grad_output / scale folded in at forward time) as device scalars â€” no host sync."""
+    go = grad_output.detach().to(device=dev, dtype=torch.float32).reshape(()).contiguous()
+    ratio = go if upstream is None else (go / upstream).contiguous()
+    return go, ratio
 
 
 def _upstream_ptr(upstream, dev):
@@ -125,7 +126,11 @@ class _LogitKD(torch.autograd.Function):
         ctx.student_shape = student.shape
         ctx.dev = dev
         ctx.upstream = up_t
-        ctx.workspace = ws      # row statistics stay alive for inspection (kd_logit_kd_rowaux_offset)
+        ctx.workspace = ws      # row statistics (kd_logit_kd_rowaux_offset), token records and the override table
+        if need_grad:           # inputs of the backward re-emission
+            ctx.rows = (t2, s2)
+            ctx.call = (n_rows, V, _dtype_code(student), float(T), float(eps), int(variant),
+                        _inv_norm(reduction, n_rows, V, batch, n_total))
         return loss
 
     @staticmethod
@@ -134,10 +139,16 @@ class _LogitKD(torch.autograd.Function):
         if grad is None:
             return (None,) * 11
         ctx.grad = None
-        go = _backward_factor(grad_output, ctx.upstream, ctx.dev)
+        go, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
+        t2, s2 = ctx.rows
+        n_rows, V, dt, T, eps, variant, inv_norm = ctx.call
+        ws = ctx.workspace
         with torch.cuda.device(ctx.dev):
-            _lib.check(_lib.load().kd_scale_rows(grad.data_ptr(), grad.stride(0), grad.shape[0], grad.shape[1],
-                                                 _dtype_code(grad), go.data_ptr(), _stream_ptr(ctx.dev)))
+            _lib.check(_lib.load().kd_logit_kd_regrad(t2.data_ptr(), t2.stride(0), s2.data_ptr(), s2.stride(0),
+                                                      grad.data_ptr(), grad.stride(0), ws.data_ptr(), ws.numel(),
+                                                      n_rows, V, dt, T, eps, variant, inv_norm, go.data_ptr(),
+                                                      ratio.data_ptr(), _stream_ptr(ctx.dev)))
+        ctx.rows = ctx.workspace = None
         return (None, grad.view(ctx.student_shape), None, None, None, None, None, None, None, None, None)
 
 
@@ -191,6 +202,7 @@ class _InfoNCE(torch.autograd.Function):
                                                float(temperature), up_ptr, 0 if need_grad else _lib.FLAG_NO_GRAD,
                                                _stream_ptr(dev)))
         ctx.grad, ctx.dev, ctx.upstream = grad, dev, up_t
+        ctx.workspace, ctx.shape3 = ws, (M, P, D)
         return loss
 
     @staticmethod
@@ -199,11 +211,13 @@ class _InfoNCE(torch.autograd.Function):
         if grad is None:
             return None, None, None, None
         ctx.grad = None
-        go = _backward_factor(grad_output, ctx.upstream, ctx.dev)
-        flat = grad.view(1, -1)
+        _, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
+        M, P, D = ctx.shape3
+        ws = ctx.workspace
         with torch.cuda.device(ctx.dev):
-            _lib.check(_lib.load().kd_scale_rows(flat.data_ptr(), flat.shape[1], 1, flat.shape[1], _dtype_code(grad),
-                                                 go.data_ptr(), _stream_ptr(ctx.dev)))
+            _lib.check(_lib.load().kd_info_nce_regrad(ws.data_ptr(), ws.numel(), grad.data_ptr(), M, P, D,
+                                                      _dtype_code(grad), ratio.data_ptr(), _stream_ptr(ctx.dev)))
+        ctx.workspace = None
         return grad, None, None, None
 
 
@@ -232,6 +246,7 @@ class _FeatureMSE(torch.autograd.Function):
                                                   loss.data_ptr(), ws.data_ptr(), ws_bytes, a.numel(), _dtype_code(a),
                                                   up_ptr, 0 if need_grad else _lib.FLAG_NO_GRAD, _stream_ptr(dev)))
         ctx.grad, ctx.dev, ctx.upstream = grad, dev, up_t
+        ctx.inputs = (a, b) if need_grad else None
         return loss
 
     @staticmethod
@@ -240,11 +255,13 @@ class _FeatureMSE(torch.autograd.Function):
         if grad is None:
             return None, None, None
         ctx.grad = None
-        go = _backward_factor(grad_output, ctx.upstream, ctx.dev)
-        flat = grad.view(1, -1)
+        go, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
+        a, b = ctx.inputs
         with torch.cuda.device(ctx.dev):
-            _lib.check(_lib.load().kd_scale_rows(flat.data_ptr(), flat.shape[1], 1, flat.shape[1], _dtype_code(grad),
-                                                 go.data_ptr(), _stream_ptr(ctx.dev)))
+            _lib.check(_lib.load().kd_feature_mse_regrad(a.data_ptr(), b.data_ptr(), grad.data_ptr(), a.numel(),
+                                                         _dtype_code(a), go.data_ptr(), ratio.data_ptr(),
+                                                         _stream_ptr(ctx.dev)))
+        ctx.inputs = None
         return grad, None, None
 
 

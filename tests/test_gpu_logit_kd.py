@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import goldens_of_kind, load_golden, rel_err
+from _util import goldens_of_kind, grad_close, load_golden, rel_err
 from oracle import kd_oracle as O
 import knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 as kd
 from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import _lib, synthetic
@@ -36,7 +36,7 @@ def test_loca_goldens(name, dtype, force_streaming):
     t, s, lab = torch.from_numpy(g["teacher"]), torch.from_numpy(g["student"]), torch.from_numpy(g["labels"])
     loss, grad = run_loca(t, s, lab, float(g["T"]), float(g["alpha"]), mode, dtype, force_streaming)
     assert abs(loss - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
-    assert rel_err(grad, g["grad"]) <= (GRAD_RTOL_BF16 if dtype == torch.bfloat16 else GRAD_RTOL_F32)
+    assert grad_close(grad, g["grad"]) if dtype == torch.bfloat16 else rel_err(grad, g["grad"]) <= GRAD_RTOL_F32
 
 
 @pytest.mark.parametrize("force_streaming", PATHS)
@@ -49,7 +49,7 @@ def test_temperature_kl_goldens(name, force_streaming):
     loss = kd.temperature_kl(t, s, float(g["T"]), log_target_quirk=quirk, force_streaming=force_streaming)
     loss.backward()
     assert abs(loss.item() - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
-    assert rel_err(s.grad.float().cpu(), g["grad"]) <= GRAD_RTOL_BF16
+    assert grad_close(s.grad.float().cpu(), g["grad"])
 
 
 @pytest.mark.parametrize("force_streaming", PATHS)
@@ -62,8 +62,8 @@ def test_loca_full_vocab_golden(name, force_streaming):
     loss, grad = run_loca(t, s, lab, float(g["T"]), float(g["alpha"]), "reference", torch.bfloat16, force_streaming)
     assert abs(loss - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
     st = int(g["grad_stride"])
-    assert rel_err(grad[:, ::st], g["grad_sample"]) <= GRAD_RTOL_BF16
-    assert rel_err(grad[:, lab], g["grad_at_labels"]) <= GRAD_RTOL_BF16
+    assert grad_close(grad[:, ::st], g["grad_sample"])
+    assert rel_err(grad[:, lab], g["grad_at_labels"]) <= 2.0 ** -8     # a handful of cells: worst-case bf16 rounding
     assert abs(grad.double().norm().item() - float(g["grad_norm"])) <= GRAD_RTOL_BF16 * float(g["grad_norm"])
 
 
@@ -82,10 +82,10 @@ def test_loca_against_oracle(N, V, T, peaked, boost, mode, force_streaming):
     ref = O.loca_kl(t, s, lab, T, 0.8, mode=mode, chunk_rows=8)
     loss, grad = run_loca(t, s, lab, T, 0.8, mode, torch.bfloat16, force_streaming)
     assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
-    assert rel_err(grad, ref.grad) <= GRAD_RTOL_BF16
+    assert grad_close(grad, ref.grad)
     # row-wise check too: no single row may hide behind the others
     row_err = (grad.double() - ref.grad).norm(dim=1) / ref.grad.norm(dim=1)
-    assert row_err.max().item() <= 2 * GRAD_RTOL_BF16
+    assert row_err.max().item() <= 2.0 ** -8
 
 
 @pytest.mark.parametrize("force_streaming", PATHS)
@@ -96,20 +96,26 @@ def test_teacher_wider_than_student_and_strided_rows(force_streaming):
     ref = O.loca_kl(t, s, lab, 2.0, 0.8)
     loss, grad = run_loca(t, s, lab, 2.0, 0.8, "reference", torch.bfloat16, force_streaming)
     assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
-    assert rel_err(grad, ref.grad) <= GRAD_RTOL_BF16
+    assert grad_close(grad, ref.grad)
     # 3-D [B,S,V] inputs and [B,S] labels, as the reference passes them
     loss3, grad3 = run_loca(t.reshape(1, N, Vt), s.reshape(1, N, V), lab.reshape(1, N), 2.0, 0.8, "reference",
                             torch.bfloat16, force_streaming)
     assert loss3 == loss and torch.equal(grad3.reshape(N, V), grad)
 
 
+@pytest.mark.parametrize("force_streaming", PATHS)
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32], ids=["f16", "f32"])
-def test_other_dtypes(dtype):
-    t, s, lab = synthetic.logit_batch(12, 5000, seed=8, dtype=dtype)
+def test_other_dtypes(dtype, force_streaming):
+    """fp16 gradients need a loss scale (they are ~1e-9 and would flush to zero): exactly what AMP does in the
+    reference (Trainer(precision="16"), TR2:145) — the scale is folded into the forward launch via ``upstream``."""
+    t, s, lab = synthetic.logit_batch(12, 8192, seed=8, dtype=dtype)
     ref = O.loca_kl(t, s, lab, 2.0, 0.8)
-    loss, grad = run_loca(t, s, lab, 2.0, 0.8, "reference", dtype)
-    assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
-    assert rel_err(grad, ref.grad) <= (1e-3 if dtype == torch.float16 else GRAD_RTOL_F32)
+    scale = 2.0 ** 20 if dtype == torch.float16 else 1.0
+    sd = s.cuda().requires_grad_(True)
+    loss = kd.loca_kl(t.cuda(), sd, lab.cuda(), 2.0, alpha=0.8, upstream=scale, force_streaming=force_streaming)
+    (loss * scale).backward()
+    assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    assert rel_err(sd.grad.float().cpu() / scale, ref.grad) <= (5e-4 if dtype == torch.float16 else GRAD_RTOL_F32)
 
 
 def test_out_of_range_label_poisons_the_loss():
@@ -129,7 +135,7 @@ def test_duplicate_labels_last_token_wins():
     ref = O.loca_kl(t, s, lab, 2.0, 0.8)
     loss, grad = run_loca(t, s, lab, 2.0, 0.8, "reference", torch.bfloat16)
     assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
-    assert rel_err(grad, ref.grad) <= GRAD_RTOL_BF16
+    assert grad_close(grad, ref.grad)
 
 
 def test_grad_output_and_upstream_scaling():
@@ -139,11 +145,17 @@ def test_grad_output_and_upstream_scaling():
     # (a) grad_output != 1 handled in backward
     sd = s.cuda().requires_grad_(True)
     (kd.loca_kl(td, sd, ld, 2.0) * 0.8 * 1024.0).backward()
-    assert rel_err(sd.grad.float().cpu() / (0.8 * 1024.0), ref.grad) <= GRAD_RTOL_BF16
-    # (b) the same scale folded into the forward launch: identical result, no rescale pass
+    assert grad_close(sd.grad.float().cpu() / (0.8 * 1024.0), ref.grad)
+    # (b) the same scale folded into the forward launch: bit-identical result, the re-emission kernel exits early
     sd2 = s.cuda().requires_grad_(True)
     (kd.loca_kl(td, sd2, ld, 2.0, upstream=0.8 * 1024.0) * 0.8 * 1024.0).backward()
-    assert rel_err(sd2.grad.float().cpu() / (0.8 * 1024.0), ref.grad) <= GRAD_RTOL_BF16
+    assert torch.equal(sd2.grad, sd.grad)
+    # (b') per-row and plain-KL variants go through the same re-emission path
+    for fn in (lambda x: kd.loca_kl(td, x, ld, 2.0, mode="per_row"), lambda x: kd.temperature_kl(td, x, 2.0)):
+        x1, x2 = s.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
+        fn(x1).backward()
+        (fn(x2) * 3.0).backward()
+        assert rel_err(x2.grad.float().cpu() / 3.0, x1.grad.float().cpu()) <= 2.0 ** -7    # both sides carry one bf16 rounding
     # (c) no grad requested: forward only
     loss = kd.loca_kl(td, s.cuda(), ld, 2.0)
     assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
@@ -157,7 +169,7 @@ def test_batchmean_and_sum_reductions():
     loss = kd.temperature_kl(t3.cuda(), sd, 2.0, reduction="batchmean")
     loss.backward()
     assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
-    assert rel_err(sd.grad.float().cpu(), ref.grad) <= GRAD_RTOL_BF16
+    assert grad_close(sd.grad.float().cpu(), ref.grad)
 
 
 def test_size_independent_properties_at_full_size():
@@ -194,4 +206,4 @@ def test_phase_split_entry_points_match_fused_call():
     loss, grad = sharded.loca_kl_token_sharded(td, sd, ld, 2.0, group=None)
     assert abs(loss.item() - full.item()) <= 1e-6 * abs(full.item())
     ref = O.loca_kl(t, s, lab, 2.0, 0.8)
-    assert rel_err(grad.float().cpu(), ref.grad) <= GRAD_RTOL_BF16
+    assert grad_close(grad.float().cpu(), ref.grad)

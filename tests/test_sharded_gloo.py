@@ -1,0 +1,82 @@
+"""World-size-2 (gloo, CPU) test of the token-sharded LoCa host logic: ragged record all-gather in global token
+order, identical table on every rank, global normaliser, loss all-reduce.  The three device phases are replaced by
+oracle-backed stand-ins (tests may use oracle/); the CUDA phases are covered by the GPU tests."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import kd_oracle as O
+from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import sharded, synthetic
+
+T, ALPHA, V = 2.0, 0.8, 257
+
+
+class OraclePhases:
+    """CPU stand-in for sharded.CudaPhases with the same record layout ([n,4] int32: label, v1 bits, k, v2 bits)."""
+
+    def teacher_stats(self, teacher, labels, T, alpha, V):
+        st = O.loca_row_stats(teacher, labels, T, alpha, V, dtype=torch.float64)
+        rec = torch.empty((labels.numel(), 4), dtype=torch.int32)
+        rec[:, 0] = st["labels"].int()
+        rec[:, 1] = st["v1"].float().view(torch.int32)
+        rec[:, 2] = st["k"].int()
+        rec[:, 3] = st["v2"].float().view(torch.int32)
+        return rec, None, None
+
+    def build_table(self, records_all, V):
+        lab, k = records_all[:, 0].long(), records_all[:, 2].long()
+        v1 = records_all[:, 1].contiguous().view(torch.float32).double()
+        v2 = records_all[:, 3].contiguous().view(torch.float32).double()
+        self.stats_all = {"labels": lab, "k": k, "v1": v1, "v2": v2}
+        return O.build_override_table(lab, k, v1, v2, V), None
+
+    def emit(self, teacher, student, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad=True, force_streaming=False):
+        lab_local = torch.zeros(student.shape[0], dtype=torch.long)     # labels only matter through the table here
+        res = O.loca_kl(teacher, student, lab_local, T, ALPHA, eps, mode=O.LOCA_REFERENCE, inv_norm=inv_norm,
+                        stats_override=self.stats_all)
+        return res.loss.float(), res.grad
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_total, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        t, s, lab = synthetic.logit_batch(n_total, V, seed=3)
+        # ragged shards on purpose: rank 0 gets fewer rows than an even split
+        cut = n_total // 3
+        lo, hi = (0, cut) if rank == 0 else (cut, n_total)
+        loss, grad = sharded.loca_kl_token_sharded(t[lo:hi], s[lo:hi], lab[lo:hi], T, ALPHA, phases=OraclePhases())
+        full = O.loca_kl(t, s, lab, T, ALPHA)
+        ok_loss = abs(loss.item() - full.loss.item()) <= 1e-6 * abs(full.loss.item())
+        ok_grad = ((grad - full.grad[lo:hi]).norm() / full.grad[lo:hi].norm()).item() <= 1e-6
+        # per-row variants: only the normaliser and the scalar sum cross ranks
+        part = sharded.per_row_token_sharded(
+            lambda a, b, n_total=None: O.temperature_kl(a, b, T, inv_norm=1.0 / (n_total * V)).loss.float(), t[lo:hi], s[lo:hi])
+        ok_kl = abs(part.item() - O.temperature_kl(t, s, T).loss.item()) <= 1e-6 * abs(part.item())
+        out[rank] = (ok_loss, ok_grad, ok_kl)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_token_sharded_loca_world_size_2():
+    world, port = 2, _free_port()
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, 23, out), nprocs=world, join=True)
+    assert dict(out) == {0: (True, True, True), 1: (True, True, True)}
+
+
+def test_single_process_passthrough():
+    rec = torch.arange(12, dtype=torch.int32).reshape(3, 4)
+    assert sharded.gather_records(rec) is rec
