@@ -277,8 +277,15 @@ def main() -> None:
             emit_ms, stats_ms = a.elapsed_time(b) / k, b.elapsed_time(c) / k
             emit_bytes = 3 * esize * V * N            # read teacher + read student + write grad
             achieved = emit_bytes / (emit_ms / 1e3) / 1e9
+            traffic = None
+            try:      # dram__bytes_read+write per row from the committed ncu --set full capture (profiles/)
+                with open(os.path.join(ROOT, "profiles", "emit_traffic.json")) as f:
+                    traffic = json.load(f)["dram_bytes_per_row"] * N
+            except Exception:  # noqa: BLE001
+                pass
             roof = {"bound": "hbm", "kernel": "LoCa emit (phase C: q/Q_r/loss/grad)", "achieved": achieved, "peak": peak_gbs,
-                    "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "algorithmic_bytes": emit_bytes,
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_token": 3 * esize * V, "kernel_ms": emit_ms}
             side["teacher_stats"] = {"kernel_ms": stats_ms, "achieved_gbs": esize * V * N / (stats_ms / 1e3) / 1e9,
                                      "frac": esize * V * N / (stats_ms / 1e3) / 1e9 / peak_gbs,

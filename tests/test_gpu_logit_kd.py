@@ -145,7 +145,7 @@ def test_grad_output_and_upstream_scaling():
     # (a) grad_output != 1 handled in backward
     sd = s.cuda().requires_grad_(True)
     (kd.loca_kl(td, sd, ld, 2.0) * 0.8 * 1024.0).backward()
-    assert grad_close(sd.grad.float().cpu() / (0.8 * 1024.0), ref.grad)
+    assert grad_close(sd.grad.float().cpu(), ref.grad * (0.8 * 1024.0))
     # (b) the same scale folded into the forward launch: bit-identical result, the re-emission kernel exits early
     sd2 = s.cuda().requires_grad_(True)
     (kd.loca_kl(td, sd2, ld, 2.0, upstream=0.8 * 1024.0) * 0.8 * 1024.0).backward()

@@ -1,0 +1,8 @@
+set -x
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
+CMD="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-secondary"
+$CMD > gpurun_out/plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+$CMD > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:row_emit_cluster -s 3 -c 1 -o gpurun_out/r1_emit_full $CMD > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
