@@ -23,6 +23,10 @@ namespace kd {
 
 namespace {
 
+#ifndef KD_SWEEP_UNROLL
+#define KD_SWEEP_UNROLL 2
+#endif
+constexpr int kSweepUnroll = KD_SWEEP_UNROLL;
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr float kPush = -3.0e38f;       // ov' * kPush drives log2 q of an overridden cell to -inf
@@ -176,8 +180,8 @@ struct SmemPlan {
 // Walk the warp's vectors v = lane, lane+32, ... keeping D loads of the primary stream in flight ahead of use.
 template <int D, typename LoadF, typename BodyF>
 __device__ __forceinline__ void pipelined_sweep(int lane, int w_n, LoadF load, BodyF body) {
-    if constexpr (D == 0) {       // shared-memory source: a plain 2x unrolled loop schedules best
-#pragma unroll 2
+    if constexpr (D == 0) {       // shared-memory source: a plain unrolled loop schedules best
+#pragma unroll kSweepUnroll
         for (int v = lane; v < w_n; v += 32) body(v, load(v));
         return;
     }
@@ -389,32 +393,44 @@ row_emit_cluster_kernel(const ClusterParams cp) {
             if (ms_s.m == -INFINITY) ms_s.s = 0.f;      // warp without cells
         }
         if constexpr (TEACHER_STATS) {
-            // online (max, sum) + runner-up tracking for the teacher slice
-            float mk_t = -INFINITY;
-            float thr_top = -INFINITY;     // lower bound of the row's runner-up value: smaller cells cannot matter
-            u64 acc_t = pk(0.f, 0.f);
-            int iter = 0;
-            pipelined_sweep<DT>(lane, w_n, load_t, [&](int v, const uint4& raw) {
-                uint32_t m2 = Pair<T>::vmax(Pair<T>::vmax(raw.x, raw.y), Pair<T>::vmax(raw.z, raw.w));
-                float m_lo, m_hi;
-                upk(Pair<T>::widen(m2), m_lo, m_hi);
-                const float vm = fmaxf(m_lo, m_hi);
-                if (vm > ms_t.m) {
-                    const float sc = ex2((ms_t.m - vm) * k2);
-                    acc_t = mul2(acc_t, pk(sc, sc));
-                    ms_t.m = vm;
-                    mk_t = -vm * k2;
-                }
-                const u64 mkp = pk(mk_t, mk_t);
-                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+            // teacher slice, same two passes; the runner-up candidates are found in pass 2 behind a threshold that pass 1
+            // makes tight: the 2nd largest of the 32 lane maxima is a lower bound of the row's runner-up value
+            uint32_t tmax2 = Pair<T>::kNegInf2;
+#pragma unroll 4
+            for (int v = lane; v < w_n; v += 32) {
+                const uint4 rt = load_t(v);
+                tmax2 = Pair<T>::vmax(tmax2, Pair<T>::vmax(Pair<T>::vmax(rt.x, rt.y), Pair<T>::vmax(rt.z, rt.w)));
+            }
+            float lo, hi;
+            upk(Pair<T>::widen(tmax2), lo, hi);
+            const float lane_tmax = fmaxf(lo, hi);
+            ms_t.m = warp_max(lane_tmax);
+            float thr_top = -INFINITY;
+            if constexpr (VARIANT == KD_LOCA_PER_ROW) {
+                // second largest lane maximum (the lane holding the maximum is masked out once)
+                const unsigned holders = __ballot_sync(0xffffffffu, lane_tmax == ms_t.m);
+                const bool is_first_holder = (holders != 0u) && (lane == __ffs(holders) - 1);
+                thr_top = warp_max(is_first_holder ? -INFINITY : lane_tmax);
+            }
+            const float mk = -ms_t.m * k2;
+            const u64 mkp = pk(mk, mk);
+            u64 acc0 = pk(0.f, 0.f), acc1 = pk(0.f, 0.f);
+#pragma unroll 2
+            for (int v = lane; v < w_n; v += 32) {
+                const uint4 rt = load_t(v);
+                const uint32_t w[4] = {rt.x, rt.y, rt.z, rt.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float e0, e1;
                     upk(fma2(Pair<T>::widen(w[i]), k2p, mkp), e0, e1);
-                    acc_t = add2(acc_t, pk(ex2(e0), ex2(e1)));
+                    if (i & 1) acc1 = add2(acc1, pk(ex2(e0), ex2(e1)));
+                    else acc0 = add2(acc0, pk(ex2(e0), ex2(e1)));
                 }
                 if constexpr (VARIANT == KD_LOCA_PER_ROW) {
-                    if (vm >= thr_top) {
+                    const uint32_t m2 = Pair<T>::vmax(Pair<T>::vmax(rt.x, rt.y), Pair<T>::vmax(rt.z, rt.w));
+                    float m_lo, m_hi;
+                    upk(Pair<T>::widen(m2), m_lo, m_hi);
+                    if (fmaxf(m_lo, m_hi) >= thr_top) {          // rare: a cell that may be best or runner-up
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             float x0, x1;
@@ -422,17 +438,13 @@ row_emit_cluster_kernel(const ClusterParams cp) {
                             top.push(x0, (g_v0 + v) * 8 + 2 * i);
                             top.push(x1, (g_v0 + v) * 8 + 2 * i + 1);
                         }
-                        thr_top = fmaxf(thr_top, top.a2);
                     }
                 }
-                (void)iter;
-            });
+            }
             float a0, a1;
-            upk(acc_t, a0, a1);
-            ms_t.s = a0 + a1;
-            const float M = warp_max(ms_t.m);
-            ms_t.s = warp_sum(ms_t.m == -INFINITY ? 0.f : ms_t.s * ex2((ms_t.m - M) * k2));
-            ms_t.m = M;
+            upk(add2(acc0, acc1), a0, a1);
+            ms_t.s = warp_sum(a0 + a1);
+            if (ms_t.m == -INFINITY) ms_t.s = 0.f;
             if constexpr (VARIANT == KD_LOCA_PER_ROW) warp_merge(top);
         }
 

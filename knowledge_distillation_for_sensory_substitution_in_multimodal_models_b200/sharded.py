@@ -71,17 +71,32 @@ def shard_rows(n_total: int, world_size: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
-def gather_records(records: torch.Tensor, group=None) -> torch.Tensor:
-    """All-gather ragged [n_i, 4] int32 record blocks in rank order (global flattened token order)."""
+_shard_counts: dict = {}     # (group id, local rows) -> rows of every rank; shard sizes are exchanged once, not per step
+
+
+def gather_records(records: torch.Tensor, group=None, counts=None) -> torch.Tensor:
+    """All-gather ragged [n_i, 4] int32 record blocks in rank order (global flattened token order).
+
+    The per-rank row counts need a host read-back, so they are exchanged only the first time a given local
+    shard size is seen for ``group`` (pass ``counts`` explicitly when ranks resize independently)."""
     if group is None and not (dist.is_available() and dist.is_initialized()):
         return records
     world = dist.get_world_size(group)
     if world == 1:
         return records
-    n_local = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    counts = [int(c.item()) for c in counts]
+    key = (id(group), int(records.shape[0]))
+    if counts is None:
+        counts = _shard_counts.get(key)
+    if counts is None:
+        n_local = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
+        gathered = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(gathered, n_local, group=group)
+        counts = [int(c.item()) for c in gathered]
+        _shard_counts[key] = counts
+    if len(set(counts)) == 1:            # even shards: one contiguous all-gather, no padding or concatenation
+        out = torch.empty((world * counts[0], 4), dtype=records.dtype, device=records.device)
+        dist.all_gather_into_tensor(out, records.contiguous(), group=group)
+        return out
     n_max = max(counts)
     padded = torch.zeros((n_max, 4), dtype=records.dtype, device=records.device)
     padded[: records.shape[0]] = records
