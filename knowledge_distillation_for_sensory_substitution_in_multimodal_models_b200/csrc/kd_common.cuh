@@ -43,16 +43,6 @@ __device__ __forceinline__ float ex2(float x) {   // MUFU.EX2, flush-to-zero; ex
     return y;
 }
 
-// packed fp32x2 FMA (Blackwell FFMA2): halves the issue slots of the scale-and-shift step
-__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
-    unsigned long long a, bb, cc, d;
-    asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(a0), "f"(a1));
-    asm("mov.b64 %0, {%1,%2};" : "=l"(bb) : "f"(b), "f"(b));
-    asm("mov.b64 %0, {%1,%2};" : "=l"(cc) : "f"(c), "f"(c));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
-}
-
 // ---------------------------------------------------------------------------------------------
 // 16-byte vector access for the three element types: a "pack" is what one 128-bit access moves
 // ---------------------------------------------------------------------------------------------
@@ -194,5 +184,60 @@ __device__ __forceinline__ void warp_merge(Top2& t) {
         t.merge(p);
     }
 }
+
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2) --------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+__device__ __forceinline__ float set_ge(float a, float b) {      // 1.0f if a >= b else 0.0f, one FSET
+    float r;
+    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+// 16-bit element pair -> packed fp32x2
+template <typename T> struct Pair;
+template <> struct Pair<__nv_bfloat16> {
+    static constexpr uint32_t kPosInf2 = 0x7f807f80u;
+    static constexpr uint32_t kNegInf2 = 0xff80ff80u;
+    static __device__ __forceinline__ uint32_t vmin(uint32_t a, uint32_t b) {
+        __nv_bfloat162 r = __hmin2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
+    static __device__ __forceinline__ u64 widen(uint32_t w) { return pk(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+    static __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) {
+        __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
+    static __device__ __forceinline__ uint32_t narrow(float lo, float hi) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+};
+template <> struct Pair<__half> {
+    static constexpr uint32_t kPosInf2 = 0x7c007c00u;
+    static constexpr uint32_t kNegInf2 = 0xfc00fc00u;
+    static __device__ __forceinline__ uint32_t vmin(uint32_t a, uint32_t b) {
+        __half2 r = __hmin2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
+    static __device__ __forceinline__ u64 widen(uint32_t w) {
+        float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+        return pk(f.x, f.y);
+    }
+    static __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) {
+        __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
+    static __device__ __forceinline__ uint32_t narrow(float lo, float hi) {
+        __half2 h = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+};
+
 
 }  // namespace kd

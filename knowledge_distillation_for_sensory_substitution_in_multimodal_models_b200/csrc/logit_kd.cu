@@ -125,6 +125,101 @@ __device__ __forceinline__ void row_stats(const T* __restrict__ row, int V, floa
     }
 }
 
+// order-preserving float <-> int map so that a shared atomicMax can carry a float bound
+__device__ __forceinline__ int float_key(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// 16-bit logits: packed min/max and fp32x2 arithmetic, lazy rescale (only when the running reference would let
+// 2^((x - ref)*k2) approach overflow).  Runner-up candidates sit behind a threshold that is (i) seeded from the first
+// batch (2nd largest of the warp's lane maxima) and (ii) shared across the CTA through `thr_shared` (atomicMax), so the
+// divergent per-cell path runs about once per warp and row instead of once per batch.
+template <typename T, int NT, bool WANT_TOP2>
+__device__ __forceinline__ void row_stats_packed(const T* __restrict__ row, int V, float k2, MaxSum& ms, Top2& top, int* thr_shared) {
+    ms.init();
+    if (WANT_TOP2) top.init();
+    const int nvec = V / 8;
+    const uint4* rv = reinterpret_cast<const uint4*>(row);
+    const u64 k2p = pk(k2, k2);
+    const float slack = 64.f / k2;          // logits may exceed the reference by this much before a rescale
+    float ref = -INFINITY, lane_max = -INFINITY, thr_top = -INFINITY;
+    u64 mkp = pk(0.f, 0.f), acc0 = pk(0.f, 0.f), acc1 = pk(0.f, 0.f);
+    auto vec_max = [&](const uint4& raw) -> float {
+        const uint32_t m2 = Pair<T>::vmax(Pair<T>::vmax(raw.x, raw.y), Pair<T>::vmax(raw.z, raw.w));
+        float m_lo, m_hi;
+        upk(Pair<T>::widen(m2), m_lo, m_hi);
+        return fmaxf(m_lo, m_hi);
+    };
+    auto consume = [&](const uint4& raw, int v) {
+        const float vm = vec_max(raw);
+        lane_max = fmaxf(lane_max, vm);
+        if (vm > ref + slack || ref == -INFINITY) {     // rare: first vector, or a cell far above the reference
+            const float sc = (ref == -INFINITY) ? 0.f : ex2((ref - vm) * k2);
+            acc0 = mul2(acc0, pk(sc, sc));
+            acc1 = mul2(acc1, pk(sc, sc));
+            ref = vm;
+            mkp = pk(-vm * k2, -vm * k2);
+        }
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float e0, e1;
+            upk(fma2(Pair<T>::widen(w[i]), k2p, mkp), e0, e1);
+            if (i & 1) acc1 = add2(acc1, pk(ex2(e0), ex2(e1)));
+            else acc0 = add2(acc0, pk(ex2(e0), ex2(e1)));
+        }
+        if (WANT_TOP2 && vm >= thr_top) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float x0, x1;
+                upk(Pair<T>::widen(w[i]), x0, x1);
+                top.push(x0, v * 8 + 2 * i);
+                top.push(x1, v * 8 + 2 * i + 1);
+            }
+            if (top.a2 > thr_top) {
+                thr_top = top.a2;
+                atomicMax(thr_shared, float_key(thr_top));
+            }
+        }
+    };
+    constexpr int U = 8;      // independent 128-bit loads in flight per thread
+    int v = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int last_lane = 31 - lane;      // warp-uniform trip count: test the warp's last lane
+    bool seeded = !WANT_TOP2;
+    for (; v + last_lane + (U - 1) * NT < nvec; v += U * NT) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) raw[u] = ldg_stream(rv + v + u * NT);
+        if (!seeded) {      // first batch: 2nd largest lane maximum of the warp is a valid lower bound of the runner-up
+            float bm = vec_max(raw[0]);
+#pragma unroll
+            for (int u = 1; u < U; ++u) bm = fmaxf(bm, vec_max(raw[u]));
+            const float wm = warp_max(bm);
+            const unsigned holders = __ballot_sync(0xffffffffu, bm == wm);
+            thr_top = warp_max((lane == __ffs(holders) - 1) ? -INFINITY : bm);
+            if (lane == 0) atomicMax(thr_shared, float_key(thr_top));
+            seeded = true;
+        }
+        if (WANT_TOP2) thr_top = fmaxf(thr_top, key_float(*reinterpret_cast<volatile int*>(thr_shared)));
+#pragma unroll
+        for (int u = 0; u < U; ++u) consume(raw[u], v + u * NT);
+    }
+    for (; v < nvec; v += NT) consume(ldg_stream(rv + v), v);
+    float a0, a1;
+    upk(add2(acc0, acc1), a0, a1);
+    // express the partial relative to the lane's true maximum (<= ref + slack, so the factor is finite)
+    ms.m = lane_max;
+    ms.s = (lane_max == -INFINITY) ? 0.f : (a0 + a1) * ex2((ref - lane_max) * k2);
+    for (int c = nvec * 8 + threadIdx.x; c < V; c += NT) {      // scalar tail (V % 8)
+        const float x = Elem<T>::to_float(row[c]);
+        const float nm = fmaxf(ms.m, x);
+        ms.s = ms.s * ex2((ms.m - nm) * k2) + ex2((x - nm) * k2);
+        if (ms.m == -INFINITY) ms.s = ex2((x - nm) * k2);
+        ms.m = nm;
+        if (WANT_TOP2) top.push(x, c);
+    }
+}
+
 __device__ __forceinline__ float lse2_of(const MaxSum& ms, float k2) { return fmaf(ms.m, k2, log2f(ms.s)); }
 
 // ------------------------------------------------------------------------------------------------
@@ -137,11 +232,17 @@ teacher_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const int64_t*
                      int64_t n_rows, int V, float k2, float alpha) {
     __shared__ float smf[2 * kMaxWarps];
     __shared__ int smi[2 * kMaxWarps];
-    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    __shared__ int thr_shared[2];        // CTA-wide runner-up bound, one slot per row parity
+    if (threadIdx.x < 2) thr_shared[threadIdx.x] = float_key(-INFINITY);
+    __syncthreads();
+    int parity = 0;
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x, parity ^= 1) {
         const T* row = teacher + r * ld_t;
         MaxSum ms;
         Top2 top;
-        row_stats<T, VEC, kStatsThreads, true>(row, V, k2, ms, top);
+        if (threadIdx.x == 0) thr_shared[parity ^ 1] = float_key(-INFINITY);    // next row's slot (rows are separated by the merges' barriers)
+        if constexpr (VEC && sizeof(T) == 2) row_stats_packed<T, kStatsThreads, true>(row, V, k2, ms, top, thr_shared + parity);
+        else row_stats<T, VEC, kStatsThreads, true>(row, V, k2, ms, top);
         ms = block_merge<kStatsThreads>(ms, k2, smf);
         top = block_merge<kStatsThreads>(top, smf, smi);
         if (threadIdx.x == 0) {

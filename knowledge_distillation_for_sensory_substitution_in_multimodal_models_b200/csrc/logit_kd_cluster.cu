@@ -89,60 +89,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
-// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2) --------------------------------------------------
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-
-__device__ __forceinline__ float set_ge(float a, float b) {      // 1.0f if a >= b else 0.0f, one FSET
-    float r;
-    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-    return r;
-}
-
-// 16-bit element pair -> packed fp32x2
-template <typename T> struct Pair;
-template <> struct Pair<__nv_bfloat16> {
-    static constexpr uint32_t kPosInf2 = 0x7f807f80u;
-    static constexpr uint32_t kNegInf2 = 0xff80ff80u;
-    static __device__ __forceinline__ uint32_t vmin(uint32_t a, uint32_t b) {
-        __nv_bfloat162 r = __hmin2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-        return *reinterpret_cast<uint32_t*>(&r);
-    }
-    static __device__ __forceinline__ u64 widen(uint32_t w) { return pk(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
-    static __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) {
-        __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-        return *reinterpret_cast<uint32_t*>(&r);
-    }
-    static __device__ __forceinline__ uint32_t narrow(float lo, float hi) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-        return *reinterpret_cast<uint32_t*>(&h);
-    }
-};
-template <> struct Pair<__half> {
-    static constexpr uint32_t kPosInf2 = 0x7c007c00u;
-    static constexpr uint32_t kNegInf2 = 0xfc00fc00u;
-    static __device__ __forceinline__ uint32_t vmin(uint32_t a, uint32_t b) {
-        __half2 r = __hmin2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
-        return *reinterpret_cast<uint32_t*>(&r);
-    }
-    static __device__ __forceinline__ u64 widen(uint32_t w) {
-        float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
-        return pk(f.x, f.y);
-    }
-    static __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) {
-        __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
-        return *reinterpret_cast<uint32_t*>(&r);
-    }
-    static __device__ __forceinline__ uint32_t narrow(float lo, float hi) {
-        __half2 h = __floats2half2_rn(lo, hi);
-        return *reinterpret_cast<uint32_t*>(&h);
-    }
-};
-
 struct ClusterParams {
     EmitParams e;
     int n_clusters;
