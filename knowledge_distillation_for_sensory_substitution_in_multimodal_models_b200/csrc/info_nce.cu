@@ -16,18 +16,17 @@ constexpr int kPoolThreads = 512;
 constexpr int kRowThreads = 256;
 constexpr float kNormEps = 1e-12f;   // F.normalize default
 
-// ---- pool + normalise: one CTA per (image, tensor) ---------------------------------------------
+// ---- pooling, split over tokens: CTA (split, image|tensor) sums its token chunk into an fp32 partial ---------------
 template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
-pool_normalize_kernel(const T* __restrict__ xs, const T* __restrict__ xt, float* __restrict__ us, float* __restrict__ ut,
-                      float* __restrict__ norm_s, int M, int P, int D, bool vec) {
-    extern __shared__ float sm[];        // [groups][D] partial sums, then the pooled vector in sm[0..D)
-    __shared__ float red[kPoolThreads / 32];
+pool_partial_kernel(const T* __restrict__ xs, const T* __restrict__ xt, float* __restrict__ partials, int M, int P, int D,
+                    int nsplit, bool vec) {
+    extern __shared__ float sm[];        // [groups][D] partial sums
     constexpr int E = Elem<T>::kPack;
-    const int m = blockIdx.x % M;
-    const bool is_teacher = blockIdx.x >= M;
-    const T* x = (is_teacher ? xt : xs) + (int64_t)m * P * D;
-    float* u = (is_teacher ? ut : us) + (int64_t)m * D;
+    const int mt = blockIdx.y, split = blockIdx.x;
+    const int m = mt % M;
+    const T* x = (mt >= M ? xt : xs) + (int64_t)m * P * D;
+    const int p0 = (int)(((int64_t)P * split) / nsplit), p1 = (int)(((int64_t)P * (split + 1)) / nsplit);
 
     const int ncol = vec ? D / E : D;                       // column slots (vector or scalar)
     const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
@@ -41,8 +40,8 @@ pool_normalize_kernel(const T* __restrict__ xs, const T* __restrict__ xt, float*
                 float acc[E];
 #pragma unroll
                 for (int i = 0; i < E; ++i) acc[i] = 0.f;
-#pragma unroll 4
-                for (int p = grp; p < P; p += groups) {
+#pragma unroll 8
+                for (int p = p0 + grp; p < p1; p += groups) {
                     float v[E];
                     Elem<T>::unpack(ldg_stream(reinterpret_cast<const uint4*>(x + (int64_t)p * D) + c), v);
 #pragma unroll
@@ -52,29 +51,46 @@ pool_normalize_kernel(const T* __restrict__ xs, const T* __restrict__ xt, float*
                 for (int i = 0; i < E; ++i) sm[grp * D + c * E + i] = acc[i];
             } else {
                 float acc = 0.f;
-                for (int p = grp; p < P; p += groups) acc += Elem<T>::to_float(x[(int64_t)p * D + c]);
+                for (int p = p0 + grp; p < p1; p += groups) acc += Elem<T>::to_float(x[(int64_t)p * D + c]);
                 sm[grp * D + c] = acc;
             }
         }
     }
     __syncthreads();
-    float ss = 0.f;
-    const float invP = 1.f / (float)P;
+    float* out = partials + ((int64_t)split * 2 * M + mt) * D;
     for (int d = threadIdx.x; d < D; d += kPoolThreads) {
         float a = 0.f;
         for (int gI = 0; gI < groups; ++gI) a += sm[gI * D + d];
+        out[d] = a;
+    }
+}
+
+// ---- finish: add the partials, take the mean, L2-normalise (F.normalize eps) -------------------------------------
+__global__ void __launch_bounds__(256)
+pool_finish_kernel(const float* __restrict__ partials, float* __restrict__ us, float* __restrict__ ut, float* __restrict__ norm_s,
+                   int M, int P, int D, int nsplit) {
+    extern __shared__ float sm[];        // [D] pooled vector
+    __shared__ float red[8];
+    const int mt = blockIdx.x, m = mt % M;
+    const bool is_teacher = mt >= M;
+    float* u = (is_teacher ? ut : us) + (int64_t)m * D;
+    const float invP = 1.f / (float)P;
+    float ss = 0.f;
+    for (int d = threadIdx.x; d < D; d += 256) {
+        float a = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) a += partials[((int64_t)sp * 2 * M + mt) * D + d];
         a *= invP;
         ss = fmaf(a, a, ss);
-        sm[d] = a;        // safe: every thread only rewrites the columns it just summed (group 0 slot)
+        sm[d] = a;
     }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
     float tot = 0.f;
-    for (int i = 0; i < kPoolThreads / 32; ++i) tot += red[i];
+    for (int i = 0; i < 8; ++i) tot += red[i];
     const float nrm = sqrtf(tot);
     const float inv = 1.f / fmaxf(nrm, kNormEps);
-    for (int d = threadIdx.x; d < D; d += kPoolThreads) u[d] = sm[d] * inv;
+    for (int d = threadIdx.x; d < D; d += 256) u[d] = sm[d] * inv;
     if (!is_teacher && threadIdx.x == 0) norm_s[m] = nrm;
 }
 
@@ -195,7 +211,8 @@ broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P
     }
 }
 
-struct NceWorkspace { size_t us, ut, norm_s, dmean, rowloss, total; };
+constexpr int kMaxPoolSplit = 8;
+struct NceWorkspace { size_t us, ut, norm_s, dmean, rowloss, partials, total; };
 NceWorkspace nce_layout(int64_t M, int64_t D) {
     NceWorkspace w{};
     size_t off = 0;
@@ -205,6 +222,7 @@ NceWorkspace nce_layout(int64_t M, int64_t D) {
     w.norm_s = take(sizeof(float) * M);
     w.dmean = take(sizeof(float) * M * D);
     w.rowloss = take(sizeof(float) * M);
+    w.partials = take(sizeof(float) * kMaxPoolSplit * 2 * M * D);
     w.total = off;
     return w;
 }
@@ -221,14 +239,25 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
     float* rowloss = reinterpret_cast<float*>(ws + w.rowloss);
     const bool vec_in = (D % E == 0) && ((reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(xt)) & 15u) == 0;
     {
+        float* partials = reinterpret_cast<float*>(ws + w.partials);
         const int ncol = vec_in ? D / E : D;
         const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
         const size_t smem = sizeof(float) * (size_t)(kPoolThreads / lanes) * D;
         KD_CHECK_ARG(smem <= 200 * 1024, "info_nce: feature dimension %d too large for the pooling kernel", D);
-        auto kfn = pool_normalize_kernel<T>;
+        // enough CTAs for ~4 per SM, but never fewer than ~64 tokens per chunk
+        int nsplit = (148 * 4 + 2 * M - 1) / (2 * M);
+        if (nsplit > kMaxPoolSplit) nsplit = kMaxPoolSplit;
+        if (nsplit > (P + 63) / 64) nsplit = (P + 63) / 64;
+        if (nsplit < 1) nsplit = 1;
+        auto kfn = pool_partial_kernel<T>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kfn<<<2 * M, kPoolThreads, smem, st>>>(static_cast<const T*>(xs), static_cast<const T*>(xt), us, ut, norm_s, M, P, D, vec_in);
-        KD_CHECK_LAUNCH("pool_normalize_kernel");
+        kfn<<<dim3(nsplit, 2 * M), kPoolThreads, smem, st>>>(static_cast<const T*>(xs), static_cast<const T*>(xt), partials, M, P, D, nsplit, vec_in);
+        KD_CHECK_LAUNCH("pool_partial_kernel");
+        KD_CHECK_ARG(sizeof(float) * (size_t)D <= 200 * 1024, "info_nce: feature dimension %d too large", D);
+        if (sizeof(float) * (size_t)D > 48 * 1024)
+            cudaFuncSetAttribute(pool_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * D));
+        pool_finish_kernel<<<2 * M, 256, sizeof(float) * (size_t)D, st>>>(partials, us, ut, norm_s, M, P, D, nsplit);
+        KD_CHECK_LAUNCH("pool_finish_kernel");
     }
     {
         const size_t smem = sizeof(float) * ((size_t)D + M);

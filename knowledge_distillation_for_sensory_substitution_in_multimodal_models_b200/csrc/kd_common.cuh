@@ -38,6 +38,9 @@ int cuda_fail(cudaError_t e, const char* what);
 // fast math
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2(float x) {   // MUFU.EX2, flush-to-zero; ex2(-inf) = 0
+#ifdef KD_ABLATE_MUFU      // timing experiment only (wrong results): take the XU pipe out of the picture
+    return x * 0.5f;
+#endif
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;

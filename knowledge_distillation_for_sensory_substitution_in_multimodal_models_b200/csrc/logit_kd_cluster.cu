@@ -13,6 +13,7 @@
 //   * a CTA runs NPIPE independent row pipelines (disjoint warps, different rows) so that one pipeline's
 //     reduction / TMA wait is covered by the other's arithmetic;
 //   * LoCa reference mode keeps its slice of the V-entry override table in shared memory for the whole kernel.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -27,7 +28,10 @@ namespace {
 #define KD_SWEEP_UNROLL 2
 #endif
 constexpr int kSweepUnroll = KD_SWEEP_UNROLL;
-constexpr int kThreads = 512;
+#ifndef KD_CLUSTER_THREADS
+#define KD_CLUSTER_THREADS 512
+#endif
+constexpr int kThreads = KD_CLUSTER_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr float kPush = -3.0e38f;       // ov' * kPush drives log2 q of an overridden cell to -inf
 constexpr float kOvFloor = 1.0e-36f;    // encoded "overridden with ~0" (must stay > 0)
@@ -67,6 +71,9 @@ __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, u
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
                  :: "r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar) : "memory");
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {     // sub-CTA barrier: one row pipeline's warps
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
 }
@@ -89,7 +96,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
+// Optional phase tracing (compile with -DKD_TRACE): lane 0 of every warp stamps %globaltimer at the phase
+// boundaries of each row into `trace` ([cta][warp][row_iter][8] u64), read back by tools/trace_emit.py.
+#ifdef KD_TRACE
+#define KD_STAMP(i) do { if (lane == 0 && cp.trace && row_iter < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    cp.trace[(((size_t)blockIdx.x * kWarps + warp) * 64 + row_iter) * 8 + (i)] = t_; } } while (0)
+#else
+#define KD_STAMP(i) do {} while (0)
+#endif
+
 struct ClusterParams {
+    unsigned long long* trace;
     EmitParams e;
     int n_clusters;
     int vpc;                      // 16-byte vectors per CTA slice
@@ -106,7 +123,7 @@ struct SmemPlan {
     static constexpr int WPP = kWarps / NPIPE;             // warps per pipeline
     static constexpr int NSLOT = CS * WPP;                  // partials per reduction
     static constexpr int kRowTensors = TSM ? 2 : 1;
-    int table, rows, bars, slotsA, slotsB, total;
+    int table, rows, bars, slotsA, slotsB, bcast, total;
     __host__ __device__ SmemPlan(int vpc) {
         int off = 0;
         table = off;
@@ -119,6 +136,8 @@ struct SmemPlan {
         off += NPIPE * NSLOT * SlotWords<VARIANT>::A * 4;
         slotsB = off;
         off += NPIPE * NSLOT * 8;
+        bcast = off;                 // per pipeline: 8 words of reduction-A results + 2 words of reduction-B results (+pad)
+        off += NPIPE * 64;
         total = off;
     }
 };
@@ -160,6 +179,10 @@ __device__ __forceinline__ uint4 ldg_l2(const uint4* p) {     // teacher slice: 
 // input so that loads of the same address in different rows are distinct values (the slice is refilled by TMA).
 __device__ __forceinline__ uint4 lds128_nv(uint32_t addr, uint32_t epoch) {
     uint4 v;
+#ifdef KD_ABLATE_LDS       // timing experiment only (wrong results): take shared-memory reads out of the picture
+    v = make_uint4(addr, epoch, addr ^ 0x3f80, 0x3f803f80u);
+    return v;
+#endif
     asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];  // epoch %5" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "r"(epoch));
     return v;
 }
@@ -191,6 +214,8 @@ row_emit_cluster_kernel(const ClusterParams cp) {
     const uint32_t bar_redB = bar_redA + 8;
     const uint32_t slotA = s_base + plan.slotsA + pipe * NSLOT * AW * 4;
     const uint32_t slotB = s_base + plan.slotsB + pipe * NSLOT * 8;
+    volatile float* bcast = reinterpret_cast<volatile float*>(smem + plan.bcast + pipe * 64);
+    const int barA = 1 + 2 * pipe, barB = 2 + 2 * pipe;     // named barriers of this pipeline (0 is __syncthreads)
 
     // this CTA's column slice and this warp's private part of it (in 16-byte vectors)
     const int cta_v0 = min((int)rank * cp.vpc, cp.nvec);
@@ -203,7 +228,7 @@ row_emit_cluster_kernel(const ClusterParams cp) {
     const int w_n = w_hi - w_lo;
     const uint32_t s_s = s_base + plan.rows + pipe * SmemPlan<VARIANT, CS, NPIPE, TSM>::kRowTensors * cp.vpc * 16 + w_lo * 16;
     const uint32_t s_t = s_s + cp.vpc * 16;          // teacher part (TSM only)
-    const uint32_t s_ov = s_table + w_lo * 32;
+    const uint32_t s_ov = s_table + w_lo * 16;           // cells 0-3; cells 4-7 live cp.vpc*16 bytes further
     const int g_v0 = cta_v0 + w_lo;                  // first global vector of the warp
 
     if (tid == 0) {
@@ -218,6 +243,8 @@ row_emit_cluster_kernel(const ClusterParams cp) {
     // LoCa reference mode: encode this CTA's table slice once (0 = not overridden, else max(ov, floor) > 0)
     bool fast_table = true;
     if constexpr (VARIANT == KD_LOCA_REFERENCE) {
+        // layout: [vpc][4] floats for cells 0-3 of every vector, then [vpc][4] for cells 4-7, so that both 128-bit
+        // reads of a sweep have a lane stride of 16 bytes (a [vpc][8] layout costs a 2-way bank conflict per read)
         float* tbl = reinterpret_cast<float*>(smem + plan.table);
         bool ok = true;
         for (int i = tid; i < cta_n * 8; i += kThreads) {
@@ -227,7 +254,8 @@ row_emit_cluster_kernel(const ClusterParams cp) {
                 ok = ok && (ov >= 0.f) && (ov <= 3.0e38f);
                 enc = fmaxf(ov, kOvFloor);
             }
-            tbl[i] = enc;
+            const int vec = i >> 3, cell = i & 7;
+            tbl[(cell >> 2) * cp.vpc * 4 + vec * 4 + (cell & 3)] = enc;
         }
         // a negative / non-finite override in this slice (alpha >= 1) forces the exact per-cell path for this CTA
         fast_table = __syncthreads_and(ok);
@@ -264,10 +292,14 @@ row_emit_cluster_kernel(const ClusterParams cp) {
     const float up = p.upstream ? *p.upstream : 1.f;
     const float g = p.gscale * up;
     const bool want_grad = !(p.flags & KD_FLAG_NO_GRAD);
+    const float inv_k2 = 1.f / k2;
     const u64 k2p = pk(k2, k2);
     uint32_t ph_full = 0, ph_red = 0;
 
+    int row_iter = -1;
     for (; r < p.n_rows; r += row_stride) {
+        ++row_iter;
+        KD_STAMP(0);
         // per-row scalars fetched early so their latency hides behind sweep A
         float lse2_t = 0.f;
         int lab = -1;
@@ -292,6 +324,7 @@ row_emit_cluster_kernel(const ClusterParams cp) {
         auto load_s = [&](int v) -> uint4 { return lds128_nv(s_s + v * 16, epoch); };
         if (w_n > 0) mbar_wait_cta(bar_full, ph_full);
         ph_full ^= 1;
+        KD_STAMP(1);
 
         // ================= sweep A: softmax statistics over the warp's slice ==========================
         // pass 1 (packed 16-bit min/max only) fixes the warp's reference maximum, pass 2 sums 2^((x - max)*k2)
@@ -394,6 +427,7 @@ row_emit_cluster_kernel(const ClusterParams cp) {
             if constexpr (VARIANT == KD_LOCA_PER_ROW) warp_merge(top);
         }
 
+        KD_STAMP(2);
         // ---- push partial A to every CTA of the cluster, then wait for all NSLOT partials --------------
         if (lane < CS) {
             const uint32_t dst = map_to_cta(slotA + (rank * WPP + pw) * AW * 4, lane);
@@ -405,9 +439,11 @@ row_emit_cluster_kernel(const ClusterParams cp) {
                 st_async_v4(dst + 16, __float_as_uint(top.a1), (uint32_t)top.i1, __float_as_uint(top.a2), (uint32_t)top.i2, rbar);
             }
         }
-        mbar_wait_cta(bar_redA, ph_red);
-        if (pw == 0 && lane == 0) mbar_expect_tx(bar_redA, NSLOT * AW * 4);      // arm the next row's phase
-        {
+        // one warp per pipeline folds the NSLOT partials and broadcasts the row statistics through shared memory; the
+        // other warps park on a named barrier instead of spinning on the mbarrier
+        if (pw == 0) {
+            mbar_wait_cta(bar_redA, ph_red);
+            if (lane == 0) mbar_expect_tx(bar_redA, NSLOT * AW * 4);      // arm the next row's phase
             const float* slots = reinterpret_cast<const float*>(smem + (slotA - s_base));
             float m_s = -INFINITY, m_t = -INFINITY;
             for (int i = lane; i < NSLOT; i += 32) {
@@ -429,13 +465,26 @@ row_emit_cluster_kernel(const ClusterParams cp) {
                     all_top.merge(o);
                 }
             }
-            ms_s.m = m_s;
-            ms_s.s = warp_sum(s_sum);
-            if constexpr (TEACHER_STATS) { ms_t.m = m_t; ms_t.s = warp_sum(t_sum); }
-            if constexpr (VARIANT == KD_LOCA_PER_ROW) { warp_merge(all_top); top = all_top; }
+            s_sum = warp_sum(s_sum);
+            if constexpr (TEACHER_STATS) t_sum = warp_sum(t_sum);
+            if constexpr (VARIANT == KD_LOCA_PER_ROW) warp_merge(all_top);
+            if (lane == 0) {
+                bcast[0] = fmaf(m_s, k2, __log2f(s_sum));
+                if constexpr (TEACHER_STATS) bcast[1] = fmaf(m_t, k2, __log2f(t_sum));
+                if constexpr (VARIANT == KD_LOCA_PER_ROW) {
+                    bcast[2] = all_top.a2;
+                    bcast[3] = __int_as_float(all_top.i2);
+                }
+            }
         }
-        const float lse2_s = fmaf(ms_s.m, k2, log2f(ms_s.s));
-        if constexpr (TEACHER_STATS) lse2_t = fmaf(ms_t.m, k2, log2f(ms_t.s));
+        named_bar_sync(barA, WPP * 32);
+        KD_STAMP(3);
+        const float lse2_s = bcast[0];
+        if constexpr (TEACHER_STATS) lse2_t = bcast[1];
+        if constexpr (VARIANT == KD_LOCA_PER_ROW) {
+            top.a2 = bcast[2];
+            top.i2 = __float_as_int(bcast[3]);
+        }
         int ov_k = -1;
         float v1 = NaN, v2 = NaN;
         if constexpr (VARIANT == KD_LOCA_PER_ROW) {
@@ -448,7 +497,7 @@ row_emit_cluster_kernel(const ClusterParams cp) {
         // the threshold -> the mask is a constant and the compare / select work disappears from sweeps B and C.
         int mask_mode = 0;
         if constexpr (LOCA) {
-            const float theta = (lse2_s + thr2) / k2;
+            const float theta = (lse2_s + thr2) * inv_k2;
             const float margin = 1e-3f * (1.f + fabsf(theta));
             if (__all_sync(0xffffffffu, lane_min >= theta + margin)) mask_mode = 1;
             else if (__all_sync(0xffffffffu, lane_max < theta - margin)) mask_mode = 2;
@@ -496,7 +545,7 @@ row_emit_cluster_kernel(const ClusterParams cp) {
                     if constexpr (MODE != 2) rs = load_s(v);
                     const uint32_t wsv[4] = {rs.x, rs.y, rs.z, rs.w};
                     uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
-                    if constexpr (VARIANT == KD_LOCA_REFERENCE) { o0 = lds128_nv(s_ov + v * 32, 0u); o1 = lds128_nv(s_ov + v * 32 + 16, 0u); }
+                    if constexpr (VARIANT == KD_LOCA_REFERENCE) { o0 = lds128_nv(s_ov + v * 16, 0u); o1 = lds128_nv(s_ov + v * 16 + cp.vpc * 16, 0u); }
                     const u64 ovp[4] = {pk(__uint_as_float(o0.x), __uint_as_float(o0.y)), pk(__uint_as_float(o0.z), __uint_as_float(o0.w)),
                                         pk(__uint_as_float(o1.x), __uint_as_float(o1.y)), pk(__uint_as_float(o1.z), __uint_as_float(o1.w))};
 #pragma unroll
@@ -540,14 +589,14 @@ row_emit_cluster_kernel(const ClusterParams cp) {
         }
         row = warp_sum(row);
         Q = warp_sum(Q);
+        KD_STAMP(4);
         if (lane < CS) {
             st_async_v2(map_to_cta(slotB + (rank * WPP + pw) * 8, lane), __float_as_uint(row), __float_as_uint(Q),
                         map_to_cta(bar_redB, lane));
         }
-        mbar_wait_cta(bar_redB, ph_red);
-        if (pw == 0 && lane == 0) mbar_expect_tx(bar_redB, NSLOT * 8);
-        ph_red ^= 1;
-        {
+        if (pw == 0) {
+            mbar_wait_cta(bar_redB, ph_red);
+            if (lane == 0) mbar_expect_tx(bar_redB, NSLOT * 8);
             float rr = 0.f, qq = 0.f;
             for (int i = lane; i < NSLOT; i += 32) {
                 const float2 sl = reinterpret_cast<const float2*>(smem + (slotB - s_base))[i];
@@ -556,32 +605,39 @@ row_emit_cluster_kernel(const ClusterParams cp) {
             }
             row = warp_sum(rr);
             Q = warp_sum(qq);
-        }
-        if (rank == 0 && pw == 0 && lane == 0) {
-            if constexpr (VARIANT == KD_LOCA_PER_ROW) {
-                if (lab >= 0) {
-                    if (ov_k != lab && v1 != 0.f) row += v1 * log2f(v1);
-                    if (v2 != 0.f) row += v2 * log2f(v2);
-                } else {
-                    row = NaN;
+            if (lane == 0) {
+                bcast[8] = Q;
+                if (rank == 0) {
+                    if constexpr (VARIANT == KD_LOCA_PER_ROW) {
+                        if (lab >= 0) {
+                            if (ov_k != lab && v1 != 0.f) row += v1 * log2f(v1);
+                            if (v2 != 0.f) row += v2 * log2f(v2);
+                        } else {
+                            row = NaN;
+                        }
+                    }
+                    p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row);
+                    if constexpr (VARIANT == KD_LOCA_PER_ROW) {
+                        if (p.records) {
+                            kd_token_record rec;
+                            rec.label = lab; rec.v1 = v1; rec.k = ov_k; rec.v2 = v2;
+                            p.records[r] = rec;
+                        }
+                    }
                 }
             }
-            p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row);
-            if constexpr (VARIANT == KD_LOCA_PER_ROW) {
-                if (p.records) {
-                    kd_token_record rec;
-                    rec.label = lab; rec.v1 = v1; rec.k = ov_k; rec.v2 = v2;
-                    p.records[r] = rec;
-                }
-            }
         }
+        named_bar_sync(barB, WPP * 32);
+        KD_STAMP(5);
+        Q = bcast[8];
+        ph_red ^= 1;
 
         // ================= sweep C: gradient, written straight to HBM ===================================
         if (want_grad) {
             const float gQ = g * Q;
             const bool fast_sign = (g > 0.f) && (gQ > 0.f) && (gQ < INFINITY);
             // fast path folds g*Q and g into the exponents: 2^(a + log2 gQ) - mask * (2^(b + log2 g) + g*ov)
-            const float lgQ = fast_sign ? log2f(gQ) : 0.f, lg = fast_sign ? log2f(g) : 0.f;
+            const float lgQ = fast_sign ? __log2f(gQ) : 0.f, lg = fast_sign ? __log2f(g) : 0.f;
             const u64 nls = pk(lgQ - lse2_s, lgQ - lse2_s), nlt = pk(lg - lse2_t, lg - lse2_t);
             const float thrC = thr2 + lgQ;          // a >= thr2  <=>  a + lgQ >= thr2 + lgQ
             const u64 gp = pk(g, g), pushp = pk(kPush, kPush), neg1 = pk(-1.f, -1.f);
@@ -626,7 +682,7 @@ row_emit_cluster_kernel(const ClusterParams cp) {
                             }
                         } else {
                             uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
-                            if constexpr (VARIANT == KD_LOCA_REFERENCE) { o0 = lds128_nv(s_ov + v * 32, 0u); o1 = lds128_nv(s_ov + v * 32 + 16, 0u); }
+                            if constexpr (VARIANT == KD_LOCA_REFERENCE) { o0 = lds128_nv(s_ov + v * 16, 0u); o1 = lds128_nv(s_ov + v * 16 + cp.vpc * 16, 0u); }
                             const u64 ovp[4] = {pk(__uint_as_float(o0.x), __uint_as_float(o0.y)), pk(__uint_as_float(o0.z), __uint_as_float(o0.w)),
                                                 pk(__uint_as_float(o1.x), __uint_as_float(o1.y)), pk(__uint_as_float(o1.z), __uint_as_float(o1.w))};
 #pragma unroll
@@ -659,6 +715,7 @@ row_emit_cluster_kernel(const ClusterParams cp) {
                 else sweepC(std::integral_constant<int, 0>{});
             }
         }
+        KD_STAMP(6);
         // ---- refill the warp's private slice with its next row (all lanes are done reading it) -----------
         __syncwarp();
         if (r + row_stride < p.n_rows) issue_load(r + row_stride);
@@ -708,6 +765,27 @@ int launch_variant(const EmitParams& e, cudaStream_t st, bool query_only, int* c
     if (max_clusters < 1) return KD_ERR_UNSUPPORTED;
     const int64_t want = (e.n_rows + NPIPE - 1) / NPIPE;
     ClusterParams cp;
+    cp.trace = nullptr;
+#ifdef KD_TRACE
+    {
+        static unsigned long long* tbuf = nullptr;
+        if (!tbuf) cudaMalloc(&tbuf, (size_t)max_clusters * CS * kWarps * 64 * 8 * sizeof(unsigned long long));
+        cp.trace = tbuf;
+        if (const char* pth = getenv("KD_TRACE_DUMP")) {       // previous launch's stamps -> file (debug only)
+            static int calls = 0;
+            if (++calls == 3) {
+                cudaDeviceSynchronize();
+                const size_t n = (size_t)max_clusters * CS * kWarps * 64 * 8;
+                unsigned long long* h = (unsigned long long*)malloc(n * 8);
+                cudaMemcpy(h, tbuf, n * 8, cudaMemcpyDeviceToHost);
+                FILE* f = fopen(pth, "wb");
+                fwrite(h, 8, n, f);
+                fclose(f);
+                free(h);
+            }
+        }
+    }
+#endif
     cp.e = e;
     cp.n_clusters = (int)(want < max_clusters ? want : max_clusters);
     cp.vpc = vpc;
