@@ -51,11 +51,16 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thread = None
         try:
+            if os.environ.get("KD_BENCH_NO_CLOCKS"):
+                raise RuntimeError("clock sampling disabled")
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # prime the two per-sample queries: the first NVML call of each kind is slow and would stall kernel launches
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         except Exception:  # noqa: BLE001
             self.nv = None
 
@@ -76,7 +81,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         if self.nv is not None:
@@ -171,7 +176,7 @@ def run_reference_arm(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="reference", choices=["reference", "per_row"])
@@ -179,6 +184,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the per_row / KL / InfoNCE / MSE side measurements")
+    ap.add_argument("--force-streaming", action="store_true", help="time the general streaming emit kernel instead of the cluster kernel")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -257,7 +263,8 @@ def main() -> None:
             inv_norm = 1.0 / (float(N) * V)
 
             def emit():
-                return phases.emit(teacher, student.detach(), lse2_t, table, consts, T_KD, 1e-8, inv_norm, None)
+                return phases.emit(teacher, student.detach(), lse2_t, table, consts, T_KD, 1e-8, inv_norm, None,
+                                   force_streaming=args.force_streaming)
 
             def stats():
                 return phases.teacher_stats(teacher, labels, T_KD, ALPHA, V)
@@ -397,7 +404,9 @@ def main() -> None:
             cpu = {"value": CPU_SAMPLE_ROWS / best, "unit": "tokens/s", "cores": threads, "kind": "port",
                    "sample": f"oracle/reference_port.py eager LoCa fwd+bwd, fp32, B=1,S={CPU_SAMPLE_ROWS},V={V} "
                              f"(BASELINE configs[0]), best of 3 after 1 warm-up = {best:.3f} s on {cpu_model_name()}"}
-        launches_per_step = 9 if mode == "reference" else 4
+        # status_clear, teacher_stats, owner_init, owner_scatter, table_fill, table_consts, queue_init, cluster emit,
+        # streaming helper emit, loss_finalize, regrad (early exit)
+        launches_per_step = 11 if mode == "reference" else 6
         out = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -106,7 +106,8 @@ int kd_loca_build_table(const kd_token_record* records_all, int64_t n_tokens_all
                         size_t workspace_bytes, void* stream);
 int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const float* lse2_t,
                  const float* table, const double* table_consts, void* grad_student, int64_t ld_g,
-                 float* loss_out, void* rowaux /* float4[n_rows] */, int64_t n_rows, int64_t V, int dtype,
+                 float* loss_out, void* rowaux /* float4[n_rows + 1]; the extra entry is scratch (row queue) */,
+                 int64_t n_rows, int64_t V, int dtype,
                  float T, float eps, double inv_norm, const float* upstream, unsigned flags, void* stream);
 
 /* Re-emission of the gradient for autograd's backward when the incoming grad_output differs from the scale that

@@ -6,6 +6,7 @@
 // sweeps (stats -> accumulate -> emit); logit_kd_cluster.cu keeps the row pair resident in the distributed
 // shared memory of a thread-block cluster so that HBM sees every byte once.
 #include <math.h>
+#include <stdlib.h>
 
 #include "logit_kd.cuh"
 
@@ -351,7 +352,31 @@ row_emit_stream_kernel(const EmitParams p) {
     const bool want_grad = !(p.flags & KD_FLAG_NO_GRAD);
     const int nvec = VEC ? V / P : 0;
 
-    for (int64_t r = blockIdx.x; r < p.n_rows; r += gridDim.x) {
+    __shared__ int next_row_sm;
+    int64_t r = blockIdx.x;
+    if (p.row_queue) {          // helper mode: rows are claimed from the queue shared with the cluster kernel
+        if (threadIdx.x == 0) {
+            // leave the last rows to the (much faster per row) cluster pipelines: no long tail behind a late claim
+            const int peek = *reinterpret_cast<volatile int*>(p.row_queue);
+            next_row_sm = (peek >= p.n_rows - p.queue_tail_reserve) ? 0x7fffffff : atomicAdd(p.row_queue, 1);
+        }
+        __syncthreads();
+        r = next_row_sm;
+    }
+    for (; r < p.n_rows;) {
+        auto advance_row = [&]() {
+            if (p.row_queue) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const int peek = *reinterpret_cast<volatile int*>(p.row_queue);
+                    next_row_sm = (peek >= p.n_rows - p.queue_tail_reserve) ? 0x7fffffff : atomicAdd(p.row_queue, 1);
+                }
+                __syncthreads();
+                r = next_row_sm;
+            } else {
+                r += gridDim.x;
+            }
+        };
         const T* trow = static_cast<const T*>(p.teacher) + r * p.ld_t;
         const T* srow = static_cast<const T*>(p.student) + r * p.ld_s;
         T* grow = static_cast<T*>(p.grad) + r * p.ld_g;
@@ -439,7 +464,7 @@ row_emit_stream_kernel(const EmitParams p) {
                 }
             }
         }
-        if (!want_grad) continue;
+        if (!want_grad) { advance_row(); continue; }
 
         // ---- sweep C: gradient ----------------------------------------------------------------------
         const float gQ = g * Q;
@@ -468,6 +493,7 @@ row_emit_stream_kernel(const EmitParams p) {
         for (int c = nvec * P + threadIdx.x; c < V; c += NT)
             grow[c] = Elem<T>::from_float(PointTerm<VARIANT>::grad(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]),
                                                                    LOCA ? override_of(c) : NaN, k2, lse2_t, lse2_s, thr2, g, gQ));
+        advance_row();
     }
 }
 
@@ -550,6 +576,7 @@ loss_finalize_kernel(const float4* __restrict__ rowaux, int64_t n_rows, double u
 }
 
 __global__ void status_clear_kernel(uint32_t* status) { *status = 0u; }
+__global__ void queue_init_kernel(int* queue, int value) { *queue = value; }
 
 // ------------------------------------------------------------------------------------------------
 // in-place scaling of a gradient (autograd backward with grad_output != 1)
@@ -593,7 +620,7 @@ int sm_count() {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {   // layout of the caller-provided logit-KD workspace
-    size_t rowaux, records, lse2_t, table_ws, table_ws_bytes, table, consts, status, total;
+    size_t rowaux, records, lse2_t, table_ws, table_ws_bytes, table, consts, status, queue, total;
 };
 
 size_t table_workspace_bytes(int64_t V) {   // owner arrays (labels pass, k pass) + per-block partial sums
@@ -613,6 +640,7 @@ Workspace workspace_layout(int64_t n_rows, int64_t V) {
     w.table = take(sizeof(float) * V);
     w.consts = take(sizeof(double) * 2);
     w.status = take(sizeof(uint32_t));
+    w.queue = take(sizeof(int));
     w.total = off;
     return w;
 }
@@ -640,7 +668,7 @@ template <int VARIANT, typename T>
 int launch_emit_stream_t(const EmitParams& p, cudaStream_t st) {
     const bool vec = rows_vectorizable<T>(p.teacher, p.ld_t) && rows_vectorizable<T>(p.student, p.ld_s) &&
                      ((p.flags & KD_FLAG_NO_GRAD) || rows_vectorizable<T>(p.grad, p.ld_g));
-    const int64_t cap = (int64_t)sm_count() * 2;
+    const int64_t cap = p.helper_ctas > 0 ? p.helper_ctas : (int64_t)sm_count() * 2;
     const int grid = static_cast<int>(p.n_rows < cap ? p.n_rows : cap);
     if (vec)
         row_emit_stream_kernel<VARIANT, T, true><<<grid, kEmitThreads, 0, st>>>(p);
@@ -662,11 +690,36 @@ int launch_emit_stream_v(const EmitParams& p, int variant, cudaStream_t st) {
     return KD_ERR_INVALID_ARGUMENT;
 }
 
-int launch_emit(const EmitParams& p, int variant, int dtype, cudaStream_t st) {
-    if (!(p.flags & KD_FLAG_FORCE_STREAMING)) {
-        const int rc = launch_emit_cluster(p, variant, dtype, st);
-        if (rc != KD_ERR_UNSUPPORTED) return rc;
+// helper stream + events for the concurrent streaming launch on the SMs the cluster kernel cannot occupy
+struct HelperStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int device = -1;
+};
+HelperStream* helper_stream() {
+    static HelperStream hs[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    HelperStream& h = hs[dev];
+    if (h.device != dev) {
+        if (cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&h.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        h.device = dev;
     }
+    return &h;
+}
+
+int spare_sm_mode() {       // KD_SPARE_SMS=0 disables the helper launch
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KD_SPARE_SMS");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
+int launch_emit_stream_any(const EmitParams& p, int variant, int dtype, cudaStream_t st) {
     switch (dtype) {
         case KD_DTYPE_BF16: return launch_emit_stream_v<__nv_bfloat16>(p, variant, st);
         case KD_DTYPE_F16: return launch_emit_stream_v<__half>(p, variant, st);
@@ -674,6 +727,47 @@ int launch_emit(const EmitParams& p, int variant, int dtype, cudaStream_t st) {
     }
     set_error("unknown dtype %d", dtype);
     return KD_ERR_INVALID_ARGUMENT;
+}
+
+// Emit = cluster-resident kernel where the shape allows it.  A cluster-of-8 launch reaches 120 of the 148 SMs, so when
+// a row queue is available the general streaming kernel runs concurrently on a helper stream over the remaining SMs and
+// both kernels claim rows from the same counter:
+//   main stream : queue_init -> [fork] -> cluster kernel -> wait(join)
+//   helper      : wait(fork) -> streaming kernel (2 CTAs per spare SM) -> [join]
+int launch_emit(const EmitParams& p_in, int variant, int dtype, cudaStream_t st, int* queue) {
+    EmitParams p = p_in;
+    p.row_queue = nullptr;
+    p.queue_tail_reserve = 0;
+    p.helper_ctas = 0;
+    if (p.flags & KD_FLAG_FORCE_STREAMING) return launch_emit_stream_any(p, variant, dtype, st);
+
+    int n_clusters = 0, cta_per = 8, pipes = 2;
+    const int shape_rc = cluster_launch_shape(p, variant, dtype, &n_clusters, &cta_per, &pipes);
+    if (shape_rc == KD_ERR_UNSUPPORTED) return launch_emit_stream_any(p, variant, dtype, st);
+    if (shape_rc != KD_OK) return shape_rc;
+
+    const int spare = sm_count() - n_clusters * cta_per;
+    HelperStream* hs = nullptr;
+    if (queue && spare_sm_mode() && spare >= 8 && p.n_rows >= (int64_t)n_clusters * pipes * 8) hs = helper_stream();
+    if (hs) {
+        queue_init_kernel<<<1, 1, 0, st>>>(queue, 2 * n_clusters * pipes);   // two static rows per cluster pipeline
+        KD_CHECK_LAUNCH("queue_init_kernel");
+        if (cudaEventRecord(hs->fork, st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaEventRecord(fork)");
+        p.row_queue = queue;
+    }
+    int rc = launch_emit_cluster(p, variant, dtype, st, nullptr, nullptr, nullptr);
+    if (rc != KD_OK) return rc;
+    if (hs && spare_sm_mode() != 2) {      // KD_SPARE_SMS=2: dynamic row queue without the helper kernel (experiment)
+        if (cudaStreamWaitEvent(hs->stream, hs->fork, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent(fork)");
+        EmitParams h = p;
+        h.queue_tail_reserve = n_clusters * pipes * 10;      // the last ~10 rows per cluster pipeline stay with the cluster kernel
+        h.helper_ctas = spare * 2;
+        rc = launch_emit_stream_any(h, variant, dtype, hs->stream);
+        if (rc != KD_OK) return rc;
+        if (cudaEventRecord(hs->join, hs->stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaEventRecord(join)");
+        if (cudaStreamWaitEvent(st, hs->join, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent(join)");
+    }
+    return KD_OK;
 }
 
 template <int VARIANT, typename T>
@@ -812,7 +906,7 @@ int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t
     p.rowaux = static_cast<float4*>(rowaux); p.upstream = upstream; p.n_rows = n_rows; p.V = (int)V;
     p.k2 = kLog2e / T; p.thr2 = log2f(eps); p.gscale = static_cast<float>(T * inv_norm); p.flags = flags;
     if (n_rows > 0) {
-        if (int rc = launch_emit(p, KD_LOCA_REFERENCE, dtype, st)) return rc;
+        if (int rc = launch_emit(p, KD_LOCA_REFERENCE, dtype, st, reinterpret_cast<int*>(p.rowaux + n_rows))) return rc;
     }
     loss_finalize_kernel<<<1, kFinalThreads, 0, st>>>(p.rowaux, n_rows, (double)kLn2, (double)T * T * inv_norm, table_consts,
                                                       nullptr, loss_out);
@@ -864,7 +958,7 @@ int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, 
         p.table = table;
     }
     if (n_rows > 0) {
-        if (int rc = launch_emit(p, variant, dtype, st)) return rc;
+        if (int rc = launch_emit(p, variant, dtype, st, reinterpret_cast<int*>(ws + w.queue))) return rc;
     }
     const double unit = (variant == KD_KL_LOG_TARGET) ? 1.0 : (double)kLn2;
     loss_finalize_kernel<<<1, kFinalThreads, 0, st>>>(rowaux, n_rows, unit, (double)T * T * inv_norm,

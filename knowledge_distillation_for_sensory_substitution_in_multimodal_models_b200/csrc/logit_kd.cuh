@@ -26,6 +26,10 @@ struct EmitParams {
     int64_t ld_g;
     float4* rowaux;             // per row: lse2_t, lse2_s, Q_r, row sum (log2 units; natural for KLLT)
     kd_token_record* records;   // per-row LoCa: {label, v1, k, v2} written for the backward re-emission (may be null)
+    int* row_queue;             // shared row counter: the cluster kernel (120 SMs) and the streaming kernel running on the
+                                // SMs a cluster-8 launch cannot reach pull rows from it; null = static striding
+    int queue_tail_reserve;     // streaming helper: stop claiming when fewer than this many rows are left
+    int helper_ctas;            // streaming helper: grid size (0 = default)
     uint32_t* status;
     const float* upstream;      // device scalar or nullptr
     int64_t n_rows;
@@ -91,7 +95,11 @@ __device__ __forceinline__ void loca_scalars(float x_label, float x_runner, floa
     v2 = sc * p_k;
 }
 
-// host-side launchers implemented in logit_kd_cluster.cu; return KD_ERR_UNSUPPORTED when the shape does not fit
-int launch_emit_cluster(const EmitParams& p, int variant, int dtype, cudaStream_t stream);
+// host-side launchers implemented in logit_kd_cluster.cu; return KD_ERR_UNSUPPORTED when the shape does not fit.
+// *first_free_row receives the first row index not statically owned by a cluster pipeline (initial queue value).
+int launch_emit_cluster(const EmitParams& p, int variant, int dtype, cudaStream_t stream, int* clusters_launched,
+                        int* ctas_per_cluster, int* first_free_row);
+// shape the cluster launch would take (no launch): KD_ERR_UNSUPPORTED when the cluster kernel does not apply
+int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clusters, int* ctas_per_cluster, int* pipelines);
 
 }  // namespace kd

@@ -135,7 +135,7 @@ struct SmemPlan {
         slotsA = off;
         off += NPIPE * NSLOT * SlotWords<VARIANT>::A * 4;
         slotsB = off;
-        off += NPIPE * NSLOT * 8;
+        off += NPIPE * (NSLOT + 1) * 8;      // +1: the leader's "next row" word rides on reduction B
         bcast = off;                 // per pipeline: 8 words of reduction-A results + 2 words of reduction-B results (+pad)
         off += NPIPE * 64;
         total = off;
@@ -188,7 +188,7 @@ __device__ __forceinline__ uint4 lds128_nv(uint32_t addr, uint32_t epoch) {
 }
 
 // --------------------------------------------------------------------------------------------------------
-template <int VARIANT, typename T, int CS, int NPIPE, bool TSM>
+template <int VARIANT, typename T, int CS, int NPIPE, bool TSM, bool DYN>
 __global__ void __launch_bounds__(kThreads, 1)
 row_emit_cluster_kernel(const ClusterParams cp) {
     constexpr bool LOCA = (VARIANT == KD_LOCA_REFERENCE || VARIANT == KD_LOCA_PER_ROW);
@@ -213,7 +213,9 @@ row_emit_cluster_kernel(const ClusterParams cp) {
     const uint32_t bar_redA = s_base + plan.bars + (kWarps + 2 * pipe) * 8;
     const uint32_t bar_redB = bar_redA + 8;
     const uint32_t slotA = s_base + plan.slotsA + pipe * NSLOT * AW * 4;
-    const uint32_t slotB = s_base + plan.slotsB + pipe * NSLOT * 8;
+    const uint32_t slotB = s_base + plan.slotsB + pipe * (NSLOT + 1) * 8;
+    constexpr bool dynamic_rows = DYN;       // rows claimed from p.row_queue (shared with the streaming helper kernel)
+    const uint32_t redB_bytes = NSLOT * 8 + (dynamic_rows ? 8 : 0);
     volatile float* bcast = reinterpret_cast<volatile float*>(smem + plan.bcast + pipe * 64);
     const int barA = 1 + 2 * pipe, barB = 2 + 2 * pipe;     // named barriers of this pipeline (0 is __syncthreads)
 
@@ -237,7 +239,7 @@ row_emit_cluster_kernel(const ClusterParams cp) {
         fence_mbar_init();
         for (int i = 0; i < NPIPE; ++i) {        // arm the first phase of every reduction barrier
             mbar_expect_tx(s_base + plan.bars + (kWarps + 2 * i) * 8, NSLOT * AW * 4);
-            mbar_expect_tx(s_base + plan.bars + (kWarps + 2 * i + 1) * 8, NSLOT * 8);
+            mbar_expect_tx(s_base + plan.bars + (kWarps + 2 * i + 1) * 8, NSLOT * 8 + (DYN ? 8 : 0));
         }
     }
     // LoCa reference mode: encode this CTA's table slice once (0 = not overridden, else max(ov, floor) > 0)
@@ -297,8 +299,15 @@ row_emit_cluster_kernel(const ClusterParams cp) {
     uint32_t ph_full = 0, ph_red = 0;
 
     int row_iter = -1;
-    for (; r < p.n_rows; r += row_stride) {
+    int64_t next_r = r + row_stride;      // dynamic mode: the first two rows of a pipeline are static, later ones are claimed
+    while (r < p.n_rows) {
         ++row_iter;
+        // dynamic mode: the leader warp (cluster rank 0, first warp of the pipeline) claims the pipeline's next row now;
+        // the index travels to every CTA with reduction B, long before the refill at the end of this row needs it
+        // (the claim is for the row AFTER the next one: the next row is already known, so its L2 warm-up starts now)
+        if (!dynamic_rows) next_r = r + row_stride;
+        int claimed = 0;
+        if (dynamic_rows && rank == 0 && pw == 0 && lane == 0) claimed = atomicAdd(p.row_queue, 1);
         KD_STAMP(0);
         // per-row scalars fetched early so their latency hides behind sweep A
         float lse2_t = 0.f;
@@ -314,7 +323,7 @@ row_emit_cluster_kernel(const ClusterParams cp) {
                 atomicOr(p.status, KD_STATUS_BAD_LABEL);
             }
         }
-        warm_l2(r + row_stride);
+        warm_l2(next_r);
         const uint32_t epoch = (uint32_t)r;
         const uint4* tvec = reinterpret_cast<const uint4*>(tbase + r * p.ld_t) + g_v0;     // this warp's teacher vectors
         auto load_t = [&](int v) -> uint4 {
@@ -593,10 +602,14 @@ row_emit_cluster_kernel(const ClusterParams cp) {
         if (lane < CS) {
             st_async_v2(map_to_cta(slotB + (rank * WPP + pw) * 8, lane), __float_as_uint(row), __float_as_uint(Q),
                         map_to_cta(bar_redB, lane));
+            if (dynamic_rows && rank == 0 && pw == 0) {
+                claimed = __shfl_sync((1u << CS) - 1u, claimed, 0);
+                st_async_v2(map_to_cta(slotB + NSLOT * 8, lane), (uint32_t)claimed, 0u, map_to_cta(bar_redB, lane));
+            }
         }
         if (pw == 0) {
             mbar_wait_cta(bar_redB, ph_red);
-            if (lane == 0) mbar_expect_tx(bar_redB, NSLOT * 8);
+            if (lane == 0) mbar_expect_tx(bar_redB, redB_bytes);
             float rr = 0.f, qq = 0.f;
             for (int i = lane; i < NSLOT; i += 32) {
                 const float2 sl = reinterpret_cast<const float2*>(smem + (slotB - s_base))[i];
@@ -607,6 +620,7 @@ row_emit_cluster_kernel(const ClusterParams cp) {
             Q = warp_sum(qq);
             if (lane == 0) {
                 bcast[8] = Q;
+                if (dynamic_rows) bcast[9] = __int_as_float(reinterpret_cast<const int*>(smem + (slotB - s_base))[NSLOT * 2]);
                 if (rank == 0) {
                     if constexpr (VARIANT == KD_LOCA_PER_ROW) {
                         if (lab >= 0) {
@@ -630,6 +644,8 @@ row_emit_cluster_kernel(const ClusterParams cp) {
         named_bar_sync(barB, WPP * 32);
         KD_STAMP(5);
         Q = bcast[8];
+        int64_t after_next = 0;
+        if (dynamic_rows) after_next = __float_as_int(bcast[9]);
         ph_red ^= 1;
 
         // ================= sweep C: gradient, written straight to HBM ===================================
@@ -718,15 +734,17 @@ row_emit_cluster_kernel(const ClusterParams cp) {
         KD_STAMP(6);
         // ---- refill the warp's private slice with its next row (all lanes are done reading it) -----------
         __syncwarp();
-        if (r + row_stride < p.n_rows) issue_load(r + row_stride);
+        if (next_r < p.n_rows) issue_load(next_r);
+        r = next_r;
+        if (dynamic_rows) next_r = after_next;
     }
     cluster_sync_all();     // nobody leaves while peers may still push into its shared memory
 }
 
 // --------------------------------------------------------------------------------------------------------
-template <int VARIANT, typename T, int CS, int NPIPE, bool TSM>
-int launch_variant(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity) {
-    auto kfn = row_emit_cluster_kernel<VARIANT, T, CS, NPIPE, TSM>;
+template <int VARIANT, typename T, int CS, int NPIPE, bool TSM, bool DYN>
+int launch_variant_d(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
+    auto kfn = row_emit_cluster_kernel<VARIANT, T, CS, NPIPE, TSM, DYN>;
     const int nvec = e.V / 8;
     const int vpc = (nvec + CS - 1) / CS;
     const SmemPlan<VARIANT, CS, NPIPE, TSM> plan(vpc);
@@ -791,9 +809,17 @@ int launch_variant(const EmitParams& e, cudaStream_t st, bool query_only, int* c
     cp.vpc = vpc;
     cp.nvec = nvec;
     cfg.gridDim = dim3(cp.n_clusters * CS);
+    if (launched) *launched = cp.n_clusters;
+    if (first_free) *first_free = 2 * cp.n_clusters * NPIPE;
     err = cudaLaunchKernelEx(&cfg, kfn, cp);
     if (err != cudaSuccess) return cuda_fail(err, "row_emit_cluster_kernel launch");
     return KD_OK;
+}
+
+template <int VARIANT, typename T, int CS, int NPIPE, bool TSM>
+int launch_variant(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched = nullptr, int* first_free = nullptr) {
+    if (e.row_queue) return launch_variant_d<VARIANT, T, CS, NPIPE, TSM, true>(e, st, query_only, capacity, launched, first_free);
+    return launch_variant_d<VARIANT, T, CS, NPIPE, TSM, false>(e, st, query_only, capacity, launched, first_free);
 }
 
 // configuration: 0 = teacher + student slices resident, 2 row pipelines; 1 = student resident, teacher via L2, 4 pipelines
@@ -807,18 +833,18 @@ int cluster_config() {
 }
 
 template <int VARIANT, typename T>
-int launch_cfg(const EmitParams& e, cudaStream_t st) {
-    if (cluster_config() == 0) return launch_variant<VARIANT, T, 8, 2, true>(e, st, false, nullptr);
-    return launch_variant<VARIANT, T, 8, 4, false>(e, st, false, nullptr);
+int launch_cfg(const EmitParams& e, cudaStream_t st, int* launched, int* first_free) {
+    if (cluster_config() == 0) return launch_variant<VARIANT, T, 8, 2, true>(e, st, false, nullptr, launched, first_free);
+    return launch_variant<VARIANT, T, 8, 4, false>(e, st, false, nullptr, launched, first_free);
 }
 
 template <typename T>
-int launch_dtype(const EmitParams& e, int variant, cudaStream_t st) {
+int launch_dtype(const EmitParams& e, int variant, cudaStream_t st, int* launched, int* first_free) {
     switch (variant) {
-        case KD_LOCA_REFERENCE: return launch_cfg<KD_LOCA_REFERENCE, T>(e, st);
-        case KD_LOCA_PER_ROW: return launch_cfg<KD_LOCA_PER_ROW, T>(e, st);
-        case KD_KL_PLAIN: return launch_cfg<KD_KL_PLAIN, T>(e, st);
-        case KD_KL_LOG_TARGET: return launch_cfg<KD_KL_LOG_TARGET, T>(e, st);
+        case KD_LOCA_REFERENCE: return launch_cfg<KD_LOCA_REFERENCE, T>(e, st, launched, first_free);
+        case KD_LOCA_PER_ROW: return launch_cfg<KD_LOCA_PER_ROW, T>(e, st, launched, first_free);
+        case KD_KL_PLAIN: return launch_cfg<KD_KL_PLAIN, T>(e, st, launched, first_free);
+        case KD_KL_LOG_TARGET: return launch_cfg<KD_KL_LOG_TARGET, T>(e, st, launched, first_free);
     }
     return KD_ERR_UNSUPPORTED;
 }
@@ -835,14 +861,40 @@ int cluster_capacity(int cluster_size, int, size_t) {
     return cap;
 }
 
-int launch_emit_cluster(const EmitParams& p, int variant, int dtype, cudaStream_t stream) {
-    if (dtype == KD_DTYPE_F32) return KD_ERR_UNSUPPORTED;                 // 16-bit logits only
-    if (p.V % 8 != 0 || p.V < 8 * 8 * 32) return KD_ERR_UNSUPPORTED;      // whole 16-byte vectors, enough columns per warp
-    if (!aligned_rows(p.teacher, p.ld_t) || !aligned_rows(p.student, p.ld_s)) return KD_ERR_UNSUPPORTED;
-    if (!(p.flags & KD_FLAG_NO_GRAD) && !aligned_rows(p.grad, p.ld_g)) return KD_ERR_UNSUPPORTED;
-    if (p.n_rows < 1) return KD_ERR_UNSUPPORTED;
-    if (dtype == KD_DTYPE_BF16) return launch_dtype<__nv_bfloat16>(p, variant, stream);
-    return launch_dtype<__half>(p, variant, stream);
+static bool cluster_eligible(const EmitParams& p, int dtype) {
+    if (dtype == KD_DTYPE_F32) return false;                                   // 16-bit logits only
+    if (p.V % 8 != 0 || p.V < 8 * 8 * 32) return false;                        // whole 16-byte vectors, enough columns per warp
+    if (!aligned_rows(p.teacher, p.ld_t) || !aligned_rows(p.student, p.ld_s)) return false;
+    if (!(p.flags & KD_FLAG_NO_GRAD) && !aligned_rows(p.grad, p.ld_g)) return false;
+    return p.n_rows >= 1;
+}
+
+int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clusters, int* ctas_per_cluster, int* pipelines) {
+    if (!cluster_eligible(p, dtype)) return KD_ERR_UNSUPPORTED;
+    int cap = 0, rc;
+    const int pipes = cluster_config() == 0 ? 2 : 4;
+#define KD_QUERY(VAR, TT) (cluster_config() == 0 ? launch_variant<VAR, TT, 8, 2, true>(p, nullptr, true, &cap) \
+                                                 : launch_variant<VAR, TT, 8, 4, false>(p, nullptr, true, &cap))
+#define KD_QUERY_T(TT) (variant == KD_LOCA_REFERENCE ? KD_QUERY(KD_LOCA_REFERENCE, TT) : variant == KD_LOCA_PER_ROW ? KD_QUERY(KD_LOCA_PER_ROW, TT) \
+                        : variant == KD_KL_PLAIN ? KD_QUERY(KD_KL_PLAIN, TT) : KD_QUERY(KD_KL_LOG_TARGET, TT))
+    rc = (dtype == KD_DTYPE_BF16) ? KD_QUERY_T(__nv_bfloat16) : KD_QUERY_T(__half);
+#undef KD_QUERY_T
+#undef KD_QUERY
+    if (rc != KD_OK) return rc;
+    if (cap < 1) return KD_ERR_UNSUPPORTED;
+    const int64_t want = (p.n_rows + pipes - 1) / pipes;
+    *n_clusters = (int)(want < cap ? want : cap);
+    *ctas_per_cluster = 8;
+    *pipelines = pipes;
+    return KD_OK;
+}
+
+int launch_emit_cluster(const EmitParams& p, int variant, int dtype, cudaStream_t stream, int* clusters_launched,
+                        int* ctas_per_cluster, int* first_free_row) {
+    if (ctas_per_cluster) *ctas_per_cluster = 8;
+    if (!cluster_eligible(p, dtype)) return KD_ERR_UNSUPPORTED;
+    if (dtype == KD_DTYPE_BF16) return launch_dtype<__nv_bfloat16>(p, variant, stream, clusters_launched, first_free_row);
+    return launch_dtype<__half>(p, variant, stream, clusters_launched, first_free_row);
 }
 
 }  // namespace kd

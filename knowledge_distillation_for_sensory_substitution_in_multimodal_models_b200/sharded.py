@@ -51,7 +51,7 @@ class CudaPhases:
         dev = student.device
         n, V = student.shape
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        rowaux = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
+        rowaux = torch.empty((n + 1, 4), dtype=torch.float32, device=dev)     # +1: scratch entry (row queue)
         grad = torch.empty((n, V), dtype=student.dtype, device=dev) if want_grad else None
         up_t, up_ptr = _upstream_ptr(upstream, dev)
         flags = (0 if want_grad else _lib.FLAG_NO_GRAD) | (_lib.FLAG_FORCE_STREAMING if force_streaming else 0)

@@ -196,7 +196,9 @@ def test_size_independent_properties_at_full_size():
     l1 = kd.loca_kl(t, s, lab, 2.0, mode="per_row")
     l3.backward()
     assert abs(l3.item() - l1.item()) <= 1e-6 * abs(l1.item())
-    assert torch.equal(sd3.grad, sd.grad[perm])
+    # rows may be claimed by either the cluster kernel or the streaming helper: same math, different evaluation order,
+    # so only cells on a bf16 rounding boundary may differ
+    assert rel_err(sd3.grad.float(), sd.grad[perm].float()) <= 1e-3
 
 
 def test_phase_split_entry_points_match_fused_call():
