@@ -102,4 +102,11 @@ int launch_emit_cluster(const EmitParams& p, int variant, int dtype, cudaStream_
 // shape the cluster launch would take (no launch): KD_ERR_UNSUPPORTED when the cluster kernel does not apply
 int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clusters, int* ctas_per_cluster, int* pipelines);
 
+
+// two-sweep kernel with the q values parked in tensor memory (logit_kd_fused.cu): applies to KD_LOCA_REFERENCE with
+// 0 <= alpha <= 1 and to KD_KL_PLAIN on 16-bit logits; same launch shape as the cluster kernel (clusters of 8, 2 pipelines)
+bool fused_applies(const EmitParams& p, int variant, int dtype);
+int launch_emit_fused(const EmitParams& p, int variant, int dtype, cudaStream_t stream, bool query_only, int* capacity,
+                      int* clusters_launched, int* first_free_row);
+
 }  // namespace kd

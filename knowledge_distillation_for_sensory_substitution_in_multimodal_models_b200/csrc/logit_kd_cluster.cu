@@ -18,6 +18,7 @@
 
 #include <type_traits>
 
+#include "cluster_prims.cuh"
 #include "logit_kd.cuh"
 
 namespace kd {
@@ -35,66 +36,6 @@ constexpr int kThreads = KD_CLUSTER_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr float kPush = -3.0e38f;       // ov' * kPush drives log2 q of an overridden cell to -inf
 constexpr float kOvFloor = 1.0e-36f;    // encoded "overridden with ~0" (must stay > 0)
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_t b) {
-    asm volatile("st.shared::cluster.v2.u32 [%0], {%1,%2};" :: "r"(addr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-// remote store that signals the destination CTA's mbarrier (complete_tx) — no fence, no cluster barrier
-__device__ __forceinline__ void st_async_v2(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t cluster_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1,%2}, [%3];"
-                 :: "r"(cluster_addr), "r"(a), "r"(b), "r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t cluster_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
-                 :: "r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {     // sub-CTA barrier: one row pipeline's warps
-    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {       // TMA completion
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
 
 // Optional phase tracing (compile with -DKD_TRACE): lane 0 of every warp stamps %globaltimer at the phase
 // boundaries of each row into `trace` ([cta][warp][row_iter][8] u64), read back by tools/trace_emit.py.
@@ -872,6 +813,13 @@ static bool cluster_eligible(const EmitParams& p, int dtype) {
 int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clusters, int* ctas_per_cluster, int* pipelines) {
     if (!cluster_eligible(p, dtype)) return KD_ERR_UNSUPPORTED;
     int cap = 0, rc;
+    if (fused_applies(p, variant, dtype) && launch_emit_fused(p, variant, dtype, nullptr, true, &cap, nullptr, nullptr) == KD_OK && cap >= 1) {
+        const int64_t want2 = (p.n_rows + 1) / 2;
+        *n_clusters = (int)(want2 < cap ? want2 : cap);
+        *ctas_per_cluster = 8;
+        *pipelines = 2;
+        return KD_OK;
+    }
     const int pipes = cluster_config() == 0 ? 2 : 4;
 #define KD_QUERY(VAR, TT) (cluster_config() == 0 ? launch_variant<VAR, TT, 8, 2, true>(p, nullptr, true, &cap) \
                                                  : launch_variant<VAR, TT, 8, 4, false>(p, nullptr, true, &cap))
@@ -893,6 +841,10 @@ int launch_emit_cluster(const EmitParams& p, int variant, int dtype, cudaStream_
                         int* ctas_per_cluster, int* first_free_row) {
     if (ctas_per_cluster) *ctas_per_cluster = 8;
     if (!cluster_eligible(p, dtype)) return KD_ERR_UNSUPPORTED;
+    if (fused_applies(p, variant, dtype)) {
+        const int rc = launch_emit_fused(p, variant, dtype, stream, false, nullptr, clusters_launched, first_free_row);
+        if (rc != KD_ERR_UNSUPPORTED) return rc;
+    }
     if (dtype == KD_DTYPE_BF16) return launch_dtype<__nv_bfloat16>(p, variant, stream, clusters_launched, first_free_row);
     return launch_dtype<__half>(p, variant, stream, clusters_launched, first_free_row);
 }
