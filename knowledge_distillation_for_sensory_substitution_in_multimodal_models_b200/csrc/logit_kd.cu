@@ -741,8 +741,8 @@ int launch_emit(const EmitParams& p_in, int variant, int dtype, cudaStream_t st,
     p.helper_ctas = 0;
     if (p.flags & KD_FLAG_FORCE_STREAMING) return launch_emit_stream_any(p, variant, dtype, st);
 
-    int n_clusters = 0, cta_per = 8, pipes = 2;
-    const int shape_rc = cluster_launch_shape(p, variant, dtype, &n_clusters, &cta_per, &pipes);
+    int n_clusters = 0, cta_per = 8, pipes = 2, static_rows = 4;
+    const int shape_rc = cluster_launch_shape(p, variant, dtype, &n_clusters, &cta_per, &pipes, &static_rows);
     if (shape_rc == KD_ERR_UNSUPPORTED) return launch_emit_stream_any(p, variant, dtype, st);
     if (shape_rc != KD_OK) return shape_rc;
 
@@ -750,7 +750,7 @@ int launch_emit(const EmitParams& p_in, int variant, int dtype, cudaStream_t st,
     HelperStream* hs = nullptr;
     if (queue && spare_sm_mode() && spare >= 8 && p.n_rows >= (int64_t)n_clusters * pipes * 8) hs = helper_stream();
     if (hs) {
-        queue_init_kernel<<<1, 1, 0, st>>>(queue, 2 * n_clusters * pipes);   // two static rows per cluster pipeline
+        queue_init_kernel<<<1, 1, 0, st>>>(queue, n_clusters * static_rows);   // the first rows of every cluster are static
         KD_CHECK_LAUNCH("queue_init_kernel");
         if (cudaEventRecord(hs->fork, st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaEventRecord(fork)");
         p.row_queue = queue;

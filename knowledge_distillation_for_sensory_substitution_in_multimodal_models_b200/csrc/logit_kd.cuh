@@ -100,13 +100,15 @@ __device__ __forceinline__ void loca_scalars(float x_label, float x_runner, floa
 int launch_emit_cluster(const EmitParams& p, int variant, int dtype, cudaStream_t stream, int* clusters_launched,
                         int* ctas_per_cluster, int* first_free_row);
 // shape the cluster launch would take (no launch): KD_ERR_UNSUPPORTED when the cluster kernel does not apply
-int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clusters, int* ctas_per_cluster, int* pipelines);
+// *static_rows = rows per cluster that are assigned statically (the row queue starts behind them)
+int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clusters, int* ctas_per_cluster, int* pipelines,
+                         int* static_rows);
 
 
 // two-sweep kernel with the q values parked in tensor memory (logit_kd_fused.cu): applies to KD_LOCA_REFERENCE with
 // 0 <= alpha <= 1 and to KD_KL_PLAIN on 16-bit logits; same launch shape as the cluster kernel (clusters of 8, 2 pipelines)
 bool fused_applies(const EmitParams& p, int variant, int dtype);
 int launch_emit_fused(const EmitParams& p, int variant, int dtype, cudaStream_t stream, bool query_only, int* capacity,
-                      int* clusters_launched, int* first_free_row);
+                      int* clusters_launched, int* first_free_row, int* rows_in_flight /* per cluster: 1 or 2 pipelines */);
 
 }  // namespace kd

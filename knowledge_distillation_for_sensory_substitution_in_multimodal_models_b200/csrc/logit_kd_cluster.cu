@@ -810,14 +810,17 @@ static bool cluster_eligible(const EmitParams& p, int dtype) {
     return p.n_rows >= 1;
 }
 
-int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clusters, int* ctas_per_cluster, int* pipelines) {
+int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clusters, int* ctas_per_cluster, int* pipelines,
+                         int* static_rows) {
     if (!cluster_eligible(p, dtype)) return KD_ERR_UNSUPPORTED;
     int cap = 0, rc;
-    if (fused_applies(p, variant, dtype) && launch_emit_fused(p, variant, dtype, nullptr, true, &cap, nullptr, nullptr) == KD_OK && cap >= 1) {
-        const int64_t want2 = (p.n_rows + 1) / 2;
+    int in_flight = 2;
+    if (fused_applies(p, variant, dtype) && launch_emit_fused(p, variant, dtype, nullptr, true, &cap, nullptr, nullptr, &in_flight) == KD_OK && cap >= 1) {
+        const int64_t want2 = (p.n_rows + in_flight - 1) / in_flight;
         *n_clusters = (int)(want2 < cap ? want2 : cap);
         *ctas_per_cluster = 8;
-        *pipelines = 2;
+        *pipelines = in_flight;
+        *static_rows = in_flight == 1 ? 3 : 4;       // pipelined kernel: 3 rows; two pipelines: 2 rows each
         return KD_OK;
     }
     const int pipes = cluster_config() == 0 ? 2 : 4;
@@ -834,6 +837,7 @@ int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clu
     *n_clusters = (int)(want < cap ? want : cap);
     *ctas_per_cluster = 8;
     *pipelines = pipes;
+    *static_rows = 2 * pipes;
     return KD_OK;
 }
 
@@ -842,7 +846,7 @@ int launch_emit_cluster(const EmitParams& p, int variant, int dtype, cudaStream_
     if (ctas_per_cluster) *ctas_per_cluster = 8;
     if (!cluster_eligible(p, dtype)) return KD_ERR_UNSUPPORTED;
     if (fused_applies(p, variant, dtype)) {
-        const int rc = launch_emit_fused(p, variant, dtype, stream, false, nullptr, clusters_launched, first_free_row);
+        const int rc = launch_emit_fused(p, variant, dtype, stream, false, nullptr, clusters_launched, first_free_row, nullptr);
         if (rc != KD_ERR_UNSUPPORTED) return rc;
     }
     if (dtype == KD_DTYPE_BF16) return launch_dtype<__nv_bfloat16>(p, variant, stream, clusters_launched, first_free_row);

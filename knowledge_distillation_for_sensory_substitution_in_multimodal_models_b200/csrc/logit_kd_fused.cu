@@ -301,7 +301,9 @@ row_emit_fused_kernel(const FusedParams cp) {
         }
         // one warp per pipeline folds the NSLOT partials and broadcasts the row statistics through shared memory
         if (pw == 0) {
+#ifndef KD_ABLATE_SYNC     // timing experiment only (wrong results): no reduction wait
             mbar_wait_cta(bar_red1, ph1);
+#endif
             if (lane == 0) mbar_expect_tx(bar_red1, RED1_BYTES);      // arm the next row's phase
             constexpr int SPL = NSLOT / 32;                            // slots per lane
             float4 sa[SPL], sb[SPL];
@@ -365,11 +367,17 @@ row_emit_fused_kernel(const FusedParams cp) {
                 if (rank == 0 && all_kept) p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row);
             }
         }
+#ifndef KD_ABLATE_SYNC
         named_bar_sync(bar1, WPP * 32);
+#endif
         const float lse2_s = bcast[0];
         if constexpr (!REF) lse2_t = bcast[1];
         float Q = bcast[2];
+#ifdef KD_ABLATE_SYNC
+        const bool all_kept = true;
+#else
         const bool all_kept = bcast[3] != 0.f;
+#endif
         int64_t after_next = 0;
         if (DYN) after_next = __float_as_int(bcast[4]);
         ph1 ^= 1;
@@ -500,6 +508,622 @@ row_emit_fused_kernel(const FusedParams cp) {
     if (warp == 1) tmem_dealloc_512(tmem_base);
 }
 
+
+// ========================================================================================================
+// Software-pipelined variant: ONE pipeline of 16 warps per CTA, rows overlapped in time instead of side by side.
+//
+//   iteration i of a cluster:   [fold(i-1)] -> (B'(i-1), push2) -> pass 0 (i) -> pass AB (i) -> push(i) -> pass C (i-1)
+//
+// The reduction of row i has the whole of pass C (i-1) and the start of the next iteration to complete, so no warp
+// waits for it and all 16 warps of the SM stay busy (the two-pipeline kernel above parks 8 of them at every
+// reduction).  Residency: student slices in a ring of 3, teacher slices in a ring of 2 (the teacher is consumed by
+// pass AB only); the TMA of row i+1 is issued at the top of iteration i by whichever warp arrives there LAST (every
+// warp is then done with the slots being refilled), one bulk copy per tensor for the whole CTA slice.  A thread
+// handles at most 5 vectors of a row, so tensor memory holds q double-buffered (2 x 40 words) AND the thread's 40
+// override-table entries (each column has exactly one owner thread now), which takes the table out of shared memory.
+// Per-row scalars every warp needs (lse2_s, g*Q and its log2, the clamp flag, the next claimed row) are computed once
+// by the folding warp — the one with the fewest vectors — and broadcast through shared memory.
+constexpr int kMaxIt = 5;
+constexpr int kTmQ = 0, kTmTable = 80;     // TMEM word offsets inside the thread's 128 words: q[2][40], table[40]
+using Int1 = std::integral_constant<int, 1>;
+using Int2 = std::integral_constant<int, 2>;
+
+template <int VARIANT, int CS>
+struct PipePlan {
+    static constexpr int NSLOT = CS * kWarps;
+    int students, teachers, bars, slots, bcast, misc, total;
+    __host__ __device__ PipePlan(int vpc) {
+        int off = 0;
+        students = off;
+        off += 3 * vpc * 16;
+        teachers = off;
+        off += 2 * vpc * 16;
+        bars = off;
+        off += 10 * 8;                    // full[2], red1[2], red2[2], res1[2], res2[2]
+        slots = off;
+        off += 2 * NSLOT * 32;            // double-buffered by row parity
+        bcast = off;
+        off += 2 * 32;
+        misc = off;                       // [0] tensor-memory base address, [1] arrival counter of the TMA election
+        off += 16;
+        total = off;
+    }
+};
+
+__device__ __forceinline__ void st_async_b32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 :: "r"(cluster_addr), "r"(v), "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t swap_halves(uint32_t w) { return __byte_perm(w, w, 0x1032); }
+
+// Sums of four per-lane values in 6 shuffles: afterwards lanes 8g..8g+7 hold the warp total of value g.
+__device__ __forceinline__ float warp_sum4_grouped(float a, float b, float c, float d, int lane) {
+    const bool hi4 = lane & 16, hi3 = lane & 8;
+    float x = hi4 ? c : a, y = hi4 ? d : b;
+    const float sx = hi4 ? a : c, sy = hi4 ? b : d;
+    x += __shfl_xor_sync(0xffffffffu, sx, 16);
+    y += __shfl_xor_sync(0xffffffffu, sy, 16);
+    float k = hi3 ? y : x;
+    const float sk = hi3 ? x : y;
+    k += __shfl_xor_sync(0xffffffffu, sk, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
+}
+
+template <int VARIANT, typename T, int CS, bool DYN>
+__global__ void __launch_bounds__(kThreads, 1)
+row_emit_pipelined_kernel(const FusedParams cp) {
+    constexpr bool REF = (VARIANT == KD_LOCA_REFERENCE);
+    constexpr int NSLOT = CS * kWarps;
+    constexpr int SPL = NSLOT / 32;                 // slots per lane in the fold
+    constexpr uint32_t RED1_BYTES = NSLOT * (REF ? 24 : 32);
+    constexpr uint32_t RED2_BYTES = NSLOT * 8;
+    constexpr int FOLD_WARP = kWarps - 2;           // a warp with the fewest vectors (the last one also runs the partial step)
+    static_assert(CS == 8, "the grouped push below addresses 8 CTAs with 3 lane bits");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const EmitParams& p = cp.e;
+    const PipePlan<VARIANT, CS> plan(cp.vpc);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x / CS;
+    const float NaN = __int_as_float(0x7fc00000);
+
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t bar_full = s_base + plan.bars;               // + par * 8
+    const uint32_t bar_red1 = s_base + plan.bars + 2 * 8;
+    const uint32_t bar_red2 = s_base + plan.bars + 4 * 8;
+    const uint32_t bar_res1 = s_base + plan.bars + 6 * 8;
+    const uint32_t bar_res2 = s_base + plan.bars + 8 * 8;
+    const uint32_t slots = s_base + plan.slots;                 // + par * NSLOT * 32
+    uint32_t* misc = reinterpret_cast<uint32_t*>(smem + plan.misc);
+
+    // this CTA's column slice; warp iterations (32 vectors each) are dealt out evenly
+    const int cta_v0 = min((int)rank * cp.vpc, cp.nvec);
+    const int cta_v1 = min(cta_v0 + cp.vpc, cp.nvec);
+    const int cta_n = cta_v1 - cta_v0;
+    const int it_total = (cta_n + 31) >> 5;
+    const int it_base = it_total / kWarps, it_extra = it_total % kWarps;
+    const int w_lo = min((warp * it_base + min(warp, it_extra)) * 32, cta_n);
+    const int w_n = max(0, min((it_base + (warp < it_extra ? 1 : 0)) * 32, cta_n - w_lo));
+    const int n_full = w_n >> 5, n_tail = w_n & 31;
+    const int g_v0 = cta_v0 + w_lo;
+    const uint32_t slice_bytes = (uint32_t)cp.vpc * 16u;
+    const uint32_t s_stu = s_base + plan.students, s_tea = s_base + plan.teachers;
+
+    if (tid == 0) {
+        for (int w = 0; w < 10; ++w) mbar_init(s_base + plan.bars + w * 8, 1);
+        misc[1] = 0u;
+        fence_mbar_init();
+        for (int par = 0; par < 2; ++par) {        // arm the first phase of every reduction barrier
+            mbar_expect_tx(bar_red1 + par * 8, RED1_BYTES);
+            mbar_expect_tx(bar_red2 + par * 8, RED2_BYTES);
+        }
+    }
+    if (warp == 1) tmem_alloc_512(s_base + plan.misc);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(misc);
+    const uint32_t tm = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(kTmemColsPerWarp * (warp >> 2));
+
+    // LoCa: the thread's own table entries go to tensor memory, encoded (0 = not overridden, else max(ov, floor) > 0)
+    float poison = 0.f;
+    if constexpr (REF) {
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < kMaxIt; ++j) {
+            uint32_t enc[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            const int v = lane + 32 * j;
+            if (v < w_n) {
+                const float4* src = reinterpret_cast<const float4*>(p.table + (int64_t)(g_v0 + v) * 8);
+                const float4 a = src[0], b = src[1];
+                const float ov[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (ov[i] == ov[i]) {
+                        ok = ok && (ov[i] >= 0.f) && (ov[i] <= 3.0e38f);
+                        enc[i] = __float_as_uint(fmaxf(ov[i], kOvFloor));
+                    }
+                }
+            }
+            __syncwarp();
+            tmem_st8(tm + kTmTable + 8 * j, enc);
+        }
+        tmem_wait_st();
+        // a negative / non-finite override (alpha > 1; the reference's loss is NaN there too) poisons the row sums
+        if (!__syncthreads_and(ok)) poison = NaN;
+    }
+    cluster_sync_all();     // barriers initialised cluster-wide before any remote push
+
+    const T* tbase = static_cast<const T*>(p.teacher);
+    const T* sbase = static_cast<const T*>(p.student);
+    // one thread loads the whole CTA slice of `row` (student -> ring slot s_dst, teacher -> t_dst)
+    auto issue_load = [&](int64_t row, uint32_t s_dst, uint32_t t_dst, uint32_t bar) {
+        const uint32_t bytes = (uint32_t)cta_n * 16u;
+        fence_proxy_async();
+        mbar_expect_tx(bar, 2u * bytes);
+        tma_load_1d(s_dst, sbase + row * p.ld_s + (int64_t)cta_v0 * 8, bytes, bar);
+        tma_load_1d(t_dst, tbase + row * p.ld_t + (int64_t)cta_v0 * 8, bytes, bar);
+    };
+
+    const float k2 = p.k2, thr2 = p.thr2;
+    const float up = p.upstream ? *p.upstream : 1.f;
+    const float g = p.gscale * up;
+    const bool want_grad = !(p.flags & KD_FLAG_NO_GRAD);
+    const u64 k2p = pk(k2, k2);
+    const u64 pushp = pk(kPush, kPush);
+    uint32_t ph2_0 = 0, ph2_1 = 0;
+
+    // rows of this cluster: the first three are static, later ones are claimed from the queue (the claim made in
+    // iteration i travels with reduction i and names the row of iteration i+3)
+    const int64_t n_rows = p.n_rows;
+    int64_t r_cur = cluster_id, r_nxt = r_cur + cp.n_clusters, r_nn = r_nxt + cp.n_clusters;
+    int64_t r_prev = -1;
+    // ring slots (byte addresses of the CTA slice): student of the current / previous / next row, teacher current / next
+    uint32_t st_cur = s_stu, st_prev = s_stu + 2 * slice_bytes, st_nxt = s_stu + slice_bytes;
+    uint32_t te_cur = s_tea, te_nxt = s_tea + slice_bytes;
+    float lse2_t_prev = 0.f, mtk_prev = 0.f, R_prev = 0.f;     // carried from pass AB (i) to pass C (i) one iteration later
+    if (tid == 0 && cta_n > 0 && r_cur < n_rows) issue_load(r_cur, st_cur, te_cur, bar_full);
+
+    for (int it = 0;; ++it) {
+        const bool have_cur = r_cur < n_rows, have_prev = r_prev >= 0;
+        if (!have_cur && !have_prev) break;
+        const int par = it & 1, ppar = par ^ 1;                 // parity of the current / previous row
+        if (have_cur) {
+            if (cta_n > 0) mbar_wait_hint(bar_full + par * 8, (it >> 1) & 1, 2000u);
+            // the LAST warp to get here knows every warp has finished iteration it-1, i.e. is done reading the student slot of
+            // row it-2 and the teacher slot of row it-1: it refills them with row it+1
+            unsigned old = 0;
+            if (lane == 0) old = atomicAdd(&misc[1], 1u);
+            if (lane == 0 && (old & (kWarps - 1)) == kWarps - 1 && cta_n > 0 && r_nxt < n_rows)
+                issue_load(r_nxt, st_nxt, te_nxt, bar_full + ppar * 8);
+            __syncwarp();
+        }
+        int claimed = 0;
+        if (DYN && have_cur && rank == 0 && warp == FOLD_WARP && lane == 0) claimed = atomicAdd(p.row_queue, 1);
+
+        // ---------------- result of the previous row's reduction (folded by one warp, long complete) ----------------
+        float lse2_s_p = 0.f, gQ_p = 0.f, lgQ_p = 0.f;
+        bool kept_p = true, fold_p = false;
+        volatile float* bc = reinterpret_cast<volatile float*>(smem + plan.bcast + ppar * 32);
+        if (have_prev) {
+            const uint32_t ph = ((it - 1) >> 1) & 1;
+            if (warp == FOLD_WARP) {
+                mbar_wait_hint(bar_red1 + ppar * 8, ph, 1000u);
+                if (lane == 0) mbar_expect_tx(bar_red1 + ppar * 8, RED1_BYTES);      // arm this parity's next use
+                const float4* slot_v = reinterpret_cast<const float4*>(smem + plan.slots + ppar * NSLOT * 32);
+                float4 sa[SPL], sb[SPL];
+                float m_s = -INFINITY, m_t = -INFINITY, mn = INFINITY;
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) {
+                    sa[i] = slot_v[2 * (lane + 32 * i)];
+                    sb[i] = slot_v[2 * (lane + 32 * i) + 1];
+                    m_s = fmaxf(m_s, sa[i].x);
+                    if constexpr (REF) mn = fminf(mn, sb[i].x);
+                    else m_t = fmaxf(m_t, sb[i].z);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {          // independent butterflies, interleaved
+                    m_s = fmaxf(m_s, __shfl_xor_sync(0xffffffffu, m_s, o));
+                    if constexpr (REF) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    else m_t = fmaxf(m_t, __shfl_xor_sync(0xffffffffu, m_t, o));
+                }
+                float s_sum = 0.f, t_sum = 0.f, Q = 0.f, A = 0.f;
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) {
+                    if (sa[i].x != -INFINITY) s_sum = fmaf(sa[i].y, ex2((sa[i].x - m_s) * k2), s_sum);
+                    if constexpr (REF) {
+                        const float mki = __fmul_rn((sa[i].x == -INFINITY) ? 0.f : sa[i].x, k2);
+                        Q += sa[i].z;
+                        A += sa[i].w - mki * sa[i].z;            // row = A + lse2_s * Q
+                    } else {
+                        if (sb[i].z != -INFINITY) t_sum = fmaf(sa[i].z, ex2((sb[i].z - m_t) * k2), t_sum);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
+                    if constexpr (REF) {
+                        Q += __shfl_xor_sync(0xffffffffu, Q, o);
+                        A += __shfl_xor_sync(0xffffffffu, A, o);
+                    } else {
+                        t_sum += __shfl_xor_sync(0xffffffffu, t_sum, o);
+                    }
+                }
+                const float lse2_s = fmaf(m_s, k2, __log2f(s_sum));
+                float lse2_t = lse2_t_prev, row;
+                if constexpr (REF) {
+                    row = fmaf(lse2_s, Q, A);
+                } else {
+                    lse2_t = fmaf(m_t, k2, __log2f(t_sum));
+                    row = 0.f;
+#pragma unroll
+                    for (int i = 0; i < SPL; ++i) {
+                        const float mki = __fmul_rn((sa[i].x == -INFINITY) ? 0.f : sa[i].x, k2);
+                        const float mti = __fmul_rn((sb[i].z == -INFINITY) ? 0.f : sb[i].z, k2);
+                        const float sc = ex2(mti - lse2_t);           // that warp's teacher partials are relative to its mt_w
+                        Q = fmaf(sc, sa[i].z, Q);
+                        row = fmaf(sc, sa[i].w + ((mti - lse2_t) - (mki - lse2_s)) * sa[i].z, row);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        Q += __shfl_xor_sync(0xffffffffu, Q, o);
+                        row += __shfl_xor_sync(0xffffffffu, row, o);
+                    }
+                }
+                // the leader's slot (cluster rank 0, fold warp) carries the claimed row index
+                int claim_all = 0;
+                if (DYN) claim_all = __shfl_sync(0xffffffffu, __float_as_int(sb[FOLD_WARP / 32].y), FOLD_WARP % 32);
+                bool all_kept = true;
+                if constexpr (REF) {
+                    const float a_min = fmaf(mn, k2, -lse2_s);
+                    all_kept = a_min >= thr2 + 1e-3f * (1.f + fabsf(thr2));       // NaN -> masked path
+                }
+                if (lane == 0) {
+                    const float gQ = g * Q;
+                    const bool fold = (g > 0.f) && (gQ > 0.f) && (gQ < INFINITY);
+                    bc[0] = lse2_s;
+                    bc[1] = lse2_t;
+                    bc[2] = gQ;
+                    bc[3] = __int_as_float((all_kept ? 1 : 0) | (fold ? 2 : 0));
+                    bc[4] = __int_as_float(claim_all);
+                    bc[5] = fold ? __log2f(gQ) : 0.f;
+                    if (rank == 0 && all_kept) p.rowaux[r_prev] = make_float4(lse2_t, lse2_s, Q, row);
+                    mbar_arrive_cta(bar_res1 + ppar * 8);
+                }
+            }
+        }
+        if (!DYN) r_nn = r_nxt + cp.n_clusters;
+        const uint32_t s_sp = st_prev + w_lo * 16;
+        auto load_sp = [&](int v) -> uint4 { return lds128_ep(s_sp + v * 16, (uint32_t)it); };
+
+        // ---------------- current row: pass 0, pass AB, push ----------------
+        float R_cur = 0.f, mtk_cur = 0.f, lse2_t_cur = 0.f;
+        float red = 0.f, m_w = -INFINITY, min_w = INFINITY, mt_w = -INFINITY;
+        if (have_cur) {
+            if constexpr (REF) lse2_t_cur = p.lse2_t_in[r_cur];
+            const uint32_t epoch = (uint32_t)it;
+            const uint32_t s_s = st_cur + w_lo * 16, s_t = te_cur + w_lo * 16;
+            auto load_s = [&](int v) -> uint4 { return lds128_ep(s_s + v * 16, epoch); };
+            auto load_t = [&](int v) -> uint4 { return lds128_ep(s_t + v * 16, epoch); };
+            // pass 0: (student max, -student min) [LoCa] or (student max, teacher max) [plain KL] ride one packed butterfly
+            {
+                uint32_t smax2 = Pair<T>::kNegInf2, smin2 = Pair<T>::kPosInf2, tmax2 = Pair<T>::kNegInf2;
+#pragma unroll
+                for (int j = 0; j < kMaxIt; ++j) {
+                    const int v = lane + 32 * j;
+                    if (v < w_n) {
+                        const uint4 rs = load_s(v);
+                        smax2 = Pair<T>::vmax(smax2, Pair<T>::vmax(Pair<T>::vmax(rs.x, rs.y), Pair<T>::vmax(rs.z, rs.w)));
+                        if constexpr (REF) {
+                            smin2 = Pair<T>::vmin(smin2, Pair<T>::vmin(Pair<T>::vmin(rs.x, rs.y), Pair<T>::vmin(rs.z, rs.w)));
+                        } else {
+                            const uint4 rt = load_t(v);
+                            tmax2 = Pair<T>::vmax(tmax2, Pair<T>::vmax(Pair<T>::vmax(rt.x, rt.y), Pair<T>::vmax(rt.z, rt.w)));
+                        }
+                    }
+                }
+                smax2 = Pair<T>::vmax(smax2, swap_halves(smax2));                 // both halves: the lane's maximum
+                uint32_t other;
+                if constexpr (REF) other = Pair<T>::vmin(smin2, swap_halves(smin2)) ^ 0x80008000u;      // -min (sign flip is exact)
+                else other = Pair<T>::vmax(tmax2, swap_halves(tmax2));
+                uint32_t both = __byte_perm(smax2, other, 0x7610);                // low half: student max, high half: the other
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) both = Pair<T>::vmax(both, __shfl_xor_sync(0xffffffffu, both, o));
+                float lo, hi;
+                upk(Pair<T>::widen(both), lo, hi);
+                m_w = lo;
+                if constexpr (REF) min_w = -hi;
+                else mt_w = hi;
+            }
+            const float mk = __fmul_rn((m_w == -INFINITY) ? 0.f : m_w, k2);
+            mtk_cur = __fmul_rn((mt_w == -INFINITY) ? 0.f : mt_w, k2);
+
+            // `red` after the grouped reduction: lanes 0-7 S_w, 8-15 Q_w, 16-23 R_w - P_w
+            {
+                const u64 nmk = pk(-mk, -mk);
+                const float tref = REF ? lse2_t_cur : mtk_cur;
+                const u64 nlt = pk(-tref, -tref);
+                u64 accS0 = pk(0.f, 0.f), accS1 = pk(0.f, 0.f), accQ = pk(0.f, 0.f), accR = pk(0.f, 0.f), accP = pk(0.f, 0.f);
+                auto ab_step = [&](int j, auto nv_tag, bool act, auto tail_tag) {
+                    constexpr int NV = decltype(nv_tag)::value;
+                    uint32_t qb[NV][8], ob[NV][8];
+                    uint4 rs[NV], rt[NV];
+#pragma unroll
+                    for (int u = 0; u < NV; ++u) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { qb[u][i] = 0u; ob[u][i] = 0u; }
+                        if constexpr (REF) tmem_ld8(tm + kTmTable + 8 * (j + u), ob[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < NV; ++u) {
+                        rs[u] = make_uint4(0, 0, 0, 0);
+                        rt[u] = rs[u];
+                        if (act) {
+                            rs[u] = load_s(lane + 32 * (j + u));
+                            rt[u] = load_t(lane + 32 * (j + u));
+                        }
+                    }
+                    if constexpr (REF) tmem_wait_ld();
+                    if (act) {
+#pragma unroll
+                        for (int u = 0; u < NV; ++u) {
+                            const uint32_t ws[4] = {rs[u].x, rs[u].y, rs[u].z, rs[u].w}, wt[4] = {rt[u].x, rt[u].y, rt[u].z, rt[u].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const u64 ovp = pk(__uint_as_float(ob[u][2 * i]), __uint_as_float(ob[u][2 * i + 1]));
+                                const u64 a2 = fma2(Pair<T>::widen(ws[i]), k2p, nmk);        // xs*k2 - m_w*k2  (<= 0)
+                                float a_lo, a_hi;
+                                upk(a2, a_lo, a_hi);
+                                const u64 e2 = pk(ex2(a_lo), ex2(a_hi));
+                                if (i & 1) accS1 = add2(accS1, e2);
+                                else accS0 = add2(accS0, e2);
+                                const u64 b2 = fma2(Pair<T>::widen(wt[i]), k2p, nlt);        // log2 tp (REF) / relative to mt_w (PLAIN)
+                                float e_lo, e_hi;
+                                if constexpr (REF) upk(fma2(ovp, pushp, b2), e_lo, e_hi);
+                                else upk(b2, e_lo, e_hi);
+                                const u64 t2 = pk(ex2(e_lo), ex2(e_hi));
+                                const u64 q2 = REF ? add2(t2, ovp) : t2;
+                                accQ = add2(accQ, q2);
+                                accR = fma2(t2, b2, accR);
+                                accP = fma2(q2, a2, accP);
+                                float q_lo, q_hi;
+                                upk(q2, q_lo, q_hi);
+                                qb[u][2 * i] = __float_as_uint(q_lo);
+                                qb[u][2 * i + 1] = __float_as_uint(q_hi);
+                            }
+                        }
+                    }
+                    if constexpr (decltype(tail_tag)::value) __syncwarp();     // reconverge before the warp-collective store
+#pragma unroll
+                    for (int u = 0; u < NV; ++u) tmem_st8(tm + kTmQ + 40 * par + 8 * (j + u), qb[u]);
+                };
+                {
+                    int j = 0;
+                    for (; j + 1 < n_full; j += 2) ab_step(j, Int2{}, true, std::false_type{});
+                    if (j < n_full) ab_step(j, Int1{}, true, std::false_type{});
+                    if (n_tail) ab_step(n_full, Int1{}, lane < n_tail, std::true_type{});
+                }
+                tmem_wait_st();
+                float s0, s1, q0, q1, r0, r1, p0, p1;
+                upk(add2(accS0, accS1), s0, s1);
+                upk(accQ, q0, q1);
+                upk(accR, r0, r1);
+                upk(accP, p0, p1);
+                R_cur = (r0 + r1) + poison;                     // lane-level share, used by pass B' of a masked row
+                red = warp_sum4_grouped(s0 + s1, q0 + q1, R_cur - (p0 + p1), 0.f, lane);
+            }
+        }
+        // ---------------- the previous row's reduction result: needed from here on (push gating, clamp flag, pass C) ----------------
+        if (have_prev) {
+            mbar_wait_hint(bar_res1 + ppar * 8, ((it - 1) >> 1) & 1, 2000u);
+            lse2_s_p = bc[0];
+            if constexpr (!REF) lse2_t_prev = bc[1];
+            gQ_p = bc[2];
+            const int fl = __float_as_int(bc[3]);
+            kept_p = fl & 1;
+            fold_p = fl & 2;
+            if (DYN) r_nn = __float_as_int(bc[4]);
+            lgQ_p = bc[5];
+        }
+        if (have_cur) {
+            // push to every CTA of the cluster.  Every warp has observed the result of row it-1 by now, which implies that every
+            // CTA's fold warp has finished reading the slots of row it-2 (same parity) before pushing its own row it-1 partial.
+            {
+                const int grp = lane >> 3;                      // lane group g pushes word g+1 (S, Q, R-P); group 3 pushes m_w (word 0)
+                const uint32_t dst_cta = lane & 7;
+                const uint32_t slot = slots + par * NSLOT * 32 + (rank * kWarps + warp) * 32;
+                const uint32_t rbar = map_to_cta(bar_red1 + par * 8, dst_cta);
+                const uint32_t word = (grp == 3) ? 0u : (uint32_t)(grp + 1);
+                const uint32_t val = (grp == 3) ? __float_as_uint(m_w) : __float_as_uint(red);
+                st_async_b32(map_to_cta(slot + word * 4, dst_cta), val, rbar);
+                if (DYN) claimed = __shfl_sync(0xffffffffu, claimed, 0);
+                if (lane < CS) {
+                    if constexpr (REF) st_async_v2(map_to_cta(slot + 16, dst_cta), __float_as_uint(min_w), (uint32_t)claimed, rbar);
+                    else st_async_v4(map_to_cta(slot + 16, dst_cta), 0u, (uint32_t)claimed, __float_as_uint(mt_w), 0u, rbar);
+                }
+            }
+        }
+
+        // ---------------- pass B' (previous row, rare): exact masked sums and a second, exposed reduction ----------------
+        if constexpr (REF) {
+            if (have_prev && !kept_p) {
+                const u64 nls = pk(-lse2_s_p, -lse2_s_p);
+                u64 accN = pk(0.f, 0.f), accM = pk(0.f, 0.f);
+                auto bp_step = [&](int j, auto nv_tag, bool act, auto tail_tag) {
+                    constexpr int NV = decltype(nv_tag)::value;
+                    uint32_t qb[NV][8];
+                    uint4 rs[NV];
+#pragma unroll
+                    for (int u = 0; u < NV; ++u) tmem_ld8(tm + kTmQ + 40 * ppar + 8 * (j + u), qb[u]);
+#pragma unroll
+                    for (int u = 0; u < NV; ++u) {
+                        rs[u] = make_uint4(0, 0, 0, 0);
+                        if (act) rs[u] = load_sp(lane + 32 * (j + u));
+                    }
+                    tmem_wait_ld();
+                    if (act) {
+#pragma unroll
+                        for (int u = 0; u < NV; ++u) {
+                            const uint32_t ws[4] = {rs[u].x, rs[u].y, rs[u].z, rs[u].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float a_lo, a_hi;
+                                upk(fma2(Pair<T>::widen(ws[i]), k2p, nls), a_lo, a_hi);
+                                const u64 q2 = pk(__uint_as_float(qb[u][2 * i]), __uint_as_float(qb[u][2 * i + 1]));
+                                accN = fma2(q2, pk(fmaxf(a_lo, thr2), fmaxf(a_hi, thr2)), accN);
+                                accM = fma2(q2, pk(set_ge(a_lo, thr2), set_ge(a_hi, thr2)), accM);
+                            }
+                        }
+                    }
+                    if constexpr (decltype(tail_tag)::value) __syncwarp();
+                };
+                {
+                    int j = 0;
+                    for (; j + 1 < n_full; j += 2) bp_step(j, Int2{}, true, std::false_type{});
+                    if (j < n_full) bp_step(j, Int1{}, true, std::false_type{});
+                    if (n_tail) bp_step(n_full, Int1{}, lane < n_tail, std::true_type{});
+                }
+                float x0, x1, y0, y1;
+                upk(accN, x0, x1);
+                upk(accM, y0, y1);
+                const float N_w = warp_sum(R_prev - (x0 + x1));        // R_prev is this lane's share of sum t*b
+                const float M_w = warp_sum(y0 + y1);
+                if (lane < CS)
+                    st_async_v2(map_to_cta(slots + ppar * NSLOT * 32 + (rank * kWarps + warp) * 32 + 24, lane), __float_as_uint(N_w),
+                                __float_as_uint(M_w), map_to_cta(bar_red2 + ppar * 8, lane));
+            }
+        }
+
+        // ---------------- previous row: second reduction result (masked rows only), then pass C ----------------
+        if (have_prev) {
+            if constexpr (REF) {
+                if (!kept_p) {
+                    const uint32_t ph2 = ppar ? ph2_1 : ph2_0;
+                    if (warp == FOLD_WARP) {
+                        mbar_wait_hint(bar_red2 + ppar * 8, ph2, 1000u);
+                        if (lane == 0) mbar_expect_tx(bar_red2 + ppar * 8, RED2_BYTES);
+                        const float4* slot_v = reinterpret_cast<const float4*>(smem + plan.slots + ppar * NSLOT * 32);
+                        float rr = 0.f, qq = 0.f;
+#pragma unroll
+                        for (int i = 0; i < SPL; ++i) {
+                            const float4 sb = slot_v[2 * (lane + 32 * i) + 1];
+                            rr += sb.z;
+                            qq += sb.w;
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            rr += __shfl_xor_sync(0xffffffffu, rr, o);
+                            qq += __shfl_xor_sync(0xffffffffu, qq, o);
+                        }
+                        if (lane == 0) {
+                            const float gQ = g * qq;
+                            const bool fold = (g > 0.f) && (gQ > 0.f) && (gQ < INFINITY);
+                            bc[2] = gQ;
+                            bc[3] = __int_as_float(fold ? 2 : 0);
+                            bc[5] = fold ? __log2f(gQ) : 0.f;
+                            if (rank == 0) p.rowaux[r_prev] = make_float4(lse2_t_prev, lse2_s_p, qq, rr);
+                            mbar_arrive_cta(bar_res2 + ppar * 8);
+                        }
+                    }
+                    mbar_wait_hint(bar_res2 + ppar * 8, ph2, 2000u);
+                    gQ_p = bc[2];
+                    fold_p = __float_as_int(bc[3]) & 2;
+                    lgQ_p = bc[5];
+                    if (ppar) ph2_1 ^= 1;
+                    else ph2_0 ^= 1;
+                }
+            }
+            if (want_grad) {
+                // fold: g*Q rides in the exponent, 2^(a + log2 gQ) - g*q;  otherwise gQ * 2^a - g*q
+                const float nl = lgQ_p - lse2_s_p;
+                const u64 nls = pk(nl, nl);
+                const float thrC = thr2 + lgQ_p;
+                const float gq = REF ? g : g * ex2(mtk_prev - lse2_t_prev);        // PLAIN: the parked values are relative to mt_w
+                const u64 negg = pk(-gq, -gq), gQp = pk(gQ_p, gQ_p);
+                T* grow = static_cast<T*>(p.grad) + r_prev * p.ld_g + (int64_t)g_v0 * 8;
+                auto sweepC = [&](auto fold_tag, auto mask_tag) {
+                    constexpr bool FOLD = decltype(fold_tag)::value;
+                    constexpr bool MASK = decltype(mask_tag)::value;
+                    auto c_step = [&](int j, auto nv_tag, bool act, auto tail_tag) {
+                        constexpr int NV = decltype(nv_tag)::value;
+                        uint32_t qb[NV][8];
+                        uint4 rs[NV];
+#pragma unroll
+                        for (int u = 0; u < NV; ++u) tmem_ld8(tm + kTmQ + 40 * ppar + 8 * (j + u), qb[u]);
+#pragma unroll
+                        for (int u = 0; u < NV; ++u) {
+                            rs[u] = make_uint4(0, 0, 0, 0);
+                            if (act) rs[u] = load_sp(lane + 32 * (j + u));
+                        }
+                        tmem_wait_ld();
+                        if (act) {
+#pragma unroll
+                            for (int u = 0; u < NV; ++u) {
+                                const uint32_t ws[4] = {rs[u].x, rs[u].y, rs[u].z, rs[u].w};
+                                uint32_t out[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    float a_lo, a_hi;
+                                    upk(fma2(Pair<T>::widen(ws[i]), k2p, nls), a_lo, a_hi);
+                                    const u64 sp2 = pk(ex2(a_lo), ex2(a_hi));
+                                    u64 q2 = pk(__uint_as_float(qb[u][2 * i]), __uint_as_float(qb[u][2 * i + 1]));
+                                    if constexpr (MASK) q2 = mul2(q2, pk(set_ge(a_lo, thrC), set_ge(a_hi, thrC)));
+                                    u64 o2;
+                                    if constexpr (FOLD) o2 = fma2(q2, negg, sp2);
+                                    else o2 = fma2(sp2, gQp, mul2(q2, negg));
+                                    float n_lo, n_hi;
+                                    upk(o2, n_lo, n_hi);
+                                    out[i] = Pair<T>::narrow(n_lo, n_hi);
+                                }
+                                stg_stream(grow + (int64_t)(lane + 32 * (j + u)) * 8, make_uint4(out[0], out[1], out[2], out[3]));
+                            }
+                        }
+                        if constexpr (decltype(tail_tag)::value) __syncwarp();
+                    };
+                    int j = 0;
+                    for (; j + 1 < n_full; j += 2) c_step(j, Int2{}, true, std::false_type{});
+                    if (j < n_full) c_step(j, Int1{}, true, std::false_type{});
+                    if (n_tail) c_step(n_full, Int1{}, lane < n_tail, std::true_type{});
+                };
+                using Yes = std::true_type;
+                using No = std::false_type;
+                if (fold_p) {
+                    if (kept_p) sweepC(Yes{}, No{});
+                    else sweepC(Yes{}, Yes{});
+                } else {
+                    if (kept_p) sweepC(No{}, No{});
+                    else sweepC(No{}, Yes{});
+                }
+            }
+        }
+        __syncwarp();
+        // advance: the current row becomes the previous one, ring slots rotate
+        r_prev = have_cur ? r_cur : -1;
+        if constexpr (REF) lse2_t_prev = lse2_t_cur;
+        mtk_prev = mtk_cur;
+        R_prev = R_cur;
+        r_cur = r_nxt;
+        r_nxt = r_nn;
+        {
+            const uint32_t t = st_prev;
+            st_prev = st_cur;
+            st_cur = st_nxt;
+            st_nxt = t;
+            const uint32_t u = te_cur;
+            te_cur = te_nxt;
+            te_nxt = u;
+        }
+    }
+    tmem_fence_before_sync();
+    cluster_sync_all();     // nobody leaves while peers may still push into its shared memory
+    tmem_fence_after_sync();
+    if (warp == 1) tmem_dealloc_512(tmem_base);
+}
+
 // --------------------------------------------------------------------------------------------------------
 template <int VARIANT, typename T, bool DYN>
 int launch_fused_d(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
@@ -571,11 +1195,76 @@ int launch_fused_t(const EmitParams& e, int variant, cudaStream_t st, bool query
     return launch_fused_v<KD_KL_PLAIN, T>(e, st, query_only, capacity, launched, first_free);
 }
 
-int fused_mode() {       // KD_FUSED=0 keeps every shape on the three-sweep cluster kernel (A/B comparisons)
+template <int VARIANT, typename T, bool DYN>
+int launch_pipe_d(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
+    constexpr int CS = 8;
+    auto kfn = row_emit_pipelined_kernel<VARIANT, T, CS, DYN>;
+    const int nvec = e.V / 8;
+    const int vpc = (nvec + CS - 1) / CS;
+    const PipePlan<VARIANT, CS> plan(vpc);
+    if ((vpc + 31) / 32 > kWarps * kMaxIt) return KD_ERR_UNSUPPORTED;      // a thread's cells must fit its tensor-memory words
+    int dev = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (plan.total > max_smem) return KD_ERR_UNSUPPORTED;
+    static int configured_dev = -1;
+    static int max_clusters = 0;
+    cudaError_t err;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = max_smem;     // one CTA per SM: it owns all 512 tensor-memory columns
+    cfg.stream = st;
+    if (configured_dev != dev) {
+        err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(pipelined kernel smem)");
+        cfg.gridDim = dim3(CS * 64);
+        err = cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg);
+        if (err != cudaSuccess || max_clusters < 1) {
+            cudaGetLastError();
+            max_clusters = 0;
+            return KD_ERR_UNSUPPORTED;
+        }
+        configured_dev = dev;
+    }
+    if (capacity) *capacity = max_clusters;
+    if (query_only) return KD_OK;
+    if (max_clusters < 1) return KD_ERR_UNSUPPORTED;
+    FusedParams cp;
+    cp.e = e;
+    cp.n_clusters = (int)(e.n_rows < max_clusters ? e.n_rows : max_clusters);
+    cp.vpc = vpc;
+    cp.nvec = nvec;
+    cfg.gridDim = dim3(cp.n_clusters * CS);
+    if (launched) *launched = cp.n_clusters;
+    if (first_free) *first_free = 3 * cp.n_clusters;
+    err = cudaLaunchKernelEx(&cfg, kfn, cp);
+    if (err != cudaSuccess) return cuda_fail(err, "row_emit_pipelined_kernel launch");
+    return KD_OK;
+}
+
+template <typename T>
+int launch_pipe_t(const EmitParams& e, int variant, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
+    if (variant == KD_LOCA_REFERENCE) {
+        if (e.row_queue) return launch_pipe_d<KD_LOCA_REFERENCE, T, true>(e, st, query_only, capacity, launched, first_free);
+        return launch_pipe_d<KD_LOCA_REFERENCE, T, false>(e, st, query_only, capacity, launched, first_free);
+    }
+    if (e.row_queue) return launch_pipe_d<KD_KL_PLAIN, T, true>(e, st, query_only, capacity, launched, first_free);
+    return launch_pipe_d<KD_KL_PLAIN, T, false>(e, st, query_only, capacity, launched, first_free);
+}
+
+// KD_FUSED: 0 = three-sweep cluster kernel everywhere, 1 = two-pipeline fused kernel, 2 = software-pipelined kernel (default)
+int fused_mode() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("KD_FUSED");
-        v = e ? atoi(e) : 1;
+        v = e ? atoi(e) : 2;
     }
     return v;
 }
@@ -593,7 +1282,15 @@ bool fused_applies(const EmitParams& p, int variant, int dtype) {
 }
 
 int launch_emit_fused(const EmitParams& p, int variant, int dtype, cudaStream_t stream, bool query_only, int* capacity,
-                      int* clusters_launched, int* first_free_row) {
+                      int* clusters_launched, int* first_free_row, int* rows_in_flight) {
+    if (fused_mode() >= 2) {
+        if (rows_in_flight) *rows_in_flight = 1;
+        const int rc = (dtype == KD_DTYPE_BF16)
+                           ? launch_pipe_t<__nv_bfloat16>(p, variant, stream, query_only, capacity, clusters_launched, first_free_row)
+                           : launch_pipe_t<__half>(p, variant, stream, query_only, capacity, clusters_launched, first_free_row);
+        if (rc != KD_ERR_UNSUPPORTED) return rc;
+    }
+    if (rows_in_flight) *rows_in_flight = 2;
     if (dtype == KD_DTYPE_BF16) return launch_fused_t<__nv_bfloat16>(p, variant, stream, query_only, capacity, clusters_launched, first_free_row);
     return launch_fused_t<__half>(p, variant, stream, query_only, capacity, clusters_launched, first_free_row);
 }
