@@ -52,7 +52,8 @@ class KDError(RuntimeError):
 
 
 def library_path() -> str:
-    return _build.LIB
+    """In-tree library; ``KD_B200_LIB`` points at an alternative build (tuning experiments)."""
+    return os.environ.get("KD_B200_LIB") or _build.LIB
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
@@ -62,7 +63,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         if _lib is not None:
             return _lib
         path = library_path()
-        if build_if_missing and _build.is_stale():
+        if build_if_missing and not os.environ.get("KD_B200_LIB") and _build.is_stale():
             try:
                 _build.build()
             except Exception as exc:  # noqa: BLE001

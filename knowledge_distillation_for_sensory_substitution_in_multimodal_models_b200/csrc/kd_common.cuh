@@ -196,6 +196,46 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f3
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
+// ---- exp2 on the FMA pipe (Cody-Waite + polynomial), two values at a time ---------------------------------
+// The fused emit kernels are bound by the XU pipe (MUFU.EX2: 16 lanes/clk/SM) inside their sweeps while issue slots are
+// free, so a fraction of the exponentials is evaluated with packed FMAs instead:  t = x + 1.5*2^23 rounds x to an integer
+// kept in t's low mantissa bits, f = x - (t - 1.5*2^23) is in [-0.5, 0.5], 2^x = p(f) with the integer added to p's
+// exponent field.  Valid for -126 <= x <= 126 (callers check the range per warp and row).  Relative error (float32
+// Horner, measured): degree 3: 7.5e-5, degree 4: 2.7e-6 (mean 3.5e-8), degree 5: 2.3e-7.
+template <int DEG>
+__device__ __forceinline__ u64 ex2_poly2(u64 x2) {
+    const u64 t = add2(x2, pk(12582912.f, 12582912.f));
+    const u64 r = add2(t, pk(-12582912.f, -12582912.f));
+    const u64 f = fma2(r, pk(-1.f, -1.f), x2);
+    u64 p;
+    if constexpr (DEG == 3) {
+        p = fma2(pk(5.517080426e-02f, 5.517080426e-02f), f, pk(2.426092774e-01f, 2.426092774e-01f));
+        p = fma2(p, f, pk(6.932609677e-01f, 6.932609677e-01f));
+        p = fma2(p, f, pk(9.999281764e-01f, 9.999281764e-01f));
+    } else if constexpr (DEG == 4) {
+        p = fma2(pk(9.570019320e-03f, 9.570019320e-03f), f, pk(5.591766536e-02f, 5.591766536e-02f));
+        p = fma2(p, f, pk(2.402474433e-01f, 2.402474433e-01f));
+        p = fma2(p, f, pk(6.931218505e-01f, 6.931218505e-01f));
+        p = fma2(p, f, pk(9.999992847e-01f, 9.999992847e-01f));
+    } else {
+        p = fma2(pk(1.327640144e-03f, 1.327640144e-03f), f, pk(9.675524198e-03f, 9.675524198e-03f));
+        p = fma2(p, f, pk(5.550713465e-02f, 5.550713465e-02f));
+        p = fma2(p, f, pk(2.402212024e-01f, 2.402212024e-01f));
+        p = fma2(p, f, pk(6.931469440e-01f, 6.931469440e-01f));
+        p = fma2(p, f, pk(1.000000119e+00f, 1.000000119e+00f));
+    }
+    float p_lo, p_hi, t_lo, t_hi;
+    upk(p, p_lo, p_hi);
+    upk(t, t_lo, t_hi);
+    return pk(__int_as_float(__float_as_int(p_lo) + (__float_as_int(t_lo) << 23)),
+              __int_as_float(__float_as_int(p_hi) + (__float_as_int(t_hi) << 23)));
+}
+__device__ __forceinline__ u64 ex2_mufu2(u64 x2) {
+    float lo, hi;
+    upk(x2, lo, hi);
+    return pk(ex2(lo), ex2(hi));
+}
+
 __device__ __forceinline__ float set_ge(float a, float b) {      // 1.0f if a >= b else 0.0f, one FSET
     float r;
     asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));

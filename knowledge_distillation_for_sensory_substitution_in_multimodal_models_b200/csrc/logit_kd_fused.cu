@@ -19,6 +19,7 @@
 //
 // Variants: KD_LOCA_REFERENCE (teacher lse2_t and the override table come from phase A) and KD_KL_PLAIN (teacher
 // statistics are folded into the same single reduction through a per-warp teacher reference maximum).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -36,8 +37,33 @@ constexpr float kPush = -3.0e38f;       // ov' * kPush drives log2 q of an overr
 constexpr float kOvFloor = 1.0e-36f;    // encoded "overridden with ~0" (must stay > 0)
 constexpr int kTmemColsPerWarp = 128;   // 512 columns / 4 warps per lane quarter
 constexpr int kMaxIters = kTmemColsPerWarp / 8;
+// exponentials evaluated on the FMA pipe instead of the XU pipe, per 8-cell vector (0-4 pairs each)
+#ifndef KD_POLY_AB
+#define KD_POLY_AB 0        // student pairs of pass AB (degree 4)
+#endif
+#ifndef KD_POLY_C
+#define KD_POLY_C 0         // student pairs of pass C (degree 3: only the bf16 gradient depends on it)
+#endif
+constexpr float kPolyFloor = -120.f;
+// two-pipeline kernel: the student exponentials of pass AB are parked next to q as fp16 pairs scaled by 2^15 (words 80..119 of
+// the thread's tensor memory), so pass C of an unclamped row needs no MUFU at all
+#ifndef KD_ECACHE
+#define KD_ECACHE 1
+#endif
+constexpr int kTmE = 80;
+constexpr float kEScaleLog2 = 15.f;    // the polynomial path needs its argument >= -126
+
+// Optional phase tracing (compile with -DKD_TRACE): lane 0 of every warp stamps %globaltimer at the phase boundaries of
+// each row into `trace` ([cta][warp][row_iter][8] u64), decoded by tools/trace_emit.py.
+#ifdef KD_TRACE
+#define KD_STAMP(i) do { if (lane == 0 && cp.trace && row_iter < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    cp.trace[(((size_t)blockIdx.x * kWarps + warp) * 64 + row_iter) * 8 + (i)] = t_; } } while (0)
+#else
+#define KD_STAMP(i) do {} while (0)
+#endif
 
 struct FusedParams {
+    unsigned long long* trace;
     EmitParams e;
     int n_clusters;
     int vpc;                      // 16-byte vectors per CTA slice
@@ -59,7 +85,7 @@ struct FusedPlan {
         rows = off;
         off += NPIPE * 2 * vpc * 16;
         bars = off;
-        off += (kWarps + 2 * NPIPE) * 8;
+        off += (kWarps + 3 * NPIPE) * 8;         // full[16], red1/red2 per pipeline, one pass-AB token per pipeline
         slots = off;
         off += NPIPE * NSLOT * 32;
         bcast = off;
@@ -108,6 +134,13 @@ row_emit_fused_kernel(const FusedParams cp) {
     const float4* slot_v = reinterpret_cast<const float4*>(smem + plan.slots + pipe * NSLOT * 32);
     volatile float* bcast = reinterpret_cast<volatile float*>(smem + plan.bcast + pipe * 32);
     const int bar1 = 1 + 2 * pipe, bar2 = 2 + 2 * pipe;     // named barriers of this pipeline (0 is __syncthreads)
+    // Ping-pong of the two pipelines: left alone they fall into lockstep (measured: both in pass AB, then both idle on their
+    // reductions, then both bursting stores).  A pipeline may start pass AB only when the other one has finished its own, so
+    // one pipeline's XU-bound sweep overlaps the other's reduction wait, pass C, refill and pass 0.
+    const uint32_t tok_mine = s_base + plan.bars + (kWarps + 2 * NPIPE + pipe) * 8;
+    const uint32_t tok_other = s_base + plan.bars + (kWarps + 2 * NPIPE + (NPIPE - 1 - pipe)) * 8;
+    volatile float* done_other = reinterpret_cast<volatile float*>(smem + plan.bcast + (NPIPE - 1 - pipe) * 32) + 7;
+    bool other_done = false;
 
     // this CTA's column slice and this warp's private part of it (in 16-byte vectors)
     const int cta_v0 = min((int)rank * cp.vpc, cp.nvec);
@@ -125,6 +158,10 @@ row_emit_fused_kernel(const FusedParams cp) {
 
     if (tid == 0) {
         for (int w = 0; w < kWarps + 2 * NPIPE; ++w) mbar_init(s_base + plan.bars + w * 8, 1);
+        for (int i = 0; i < NPIPE; ++i) {
+            mbar_init(s_base + plan.bars + (kWarps + 2 * NPIPE + i) * 8, WPP);      // one arrival per warp of the other pipeline
+            reinterpret_cast<volatile float*>(smem + plan.bcast + i * 32)[7] = 0.f;     // "this pipeline has left its row loop"
+        }
         fence_mbar_init();
         for (int i = 0; i < NPIPE; ++i) {        // arm the first phase of every reduction barrier
             mbar_expect_tx(s_base + plan.bars + (kWarps + 2 * i) * 8, RED1_BYTES);
@@ -163,14 +200,26 @@ row_emit_fused_kernel(const FusedParams cp) {
     int64_t r = (int64_t)cluster_id * NPIPE + pipe;
     const T* tbase = static_cast<const T*>(p.teacher);
     const T* sbase = static_cast<const T*>(p.student);
-    auto issue_load = [&](int64_t row) {
+    // the refill of a warp's private slices is split: the teacher part can go as soon as pass AB is done with it, the
+    // student part once no later pass of the row will read it (both complete on the warp's mbarrier, armed by the first)
+    auto issue_teacher = [&](int64_t row) {
         if (lane == 0 && w_n > 0) {
             const uint32_t bytes = (uint32_t)w_n * 16u;
             fence_proxy_async();
             mbar_expect_tx(bar_full, 2u * bytes);
-            tma_load_1d(s_s, sbase + row * p.ld_s + (int64_t)g_v0 * 8, bytes, bar_full);
             tma_load_1d(s_t, tbase + row * p.ld_t + (int64_t)g_v0 * 8, bytes, bar_full);
         }
+    };
+    auto issue_student = [&](int64_t row) {
+        if (lane == 0 && w_n > 0) {
+            const uint32_t bytes = (uint32_t)w_n * 16u;
+            fence_proxy_async();
+            tma_load_1d(s_s, sbase + row * p.ld_s + (int64_t)g_v0 * 8, bytes, bar_full);
+        }
+    };
+    auto issue_load = [&](int64_t row) {
+        issue_teacher(row);
+        issue_student(row);
     };
     auto warm_l2 = [&](int64_t row) {           // bring the warp's slice of `row` into L2 ahead of its use
         if (lane == 0 && w_n > 0 && row < p.n_rows) {
@@ -189,7 +238,10 @@ row_emit_fused_kernel(const FusedParams cp) {
     uint32_t ph_full = 0, ph1 = 0, ph2 = 0;
 
     int64_t next_r = r + row_stride;      // dynamic mode: the first two rows of a pipeline are static, later ones are claimed
+    int row_iter = -1;
     while (r < p.n_rows) {
+        ++row_iter;
+        KD_STAMP(0);
         if (!DYN) next_r = r + row_stride;
         int claimed = 0;
         if (DYN && rank == 0 && pw == 0 && lane == 0) claimed = atomicAdd(p.row_queue, 1);
@@ -201,6 +253,7 @@ row_emit_fused_kernel(const FusedParams cp) {
         auto load_t = [&](int v) -> uint4 { return lds128_ep(s_t + v * 16, epoch); };
         if (w_n > 0) mbar_wait_cta(bar_full, ph_full);
         ph_full ^= 1;
+        KD_STAMP(1);
 
         // ================= pass 0: reference maxima (and the student minimum) of the warp's slice ==============
         float m_w, min_w = INFINITY, mt_w = -INFINITY;
@@ -228,6 +281,16 @@ row_emit_fused_kernel(const FusedParams cp) {
                 mt_w = warp_max(fmaxf(lo, hi));
             }
         }
+        KD_STAMP(2);
+        if constexpr (NPIPE == 2) {
+            // pipeline 1 runs its n-th pass AB after pipeline 0's n-th, pipeline 0 its n-th after pipeline 1's (n-1)-th
+            const int need = (pipe == 1) ? row_iter : row_iter - 1;
+            if (need >= 0 && !other_done) {
+                while (!mbar_try_wait(tok_mine, (uint32_t)need & 1u)) {
+                    if (*done_other != 0.f) { other_done = true; break; }
+                }
+            }
+        }
         // exponent references (a warp whose cells are all -inf, or that has no cells, uses 0)
         const float mk = __fmul_rn((m_w == -INFINITY) ? 0.f : m_w, k2);
         const float mtk = __fmul_rn((mt_w == -INFINITY) ? 0.f : mt_w, k2);
@@ -235,12 +298,17 @@ row_emit_fused_kernel(const FusedParams cp) {
         // ================= pass AB: statistics + accumulation in one sweep, q parked in tensor memory ==========
         float S_w, Q_w, R_w, P_w;
         {
-            const u64 nmk = pk(-mk, -mk);
+            constexpr bool ECACHE = REF && KD_ECACHE;
+            // with the exponent cache the student argument carries +15 (e is parked as fp16(e * 2^15)); S_w and P_w are corrected below
+            const float esh = ECACHE ? kEScaleLog2 : 0.f;
+            const u64 nmk = pk(esh - mk, esh - mk);
             const float tref = REF ? lse2_t : mtk;
             const u64 nlt = pk(-tref, -tref);
             u64 accS0 = pk(0.f, 0.f), accS1 = pk(0.f, 0.f), accQ = pk(0.f, 0.f), accR = pk(0.f, 0.f), accP = pk(0.f, 0.f);
-            auto ab_body = [&](int j, bool act, auto tail_tag) {
+            auto ab_body = [&](int j, bool act, auto tail_tag, auto poly_tag) {
+                constexpr bool POLY = decltype(poly_tag)::value;
                 uint32_t qb[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                uint32_t eb[4] = {0u, 0u, 0u, 0u};
                 if (act) {
                     const int v = lane + 32 * j;
                     const uint4 rs = load_s(v), rt = load_t(v);
@@ -252,9 +320,13 @@ row_emit_fused_kernel(const FusedParams cp) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const u64 a2 = fma2(Pair<T>::widen(ws[i]), k2p, nmk);        // xs*k2 - m_w*k2  (<= 0)
-                        float a_lo, a_hi;
-                        upk(a2, a_lo, a_hi);
-                        const u64 e2 = pk(ex2(a_lo), ex2(a_hi));
+                        const u64 e2 = (POLY && i >= 4 - KD_POLY_AB) ? ex2_poly2<4>(a2) : ex2_mufu2(a2);
+                        if constexpr (ECACHE) {
+                            float e_lo2, e_hi2;
+                            upk(e2, e_lo2, e_hi2);
+                            const __half2 h = __floats2half2_rn(e_lo2, e_hi2);
+                            eb[i] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
                         if (i & 1) accS1 = add2(accS1, e2);
                         else accS0 = add2(accS0, e2);
                         const u64 b2 = fma2(Pair<T>::widen(wt[i]), k2p, nlt);        // log2 tp (REF) / relative to mt_w (PLAIN)
@@ -274,22 +346,35 @@ row_emit_fused_kernel(const FusedParams cp) {
                 }
                 if constexpr (decltype(tail_tag)::value) __syncwarp();     // reconverge before the warp-collective store
                 tmem_st8(tq + 8 * j, qb);
+                if constexpr (ECACHE) tmem_st4(tq + kTmE + 4 * j, eb);
             };
+            // the FMA-pipe exponentials need xs*k2 - m_w*k2 >= -126 for every cell of the warp's slice
+            const bool poly_ab = REF && KD_POLY_AB > 0 && (fmaf(min_w, k2, esh - mk) >= kPolyFloor);
+            if (poly_ab) {
 #pragma unroll 2
-            for (int j = 0; j < n_full; ++j) ab_body(j, true, std::false_type{});
-            if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{});
+                for (int j = 0; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::true_type{});
+                if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::true_type{});
+            } else {
+#pragma unroll 2
+                for (int j = 0; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::false_type{});
+                if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::false_type{});
+            }
             tmem_wait_st();
+            __syncwarp();
+            if (next_r < p.n_rows) issue_teacher(next_r);      // nobody reads the teacher slice after pass AB
+            if (NPIPE == 2 && lane == 0) mbar_arrive_cta(tok_other);
             float x0, x1;
             upk(add2(accS0, accS1), x0, x1);
-            S_w = warp_sum(x0 + x1);
+            S_w = warp_sum(x0 + x1) * (ECACHE ? 1.f / 32768.f : 1.f);
             upk(accQ, x0, x1);
             Q_w = warp_sum(x0 + x1);
             upk(accR, x0, x1);
             R_w = warp_sum(x0 + x1) + poison;
             upk(accP, x0, x1);
-            P_w = warp_sum(x0 + x1);
+            P_w = warp_sum(x0 + x1) - esh * Q_w;          // sum q*(a + 15) -> sum q*a
         }
 
+        KD_STAMP(3);
         // ---- the single reduction: push the warp's partial to every CTA of the cluster ---------------------------
         if (DYN) claimed = __shfl_sync(0xffffffffu, claimed, 0);
         if (lane < CS) {
@@ -301,9 +386,8 @@ row_emit_fused_kernel(const FusedParams cp) {
         }
         // one warp per pipeline folds the NSLOT partials and broadcasts the row statistics through shared memory
         if (pw == 0) {
-#ifndef KD_ABLATE_SYNC     // timing experiment only (wrong results): no reduction wait
             mbar_wait_cta(bar_red1, ph1);
-#endif
+            KD_STAMP(7);
             if (lane == 0) mbar_expect_tx(bar_red1, RED1_BYTES);      // arm the next row's phase
             constexpr int SPL = NSLOT / 32;                            // slots per lane
             float4 sa[SPL], sb[SPL];
@@ -367,17 +451,12 @@ row_emit_fused_kernel(const FusedParams cp) {
                 if (rank == 0 && all_kept) p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row);
             }
         }
-#ifndef KD_ABLATE_SYNC
         named_bar_sync(bar1, WPP * 32);
-#endif
+        KD_STAMP(4);
         const float lse2_s = bcast[0];
         if constexpr (!REF) lse2_t = bcast[1];
         float Q = bcast[2];
-#ifdef KD_ABLATE_SYNC
-        const bool all_kept = true;
-#else
         const bool all_kept = bcast[3] != 0.f;
-#endif
         int64_t after_next = 0;
         if (DYN) after_next = __float_as_int(bcast[4]);
         ph1 ^= 1;
@@ -441,6 +520,7 @@ row_emit_fused_kernel(const FusedParams cp) {
         }
 
         // ================= pass C: gradient, written straight to HBM ===========================================
+        bool student_refilled = false;
         if (want_grad) {
             const float gQ = g * Q;
             const bool fold = (g > 0.f) && (gQ > 0.f) && (gQ < INFINITY);
@@ -451,9 +531,10 @@ row_emit_fused_kernel(const FusedParams cp) {
             const float gq = REF ? g : g * ex2(mtk - lse2_t);        // PLAIN: the parked values are relative to mt_w
             const u64 negg = pk(-gq, -gq), gQp = pk(gQ, gQ);
             T* grow = static_cast<T*>(p.grad) + r * p.ld_g + (int64_t)g_v0 * 8;
-            auto sweepC = [&](auto fold_tag, auto mask_tag) {
+            auto sweepC = [&](auto fold_tag, auto mask_tag, auto poly_tag) {
                 constexpr bool FOLD = decltype(fold_tag)::value;
                 constexpr bool MASK = decltype(mask_tag)::value;
+                constexpr bool POLY = decltype(poly_tag)::value;
                 auto c_body = [&](int j, bool act, auto tail_tag) {
                     uint32_t qb[8];
                     tmem_ld8(tq + 8 * j, qb);
@@ -466,9 +547,10 @@ row_emit_fused_kernel(const FusedParams cp) {
                         uint32_t out[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
+                            const u64 a2 = fma2(Pair<T>::widen(ws[i]), k2p, nls);
                             float a_lo, a_hi;
-                            upk(fma2(Pair<T>::widen(ws[i]), k2p, nls), a_lo, a_hi);
-                            const u64 sp2 = pk(ex2(a_lo), ex2(a_hi));
+                            upk(a2, a_lo, a_hi);
+                            const u64 sp2 = (POLY && i >= 4 - KD_POLY_C) ? ex2_poly2<3>(a2) : ex2_mufu2(a2);
                             u64 q2 = pk(__uint_as_float(qb[2 * i]), __uint_as_float(qb[2 * i + 1]));
                             if constexpr (MASK) q2 = mul2(q2, pk(set_ge(a_lo, thrC), set_ge(a_hi, thrC)));
                             u64 o2;
@@ -486,22 +568,63 @@ row_emit_fused_kernel(const FusedParams cp) {
                 for (int j = 0; j < n_full; ++j) c_body(j, true, std::false_type{});
                 if (n_tail) c_body(n_full, lane < n_tail, std::true_type{});
             };
+            // unclamped row with the exponent cache: g*Q*sp = fp16 e' * 2^(m_w*k2 - 15 - lse2_s + log2 gQ), no shared memory, no MUFU
+            auto sweepC_cached = [&]() {
+                const float ce = ex2((mk - kEScaleLog2) + (lgQ - lse2_s));
+                const u64 cep = pk(ce, ce);
+                auto c_body = [&](int j, bool act, auto tail_tag) {
+                    uint32_t qb[8], eb[4];
+                    tmem_ld8(tq + 8 * j, qb);
+                    tmem_ld4(tq + kTmE + 4 * j, eb);
+                    tmem_wait_ld();
+                    if (act) {
+                        uint32_t out[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 ef = __half22float2(*reinterpret_cast<const __half2*>(&eb[i]));
+                            const u64 q2 = pk(__uint_as_float(qb[2 * i]), __uint_as_float(qb[2 * i + 1]));
+                            float n_lo, n_hi;
+                            upk(fma2(pk(ef.x, ef.y), cep, mul2(q2, negg)), n_lo, n_hi);
+                            out[i] = Pair<T>::narrow(n_lo, n_hi);
+                        }
+                        stg_stream(grow + (int64_t)(lane + 32 * j) * 8, make_uint4(out[0], out[1], out[2], out[3]));
+                    }
+                    if constexpr (decltype(tail_tag)::value) __syncwarp();
+                };
+#pragma unroll 2
+                for (int j = 0; j < n_full; ++j) c_body(j, true, std::false_type{});
+                if (n_tail) c_body(n_full, lane < n_tail, std::true_type{});
+            };
             using Yes = std::true_type;
             using No = std::false_type;
+            // FMA-pipe exponentials in the common (folded, unmasked) sweep when log2(g*Q*sp) >= -126 for the whole slice
+            const bool poly_c = REF && KD_POLY_C > 0 && (fmaf(min_w, k2, lgQ - lse2_s) >= kPolyFloor);
             if (fold) {
-                if (all_kept) sweepC(Yes{}, No{});
-                else sweepC(Yes{}, Yes{});
+                if (all_kept) {
+                    if (REF && KD_ECACHE) {
+                        if (next_r < p.n_rows) issue_student(next_r);       // the cached sweep reads tensor memory only
+                        student_refilled = true;
+                        sweepC_cached();
+                    }
+                    else if (poly_c) sweepC(Yes{}, No{}, Yes{});
+                    else sweepC(Yes{}, No{}, No{});
+                } else {
+                    sweepC(Yes{}, Yes{}, No{});
+                }
             } else {
-                if (all_kept) sweepC(No{}, No{});
-                else sweepC(No{}, Yes{});
+                if (all_kept) sweepC(No{}, No{}, No{});
+                else sweepC(No{}, Yes{}, No{});
             }
         }
+        KD_STAMP(5);
         // ---- refill the warp's private slice with its next row (all lanes are done reading it) -------------------
         __syncwarp();
-        if (next_r < p.n_rows) issue_load(next_r);
+        if (!student_refilled && next_r < p.n_rows) issue_student(next_r);
         r = next_r;
         if (DYN) next_r = after_next;
+        KD_STAMP(6);
     }
+    if (pw == 0 && lane == 0) reinterpret_cast<volatile float*>(smem + plan.bcast + pipe * 32)[7] = 1.f;      // releases a partner waiting for our pass AB
     tmem_fence_before_sync();
     cluster_sync_all();     // nobody leaves while peers may still push into its shared memory
     tmem_fence_after_sync();
@@ -685,7 +808,7 @@ row_emit_pipelined_kernel(const FusedParams cp) {
     // ring slots (byte addresses of the CTA slice): student of the current / previous / next row, teacher current / next
     uint32_t st_cur = s_stu, st_prev = s_stu + 2 * slice_bytes, st_nxt = s_stu + slice_bytes;
     uint32_t te_cur = s_tea, te_nxt = s_tea + slice_bytes;
-    float lse2_t_prev = 0.f, mtk_prev = 0.f, R_prev = 0.f;     // carried from pass AB (i) to pass C (i) one iteration later
+    float lse2_t_prev = 0.f, mtk_prev = 0.f, R_prev = 0.f, min_prev = 0.f;     // carried from pass AB (i) to pass C (i) one iteration later
     if (tid == 0 && cta_n > 0 && r_cur < n_rows) issue_load(r_cur, st_cur, te_cur, bar_full);
 
     for (int it = 0;; ++it) {
@@ -848,8 +971,9 @@ row_emit_pipelined_kernel(const FusedParams cp) {
                 const float tref = REF ? lse2_t_cur : mtk_cur;
                 const u64 nlt = pk(-tref, -tref);
                 u64 accS0 = pk(0.f, 0.f), accS1 = pk(0.f, 0.f), accQ = pk(0.f, 0.f), accR = pk(0.f, 0.f), accP = pk(0.f, 0.f);
-                auto ab_step = [&](int j, auto nv_tag, bool act, auto tail_tag) {
+                auto ab_step = [&](int j, auto nv_tag, bool act, auto tail_tag, auto poly_tag) {
                     constexpr int NV = decltype(nv_tag)::value;
+                    constexpr bool POLY = decltype(poly_tag)::value;
                     uint32_t qb[NV][8], ob[NV][8];
                     uint4 rs[NV], rt[NV];
 #pragma unroll
@@ -876,9 +1000,7 @@ row_emit_pipelined_kernel(const FusedParams cp) {
                             for (int i = 0; i < 4; ++i) {
                                 const u64 ovp = pk(__uint_as_float(ob[u][2 * i]), __uint_as_float(ob[u][2 * i + 1]));
                                 const u64 a2 = fma2(Pair<T>::widen(ws[i]), k2p, nmk);        // xs*k2 - m_w*k2  (<= 0)
-                                float a_lo, a_hi;
-                                upk(a2, a_lo, a_hi);
-                                const u64 e2 = pk(ex2(a_lo), ex2(a_hi));
+                                const u64 e2 = (POLY && i >= 4 - KD_POLY_AB) ? ex2_poly2<4>(a2) : ex2_mufu2(a2);
                                 if (i & 1) accS1 = add2(accS1, e2);
                                 else accS0 = add2(accS0, e2);
                                 const u64 b2 = fma2(Pair<T>::widen(wt[i]), k2p, nlt);        // log2 tp (REF) / relative to mt_w (PLAIN)
@@ -901,11 +1023,17 @@ row_emit_pipelined_kernel(const FusedParams cp) {
 #pragma unroll
                     for (int u = 0; u < NV; ++u) tmem_st8(tm + kTmQ + 40 * par + 8 * (j + u), qb[u]);
                 };
-                {
+                const bool poly_ab = REF && KD_POLY_AB > 0 && (fmaf(min_w, k2, -mk) >= kPolyFloor);
+                if (poly_ab) {
                     int j = 0;
-                    for (; j + 1 < n_full; j += 2) ab_step(j, Int2{}, true, std::false_type{});
-                    if (j < n_full) ab_step(j, Int1{}, true, std::false_type{});
-                    if (n_tail) ab_step(n_full, Int1{}, lane < n_tail, std::true_type{});
+                    for (; j + 1 < n_full; j += 2) ab_step(j, Int2{}, true, std::false_type{}, std::true_type{});
+                    if (j < n_full) ab_step(j, Int1{}, true, std::false_type{}, std::true_type{});
+                    if (n_tail) ab_step(n_full, Int1{}, lane < n_tail, std::true_type{}, std::true_type{});
+                } else {
+                    int j = 0;
+                    for (; j + 1 < n_full; j += 2) ab_step(j, Int2{}, true, std::false_type{}, std::false_type{});
+                    if (j < n_full) ab_step(j, Int1{}, true, std::false_type{}, std::false_type{});
+                    if (n_tail) ab_step(n_full, Int1{}, lane < n_tail, std::true_type{}, std::false_type{});
                 }
                 tmem_wait_st();
                 float s0, s1, q0, q1, r0, r1, p0, p1;
@@ -1045,9 +1173,10 @@ row_emit_pipelined_kernel(const FusedParams cp) {
                 const float gq = REF ? g : g * ex2(mtk_prev - lse2_t_prev);        // PLAIN: the parked values are relative to mt_w
                 const u64 negg = pk(-gq, -gq), gQp = pk(gQ_p, gQ_p);
                 T* grow = static_cast<T*>(p.grad) + r_prev * p.ld_g + (int64_t)g_v0 * 8;
-                auto sweepC = [&](auto fold_tag, auto mask_tag) {
+                auto sweepC = [&](auto fold_tag, auto mask_tag, auto poly_tag) {
                     constexpr bool FOLD = decltype(fold_tag)::value;
                     constexpr bool MASK = decltype(mask_tag)::value;
+                    constexpr bool POLY = decltype(poly_tag)::value;
                     auto c_step = [&](int j, auto nv_tag, bool act, auto tail_tag) {
                         constexpr int NV = decltype(nv_tag)::value;
                         uint32_t qb[NV][8];
@@ -1067,9 +1196,10 @@ row_emit_pipelined_kernel(const FusedParams cp) {
                                 uint32_t out[4];
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
+                                    const u64 a2 = fma2(Pair<T>::widen(ws[i]), k2p, nls);
                                     float a_lo, a_hi;
-                                    upk(fma2(Pair<T>::widen(ws[i]), k2p, nls), a_lo, a_hi);
-                                    const u64 sp2 = pk(ex2(a_lo), ex2(a_hi));
+                                    upk(a2, a_lo, a_hi);
+                                    const u64 sp2 = (POLY && i >= 4 - KD_POLY_C) ? ex2_poly2<3>(a2) : ex2_mufu2(a2);
                                     u64 q2 = pk(__uint_as_float(qb[u][2 * i]), __uint_as_float(qb[u][2 * i + 1]));
                                     if constexpr (MASK) q2 = mul2(q2, pk(set_ge(a_lo, thrC), set_ge(a_hi, thrC)));
                                     u64 o2;
@@ -1091,12 +1221,17 @@ row_emit_pipelined_kernel(const FusedParams cp) {
                 };
                 using Yes = std::true_type;
                 using No = std::false_type;
+                const bool poly_c = REF && KD_POLY_C > 0 && (fmaf(min_prev, k2, nl) >= kPolyFloor);
                 if (fold_p) {
-                    if (kept_p) sweepC(Yes{}, No{});
-                    else sweepC(Yes{}, Yes{});
+                    if (kept_p) {
+                        if (poly_c) sweepC(Yes{}, No{}, Yes{});
+                        else sweepC(Yes{}, No{}, No{});
+                    } else {
+                        sweepC(Yes{}, Yes{}, No{});
+                    }
                 } else {
-                    if (kept_p) sweepC(No{}, No{});
-                    else sweepC(No{}, Yes{});
+                    if (kept_p) sweepC(No{}, No{}, No{});
+                    else sweepC(No{}, Yes{}, No{});
                 }
             }
         }
@@ -1106,6 +1241,7 @@ row_emit_pipelined_kernel(const FusedParams cp) {
         if constexpr (REF) lse2_t_prev = lse2_t_cur;
         mtk_prev = mtk_cur;
         R_prev = R_cur;
+        min_prev = min_w;
         r_cur = r_nxt;
         r_nxt = r_nn;
         {
@@ -1171,6 +1307,27 @@ int launch_fused_d(const EmitParams& e, cudaStream_t st, bool query_only, int* c
     if (max_clusters < 1) return KD_ERR_UNSUPPORTED;
     const int64_t want = (e.n_rows + NPIPE - 1) / NPIPE;
     FusedParams cp;
+    cp.trace = nullptr;
+#ifdef KD_TRACE
+    {
+        static unsigned long long* tbuf = nullptr;
+        const size_t n = (size_t)max_clusters * CS * kWarps * 64 * 8;
+        if (!tbuf) { cudaMalloc(&tbuf, n * sizeof(unsigned long long)); cudaMemset(tbuf, 0, n * sizeof(unsigned long long)); }
+        cp.trace = tbuf;
+        if (const char* pth = getenv("KD_TRACE_DUMP")) {       // previous launch's stamps -> file (debug only)
+            static int calls = 0;
+            if (++calls == 3) {
+                cudaDeviceSynchronize();
+                unsigned long long* h = (unsigned long long*)malloc(n * 8);
+                cudaMemcpy(h, tbuf, n * 8, cudaMemcpyDeviceToHost);
+                FILE* f = fopen(pth, "wb");
+                fwrite(h, 8, n, f);
+                fclose(f);
+                free(h);
+            }
+        }
+    }
+#endif
     cp.e = e;
     cp.n_clusters = (int)(want < max_clusters ? want : max_clusters);
     cp.vpc = vpc;
@@ -1237,6 +1394,7 @@ int launch_pipe_d(const EmitParams& e, cudaStream_t st, bool query_only, int* ca
     if (query_only) return KD_OK;
     if (max_clusters < 1) return KD_ERR_UNSUPPORTED;
     FusedParams cp;
+    cp.trace = nullptr;
     cp.e = e;
     cp.n_clusters = (int)(e.n_rows < max_clusters ? e.n_rows : max_clusters);
     cp.vpc = vpc;
@@ -1259,12 +1417,12 @@ int launch_pipe_t(const EmitParams& e, int variant, cudaStream_t st, bool query_
     return launch_pipe_d<KD_KL_PLAIN, T, false>(e, st, query_only, capacity, launched, first_free);
 }
 
-// KD_FUSED: 0 = three-sweep cluster kernel everywhere, 1 = two-pipeline fused kernel, 2 = software-pipelined kernel (default)
+// KD_FUSED: 0 = three-sweep cluster kernel everywhere, 1 = two-pipeline fused kernel (default), 2 = software-pipelined kernel
 int fused_mode() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("KD_FUSED");
-        v = e ? atoi(e) : 2;
+        v = e ? atoi(e) : 1;
     }
     return v;
 }
