@@ -68,6 +68,7 @@ struct FusedParams {
     int n_clusters;
     int vpc;                      // 16-byte vectors per CTA slice
     int nvec;                     // 16-byte vectors per row
+    int tok_after;                // two-pipeline kernel: hand the pass-AB token over this many iterations early (KD_TOKEN_EARLY)
 };
 
 // Shared-memory plan (dynamic, byte offsets).  A reduction slot is 8 words:
@@ -350,19 +351,28 @@ row_emit_fused_kernel(const FusedParams cp) {
             };
             // the FMA-pipe exponentials need xs*k2 - m_w*k2 >= -126 for every cell of the warp's slice
             const bool poly_ab = REF && KD_POLY_AB > 0 && (fmaf(min_w, k2, esh - mk) >= kPolyFloor);
+            bool token_given = false;
             if (poly_ab) {
 #pragma unroll 2
                 for (int j = 0; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::true_type{});
                 if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::true_type{});
             } else {
+                // the other pipeline may start its pass AB once this warp has `tok_after` iterations left (0 = strict alternation)
+                const int j_split = max(0, n_full - cp.tok_after);
 #pragma unroll 2
-                for (int j = 0; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::false_type{});
+                for (int j = 0; j < j_split; ++j) ab_body(j, true, std::false_type{}, std::false_type{});
+                if (NPIPE == 2 && cp.tok_after > 0) {
+                    if (lane == 0) mbar_arrive_cta(tok_other);
+                    token_given = true;
+                }
+#pragma unroll 2
+                for (int j = j_split; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::false_type{});
                 if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::false_type{});
             }
             tmem_wait_st();
             __syncwarp();
             if (next_r < p.n_rows) issue_teacher(next_r);      // nobody reads the teacher slice after pass AB
-            if (NPIPE == 2 && lane == 0) mbar_arrive_cta(tok_other);
+            if (NPIPE == 2 && !token_given && lane == 0) mbar_arrive_cta(tok_other);
             float x0, x1;
             upk(add2(accS0, accS1), x0, x1);
             S_w = warp_sum(x0 + x1) * (ECACHE ? 1.f / 32768.f : 1.f);
@@ -400,30 +410,41 @@ row_emit_fused_kernel(const FusedParams cp) {
                 if constexpr (REF) mn = fminf(mn, sb[i].x);
                 else m_t = fmaxf(m_t, sb[i].z);
             }
-            m_s = warp_max(m_s);
-            if constexpr (REF) mn = warp_min(mn);
-            else m_t = warp_max(m_t);
-            float s_sum = 0.f, t_sum = 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {          // independent butterflies, interleaved
+                m_s = fmaxf(m_s, __shfl_xor_sync(0xffffffffu, m_s, o));
+                if constexpr (REF) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                else m_t = fmaxf(m_t, __shfl_xor_sync(0xffffffffu, m_t, o));
+            }
+            float s_sum = 0.f, t_sum = 0.f, Q = 0.f, A = 0.f;
 #pragma unroll
             for (int i = 0; i < SPL; ++i) {
                 if (sa[i].x != -INFINITY) s_sum = fmaf(sa[i].y, ex2((sa[i].x - m_s) * k2), s_sum);
-                if constexpr (!REF) {
+                if constexpr (REF) {
+                    const float mki = __fmul_rn((sa[i].x == -INFINITY) ? 0.f : sa[i].x, k2);
+                    Q += sa[i].z;
+                    A += sa[i].w - mki * sa[i].z;            // row = A + lse2_s * Q
+                } else {
                     if (sb[i].z != -INFINITY) t_sum = fmaf(sa[i].z, ex2((sb[i].z - m_t) * k2), t_sum);
                 }
             }
-            s_sum = warp_sum(s_sum);
-            const float lse2_s = fmaf(m_s, k2, __log2f(s_sum));
-            float Q = 0.f, row = 0.f;
-            if constexpr (REF) {
 #pragma unroll
-                for (int i = 0; i < SPL; ++i) {
-                    const float mki = __fmul_rn((sa[i].x == -INFINITY) ? 0.f : sa[i].x, k2);
-                    Q += sa[i].z;
-                    row += sa[i].w - (mki - lse2_s) * sa[i].z;
+            for (int o = 16; o > 0; o >>= 1) {
+                s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
+                if constexpr (REF) {
+                    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+                    A += __shfl_xor_sync(0xffffffffu, A, o);
+                } else {
+                    t_sum += __shfl_xor_sync(0xffffffffu, t_sum, o);
                 }
+            }
+            const float lse2_s = fmaf(m_s, k2, __log2f(s_sum));
+            float row;
+            if constexpr (REF) {
+                row = fmaf(lse2_s, Q, A);
             } else {
-                t_sum = warp_sum(t_sum);
                 lse2_t = fmaf(m_t, k2, __log2f(t_sum));
+                row = 0.f;
 #pragma unroll
                 for (int i = 0; i < SPL; ++i) {
                     const float mki = __fmul_rn((sa[i].x == -INFINITY) ? 0.f : sa[i].x, k2);
@@ -432,9 +453,12 @@ row_emit_fused_kernel(const FusedParams cp) {
                     Q = fmaf(sc, sa[i].z, Q);
                     row = fmaf(sc, sa[i].w + ((mti - lse2_t) - (mki - lse2_s)) * sa[i].z, row);
                 }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+                    row += __shfl_xor_sync(0xffffffffu, row, o);
+                }
             }
-            Q = warp_sum(Q);
-            row = warp_sum(row);
             int claim_all = 0;
             if (DYN) claim_all = __shfl_sync(0xffffffffu, __float_as_int(sb[0].y), 0);     // slot 0 = (rank 0, warp 0)
             bool all_kept = true;
@@ -572,28 +596,40 @@ row_emit_fused_kernel(const FusedParams cp) {
             auto sweepC_cached = [&]() {
                 const float ce = ex2((mk - kEScaleLog2) + (lgQ - lse2_s));
                 const u64 cep = pk(ce, ce);
-                auto c_body = [&](int j, bool act, auto tail_tag) {
-                    uint32_t qb[8], eb[4];
-                    tmem_ld8(tq + 8 * j, qb);
-                    tmem_ld4(tq + kTmE + 4 * j, eb);
+                auto c_step = [&](int j, auto nv_tag, bool act, auto tail_tag) {
+                    constexpr int NV = decltype(nv_tag)::value;       // vectors per tensor-memory wait
+                    uint32_t qb[NV][8], eb[NV][4];
+#pragma unroll
+                    for (int u = 0; u < NV; ++u) {
+                        tmem_ld8(tq + 8 * (j + u), qb[u]);
+                        tmem_ld4(tq + kTmE + 4 * (j + u), eb[u]);
+                    }
                     tmem_wait_ld();
                     if (act) {
-                        uint32_t out[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 ef = __half22float2(*reinterpret_cast<const __half2*>(&eb[i]));
-                            const u64 q2 = pk(__uint_as_float(qb[2 * i]), __uint_as_float(qb[2 * i + 1]));
-                            float n_lo, n_hi;
-                            upk(fma2(pk(ef.x, ef.y), cep, mul2(q2, negg)), n_lo, n_hi);
-                            out[i] = Pair<T>::narrow(n_lo, n_hi);
+                        for (int u = 0; u < NV; ++u) {
+                            uint32_t out[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 ef = __half22float2(*reinterpret_cast<const __half2*>(&eb[u][i]));
+                                const u64 q2 = pk(__uint_as_float(qb[u][2 * i]), __uint_as_float(qb[u][2 * i + 1]));
+                                float n_lo, n_hi;
+                                upk(fma2(pk(ef.x, ef.y), cep, mul2(q2, negg)), n_lo, n_hi);
+                                out[i] = Pair<T>::narrow(n_lo, n_hi);
+                            }
+                            stg_stream(grow + (int64_t)(lane + 32 * (j + u)) * 8, make_uint4(out[0], out[1], out[2], out[3]));
                         }
-                        stg_stream(grow + (int64_t)(lane + 32 * j) * 8, make_uint4(out[0], out[1], out[2], out[3]));
                     }
                     if constexpr (decltype(tail_tag)::value) __syncwarp();
                 };
-#pragma unroll 2
-                for (int j = 0; j < n_full; ++j) c_body(j, true, std::false_type{});
-                if (n_tail) c_body(n_full, lane < n_tail, std::true_type{});
+                using V4 = std::integral_constant<int, 4>;
+                using V2 = std::integral_constant<int, 2>;
+                using V1 = std::integral_constant<int, 1>;
+                int j = 0;
+                for (; j + 3 < n_full; j += 4) c_step(j, V4{}, true, std::false_type{});
+                if (j + 1 < n_full) { c_step(j, V2{}, true, std::false_type{}); j += 2; }
+                if (j < n_full) c_step(j, V1{}, true, std::false_type{});
+                if (n_tail) c_step(n_full, V1{}, lane < n_tail, std::true_type{});
             };
             using Yes = std::true_type;
             using No = std::false_type;
@@ -1329,6 +1365,11 @@ int launch_fused_d(const EmitParams& e, cudaStream_t st, bool query_only, int* c
     }
 #endif
     cp.e = e;
+    {
+        static int early = -1;
+        if (early < 0) { const char* ev = getenv("KD_TOKEN_EARLY"); early = ev ? atoi(ev) : 0; }
+        cp.tok_after = early;
+    }
     cp.n_clusters = (int)(want < max_clusters ? want : max_clusters);
     cp.vpc = vpc;
     cp.nvec = nvec;
@@ -1395,6 +1436,7 @@ int launch_pipe_d(const EmitParams& e, cudaStream_t st, bool query_only, int* ca
     if (max_clusters < 1) return KD_ERR_UNSUPPORTED;
     FusedParams cp;
     cp.trace = nullptr;
+    cp.tok_after = 0;
     cp.e = e;
     cp.n_clusters = (int)(e.n_rows < max_clusters ? e.n_rows : max_clusters);
     cp.vpc = vpc;

@@ -59,7 +59,8 @@ keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
 lines = [f"# {tag}: ncu --set full, dominant kernel `{short(rr[2][rr[0].index('Kernel Name')])}`", "",
          f"capture: {rows_in_capture} rows x {V} columns bf16 (one launch)", "", "| metric | value | unit |", "|---|---|---|"]
 for k in keys:
@@ -73,7 +74,7 @@ per_row = traffic / rows_in_capture
 lines += ["", f"DRAM traffic per launch: {traffic / 1e9:.3f} GB = {per_row:.0f} B/row (algorithmic 6*V = {6 * V} B/row)",
           f"thread instructions per (row, column) cell: {f('thread_inst_executed') / (rows_in_capture * V):.2f}"]
 open(f"profiles/{tag}_emit_full.md", "w").write("\n".join(lines) + "\n")
-json.dump({"kernel": "row_emit_cluster_kernel", "dram_bytes_per_row": per_row, "rows_in_capture": rows_in_capture,
+json.dump({"kernel": short(rr[2][rr[0].index('Kernel Name')]), "dram_bytes_per_row": per_row, "rows_in_capture": rows_in_capture,
            "source": f"profiles/{tag}_emit_full.md"}, open("profiles/emit_traffic.json", "w"))
 print("\n".join(out[-8:]))
 print("\n".join(lines[-3:]))
