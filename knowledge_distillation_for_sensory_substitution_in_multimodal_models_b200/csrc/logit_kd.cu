@@ -1172,16 +1172,28 @@ int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, 
     p.gscale = static_cast<float>(T * inv_norm); p.flags = flags;
     p.records = reinterpret_cast<kd_token_record*>(ws + w.records);
 
-    if (variant == KD_LOCA_REFERENCE) {
+    // per-row LoCa on the fused kernel: phase A supplies lse2_t and the token records {label, v1, k, v2}, the emit patches
+    // the row's own override cells after its sweep (8V bytes/token instead of 6V, but half the arithmetic of the 3-sweep kernel)
+    bool per_row_two_phase = false;
+    if (variant == KD_LOCA_PER_ROW && n_rows > 0 && !(flags & KD_FLAG_FORCE_STREAMING)) {
+        EmitParams probe = p;
+        probe.lse2_t_in = reinterpret_cast<float*>(ws + w.lse2_t);
+        int nc = 0, cpc = 0, pipes = 0, srows = 0;
+        per_row_two_phase = fused_applies(probe, variant, dtype) &&
+                            cluster_launch_shape(probe, variant, dtype, &nc, &cpc, &pipes, &srows) == KD_OK;
+    }
+    if (variant == KD_LOCA_REFERENCE || per_row_two_phase) {
         kd_token_record* rec = reinterpret_cast<kd_token_record*>(ws + w.records);
         float* lse2_t = reinterpret_cast<float*>(ws + w.lse2_t);
-        float* table = reinterpret_cast<float*>(ws + w.table);
         if (n_rows > 0) {
             if (int rc = kd_loca_teacher_stats(teacher, ld_t, labels, rec, lse2_t, status, n_rows, V, dtype, T, alpha, stream)) return rc;
         }
-        if (int rc = kd_loca_build_table(rec, n_rows, V, table, consts, ws + w.table_ws, w.table_ws_bytes, stream)) return rc;
         p.lse2_t_in = lse2_t;
-        p.table = table;
+        if (variant == KD_LOCA_REFERENCE) {
+            float* table = reinterpret_cast<float*>(ws + w.table);
+            if (int rc = kd_loca_build_table(rec, n_rows, V, table, consts, ws + w.table_ws, w.table_ws_bytes, stream)) return rc;
+            p.table = table;
+        }
     }
     if (n_rows > 0) {
         if (int rc = launch_emit(p, variant, dtype, st, reinterpret_cast<int*>(ws + w.queue))) return rc;

@@ -111,10 +111,12 @@ __device__ __forceinline__ float warp_min(float v) {
 template <int VARIANT, typename T, int CS, int NPIPE, bool DYN>
 __global__ void __launch_bounds__(kThreads, 1)
 row_emit_fused_kernel(const FusedParams cp) {
-    constexpr bool REF = (VARIANT == KD_LOCA_REFERENCE);
+    constexpr bool TAB = (VARIANT == KD_LOCA_REFERENCE);            // shared override table (phase A + build_table)
+    constexpr bool PER_ROW = (VARIANT == KD_LOCA_PER_ROW);          // the row's own label / runner-up cells only
+    constexpr bool LOCA = TAB || PER_ROW;                           // teacher statistics and records come from phase A
     constexpr int WPP = kWarps / NPIPE;
     constexpr int NSLOT = CS * WPP;
-    constexpr uint32_t RED1_BYTES = NSLOT * (REF ? 24 : 32);
+    constexpr uint32_t RED1_BYTES = NSLOT * (LOCA ? 24 : 32);
     constexpr uint32_t RED2_BYTES = NSLOT * 8;
     static_assert(NSLOT % 32 == 0, "the fold assumes whole warps of slots");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -172,7 +174,7 @@ row_emit_fused_kernel(const FusedParams cp) {
     if (warp == 1) tmem_alloc_512(s_base + plan.tmem_word);
     // LoCa: encode this CTA's table slice once (0 = not overridden, else max(ov, floor) > 0); layout as in logit_kd_cluster.cu
     float poison = 0.f;
-    if constexpr (REF) {
+    if constexpr (TAB) {
         float* tbl = reinterpret_cast<float*>(smem + plan.table);
         bool ok = true;
         for (int i = tid; i < cta_n * 8; i += kThreads) {
@@ -247,7 +249,10 @@ row_emit_fused_kernel(const FusedParams cp) {
         int claimed = 0;
         if (DYN && rank == 0 && pw == 0 && lane == 0) claimed = atomicAdd(p.row_queue, 1);
         float lse2_t = 0.f;
-        if constexpr (REF) lse2_t = p.lse2_t_in[r];
+        if constexpr (LOCA) lse2_t = p.lse2_t_in[r];
+        kd_token_record rec_r;
+        rec_r.label = -1; rec_r.k = -1; rec_r.v1 = NaN; rec_r.v2 = NaN;
+        if constexpr (PER_ROW) rec_r = p.records[r];
         warm_l2(next_r);
         const uint32_t epoch = (uint32_t)r;
         auto load_s = [&](int v) -> uint4 { return lds128_ep(s_s + v * 16, epoch); };
@@ -264,7 +269,7 @@ row_emit_fused_kernel(const FusedParams cp) {
             for (int v = lane; v < w_n; v += 32) {
                 const uint4 rs = load_s(v);
                 smax2 = Pair<T>::vmax(smax2, Pair<T>::vmax(Pair<T>::vmax(rs.x, rs.y), Pair<T>::vmax(rs.z, rs.w)));
-                if constexpr (REF) {
+                if constexpr (LOCA) {
                     smin2 = Pair<T>::vmin(smin2, Pair<T>::vmin(Pair<T>::vmin(rs.x, rs.y), Pair<T>::vmin(rs.z, rs.w)));
                 } else {
                     const uint4 rt = load_t(v);
@@ -274,7 +279,7 @@ row_emit_fused_kernel(const FusedParams cp) {
             float lo, hi;
             upk(Pair<T>::widen(smax2), lo, hi);
             m_w = warp_max(fmaxf(lo, hi));
-            if constexpr (REF) {
+            if constexpr (LOCA) {
                 upk(Pair<T>::widen(smin2), lo, hi);
                 min_w = warp_min(fminf(lo, hi));
             } else {
@@ -299,11 +304,11 @@ row_emit_fused_kernel(const FusedParams cp) {
         // ================= pass AB: statistics + accumulation in one sweep, q parked in tensor memory ==========
         float S_w, Q_w, R_w, P_w;
         {
-            constexpr bool ECACHE = REF && KD_ECACHE;
+            constexpr bool ECACHE = LOCA && KD_ECACHE;
             // with the exponent cache the student argument carries +15 (e is parked as fp16(e * 2^15)); S_w and P_w are corrected below
             const float esh = ECACHE ? kEScaleLog2 : 0.f;
             const u64 nmk = pk(esh - mk, esh - mk);
-            const float tref = REF ? lse2_t : mtk;
+            const float tref = LOCA ? lse2_t : mtk;
             const u64 nlt = pk(-tref, -tref);
             u64 accS0 = pk(0.f, 0.f), accS1 = pk(0.f, 0.f), accQ = pk(0.f, 0.f), accR = pk(0.f, 0.f), accP = pk(0.f, 0.f);
             auto ab_body = [&](int j, bool act, auto tail_tag, auto poly_tag) {
@@ -314,7 +319,7 @@ row_emit_fused_kernel(const FusedParams cp) {
                     const int v = lane + 32 * j;
                     const uint4 rs = load_s(v), rt = load_t(v);
                     uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
-                    if constexpr (REF) { o0 = lds128_ep(s_ov + v * 16, 0u); o1 = lds128_ep(s_ov + v * 16 + cp.vpc * 16, 0u); }
+                    if constexpr (TAB) { o0 = lds128_ep(s_ov + v * 16, 0u); o1 = lds128_ep(s_ov + v * 16 + cp.vpc * 16, 0u); }
                     const uint32_t ws[4] = {rs.x, rs.y, rs.z, rs.w}, wt[4] = {rt.x, rt.y, rt.z, rt.w};
                     const u64 ovp[4] = {pk(__uint_as_float(o0.x), __uint_as_float(o0.y)), pk(__uint_as_float(o0.z), __uint_as_float(o0.w)),
                                         pk(__uint_as_float(o1.x), __uint_as_float(o1.y)), pk(__uint_as_float(o1.z), __uint_as_float(o1.w))};
@@ -330,12 +335,12 @@ row_emit_fused_kernel(const FusedParams cp) {
                         }
                         if (i & 1) accS1 = add2(accS1, e2);
                         else accS0 = add2(accS0, e2);
-                        const u64 b2 = fma2(Pair<T>::widen(wt[i]), k2p, nlt);        // log2 tp (REF) / relative to mt_w (PLAIN)
+                        const u64 b2 = fma2(Pair<T>::widen(wt[i]), k2p, nlt);        // log2 tp (LOCA) / relative to mt_w (PLAIN)
                         float e_lo, e_hi;
-                        if constexpr (REF) upk(fma2(ovp[i], pushp, b2), e_lo, e_hi);
+                        if constexpr (TAB) upk(fma2(ovp[i], pushp, b2), e_lo, e_hi);
                         else upk(b2, e_lo, e_hi);
                         const u64 t2 = pk(ex2(e_lo), ex2(e_hi));
-                        const u64 q2 = REF ? add2(t2, ovp[i]) : t2;
+                        const u64 q2 = TAB ? add2(t2, ovp[i]) : t2;
                         accQ = add2(accQ, q2);
                         accR = fma2(t2, b2, accR);
                         accP = fma2(q2, a2, accP);
@@ -350,7 +355,7 @@ row_emit_fused_kernel(const FusedParams cp) {
                 if constexpr (ECACHE) tmem_st4(tq + kTmE + 4 * j, eb);
             };
             // the FMA-pipe exponentials need xs*k2 - m_w*k2 >= -126 for every cell of the warp's slice
-            const bool poly_ab = REF && KD_POLY_AB > 0 && (fmaf(min_w, k2, esh - mk) >= kPolyFloor);
+            const bool poly_ab = LOCA && KD_POLY_AB > 0 && (fmaf(min_w, k2, esh - mk) >= kPolyFloor);
             bool token_given = false;
             if (poly_ab) {
 #pragma unroll 2
@@ -370,20 +375,63 @@ row_emit_fused_kernel(const FusedParams cp) {
                 if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::false_type{});
             }
             tmem_wait_st();
-            __syncwarp();
-            if (next_r < p.n_rows) issue_teacher(next_r);      // nobody reads the teacher slice after pass AB
+            if constexpr (!PER_ROW) {
+                __syncwarp();
+                if (next_r < p.n_rows) issue_teacher(next_r);      // nobody reads the teacher slice after pass AB
+            }
             if (NPIPE == 2 && !token_given && lane == 0) mbar_arrive_cta(tok_other);
             float x0, x1;
             upk(add2(accS0, accS1), x0, x1);
             S_w = warp_sum(x0 + x1) * (ECACHE ? 1.f / 32768.f : 1.f);
+            float q_l, r_l, p_l;                       // this lane's shares of Q_w, R_w, P_w
             upk(accQ, x0, x1);
-            Q_w = warp_sum(x0 + x1);
+            q_l = x0 + x1;
             upk(accR, x0, x1);
-            R_w = warp_sum(x0 + x1) + poison;
+            r_l = x0 + x1;
             upk(accP, x0, x1);
-            P_w = warp_sum(x0 + x1) - esh * Q_w;          // sum q*(a + 15) -> sum q*a
+            p_l = x0 + x1;
+            if constexpr (PER_ROW) {
+                // The sweep treated every cell as q = tp.  The row's own override cells (label -> v1, then runner-up -> v2,
+                // P1:184-185 applied per row) are patched now: the owning lane corrects its sums and the parked q.
+                if (rec_r.label >= 0) {
+                    const bool same = (rec_r.k == rec_r.label);
+#pragma unroll
+                    for (int which = 0; which < 2; ++which) {
+                        const int c = which ? rec_r.k : rec_r.label;
+                        const float ov = which ? rec_r.v2 : rec_r.v1;
+                        const int v = (c >> 3) - g_v0;                        // warp-uniform
+                        if ((which == 1 || !same) && c >= 0 && v >= 0 && v < w_n) {
+                            const int j = v >> 5, cell = c & 7;
+                            uint32_t qb[8];
+                            tmem_ld8(tq + 8 * j, qb);
+                            tmem_wait_ld();
+                            if (lane == (v & 31)) {
+                                const float xs = Elem<T>::to_float(*reinterpret_cast<const T*>(smem + (s_s - s_base) + v * 16 + cell * 2));
+                                const float xt = Elem<T>::to_float(*reinterpret_cast<const T*>(smem + (s_t - s_base) + v * 16 + cell * 2));
+                                const float b = fmaf(xt, k2, -lse2_t), t = ex2(b);
+                                const float a = fmaf(xs, k2, esh - mk);
+                                q_l += ov - t;
+                                r_l -= t * b;
+                                p_l = fmaf(ov - t, a, p_l);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if (i == cell) qb[i] = __float_as_uint(ov);
+                            }
+                            __syncwarp();
+                            tmem_st8(tq + 8 * j, qb);
+                            tmem_wait_st();
+                        }
+                    }
+                }
+            }
+            Q_w = warp_sum(q_l);
+            R_w = warp_sum(r_l) + poison;
+            P_w = warp_sum(p_l) - esh * Q_w;          // sum q*(a + 15) -> sum q*a
         }
-
+        if constexpr (PER_ROW) {
+            __syncwarp();
+            if (next_r < p.n_rows) issue_teacher(next_r);          // after the override fix-up, which still reads the teacher slice
+        }
         KD_STAMP(3);
         // ---- the single reduction: push the warp's partial to every CTA of the cluster ---------------------------
         if (DYN) claimed = __shfl_sync(0xffffffffu, claimed, 0);
@@ -391,9 +439,22 @@ row_emit_fused_kernel(const FusedParams cp) {
             const uint32_t dst = map_to_cta(slots + (rank * WPP + pw) * 32, lane);
             const uint32_t rbar = map_to_cta(bar_red1, lane);
             st_async_v4(dst, __float_as_uint(m_w), __float_as_uint(S_w), __float_as_uint(Q_w), __float_as_uint(R_w - P_w), rbar);
-            if constexpr (REF) st_async_v2(dst + 16, __float_as_uint(min_w), (uint32_t)claimed, rbar);
+            if constexpr (LOCA) st_async_v2(dst + 16, __float_as_uint(min_w), (uint32_t)claimed, rbar);
             else st_async_v4(dst + 16, 0u, (uint32_t)claimed, __float_as_uint(mt_w), 0u, rbar);
         }
+        // xlogy(v, v) of the row's own override cells (log2 units); a bad label poisons the row like the reference's gather would raise
+        auto own_xlogy_of = [&]() -> float {
+            float x = 0.f;
+            if constexpr (PER_ROW) {
+                if (rec_r.label >= 0) {
+                    if (rec_r.k != rec_r.label && rec_r.v1 != 0.f) x += rec_r.v1 * log2f(rec_r.v1);
+                    if (rec_r.v2 != 0.f) x += rec_r.v2 * log2f(rec_r.v2);
+                } else {
+                    x = NaN;
+                }
+            }
+            return x;
+        };
         // one warp per pipeline folds the NSLOT partials and broadcasts the row statistics through shared memory
         if (pw == 0) {
             mbar_wait_cta(bar_red1, ph1);
@@ -407,20 +468,20 @@ row_emit_fused_kernel(const FusedParams cp) {
                 sa[i] = slot_v[2 * (lane + 32 * i)];
                 sb[i] = slot_v[2 * (lane + 32 * i) + 1];
                 m_s = fmaxf(m_s, sa[i].x);
-                if constexpr (REF) mn = fminf(mn, sb[i].x);
+                if constexpr (LOCA) mn = fminf(mn, sb[i].x);
                 else m_t = fmaxf(m_t, sb[i].z);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {          // independent butterflies, interleaved
                 m_s = fmaxf(m_s, __shfl_xor_sync(0xffffffffu, m_s, o));
-                if constexpr (REF) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                if constexpr (LOCA) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
                 else m_t = fmaxf(m_t, __shfl_xor_sync(0xffffffffu, m_t, o));
             }
             float s_sum = 0.f, t_sum = 0.f, Q = 0.f, A = 0.f;
 #pragma unroll
             for (int i = 0; i < SPL; ++i) {
                 if (sa[i].x != -INFINITY) s_sum = fmaf(sa[i].y, ex2((sa[i].x - m_s) * k2), s_sum);
-                if constexpr (REF) {
+                if constexpr (LOCA) {
                     const float mki = __fmul_rn((sa[i].x == -INFINITY) ? 0.f : sa[i].x, k2);
                     Q += sa[i].z;
                     A += sa[i].w - mki * sa[i].z;            // row = A + lse2_s * Q
@@ -431,7 +492,7 @@ row_emit_fused_kernel(const FusedParams cp) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
-                if constexpr (REF) {
+                if constexpr (LOCA) {
                     Q += __shfl_xor_sync(0xffffffffu, Q, o);
                     A += __shfl_xor_sync(0xffffffffu, A, o);
                 } else {
@@ -440,7 +501,7 @@ row_emit_fused_kernel(const FusedParams cp) {
             }
             const float lse2_s = fmaf(m_s, k2, __log2f(s_sum));
             float row;
-            if constexpr (REF) {
+            if constexpr (LOCA) {
                 row = fmaf(lse2_s, Q, A);
             } else {
                 lse2_t = fmaf(m_t, k2, __log2f(t_sum));
@@ -459,10 +520,11 @@ row_emit_fused_kernel(const FusedParams cp) {
                     row += __shfl_xor_sync(0xffffffffu, row, o);
                 }
             }
+            const float own_xlogy = own_xlogy_of();
             int claim_all = 0;
             if (DYN) claim_all = __shfl_sync(0xffffffffu, __float_as_int(sb[0].y), 0);     // slot 0 = (rank 0, warp 0)
             bool all_kept = true;
-            if constexpr (REF) {
+            if constexpr (LOCA) {
                 const float a_min = fmaf(mn, k2, -lse2_s);
                 all_kept = a_min >= thr2 + 1e-3f * (1.f + fabsf(thr2));       // NaN -> masked path
             }
@@ -472,13 +534,13 @@ row_emit_fused_kernel(const FusedParams cp) {
                 bcast[2] = Q;
                 bcast[3] = all_kept ? 1.f : 0.f;
                 bcast[4] = __int_as_float(claim_all);
-                if (rank == 0 && all_kept) p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row);
+                if (rank == 0 && all_kept) p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row + own_xlogy);
             }
         }
         named_bar_sync(bar1, WPP * 32);
         KD_STAMP(4);
         const float lse2_s = bcast[0];
-        if constexpr (!REF) lse2_t = bcast[1];
+        if constexpr (!LOCA) lse2_t = bcast[1];
         float Q = bcast[2];
         const bool all_kept = bcast[3] != 0.f;
         int64_t after_next = 0;
@@ -486,7 +548,7 @@ row_emit_fused_kernel(const FusedParams cp) {
         ph1 ^= 1;
 
         // ================= pass B' (rare): exact masked sums for rows the sp >= eps clamp touches =================
-        if constexpr (REF) {
+        if constexpr (LOCA) {
             if (!all_kept) {
                 const u64 nls = pk(-lse2_s, -lse2_s);
                 u64 accN = pk(0.f, 0.f), accM = pk(0.f, 0.f);
@@ -534,7 +596,7 @@ row_emit_fused_kernel(const FusedParams cp) {
                     qq = warp_sum(qq);
                     if (lane == 0) {
                         bcast[2] = qq;
-                        if (rank == 0) p.rowaux[r] = make_float4(lse2_t, lse2_s, qq, rr);
+                        if (rank == 0) p.rowaux[r] = make_float4(lse2_t, lse2_s, qq, rr + own_xlogy_of());
                     }
                 }
                 named_bar_sync(bar2, WPP * 32);
@@ -552,7 +614,7 @@ row_emit_fused_kernel(const FusedParams cp) {
             const float lgQ = fold ? __log2f(gQ) : 0.f;
             const u64 nls = pk(lgQ - lse2_s, lgQ - lse2_s);
             const float thrC = thr2 + lgQ;
-            const float gq = REF ? g : g * ex2(mtk - lse2_t);        // PLAIN: the parked values are relative to mt_w
+            const float gq = LOCA ? g : g * ex2(mtk - lse2_t);        // PLAIN: the parked values are relative to mt_w
             const u64 negg = pk(-gq, -gq), gQp = pk(gQ, gQ);
             T* grow = static_cast<T*>(p.grad) + r * p.ld_g + (int64_t)g_v0 * 8;
             auto sweepC = [&](auto fold_tag, auto mask_tag, auto poly_tag) {
@@ -634,10 +696,10 @@ row_emit_fused_kernel(const FusedParams cp) {
             using Yes = std::true_type;
             using No = std::false_type;
             // FMA-pipe exponentials in the common (folded, unmasked) sweep when log2(g*Q*sp) >= -126 for the whole slice
-            const bool poly_c = REF && KD_POLY_C > 0 && (fmaf(min_w, k2, lgQ - lse2_s) >= kPolyFloor);
+            const bool poly_c = LOCA && KD_POLY_C > 0 && (fmaf(min_w, k2, lgQ - lse2_s) >= kPolyFloor);
             if (fold) {
                 if (all_kept) {
-                    if (REF && KD_ECACHE) {
+                    if (LOCA && KD_ECACHE) {
                         if (next_r < p.n_rows) issue_student(next_r);       // the cached sweep reads tensor memory only
                         student_refilled = true;
                         sweepC_cached();
@@ -1390,6 +1452,7 @@ int launch_fused_v(const EmitParams& e, cudaStream_t st, bool query_only, int* c
 template <typename T>
 int launch_fused_t(const EmitParams& e, int variant, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
     if (variant == KD_LOCA_REFERENCE) return launch_fused_v<KD_LOCA_REFERENCE, T>(e, st, query_only, capacity, launched, first_free);
+    if (variant == KD_LOCA_PER_ROW) return launch_fused_v<KD_LOCA_PER_ROW, T>(e, st, query_only, capacity, launched, first_free);
     return launch_fused_v<KD_KL_PLAIN, T>(e, st, query_only, capacity, launched, first_free);
 }
 
@@ -1475,6 +1538,8 @@ bool fused_applies(const EmitParams& p, int variant, int dtype) {
     if (!fused_mode()) return false;
     if (variant == KD_LOCA_REFERENCE) {
         if (!(p.alpha >= 0.f && p.alpha <= 1.f)) return false;      // overrides outside [0, 1]: exact per-cell path
+    } else if (variant == KD_LOCA_PER_ROW) {
+        if (!p.lse2_t_in || !p.records) return false;               // needs phase A (teacher statistics + token records)
     } else if (variant != KD_KL_PLAIN) {
         return false;
     }
@@ -1483,7 +1548,7 @@ bool fused_applies(const EmitParams& p, int variant, int dtype) {
 
 int launch_emit_fused(const EmitParams& p, int variant, int dtype, cudaStream_t stream, bool query_only, int* capacity,
                       int* clusters_launched, int* first_free_row, int* rows_in_flight) {
-    if (fused_mode() >= 2) {
+    if (fused_mode() >= 2 && variant != KD_LOCA_PER_ROW) {
         if (rows_in_flight) *rows_in_flight = 1;
         const int rc = (dtype == KD_DTYPE_BF16)
                            ? launch_pipe_t<__nv_bfloat16>(p, variant, stream, query_only, capacity, clusters_launched, first_free_row)
