@@ -108,6 +108,7 @@ int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clu
 // two-sweep kernel with the q values parked in tensor memory (logit_kd_fused.cu): applies to KD_LOCA_REFERENCE with
 // 0 <= alpha <= 1 and to KD_KL_PLAIN on 16-bit logits; same launch shape as the cluster kernel (clusters of 8, 2 pipelines)
 bool fused_applies(const EmitParams& p, int variant, int dtype);
+int fused_cluster_size();      // CTAs per cluster chosen by the last launch_emit_fused call (8 or 9)
 int launch_emit_fused(const EmitParams& p, int variant, int dtype, cudaStream_t stream, bool query_only, int* capacity,
                       int* clusters_launched, int* first_free_row, int* rows_in_flight /* per cluster: 1 or 2 pipelines */);
 

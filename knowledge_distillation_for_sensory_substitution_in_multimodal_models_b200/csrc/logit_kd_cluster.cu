@@ -818,7 +818,7 @@ int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clu
     if (fused_applies(p, variant, dtype) && launch_emit_fused(p, variant, dtype, nullptr, true, &cap, nullptr, nullptr, &in_flight) == KD_OK && cap >= 1) {
         const int64_t want2 = (p.n_rows + in_flight - 1) / in_flight;
         *n_clusters = (int)(want2 < cap ? want2 : cap);
-        *ctas_per_cluster = 8;
+        *ctas_per_cluster = fused_cluster_size();
         *pipelines = in_flight;
         *static_rows = in_flight == 1 ? 3 : 4;       // pipelined kernel: 3 rows; two pipelines: 2 rows each
         return KD_OK;

@@ -102,6 +102,11 @@ __device__ __forceinline__ uint4 lds128_ep(uint32_t addr, uint32_t epoch) {     
     asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];  // epoch %5" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "r"(epoch));
     return v;
 }
+// one-instruction warp max / min of floats through an order-preserving integer key (redux.sync); NaN is not ordered
+__device__ __forceinline__ int fkey(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
+__device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+__device__ __forceinline__ float warp_max_redux(float v) { return fkey_inv(__reduce_max_sync(0xffffffffu, fkey(v))); }
+__device__ __forceinline__ float warp_min_redux(float v) { return fkey_inv(__reduce_min_sync(0xffffffffu, fkey(v))); }
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -118,7 +123,6 @@ row_emit_fused_kernel(const FusedParams cp) {
     constexpr int NSLOT = CS * WPP;
     constexpr uint32_t RED1_BYTES = NSLOT * (LOCA ? 24 : 32);
     constexpr uint32_t RED2_BYTES = NSLOT * 8;
-    static_assert(NSLOT % 32 == 0, "the fold assumes whole warps of slots");
     extern __shared__ __align__(128) unsigned char smem[];
     const EmitParams& p = cp.e;
     const FusedPlan<VARIANT, CS, NPIPE> plan(cp.vpc);
@@ -276,16 +280,19 @@ row_emit_fused_kernel(const FusedParams cp) {
                     tmax2 = Pair<T>::vmax(tmax2, Pair<T>::vmax(Pair<T>::vmax(rt.x, rt.y), Pair<T>::vmax(rt.z, rt.w)));
                 }
             }
+            // (student max, -student min) [LoCa] or (student max, teacher max) [plain KL] ride one packed butterfly
+            smax2 = Pair<T>::vmax(smax2, __byte_perm(smax2, smax2, 0x1032));                 // both halves: the lane's maximum
+            uint32_t other;
+            if constexpr (LOCA) other = Pair<T>::vmin(smin2, __byte_perm(smin2, smin2, 0x1032)) ^ 0x80008000u;      // -min (exact)
+            else other = Pair<T>::vmax(tmax2, __byte_perm(tmax2, tmax2, 0x1032));
+            uint32_t both = __byte_perm(smax2, other, 0x7610);                                // low half: student max, high half: the other
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) both = Pair<T>::vmax(both, __shfl_xor_sync(0xffffffffu, both, o));
             float lo, hi;
-            upk(Pair<T>::widen(smax2), lo, hi);
-            m_w = warp_max(fmaxf(lo, hi));
-            if constexpr (LOCA) {
-                upk(Pair<T>::widen(smin2), lo, hi);
-                min_w = warp_min(fminf(lo, hi));
-            } else {
-                upk(Pair<T>::widen(tmax2), lo, hi);
-                mt_w = warp_max(fmaxf(lo, hi));
-            }
+            upk(Pair<T>::widen(both), lo, hi);
+            m_w = lo;
+            if constexpr (LOCA) min_w = -hi;
+            else mt_w = hi;
         }
         KD_STAMP(2);
         if constexpr (NPIPE == 2) {
@@ -460,23 +467,25 @@ row_emit_fused_kernel(const FusedParams cp) {
             mbar_wait_cta(bar_red1, ph1);
             KD_STAMP(7);
             if (lane == 0) mbar_expect_tx(bar_red1, RED1_BYTES);      // arm the next row's phase
-            constexpr int SPL = NSLOT / 32;                            // slots per lane
+            constexpr int SPL = (NSLOT + 31) / 32;                     // slots per lane (the last ones may not exist: neutral values)
             float4 sa[SPL], sb[SPL];
             float m_s = -INFINITY, m_t = -INFINITY, mn = INFINITY;
 #pragma unroll
             for (int i = 0; i < SPL; ++i) {
-                sa[i] = slot_v[2 * (lane + 32 * i)];
-                sb[i] = slot_v[2 * (lane + 32 * i) + 1];
+                const int idx = lane + 32 * i;
+                sa[i] = make_float4(-INFINITY, 0.f, 0.f, 0.f);
+                sb[i] = make_float4(INFINITY, 0.f, -INFINITY, 0.f);
+                if (NSLOT % 32 == 0 || idx < NSLOT) {
+                    sa[i] = slot_v[2 * idx];
+                    sb[i] = slot_v[2 * idx + 1];
+                }
                 m_s = fmaxf(m_s, sa[i].x);
                 if constexpr (LOCA) mn = fminf(mn, sb[i].x);
                 else m_t = fmaxf(m_t, sb[i].z);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {          // independent butterflies, interleaved
-                m_s = fmaxf(m_s, __shfl_xor_sync(0xffffffffu, m_s, o));
-                if constexpr (LOCA) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                else m_t = fmaxf(m_t, __shfl_xor_sync(0xffffffffu, m_t, o));
-            }
+            m_s = warp_max_redux(m_s);
+            if constexpr (LOCA) mn = warp_min_redux(mn);
+            else m_t = warp_max_redux(m_t);
             float s_sum = 0.f, t_sum = 0.f, Q = 0.f, A = 0.f;
 #pragma unroll
             for (int i = 0; i < SPL; ++i) {
@@ -587,10 +596,13 @@ row_emit_fused_kernel(const FusedParams cp) {
                     if (lane == 0) mbar_expect_tx(bar_red2, RED2_BYTES);
                     float rr = 0.f, qq = 0.f;
 #pragma unroll
-                    for (int i = 0; i < NSLOT / 32; ++i) {
-                        const float4 sb = slot_v[2 * (lane + 32 * i) + 1];
-                        rr += sb.z;
-                        qq += sb.w;
+                    for (int i = 0; i < (NSLOT + 31) / 32; ++i) {
+                        const int idx = lane + 32 * i;
+                        if (NSLOT % 32 == 0 || idx < NSLOT) {
+                            const float4 sb = slot_v[2 * idx + 1];
+                            rr += sb.z;
+                            qq += sb.w;
+                        }
                     }
                     rr = warp_sum(rr);
                     qq = warp_sum(qq);
@@ -1359,9 +1371,9 @@ row_emit_pipelined_kernel(const FusedParams cp) {
 }
 
 // --------------------------------------------------------------------------------------------------------
-template <int VARIANT, typename T, bool DYN>
+template <int VARIANT, typename T, int CS, bool DYN>
 int launch_fused_d(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
-    constexpr int CS = 8, NPIPE = 2;
+    constexpr int NPIPE = 2;
     auto kfn = row_emit_fused_kernel<VARIANT, T, CS, NPIPE, DYN>;
     const int nvec = e.V / 8;
     const int vpc = (nvec + CS - 1) / CS;
@@ -1391,6 +1403,10 @@ int launch_fused_d(const EmitParams& e, cudaStream_t st, bool query_only, int* c
     if (configured_dev != dev) {
         err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(fused kernel smem)");
+        if (CS > 8) {       // clusters of 9 are "non-portable": B200 co-schedules 15 of them (135 SMs) against 15 x 8 = 120
+            err = cudaFuncSetAttribute(kfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (err != cudaSuccess) { cudaGetLastError(); return KD_ERR_UNSUPPORTED; }
+        }
         cfg.gridDim = dim3(CS * 64);
         err = cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg);
         if (err != cudaSuccess || max_clusters < 1) {
@@ -1443,10 +1459,26 @@ int launch_fused_d(const EmitParams& e, cudaStream_t st, bool query_only, int* c
     return KD_OK;
 }
 
+template <int VARIANT, typename T, int CS>
+int launch_fused_c(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
+    if (e.row_queue) return launch_fused_d<VARIANT, T, CS, true>(e, st, query_only, capacity, launched, first_free);
+    return launch_fused_d<VARIANT, T, CS, false>(e, st, query_only, capacity, launched, first_free);
+}
+
+// cluster size: whichever of 8 / 9 puts more SMs to work for this shape (KD_CLUSTER_SIZE=8|9 forces one)
+int g_last_cluster_size = 8;
 template <int VARIANT, typename T>
 int launch_fused_v(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
-    if (e.row_queue) return launch_fused_d<VARIANT, T, true>(e, st, query_only, capacity, launched, first_free);
-    return launch_fused_d<VARIANT, T, false>(e, st, query_only, capacity, launched, first_free);
+    static int forced = -1;
+    if (forced < 0) { const char* ev = getenv("KD_CLUSTER_SIZE"); forced = ev ? atoi(ev) : 0; }
+    int cap8 = 0, cap9 = 0;
+    const int rc8 = (forced == 9) ? KD_ERR_UNSUPPORTED : launch_fused_c<VARIANT, T, 8>(e, st, true, &cap8, nullptr, nullptr);
+    const int rc9 = (forced == 8) ? KD_ERR_UNSUPPORTED : launch_fused_c<VARIANT, T, 9>(e, st, true, &cap9, nullptr, nullptr);
+    const bool use9 = (rc9 == KD_OK) && (rc8 != KD_OK || cap9 * 9 > cap8 * 8);
+    if (!use9 && rc8 != KD_OK) return rc8;
+    g_last_cluster_size = use9 ? 9 : 8;
+    if (use9) return launch_fused_c<VARIANT, T, 9>(e, st, query_only, capacity, launched, first_free);
+    return launch_fused_c<VARIANT, T, 8>(e, st, query_only, capacity, launched, first_free);
 }
 
 template <typename T>
@@ -1546,8 +1578,11 @@ bool fused_applies(const EmitParams& p, int variant, int dtype) {
     return dtype == KD_DTYPE_BF16 || dtype == KD_DTYPE_F16;
 }
 
+int fused_cluster_size() { return g_last_cluster_size; }
+
 int launch_emit_fused(const EmitParams& p, int variant, int dtype, cudaStream_t stream, bool query_only, int* capacity,
                       int* clusters_launched, int* first_free_row, int* rows_in_flight) {
+    g_last_cluster_size = 8;
     if (fused_mode() >= 2 && variant != KD_LOCA_PER_ROW) {
         if (rows_in_flight) *rows_in_flight = 1;
         const int rc = (dtype == KD_DTYPE_BF16)

@@ -10,9 +10,9 @@ int main() {
     printf("name=%s sms=%d l2=%d MB smem_optin=%zu regs/sm=%d clock=%d kHz mem_clock=%d kHz bus=%d\n", pr.name,
            pr.multiProcessorCount, pr.l2CacheSize >> 20, pr.sharedMemPerBlockOptin, pr.regsPerMultiprocessor, pr.clockRate,
            pr.memoryClockRate, pr.memoryBusWidth);
-    const int sizes[] = {1, 2, 4, 8, 16};
-    const int smems[] = {48 * 1024, 100 * 1024, 160 * 1024, 200 * 1024, 227 * 1024};
-    const int threads[] = {256, 512, 1024};
+    const int sizes[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16};
+    const int smems[] = {160 * 1024, 200 * 1024, 227 * 1024};
+    const int threads[] = {512};
     cudaFuncSetAttribute(dummy_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     for (int cs : sizes)
         for (int sm : smems)
