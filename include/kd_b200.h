@@ -120,6 +120,38 @@ int kd_logit_kd_regrad(const void* teacher, int64_t ld_t, const void* student, i
                        int dtype, float T, float eps, int variant, double inv_norm, const float* upstream,
                        const float* skip_if_one, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------
+ * Vocabulary-sharded logit KD (BASELINE.json configs[4]): every rank holds all n_rows rows but only
+ * columns [col0, col0 + V_local) of both logit tensors.  Same reference methods as above (P1:141-194, P1:331-343,
+ * FB:206-219); the per-row quantities that couple the shards cross ranks twice, the caller does the two collectives:
+ *   kd_vshard_stats   -> stats[n_rows][12] floats  (local max/sum-exp of both rows, local best + runner-up teacher cells
+ *                        with GLOBAL column indices, the teacher logit at the label if this shard owns it)
+ *   [all-gather the stats blocks in shard order: stats_all[n_shards][n_rows][12]]
+ *   kd_vshard_combine -> lse2[n_rows][2] = (lse2_t, lse2_s), token records (global indices, P1:166-185), rowconst[n_rows]
+ *                        (per-row mode: xlogy(v,v) of the row's own override cells in log2 units; NaN for a bad label)
+ *   [as-written mode: kd_loca_build_table(records, n_rows, V_total, ...) — every rank holds all rows]
+ *   kd_vshard_accum   -> partial[n_rows][2] = (local part of the row sum in log2 units [natural for KD_KL_LOG_TARGET],
+ *                        local part of Q_r)
+ *   [all-reduce(SUM) Q_r over the shards]
+ *   kd_vshard_emit    -> gradient of the local columns: upstream * T * inv_norm * (sp * Q_r - w)
+ *   loss = T^2 * inv_norm * ( unit * sum over shards and rows of partial.row + ln2 * sum_r rowconst + n_rows * table_consts[0] ),
+ *   unit = ln2 (1 for KD_KL_LOG_TARGET).  `table` is the full V_total-entry table (the kernels index it at col0 + c).
+ * ---------------------------------------------------------------------------------------------------- */
+#define KD_VSHARD_STAT_WORDS 12
+int kd_vshard_stats(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* labels /* may be NULL */,
+                    int64_t col0, float* stats, int64_t n_rows, int64_t V_local, int dtype, float T, void* stream);
+int kd_vshard_combine(const float* stats_all, int n_shards, int64_t n_rows, const int64_t* labels, int64_t V_total, float T,
+                      float alpha, int variant, kd_token_record* records, float* lse2, float* rowconst, uint32_t* status,
+                      void* stream);
+int kd_vshard_accum(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const float* lse2,
+                    const kd_token_record* records, const float* table, int64_t col0, float* partial, int64_t n_rows,
+                    int64_t V_local, int dtype, float T, float eps, int variant, void* stream);
+int kd_vshard_emit(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const float* lse2, const float* Q_rows,
+                   const kd_token_record* records, const float* table, int64_t col0, void* grad_student, int64_t ld_g,
+                   int64_t n_rows, int64_t V_local, int dtype, float T, float eps, int variant, double inv_norm,
+                   const float* upstream, void* stream);
+
 /* grad *= (*factor) in place, skipped on device when *factor == 1 (kept for callers that accept double rounding). */
 int kd_scale_rows(void* grad, int64_t ld_g, int64_t n_rows, int64_t V, int dtype, const float* factor, void* stream);
 

@@ -20,6 +20,7 @@ LOCA_REFERENCE, LOCA_PER_ROW, KL_PLAIN, KL_LOG_TARGET = 0, 1, 2, 3
 FLAG_NO_GRAD, FLAG_FORCE_STREAMING = 1, 2
 STATUS_BAD_LABEL = 1
 TOKEN_RECORD_BYTES = 16
+VSHARD_STAT_WORDS = 12
 
 _p, _i64, _sz, _f, _d, _i, _u = C.c_void_p, C.c_int64, C.c_size_t, C.c_float, C.c_double, C.c_int, C.c_uint
 
@@ -38,6 +39,10 @@ SIGNATURES = {
     "kd_loca_emit": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i, _f, _f, _d, _p, _u, _p]),
     "kd_logit_kd_regrad": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _sz, _i64, _i64, _i, _f, _f, _i, _d, _p, _p, _p]),
     "kd_scale_rows": (_i, [_p, _i64, _i64, _i64, _i, _p, _p]),
+    "kd_vshard_stats": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i, _f, _p]),
+    "kd_vshard_combine": (_i, [_p, _i, _i64, _p, _i64, _f, _f, _i, _p, _p, _p, _p, _p]),
+    "kd_vshard_accum": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i, _f, _f, _i, _p]),
+    "kd_vshard_emit": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i, _f, _f, _i, _d, _p, _p]),
     "kd_info_nce_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "kd_info_nce_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i64, _i64, _i64, _i, _f, _p, _u, _p]),
     "kd_info_nce_regrad": (_i, [_p, _sz, _p, _i64, _i64, _i64, _i, _p, _p]),

@@ -148,3 +148,134 @@ def per_row_token_sharded(fn, teacher, student, *args, group=None, reduce_loss=T
         dist.all_reduce(red, group=group)
         loss = loss + (red - loss.detach())       # value = global sum, gradient = local path
     return loss
+
+
+# =====================================================================================================================
+# Vocabulary-sharded execution (BASELINE.json configs[4]): every rank holds ALL rows but only columns
+# [col0, col0 + V_local) of both logit tensors — what a vocabulary-parallel lm_head produces.  Two exchanges per step:
+# an all-gather of 48-byte per-row statistics and an all-reduce of one float per row (Q_r); the loss is a scalar sum.
+# =====================================================================================================================
+
+_VS_VARIANTS = {"reference": _lib.LOCA_REFERENCE, "per_row": _lib.LOCA_PER_ROW, "kl": _lib.KL_PLAIN,
+                "kl_log_target": _lib.KL_LOG_TARGET}
+_LN2 = 0.6931471805599453
+
+
+class CudaVocabPhases:
+    """The four phase calls of the vocabulary-sharded path (kd_vshard_stats / _combine / _accum / _emit)."""
+
+    def stats(self, teacher, student, labels, col0, T):
+        dev = student.device
+        n, v_local = student.shape
+        out = torch.empty((n, _lib.VSHARD_STAT_WORDS), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().kd_vshard_stats(teacher.data_ptr(), teacher.stride(0), student.data_ptr(), student.stride(0),
+                                                   labels.data_ptr() if labels is not None else None, int(col0), out.data_ptr(),
+                                                   n, v_local, _dtype_code(student), float(T), _stream_ptr(dev)))
+        return out
+
+    def combine(self, stats_all, labels, V_total, T, alpha, variant):
+        dev = stats_all.device
+        g, n = stats_all.shape[0], stats_all.shape[1]
+        rec = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        lse2 = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        rowconst = torch.empty((n,), dtype=torch.float32, device=dev)
+        status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().kd_vshard_combine(stats_all.data_ptr(), g, n, labels.data_ptr() if labels is not None else None,
+                                                     int(V_total), float(T), float(alpha), variant, rec.data_ptr(), lse2.data_ptr(),
+                                                     rowconst.data_ptr(), status.data_ptr(), _stream_ptr(dev)))
+        return rec, lse2, rowconst, status
+
+    def build_table(self, records, V_total):
+        return CudaPhases().build_table(records, V_total)
+
+    def accum(self, teacher, student, lse2, rec, table, col0, T, eps, variant):
+        dev = student.device
+        n, v_local = student.shape
+        partial = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().kd_vshard_accum(teacher.data_ptr(), teacher.stride(0), student.data_ptr(), student.stride(0),
+                                                   lse2.data_ptr(), rec.data_ptr(), table.data_ptr() if table is not None else None,
+                                                   int(col0), partial.data_ptr(), n, v_local, _dtype_code(student), float(T),
+                                                   float(eps), variant, _stream_ptr(dev)))
+        return partial
+
+    def emit(self, teacher, student, lse2, q_rows, rec, table, col0, T, eps, variant, inv_norm, upstream):
+        dev = student.device
+        n, v_local = student.shape
+        grad = torch.empty((n, v_local), dtype=student.dtype, device=dev)
+        up_t, up_ptr = _upstream_ptr(upstream, dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().kd_vshard_emit(teacher.data_ptr(), teacher.stride(0), student.data_ptr(), student.stride(0),
+                                                  lse2.data_ptr(), q_rows.data_ptr(), rec.data_ptr(),
+                                                  table.data_ptr() if table is not None else None, int(col0), grad.data_ptr(),
+                                                  grad.stride(0), n, v_local, _dtype_code(student), float(T), float(eps), variant,
+                                                  float(inv_norm), up_ptr, _stream_ptr(dev)))
+        return grad
+
+
+class DistCollectives:
+    """The two data-path exchanges + the scalar loss sum over ``group`` (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def gather_stats(self, stats: torch.Tensor) -> torch.Tensor:
+        if not self.active:
+            return stats.unsqueeze(0)
+        world = dist.get_world_size(self.group)
+        out = torch.empty((world * stats.shape[0],) + tuple(stats.shape[1:]), dtype=stats.dtype, device=stats.device)
+        dist.all_gather_into_tensor(out, stats.contiguous(), group=self.group)      # concatenated along dim 0, shard-major
+        return out.view((world,) + tuple(stats.shape))
+
+    def sum_(self, x: torch.Tensor) -> torch.Tensor:
+        if self.active:
+            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
+        return x
+
+
+def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, T, mode="reference", alpha=0.8, eps=1e-8,
+                           n_rows_norm=None, reduction="mean", upstream=None, group=None, phases=None, collectives=None,
+                           want_grad=True):
+    """Logit KD over logits sharded along the vocabulary.
+
+    ``teacher_shard`` / ``student_shard``: this rank's columns ``[col0, col0 + V_local)`` of all rows; ``labels``: all rows'
+    labels (LoCa modes), global class indices.  ``mode``: ``"reference"`` (as written, P1:184-185), ``"per_row"``, ``"kl"``
+    (P1:331-343) or ``"kl_log_target"`` (FB:206-219).  Returns ``(loss, grad_shard)``: the GLOBAL loss (identical on every
+    rank) and the gradient w.r.t. this rank's student columns.
+    """
+    variant = _VS_VARIANTS[mode]
+    if phases is None:
+        phases = CudaVocabPhases()
+        _require_cuda(teacher_shard, student_shard, labels)
+    if collectives is None:
+        collectives = DistCollectives(group)
+    t2, s2 = _rows(teacher_shard), _rows(student_shard)
+    n = s2.shape[0]
+    loca = variant in (_lib.LOCA_REFERENCE, _lib.LOCA_PER_ROW)
+    lab = labels.reshape(-1).to(torch.int64).contiguous() if (loca and labels is not None) else None
+    if loca and lab is None:
+        raise ValueError("the LoCa modes need labels")
+    if reduction == "mean":
+        inv_norm = 1.0 / (float(n if n_rows_norm is None else n_rows_norm) * float(V_total))
+    elif reduction == "batchmean":
+        inv_norm = 1.0 / float(n if n_rows_norm is None else n_rows_norm)
+    else:
+        raise ValueError(f"unknown reduction {reduction!r}")
+
+    stats = phases.stats(t2, s2, lab, col0, T)
+    stats_all = collectives.gather_stats(stats)                             # exchange 1: [G, n, 12]
+    rec, lse2, rowconst, _status = phases.combine(stats_all, lab, V_total, T, alpha, variant)
+    table, table_const = None, 0.0
+    if variant == _lib.LOCA_REFERENCE:
+        table, consts = phases.build_table(rec, V_total)
+        table_const = consts[0].double() if consts is not None else 0.0
+    partial = phases.accum(t2, s2, lse2, rec, table, col0, T, eps, variant)
+    q_rows = collectives.sum_(partial[:, 1].contiguous())                    # exchange 2: Q_r
+    grad = phases.emit(t2, s2, lse2, q_rows, rec, table, col0, T, eps, variant, inv_norm, upstream) if want_grad else None
+    unit = 1.0 if variant == _lib.KL_LOG_TARGET else _LN2
+    rows = collectives.sum_(partial[:, 0].double().sum().reshape(1) * unit)[0]
+    loss = (rows + rowconst.double().sum() * _LN2 + float(n) * table_const) * (float(T) * float(T) * inv_norm)
+    return loss.float(), grad
