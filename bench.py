@@ -185,6 +185,8 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the per_row / KL / InfoNCE / MSE side measurements")
     ap.add_argument("--force-streaming", action="store_true", help="time the general streaming emit kernel instead of the cluster kernel")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1, as-written mode: record all-gather by peer stores from the phase-A kernel (NVLink symmetric memory) or by NCCL")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -215,6 +217,18 @@ def main() -> None:
     student.requires_grad_(True)
     n_total = N * world
     phases = sharded.CudaPhases()
+    exchange = args.exchange if world > 1 else "none"
+    if world > 1 and mode == "reference" and exchange == "peer":
+        try:        # symmetric memory needs P2P access between the ranks' GPUs; fall back to the NCCL all-gather otherwise
+            sharded.loca_kl_token_sharded(teacher[:64], student.detach()[:64], labels[:64], T_KD, ALPHA, phases=phases, exchange="peer")
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] peer exchange unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+            exchange = "nccl"
+        flag = torch.tensor([1 if exchange == "peer" else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange = "peer" if int(flag.item()) == 1 else "nccl"
 
     def step():
         """The public call a user makes: forward + backward through the autograd Function(s)."""
@@ -223,7 +237,7 @@ def main() -> None:
             loss = kd.loca_kl(teacher, student, labels, T_KD, alpha=ALPHA, mode=mode)
             loss.backward()
         elif mode == "reference":
-            loss, grad = sharded.loca_kl_token_sharded(teacher, student.detach(), labels, T_KD, ALPHA, phases=phases)
+            loss, grad = sharded.loca_kl_token_sharded(teacher, student.detach(), labels, T_KD, ALPHA, phases=phases, exchange=exchange)
             student.grad = grad
         else:
             loss = sharded.per_row_token_sharded(kd.loca_kl, teacher, student, labels, T_KD, alpha=ALPHA, mode="per_row")
@@ -413,6 +427,8 @@ def main() -> None:
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"LoCa logit-KD fwd+bwd, B=8,S=2048 ({N} rows/GPU), V={V}, T={T_KD}, alpha={ALPHA}",
                        "mode": mode, "parallelism": f"token-sharded x{world}" if world > 1 else "single GPU",
+                       **({"exchange": "phase A stores records into every rank's buffer over NVLink (symmetric memory) + device barrier"
+                           if exchange == "peer" else "NCCL all-gather of 16 B/token records"} if (world > 1 and mode == "reference") else {}),
                        "l2": "inputs (2 x 4.98 GB/GPU) exceed the 126 MB L2; no flush needed"},
             "loss": loss_value, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary(), "secondary": side,

@@ -100,6 +100,13 @@ typedef struct {
 int kd_loca_teacher_stats(const void* teacher, int64_t ld_t, const int64_t* labels, kd_token_record* records,
                           float* lse2_t, uint32_t* status, int64_t n_rows, int64_t V, int dtype, float T,
                           float alpha, void* stream);
+/* Phase A fused with the record all-gather: every record is stored into peer_records[g][row_offset + r] for all n_peers ranks
+ * (device array of device pointers to each rank's [n_tokens_all] record buffer — peer-mapped memory, e.g. CUDA IPC / symmetric
+ * memory over NVLink — including this rank's own).  The caller separates phase A from kd_loca_build_table with a cross-GPU
+ * barrier; no NCCL all-gather is needed. */
+int kd_loca_teacher_stats_peers(const void* teacher, int64_t ld_t, const int64_t* labels, kd_token_record* const* peer_records,
+                                int n_peers, int64_t row_offset, float* lse2_t, uint32_t* status, int64_t n_rows, int64_t V,
+                                int dtype, float T, float alpha, void* stream);
 int kd_loca_table_workspace_bytes(int64_t V, size_t* bytes);
 int kd_loca_build_table(const kd_token_record* records_all, int64_t n_tokens_all, int64_t V, float* table,
                         double* table_consts /* [2]: sum xlogy(ov,ov), sum ov */, void* workspace,

@@ -34,6 +34,7 @@ SIGNATURES = {
     "kd_logit_kd_rowaux_offset": (_i, [_i64, _i64, C.POINTER(_sz)]),
     "kd_logit_kd_fwd_bwd": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _sz, _i64, _i64, _i, _f, _f, _f, _i, _d, _p, _u, _p]),
     "kd_loca_teacher_stats": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _p]),
+    "kd_loca_teacher_stats_peers": (_i, [_p, _i64, _p, _p, _i, _i64, _p, _p, _i64, _i64, _i, _f, _f, _p]),
     "kd_loca_table_workspace_bytes": (_i, [_i64, C.POINTER(_sz)]),
     "kd_loca_build_table": (_i, [_p, _i64, _i64, _p, _p, _p, _sz, _p]),
     "kd_loca_emit": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i, _f, _f, _d, _p, _u, _p]),

@@ -231,7 +231,8 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(kStatsThreads)
 teacher_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const int64_t* __restrict__ labels,
                      kd_token_record* __restrict__ rec, float* __restrict__ lse2_t, uint32_t* status,
-                     int64_t n_rows, int V, float k2, float alpha) {
+                     int64_t n_rows, int V, float k2, float alpha, kd_token_record* const* __restrict__ peers, int n_peers,
+                     int64_t row_offset) {
     __shared__ float smf[2 * kMaxWarps];
     __shared__ int smi[2 * kMaxWarps];
     __shared__ int thr_shared[2];        // CTA-wide runner-up bound, one slot per row parity
@@ -265,7 +266,12 @@ teacher_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const int64_t*
                 out.k = (V > 1) ? top.i2 : 0;
                 out.v2 = v2;
             }
-            rec[r] = out;
+            if (peers) {        // fused all-gather: the record goes straight into every rank's buffer (peer stores over NVLink)
+                // (visibility to the peers: kernel completion in stream order + the system-scope release of the barrier that follows)
+                for (int gp = 0; gp < n_peers; ++gp) peers[gp][row_offset + r] = out;
+            } else {
+                rec[r] = out;
+            }
             lse2_t[r] = l2;
         }
     }
@@ -856,14 +862,15 @@ bool rows_vectorizable(const void* base, int64_t ld) {
 
 template <typename T>
 int launch_teacher_stats(const void* teacher, int64_t ld_t, const int64_t* labels, kd_token_record* rec, float* lse2_t,
-                         uint32_t* status, int64_t n_rows, int V, float k2, float alpha, cudaStream_t st) {
+                         uint32_t* status, int64_t n_rows, int V, float k2, float alpha, cudaStream_t st,
+                         kd_token_record* const* peers = nullptr, int n_peers = 0, int64_t row_offset = 0) {
     if constexpr (sizeof(T) == 2) {
         // KD_STATS_TMA=1 selects the TMA-fed kernel.  Measured on B200 (16 384 x 151 936 bf16): 1.046 ms at best (512 consumers,
         // 3 stages, 2 CTAs/SM) against 0.998 ms for the register-staged kernel — phase A is bound by issue slots + the XU pipe at
         // limited occupancy, not by load latency — so the register-staged kernel stays the default.
         static int use_tma = -1;
         if (use_tma < 0) { const char* e = getenv("KD_STATS_TMA"); use_tma = e ? atoi(e) : 0; }
-        if (use_tma && rows_vectorizable<T>(teacher, ld_t) && V % 8 == 0 && V >= 8 * kTmaConsumers) {
+        if (use_tma && !peers && rows_vectorizable<T>(teacher, ld_t) && V % 8 == 0 && V >= 8 * kTmaConsumers) {
             auto kfn = teacher_stats_tma_kernel<T>;
             const int smem = kTmaStages * kTmaChunkVec * 16;
             static bool configured = false;
@@ -882,10 +889,10 @@ int launch_teacher_stats(const void* teacher, int64_t ld_t, const int64_t* label
     const int grid = static_cast<int>(n_rows < (int64_t)sm_count() * 8 ? n_rows : (int64_t)sm_count() * 8);
     if (rows_vectorizable<T>(teacher, ld_t))
         teacher_stats_kernel<T, true><<<grid, kStatsThreads, 0, st>>>(static_cast<const T*>(teacher), ld_t, labels, rec,
-                                                                      lse2_t, status, n_rows, V, k2, alpha);
+                                                                      lse2_t, status, n_rows, V, k2, alpha, peers, n_peers, row_offset);
     else
         teacher_stats_kernel<T, false><<<grid, kStatsThreads, 0, st>>>(static_cast<const T*>(teacher), ld_t, labels, rec,
-                                                                       lse2_t, status, n_rows, V, k2, alpha);
+                                                                       lse2_t, status, n_rows, V, k2, alpha, peers, n_peers, row_offset);
     KD_CHECK_LAUNCH("teacher_stats_kernel");
     return KD_OK;
 }
@@ -1074,6 +1081,23 @@ int kd_loca_teacher_stats(const void* teacher, int64_t ld_t, const int64_t* labe
         case KD_DTYPE_BF16: return launch_teacher_stats<__nv_bfloat16>(teacher, ld_t, labels, records, lse2_t, status, n_rows, (int)V, k2, alpha, st);
         case KD_DTYPE_F16: return launch_teacher_stats<__half>(teacher, ld_t, labels, records, lse2_t, status, n_rows, (int)V, k2, alpha, st);
         default: return launch_teacher_stats<float>(teacher, ld_t, labels, records, lse2_t, status, n_rows, (int)V, k2, alpha, st);
+    }
+}
+
+int kd_loca_teacher_stats_peers(const void* teacher, int64_t ld_t, const int64_t* labels, kd_token_record* const* peer_records,
+                                int n_peers, int64_t row_offset, float* lse2_t, uint32_t* status, int64_t n_rows, int64_t V,
+                                int dtype, float T, float alpha, void* stream) {
+    if (int rc = check_common(n_rows, V, dtype, T)) return rc;
+    KD_CHECK_ARG(teacher && labels && peer_records && lse2_t && status, "kd_loca_teacher_stats_peers: null pointer");
+    KD_CHECK_ARG(n_peers >= 1 && row_offset >= 0, "kd_loca_teacher_stats_peers: bad peer layout");
+    KD_CHECK_ARG(ld_t >= V, "teacher leading dimension %lld < V %lld", (long long)ld_t, (long long)V);
+    if (n_rows == 0) return KD_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float k2 = kLog2e / T;
+    switch (dtype) {
+        case KD_DTYPE_BF16: return launch_teacher_stats<__nv_bfloat16>(teacher, ld_t, labels, nullptr, lse2_t, status, n_rows, (int)V, k2, alpha, st, peer_records, n_peers, row_offset);
+        case KD_DTYPE_F16: return launch_teacher_stats<__half>(teacher, ld_t, labels, nullptr, lse2_t, status, n_rows, (int)V, k2, alpha, st, peer_records, n_peers, row_offset);
+        default: return launch_teacher_stats<float>(teacher, ld_t, labels, nullptr, lse2_t, status, n_rows, (int)V, k2, alpha, st, peer_records, n_peers, row_offset);
     }
 }
 

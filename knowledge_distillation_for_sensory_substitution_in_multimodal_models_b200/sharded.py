@@ -35,6 +35,19 @@ class CudaPhases:
                                                          _dtype_code(teacher), float(T), float(alpha), _stream_ptr(dev)))
         return rec, lse2, status
 
+    def teacher_stats_peers(self, teacher, labels, T, alpha, V, peer_ptrs_dev, n_peers, row_offset):
+        """Phase A that stores its records into every rank's buffer (peer-mapped memory) instead of a local one."""
+        dev = teacher.device
+        n = teacher.shape[0]
+        lse2 = torch.empty((n,), dtype=torch.float32, device=dev)
+        status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().kd_loca_teacher_stats_peers(teacher.data_ptr(), teacher.stride(0), labels.data_ptr(),
+                                                               int(peer_ptrs_dev), int(n_peers), int(row_offset), lse2.data_ptr(),
+                                                               status.data_ptr(), n, V, _dtype_code(teacher), float(T), float(alpha),
+                                                               _stream_ptr(dev)))
+        return lse2, status
+
     def build_table(self, records_all, V):
         dev = records_all.device
         table = torch.empty((V,), dtype=torch.float32, device=dev)
@@ -105,14 +118,55 @@ def gather_records(records: torch.Tensor, group=None, counts=None) -> torch.Tens
     return torch.cat([b[:c] for b, c in zip(blocks, counts)], dim=0).contiguous()
 
 
+class PeerRecordExchange:
+    """Record all-gather fused into phase A over NVLink peer memory (torch symmetric memory).
+
+    Every rank owns two [n_total, 4] int32 record buffers in symmetric memory, used alternately step by step; the phase-A
+    kernel of rank g stores its records at rows [offset_g, offset_g + n_g) of EVERY rank's current buffer (16-byte peer stores),
+    and a device-side barrier on the launch stream separates phase A from the table build.  Two buffers are enough: to write the
+    buffer of step i+2 a rank must have passed the barrier of step i+1, which every rank reaches only after its table build of
+    step i has read that buffer.
+    """
+
+    def __init__(self, n_local: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        counts = torch.zeros(self.world, dtype=torch.int64, device=device)
+        counts[self.rank] = n_local
+        dist.all_reduce(counts, group=self.group)
+        self.counts = [int(c) for c in counts.tolist()]
+        self.offset, self.n_total = sum(self.counts[: self.rank]), sum(self.counts)
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            buf = symm_mem.empty((self.n_total, 4), dtype=torch.int32, device=device)
+            self.handles.append(symm_mem.rendezvous(buf, self.group.group_name))
+            self.bufs.append(buf)
+        self.step = 0
+
+    def run(self, phases, teacher, labels, T, alpha, V):
+        """Returns (records of ALL tokens in global order, lse2_t of the local rows)."""
+        i = self.step & 1
+        self.step += 1
+        hdl = self.handles[i]
+        lse2_t, _status = phases.teacher_stats_peers(teacher, labels, T, alpha, V, hdl.buffer_ptrs_dev, self.world, self.offset)
+        hdl.barrier(channel=0)
+        return self.bufs[i], lse2_t
+
+
+_peer_exchanges: dict = {}
+
+
 def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, group=None, upstream=None,
-                          phases=None, reduce_loss=True, want_grad=True, n_total=None):
+                          phases=None, reduce_loss=True, want_grad=True, n_total=None, exchange="nccl"):
     """As-written LoCa over tokens sharded across the ranks of ``group``.
 
     ``teacher``/``student``/``labels`` hold this rank's rows.  Returns ``(loss, grad_local)`` where
     ``loss`` is the GLOBAL loss (identical on every rank) when ``reduce_loss`` and the local partial otherwise.
     ``phases`` injects the three phase implementations (tests run the host logic on CPU with an
-    oracle-backed stand-in; the product default is :class:`CudaPhases`).
+    oracle-backed stand-in; the product default is :class:`CudaPhases`).  ``exchange="peer"`` replaces the NCCL
+    all-gather of the records by peer stores issued from the phase-A kernel itself (:class:`PeerRecordExchange`).
     """
     if phases is None:
         phases = CudaPhases()
@@ -120,8 +174,17 @@ def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, grou
     t2, s2 = _rows(teacher), _rows(student)
     V = s2.shape[1]
     lab = labels.reshape(-1).to(torch.int64).contiguous()
-    rec, lse2_t, _status = phases.teacher_stats(t2, lab, T, alpha, V)
-    rec_all = gather_records(rec, group)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if exchange == "peer" and multi:
+        # phase A + all-gather in one kernel: records go straight into every rank's buffer over NVLink
+        key = (id(group), int(t2.shape[0]), t2.device.index)
+        ex = _peer_exchanges.get(key)
+        if ex is None:
+            ex = _peer_exchanges[key] = PeerRecordExchange(int(t2.shape[0]), t2.device, group)
+        rec_all, lse2_t = ex.run(phases, t2, lab, T, alpha, V)
+    else:
+        rec, lse2_t, _status = phases.teacher_stats(t2, lab, T, alpha, V)
+        rec_all = gather_records(rec, group)
     if n_total is None:
         n_total = rec_all.shape[0]
     table, consts = phases.build_table(rec_all, V)
@@ -139,9 +202,12 @@ def per_row_token_sharded(fn, teacher, student, *args, group=None, reduce_loss=T
     n_local = _rows(student).shape[0]
     n_total = n_local
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        t = torch.tensor([n_local], dtype=torch.int64, device=student.device)
-        dist.all_reduce(t, group=group)
-        n_total = int(t.item())
+        key = ("n_total", id(group), n_local)
+        n_total = _shard_counts.get(key)
+        if n_total is None:      # the global token count needs a host read-back: exchanged once per shard size, not per step
+            t = torch.tensor([n_local], dtype=torch.int64, device=student.device)
+            dist.all_reduce(t, group=group)
+            n_total = _shard_counts[key] = int(t.item())
     loss = fn(teacher, student, *args, n_total=n_total, **kw)
     if reduce_loss and n_total != n_local:
         red = loss.detach().clone()
