@@ -13,7 +13,7 @@ namespace kd {
 namespace {
 
 constexpr int kPoolThreads = 512;
-constexpr int kRowThreads = 256;
+constexpr int kRowThreads = 1024;   // 32 warps: two similarity columns per warp at M = 64, one gradient column per thread at D ~ 1k
 constexpr float kNormEps = 1e-12f;   // F.normalize default
 
 // ---- pooling, split over tokens: CTA (split, image|tensor) sums its token chunk into an fp32 partial ---------------
@@ -108,10 +108,21 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     for (int d = threadIdx.x; d < D; d += kRowThreads) su[d] = us[(int64_t)i * D + d];
     __syncthreads();
+    const bool vec4 = (D % 4 == 0);
     for (int j = w; j < M; j += kRowThreads / 32) {
         const float* t = ut + (int64_t)j * D;
         float acc = 0.f;
-        for (int d = l; d < D; d += 32) acc = fmaf(su[d], t[d], acc);
+        if (vec4) {
+            const float4* t4 = reinterpret_cast<const float4*>(t);
+            const float4* s4 = reinterpret_cast<const float4*>(su);
+#pragma unroll 4
+            for (int d = l; d < D / 4; d += 32) {
+                const float4 a = s4[d], b = __ldg(t4 + d);
+                acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+            }
+        } else {
+            for (int d = l; d < D; d += 32) acc = fmaf(su[d], t[d], acc);
+        }
         acc = warp_sum(acc);
         if (l == 0) sl[j] = acc * inv_temp;
     }
@@ -152,7 +163,8 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
     float dots = 0.f;
     for (int d = threadIdx.x; d < D; d += kRowThreads) {
         float acc = 0.f;
-        for (int j = 0; j < M; ++j) acc = fmaf(sl[j], ut[(int64_t)j * D + d], acc);
+#pragma unroll 8
+        for (int j = 0; j < M; ++j) acc = fmaf(sl[j], __ldg(ut + (int64_t)j * D + d), acc);
         dots = fmaf(acc, su[d], dots);
         dmean[(int64_t)i * D + d] = acc;
     }
@@ -182,6 +194,8 @@ __global__ void nce_finalize_kernel(const float* __restrict__ rowloss, int M, fl
 }
 
 // ---- dx[m,p,:] = dmean[m,:] -----------------------------------------------------------------------
+// A thread owns one 16-byte column slot of the row: it converts its source values once and then only stores, token after
+// token (the previous version recomputed idx % ncol and re-read the source for every store: 1.8 TB/s).
 template <typename T>
 __global__ void __launch_bounds__(256)
 broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P, int D, bool vec, const float* ratio) {
@@ -196,13 +210,18 @@ broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P
     T* dst = dx + (int64_t)m * P * D;
     if (vec) {
         const int ncol = D / E;
-        const int64_t total = (int64_t)P * ncol;
-        for (int64_t idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-            const int c = (int)(idx % ncol);
+        const int lanes = ncol < 256 ? ncol : 256;          // column slots handled side by side
+        const int slots = 256 / lanes;                       // token rows handled side by side
+        const int c0 = threadIdx.x % lanes, slot = threadIdx.x / lanes;
+        if (slot >= slots) return;
+        for (int c = c0; c < ncol; c += lanes) {
             float v[E];
 #pragma unroll
             for (int i = 0; i < E; ++i) v[i] = src[c * E + i] * f;
-            stg_stream(reinterpret_cast<uint4*>(dst) + idx, Elem<T>::pack(v));
+            const uint4 packed = Elem<T>::pack(v);
+            uint4* col = reinterpret_cast<uint4*>(dst) + c;
+#pragma unroll 4
+            for (int p = blockIdx.x * slots + slot; p < P; p += gridDim.x * slots) stg_stream(col + (int64_t)p * ncol, packed);
         }
     } else {
         const int64_t total = (int64_t)P * D;
@@ -244,8 +263,9 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
         const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
         const size_t smem = sizeof(float) * (size_t)(kPoolThreads / lanes) * D;
         KD_CHECK_ARG(smem <= 200 * 1024, "info_nce: feature dimension %d too large for the pooling kernel", D);
-        // enough CTAs for ~4 per SM, but never fewer than ~64 tokens per chunk
-        int nsplit = (148 * 4 + 2 * M - 1) / (2 * M);
+        // one wave: at most 4 resident CTAs (512 threads) per SM on 148 SMs — a partial second wave doubled the time —
+        // and never fewer than ~64 tokens per chunk
+        int nsplit = (148 * 4) / (2 * M);
         if (nsplit > kMaxPoolSplit) nsplit = kMaxPoolSplit;
         if (nsplit > (P + 63) / 64) nsplit = (P + 63) / 64;
         if (nsplit < 1) nsplit = 1;
@@ -271,8 +291,8 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
     KD_CHECK_LAUNCH("nce_finalize_kernel");
     if (want_grad) {
         const bool vec_out = (D % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
-        int bx = (int)(((int64_t)P * (D / (vec_out ? E : 1)) + 255) / 256);
-        if (bx > 64) bx = 64;
+        int bx = vec_out ? (P + 15) / 16 : (int)(((int64_t)P * D + 255) / 256);      // >= 16 tokens per CTA and row
+        if (bx > 32) bx = 32;
         if (bx < 1) bx = 1;
         broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, nullptr);
         KD_CHECK_LAUNCH("broadcast_rows_kernel");
@@ -284,8 +304,8 @@ template <typename T>
 int run_regrad(const float* dmean, void* dx, int M, int P, int D, const float* ratio, cudaStream_t st) {
     constexpr int E = Elem<T>::kPack;
     const bool vec_out = (D % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
-    int bx = (int)(((int64_t)P * (D / (vec_out ? E : 1)) + 255) / 256);
-    bx = bx > 64 ? 64 : (bx < 1 ? 1 : bx);
+    int bx = vec_out ? (P + 15) / 16 : (int)(((int64_t)P * D + 255) / 256);
+    bx = bx > 32 ? 32 : (bx < 1 ? 1 : bx);
     broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, ratio);
     KD_CHECK_LAUNCH("broadcast_rows_kernel");
     return KD_OK;
