@@ -183,7 +183,10 @@ __device__ __forceinline__ void row_stats_packed(const T* __restrict__ row, int 
             }
         }
     };
-    constexpr int U = 8;      // independent 128-bit loads in flight per thread
+#ifndef KD_STATS_U
+#define KD_STATS_U 8
+#endif
+    constexpr int U = KD_STATS_U;      // independent 128-bit loads in flight per thread
     int v = threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int last_lane = 31 - lane;      // warp-uniform trip count: test the warp's last lane
@@ -227,8 +230,13 @@ __device__ __forceinline__ float lse2_of(const MaxSum& ms, float k2) { return fm
 // ------------------------------------------------------------------------------------------------
 // Phase A of the LoCa reference mode: teacher row -> token record {label, v1, k, v2} and lse2_t
 // ------------------------------------------------------------------------------------------------
+// 4 CTAs (32 warps) per SM: 64 registers, no spills.  Measured 0.88 ms (5.65 TB/s, 86 % of the measured HBM peak) against
+// 1.00 ms with the compiler's own choice of 76 registers / 3 CTAs — the kernel is latency-bound, occupancy buys the difference.
+#ifndef KD_STATS_MIN_CTAS
+#define KD_STATS_MIN_CTAS 4
+#endif
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(kStatsThreads)
+__global__ void __launch_bounds__(kStatsThreads, KD_STATS_MIN_CTAS)
 teacher_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const int64_t* __restrict__ labels,
                      kd_token_record* __restrict__ rec, float* __restrict__ lse2_t, uint32_t* status,
                      int64_t n_rows, int V, float k2, float alpha, kd_token_record* const* __restrict__ peers, int n_peers,
