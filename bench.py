@@ -392,7 +392,7 @@ def main() -> None:
                 l_ = kd.loca_kl(dt_, ds_, dl_, T_KD, alpha=ALPHA, mode=mode, n_total=n_total)
                 l_.backward()
             else:
-                l_, g_ = sharded.loca_kl_token_sharded(dt_, ds_.detach(), dl_, T_KD, ALPHA, phases=phases)
+                l_, g_ = sharded.loca_kl_token_sharded(dt_, ds_.detach(), dl_, T_KD, ALPHA, phases=phases, exchange=exchange)
             return float(l_.item())          # device -> host read of the step's result
 
         ke = max(2, min(args.steps, 5))
@@ -408,7 +408,9 @@ def main() -> None:
             dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
         e2e = {"value": n_total / (ms_e.item() / 1e3), "unit": "tokens/s", "ms_per_step": ms_e.item(),
                "h2d_bytes_per_step": 2 * N * V * 2 + N * 8, "d2h_bytes_per_step": 4, "steps": ke,
-               "note": "pinned host logits + labels copied H2D every step, loss read back; per-GPU bytes"}
+               "h2d_gbs": (2 * N * V * 2 + N * 8) / (ms_e.item() / 1e3) / 1e9,
+               "note": "pinned host logits + labels copied H2D every step, loss read back; per-GPU bytes; the step is the "
+                       "host->device copy of 9.96 GB (h2d_gbs = the PCIe rate it ran at) plus ~4 ms of kernels"}
         del ht, hs, hl, dt_, ds_, dl_
 
     if rank == 0:
