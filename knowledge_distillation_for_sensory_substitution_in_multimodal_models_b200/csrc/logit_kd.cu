@@ -989,7 +989,11 @@ int launch_emit(const EmitParams& p_in, int variant, int dtype, cudaStream_t st,
 
     const int spare = sm_count() - n_clusters * cta_per;
     HelperStream* hs = nullptr;
-    if (queue && spare_sm_mode() && spare >= 8 && p.n_rows >= (int64_t)n_clusters * pipes * 8) hs = helper_stream();
+    // The helper pays off when a fifth of the machine would otherwise idle (clusters of 8: 28 spare SMs, emit 3.07 -> 3.00 ms); with
+    // clusters of 9 only 13 SMs are spare and the extra stream / event traffic costs as much as their rows bring (measured: step
+    // 3.79-3.85 ms without against 3.86-3.91 ms with, CUDA-graph replay).  KD_SPARE_SMS=1 forces it on, 0 off, default: automatic.
+    const int min_spare = (spare_sm_mode() == 1 && getenv("KD_SPARE_SMS")) ? 8 : 20;
+    if (queue && spare_sm_mode() && spare >= min_spare && p.n_rows >= (int64_t)n_clusters * pipes * 8) hs = helper_stream();
     if (hs) {
         queue_init_kernel<<<1, 1, 0, st>>>(queue, n_clusters * static_rows);   // the first rows of every cluster are static
         KD_CHECK_LAUNCH("queue_init_kernel");
@@ -1001,7 +1005,11 @@ int launch_emit(const EmitParams& p_in, int variant, int dtype, cudaStream_t st,
     if (hs && spare_sm_mode() != 2) {      // KD_SPARE_SMS=2: dynamic row queue without the helper kernel (experiment)
         if (cudaStreamWaitEvent(hs->stream, hs->fork, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent(fork)");
         EmitParams h = p;
-        h.queue_tail_reserve = n_clusters * pipes * 10;      // the last ~10 rows per cluster pipeline stay with the cluster kernel
+        // the helper stops claiming near the end: one of its rows takes far longer than a cluster row, and a late claim would leave the
+        // cluster SMs idle behind it (KD_HELPER_RESERVE = rows per cluster pipeline that stay with the cluster kernel)
+        static int reserve = -1;
+        if (reserve < 0) { const char* e = getenv("KD_HELPER_RESERVE"); reserve = e ? atoi(e) : 10; }
+        h.queue_tail_reserve = n_clusters * pipes * reserve;
         h.helper_ctas = spare * 2;
         rc = launch_emit_stream_any(h, variant, dtype, hs->stream);
         if (rc != KD_OK) return rc;

@@ -1,0 +1,7 @@
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+for i in 1 2; do
+timeout 300 python bench.py --steps 40 --warmup 5 --no-e2e --no-cpu-baseline --no-secondary > gpurun_out/b42.log 2>&1; tail -1 gpurun_out/b42.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('RESULT ms/step %.3f tok/s %.0f emit %.3f frac %.3f'%(d['ms_per_step'],d['value'],d['roofline']['kernel_ms'],d['roofline']['frac']))"
+done
