@@ -88,8 +88,10 @@ struct PointTerm {
 // per-row LoCa calibration scalars from (lse2_t, label logit, runner-up logit) — P1:166-185
 __device__ __forceinline__ void loca_scalars(float x_label, float x_runner, float lse2_t, float k2, float alpha,
                                              float& v1, float& v2) {
-    const float p_gt = ex2(fmaf(x_label, k2, -lse2_t));
-    const float p_k = ex2(fmaf(x_runner, k2, -lse2_t));
+    // softmax values never exceed 1; 2^(x*k2 - lse2) can by an ulp when the row is a near one-hot, which would turn
+    // 1 - p_gt negative and v2 into a tiny negative number (found by tests/test_gpu_logit_kd.py::test_extreme_but_finite_logits)
+    const float p_gt = fminf(ex2(fmaf(x_label, k2, -lse2_t)), 1.f);
+    const float p_k = fminf(ex2(fmaf(x_runner, k2, -lse2_t)), 1.f);
     const float sc = alpha / (1.f - p_gt + p_k);
     v1 = 1.f - sc * (1.f - p_gt);     // sum_v tp taken as 1
     v2 = sc * p_k;

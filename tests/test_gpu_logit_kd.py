@@ -211,3 +211,30 @@ def test_phase_split_entry_points_match_fused_call():
     assert abs(loss.item() - full.item()) <= 1e-6 * abs(full.item())
     ref = O.loca_kl(t, s, lab, 2.0, 0.8)
     assert grad_close(grad.float().cpu(), ref.grad)
+
+
+@pytest.mark.parametrize("mode", ["reference", "per_row"])
+@pytest.mark.parametrize("T", [2.0, 0.8])
+def test_extreme_but_finite_logits(mode, T):
+    """Cells far outside the usual range (student columns at -3e4 / +60, teacher columns at -2e4, a teacher row that is a
+    near one-hot): the clamp decision, the FMA/XU range checks and the tensor-memory caches must not produce NaN/inf and
+    must stay within the gates."""
+    N, V = 20, 151936
+    t, s, lab = synthetic.logit_batch(N, V, seed=77)
+    s, t = s.float(), t.float()
+    g = torch.Generator().manual_seed(5)
+    cols = torch.randint(0, V, (N, 64), generator=g)
+    rows = torch.arange(N)[:, None]
+    s[rows, cols[:, :32]] = -3.0e4
+    s[rows, cols[:, 32:40]] = 60.0
+    t[rows, cols[:, 40:]] = -2.0e4
+    # (p_gt -> 1 is outside the domain where parity is defined: the reference's 1 - p_gt + p_k and sum(tp) - p_gt cancel
+    #  catastrophically there — in its own fp32 arithmetic already at 1 - p_gt ~ 1e-6 — so the label gets p_gt ~ 0.7-0.97)
+    t[3, lab[3]] += 16.0 * T        # teacher confident of the label
+    t[4, (lab[4] + 1) % V] += 60.0  # teacher almost certain of another class
+    t, s = t.to(torch.bfloat16), s.to(torch.bfloat16)
+    ref = O.loca_kl(t, s, lab, T, 0.8, mode=mode, chunk_rows=4)
+    loss, grad = run_loca(t, s, lab, T, 0.8, mode, torch.bfloat16)
+    assert torch.isfinite(grad).all() and loss == loss
+    assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    assert grad_close(grad, ref.grad)
