@@ -238,3 +238,47 @@ def test_extreme_but_finite_logits(mode, T):
     assert torch.isfinite(grad).all() and loss == loss
     assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
     assert grad_close(grad, ref.grad)
+
+
+_FUZZ = [
+    # N, V, T, alpha, mode, peaked, dtype
+    (1, 2048, 2.0, 0.8, "reference", False, torch.bfloat16),      # smallest shape the cluster kernels take: most warps hold no cell
+    (2, 2056, 0.8, 0.8, "reference", True, torch.bfloat16),       # 257 vectors: ragged CTA slices
+    (3, 4104, 1.0, 0.0, "reference", False, torch.bfloat16),      # alpha = 0: v1 = 1, v2 = 0 (override encoded with the floor)
+    (5, 9000, 2.0, 1.0, "reference", True, torch.bfloat16),       # alpha = 1: edge of the fused kernel's table range
+    (7, 18000, 0.5, 0.8, "per_row", True, torch.bfloat16),        # sharp temperature: every row clamped
+    (9, 40000, 4.0, 0.5, "per_row", False, torch.bfloat16),
+    (31, 65536, 2.0, 0.8, "reference", False, torch.float16),     # fp16 logits through the fused kernel
+    (61, 151936, 1.0, 0.3, "reference", True, torch.bfloat16),    # odd row count: pipelines / clusters end at different rows
+    (16, 163840, 2.0, 0.8, "reference", False, torch.bfloat16),   # largest V the thread's tensor-memory words hold (10 iterations at 9 CTAs)
+    (4, 200000, 2.0, 0.8, "reference", False, torch.bfloat16),    # beyond shared memory: falls back, same result
+    (6, 30001, 2.0, 0.8, "per_row", False, torch.bfloat16),       # V not a multiple of 8: streaming kernel
+]
+
+
+@pytest.mark.parametrize("N,V,T,alpha,mode,peaked,dtype", _FUZZ)
+def test_shape_and_parameter_sweep(N, V, T, alpha, mode, peaked, dtype):
+    t, s, lab = synthetic.logit_batch(N, V, seed=1000 + N + V % 97, peaked=peaked, dtype=dtype)
+    ref = O.loca_kl(t, s, lab, T, alpha, mode=mode, chunk_rows=4)
+    scale = 2.0 ** 20 if dtype == torch.float16 else 1.0            # fp16 gradients need a loss scale (see test_other_dtypes)
+    sd = s.cuda().requires_grad_(True)
+    loss = kd.loca_kl(t.cuda(), sd, lab.cuda(), T, alpha=alpha, mode=mode, upstream=scale if scale != 1.0 else None)
+    (loss * scale).backward()
+    assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    g = sd.grad.float().cpu() / scale
+    if dtype == torch.float16:
+        assert rel_err(g, ref.grad) <= 5e-4
+    else:
+        assert grad_close(g, ref.grad)
+
+
+@pytest.mark.parametrize("N,V,T", [(3, 2048, 0.8), (11, 50000, 2.0), (40, 151936, 0.8)])
+@pytest.mark.parametrize("quirk", [False, True], ids=["kl", "kl_log_target"])
+def test_temperature_kl_sweep(N, V, T, quirk):
+    t, s, _ = synthetic.logit_batch(N, V, seed=40 + N)
+    ref = O.temperature_kl(t, s, T, log_target_quirk=quirk, chunk_rows=4)
+    sd = s.cuda().requires_grad_(True)
+    loss = kd.temperature_kl(t.cuda(), sd, T, log_target_quirk=quirk)
+    loss.backward()
+    assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    assert grad_close(sd.grad.float().cpu(), ref.grad)
