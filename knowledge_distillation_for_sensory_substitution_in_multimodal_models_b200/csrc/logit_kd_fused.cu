@@ -557,8 +557,14 @@ row_emit_fused_kernel(const FusedParams cp) {
         ph1 ^= 1;
 
         // ================= pass B' (rare): exact masked sums for rows the sp >= eps clamp touches =================
+        // With the exponent cache the exact mask is applied to the parked q right here (q <- q*[a >= thr2], written back to
+        // tensor memory), so the gradient pass of a clamped row is the same cached, MUFU-free sweep as for an unclamped row and
+        // the student slice can be re-armed before the second reduction.
+        bool student_refilled = false;
+        bool q_masked = false;
         if constexpr (LOCA) {
             if (!all_kept) {
+                constexpr bool WRITE_BACK = LOCA && KD_ECACHE;
                 const u64 nls = pk(-lse2_s, -lse2_s);
                 u64 accN = pk(0.f, 0.f), accM = pk(0.f, 0.f);
                 auto bp_body = [&](int j, bool act, auto tail_tag) {
@@ -574,20 +580,39 @@ row_emit_fused_kernel(const FusedParams cp) {
                             float a_lo, a_hi;
                             upk(fma2(Pair<T>::widen(ws[i]), k2p, nls), a_lo, a_hi);
                             const u64 q2 = pk(__uint_as_float(qb[2 * i]), __uint_as_float(qb[2 * i + 1]));
-                            accN = fma2(q2, pk(fmaxf(a_lo, thr2), fmaxf(a_hi, thr2)), accN);
-                            accM = fma2(q2, pk(set_ge(a_lo, thr2), set_ge(a_hi, thr2)), accM);
+                            // max(a, thr2) = a*m + thr2*(1 - m):  sum q*max(a, thr2) = sum (q*m)*a + thr2 * (Q_w - sum q*m)
+                            const u64 a2 = pk(a_lo, a_hi);
+                            const u64 qm2 = mul2(q2, pk(set_ge(a_lo, thr2), set_ge(a_hi, thr2)));
+                            accN = fma2(qm2, a2, accN);
+                            accM = add2(accM, qm2);
+                            if constexpr (WRITE_BACK) {
+                                float m_lo, m_hi;
+                                upk(qm2, m_lo, m_hi);
+                                qb[2 * i] = __float_as_uint(m_lo);
+                                qb[2 * i + 1] = __float_as_uint(m_hi);
+                            }
                         }
                     }
                     if constexpr (decltype(tail_tag)::value) __syncwarp();
+                    if constexpr (WRITE_BACK) tmem_st8(tq + 8 * j, qb);
                 };
 #pragma unroll 2
                 for (int j = 0; j < n_full; ++j) bp_body(j, true, std::false_type{});
                 if (n_tail) bp_body(n_full, lane < n_tail, std::true_type{});
+                if constexpr (WRITE_BACK) {
+                    tmem_wait_st();
+                    q_masked = true;
+                    if (want_grad) {            // nothing reads the student slice any more: the cached gradient sweep will run
+                        __syncwarp();
+                        if (next_r < p.n_rows) issue_student(next_r);
+                        student_refilled = true;
+                    }
+                }
                 float x0, x1;
-                upk(accN, x0, x1);
-                const float N_w = warp_sum(x0 + x1);
                 upk(accM, x0, x1);
                 const float M_w = warp_sum(x0 + x1);
+                upk(accN, x0, x1);
+                const float N_w = warp_sum(x0 + x1) + thr2 * (Q_w - M_w);
                 if (lane < CS)
                     st_async_v2(map_to_cta(slots + (rank * WPP + pw) * 32 + 24, lane), __float_as_uint(R_w - N_w), __float_as_uint(M_w),
                                 map_to_cta(bar_red2, lane));
@@ -618,7 +643,6 @@ row_emit_fused_kernel(const FusedParams cp) {
         }
 
         // ================= pass C: gradient, written straight to HBM ===========================================
-        bool student_refilled = false;
         if (want_grad) {
             const float gQ = g * Q;
             const bool fold = (g > 0.f) && (gQ > 0.f) && (gQ < INFINITY);
@@ -666,9 +690,8 @@ row_emit_fused_kernel(const FusedParams cp) {
                 for (int j = 0; j < n_full; ++j) c_body(j, true, std::false_type{});
                 if (n_tail) c_body(n_full, lane < n_tail, std::true_type{});
             };
-            // unclamped row with the exponent cache: g*Q*sp = fp16 e' * 2^(m_w*k2 - 15 - lse2_s + log2 gQ), no shared memory, no MUFU
-            auto sweepC_cached = [&]() {
-                const float ce = ex2((mk - kEScaleLog2) + (lgQ - lse2_s));
+            // exponent cache (unclamped rows, and clamped rows whose q was masked by pass B'): no shared memory, no MUFU
+            auto sweepC_cached_impl = [&](float ce) {
                 const u64 cep = pk(ce, ce);
                 auto c_step = [&](int j, auto nv_tag, bool act, auto tail_tag) {
                     constexpr int NV = decltype(nv_tag)::value;       // vectors per tensor-memory wait
@@ -705,18 +728,21 @@ row_emit_fused_kernel(const FusedParams cp) {
                 if (j < n_full) c_step(j, V1{}, true, std::false_type{});
                 if (n_tail) c_step(n_full, V1{}, lane < n_tail, std::true_type{});
             };
+            // g*Q*sp = gQ * e' * 2^(m_w*k2 - 15 - lse2_s): valid for any sign of g and g*Q
+            auto sweepC_cached = [&]() { sweepC_cached_impl(gQ * ex2((mk - kEScaleLog2) - lse2_s)); };
             using Yes = std::true_type;
             using No = std::false_type;
             // FMA-pipe exponentials in the common (folded, unmasked) sweep when log2(g*Q*sp) >= -126 for the whole slice
             const bool poly_c = LOCA && KD_POLY_C > 0 && (fmaf(min_w, k2, lgQ - lse2_s) >= kPolyFloor);
-            if (fold) {
+            if ((all_kept || q_masked) && LOCA && KD_ECACHE) {
+                if (!student_refilled) {
+                    if (next_r < p.n_rows) issue_student(next_r);       // the cached sweep reads tensor memory only
+                    student_refilled = true;
+                }
+                sweepC_cached();
+            } else if (fold) {
                 if (all_kept) {
-                    if (LOCA && KD_ECACHE) {
-                        if (next_r < p.n_rows) issue_student(next_r);       // the cached sweep reads tensor memory only
-                        student_refilled = true;
-                        sweepC_cached();
-                    }
-                    else if (poly_c) sweepC(Yes{}, No{}, Yes{});
+                    if (poly_c) sweepC(Yes{}, No{}, Yes{});
                     else sweepC(Yes{}, No{}, No{});
                 } else {
                     sweepC(Yes{}, Yes{}, No{});

@@ -1,0 +1,2 @@
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+python tools/time_t08.py 2>&1 | tail -3
