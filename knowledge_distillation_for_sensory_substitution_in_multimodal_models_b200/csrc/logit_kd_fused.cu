@@ -311,7 +311,7 @@ row_emit_fused_kernel(const FusedParams cp) {
         // ================= pass AB: statistics + accumulation in one sweep, q parked in tensor memory ==========
         float S_w, Q_w, R_w, P_w;
         {
-            constexpr bool ECACHE = LOCA && KD_ECACHE;
+            constexpr bool ECACHE = KD_ECACHE;        // every variant of this kernel parks its student exponentials
             // with the exponent cache the student argument carries +15 (e is parked as fp16(e * 2^15)); S_w and P_w are corrected below
             const float esh = ECACHE ? kEScaleLog2 : 0.f;
             const u64 nmk = pk(esh - mk, esh - mk);
@@ -734,7 +734,7 @@ row_emit_fused_kernel(const FusedParams cp) {
             using No = std::false_type;
             // FMA-pipe exponentials in the common (folded, unmasked) sweep when log2(g*Q*sp) >= -126 for the whole slice
             const bool poly_c = LOCA && KD_POLY_C > 0 && (fmaf(min_w, k2, lgQ - lse2_s) >= kPolyFloor);
-            if ((all_kept || q_masked) && LOCA && KD_ECACHE) {
+            if ((all_kept || q_masked) && KD_ECACHE) {
                 if (!student_refilled) {
                     if (next_r < p.n_rows) issue_student(next_r);       // the cached sweep reads tensor memory only
                     student_refilled = true;
@@ -1406,7 +1406,9 @@ int launch_fused_d(const EmitParams& e, cudaStream_t st, bool query_only, int* c
     const FusedPlan<VARIANT, CS, NPIPE> plan(vpc);
     constexpr int WPP = kWarps / NPIPE;
     const int w_chunk = ((vpc + WPP * 32 - 1) / (WPP * 32)) * 32;
-    if (w_chunk / 32 > kMaxIters) return KD_ERR_UNSUPPORTED;        // the thread's q cells must fit its 128 TMEM words
+    // the thread's q cells (8 words per iteration, from word 0) and fp16 exponent pairs (4 per iteration, from word kTmE)
+    // must fit its 128 tensor-memory words without overlapping
+    if (w_chunk / 32 > (KD_ECACHE ? kTmE / 8 : kMaxIters)) return KD_ERR_UNSUPPORTED;
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
