@@ -28,17 +28,44 @@ constexpr int kVsWarps = kVsThreads / 32;
 constexpr int kStatWords = 12;      // m_t, S_t, a1, i1, a2, i2, x_label, m_s, S_s, pad x3
 
 template <typename T>
+__device__ __forceinline__ bool vec_ok(const T* row, int n) {        // 16-byte accesses over the whole local row
+    return (reinterpret_cast<uintptr_t>(row) & 15u) == 0 && n % Elem<T>::kPack == 0;
+}
+
+template <typename T>
 __device__ __forceinline__ void shard_row_stats(const T* __restrict__ row, int n, float k2, MaxSum& ms, Top2* top, int col0) {
+    constexpr int P = Elem<T>::kPack;
     ms.init();
     if (top) top->init();
-    for (int c = threadIdx.x; c < n; c += kVsThreads) {
-        const float x = Elem<T>::to_float(row[c]);
+    auto one = [&](float x, int c) {
         if (x > ms.m) {
             ms.s = (ms.m == -INFINITY) ? 0.f : ms.s * ex2((ms.m - x) * k2);
             ms.m = x;
         }
         ms.s += ex2((x - ms.m) * k2);
         if (top) top->push(x, col0 + c);
+    };
+    if (vec_ok(row, n)) {
+        const uint4* rv = reinterpret_cast<const uint4*>(row);
+        for (int v = threadIdx.x; v < n / P; v += kVsThreads) {
+            float x[P];
+            Elem<T>::unpack(ldg_stream(rv + v), x);
+            float vm = x[0];
+#pragma unroll
+            for (int i = 1; i < P; ++i) vm = fmaxf(vm, x[i]);
+            if (vm > ms.m) {                      // one rescale per vector instead of one per cell
+                ms.s = (ms.m == -INFINITY) ? 0.f : ms.s * ex2((ms.m - vm) * k2);
+                ms.m = vm;
+            }
+#pragma unroll
+            for (int i = 0; i < P; ++i) ms.s += ex2((x[i] - ms.m) * k2);
+            if (top && vm >= top->a2) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) top->push(x[i], col0 + v * P + i);
+            }
+        }
+    } else {
+        for (int c = threadIdx.x; c < n; c += kVsThreads) one(Elem<T>::to_float(row[c]), c);
     }
 }
 
@@ -194,9 +221,24 @@ vshard_accum_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __rest
         const T* trow = teacher + r * ld_t;
         const T* srow = student + r * ld_s;
         float row = 0.f, Q = 0.f;
-        for (int c = threadIdx.x; c < V_local; c += kVsThreads)
-            PointTerm<VARIANT>::accum(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]), LOCA ? ov.of(c) : NaN, k2, l2.x, l2.y,
-                                      thr2, row, Q);
+        if (vec_ok(trow, V_local) && vec_ok(srow, V_local)) {
+            constexpr int P = Elem<T>::kPack;
+            const uint4* tv = reinterpret_cast<const uint4*>(trow);
+            const uint4* sv = reinterpret_cast<const uint4*>(srow);
+#pragma unroll 2
+            for (int v = threadIdx.x; v < V_local / P; v += kVsThreads) {
+                float xt[P], xs[P];
+                Elem<T>::unpack(ldg_stream(tv + v), xt);
+                Elem<T>::unpack(ldg_stream(sv + v), xs);
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+                    PointTerm<VARIANT>::accum(xt[i], xs[i], LOCA ? ov.of(v * P + i) : NaN, k2, l2.x, l2.y, thr2, row, Q);
+            }
+        } else {
+            for (int c = threadIdx.x; c < V_local; c += kVsThreads)
+                PointTerm<VARIANT>::accum(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]), LOCA ? ov.of(c) : NaN, k2, l2.x, l2.y,
+                                          thr2, row, Q);
+        }
         row = warp_sum(row);
         Q = warp_sum(Q);
         const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -229,9 +271,26 @@ vshard_emit_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __restr
         const T* trow = teacher + r * ld_t;
         const T* srow = student + r * ld_s;
         T* grow = grad + r * ld_g;
-        for (int c = blockIdx.x * kVsThreads + threadIdx.x; c < V_local; c += gridDim.x * kVsThreads)
-            grow[c] = Elem<T>::from_float(PointTerm<VARIANT>::grad(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]),
-                                                                   LOCA ? ov.of(c) : NaN, k2, l2.x, l2.y, thr2, g, gQ));
+        if (vec_ok(trow, V_local) && vec_ok(srow, V_local) && vec_ok(grow, V_local)) {
+            constexpr int P = Elem<T>::kPack;
+            const uint4* tv = reinterpret_cast<const uint4*>(trow);
+            const uint4* sv = reinterpret_cast<const uint4*>(srow);
+            uint4* gv = reinterpret_cast<uint4*>(grow);
+#pragma unroll 2
+            for (int v = blockIdx.x * kVsThreads + threadIdx.x; v < V_local / P; v += gridDim.x * kVsThreads) {
+                float xt[P], xs[P], o[P];
+                Elem<T>::unpack(ldg_stream(tv + v), xt);
+                Elem<T>::unpack(ldg_stream(sv + v), xs);
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+                    o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? ov.of(v * P + i) : NaN, k2, l2.x, l2.y, thr2, g, gQ);
+                stg_stream(gv + v, Elem<T>::pack(o));
+            }
+        } else {
+            for (int c = blockIdx.x * kVsThreads + threadIdx.x; c < V_local; c += gridDim.x * kVsThreads)
+                grow[c] = Elem<T>::from_float(PointTerm<VARIANT>::grad(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]),
+                                                                       LOCA ? ov.of(c) : NaN, k2, l2.x, l2.y, thr2, g, gQ));
+        }
     }
 }
 

@@ -345,3 +345,42 @@ def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, 
     rows = collectives.sum_(partial[:, 0].double().sum().reshape(1) * unit)[0]
     loss = (rows + rowconst.double().sum() * _LN2 + float(n) * table_const) * (float(T) * float(T) * inv_norm)
     return loss.float(), grad
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Vocabulary-parallel student lm_head feeding the vocabulary-sharded KD loss (BASELINE.json configs[4], library-GEMM form):
+# logits_shard = hidden @ weight_shard^T is produced per rank (cuBLAS through torch.matmul — a plain library GEMM), the loss
+# and d loss / d logits_shard come from logit_kd_vocab_sharded, and the two weight-side GEMMs of the backward close the loop
+# (dH needs the sum over the vocabulary shards: one all-reduce of [n_rows, hidden]).  The tcgen05 kernel that folds the
+# forward GEMM into kd_vshard_stats — so the logits never reach HBM — is the next step.
+# ---------------------------------------------------------------------------------------------------------------------
+
+class _LmHeadVocabShardedKD(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, weight_shard, teacher_shard, labels, col0, V_total, T, mode, alpha, eps, n_rows_norm, reduction,
+                group, phases, collectives):
+        logits = torch.matmul(hidden.detach(), weight_shard.detach().t())          # [n_rows, V_local], the student's dtype
+        loss, grad_logits = logit_kd_vocab_sharded(teacher_shard, logits, labels, col0, V_total, T, mode=mode, alpha=alpha, eps=eps,
+                                                   n_rows_norm=n_rows_norm, reduction=reduction, group=group, phases=phases,
+                                                   collectives=collectives)
+        ctx.save_for_backward(hidden, weight_shard, grad_logits)
+        ctx.collectives = collectives if collectives is not None else DistCollectives(group)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        hidden, weight_shard, grad_logits = ctx.saved_tensors
+        g = grad_logits.to(hidden.dtype) * grad_output.to(hidden.dtype)
+        d_hidden = torch.matmul(g, weight_shard.detach())                           # partial over this rank's columns
+        d_hidden = ctx.collectives.sum_(d_hidden.contiguous())                      # sum over the vocabulary shards
+        d_weight = torch.matmul(g.t(), hidden.detach())
+        return (d_hidden, d_weight) + (None,) * 13
+
+
+def lm_head_kd_vocab_sharded(hidden, weight_shard, teacher_shard, labels, col0, V_total, T, mode="reference", alpha=0.8,
+                             eps=1e-8, n_rows_norm=None, reduction="mean", group=None, phases=None, collectives=None):
+    """KD loss of a vocabulary-parallel student ``lm_head``: ``hidden`` [n_rows, K] (replicated), ``weight_shard`` [V_local, K] (this
+    rank's rows of the 151 936 x 896 head), ``teacher_shard`` [n_rows, V_local].  Differentiable w.r.t. ``hidden`` and
+    ``weight_shard``; the returned loss is the global one."""
+    return _LmHeadVocabShardedKD.apply(hidden, weight_shard, teacher_shard, labels, int(col0), int(V_total), float(T), mode,
+                                       float(alpha), float(eps), n_rows_norm, reduction, group, phases, collectives)

@@ -113,3 +113,44 @@ def test_cuda_phases_two_simulated_shards(mode, n, V, cuts, Tk):
     for loss, _ in res:
         assert abs(loss.item() - ref.loss.item()) <= 1e-5 * abs(ref.loss.item())
     assert grad_close(grad, ref.grad)
+
+
+def test_vocab_parallel_lm_head_gradients_cpu():
+    """hidden @ weight_shard^T -> vocabulary-sharded KD: loss, d/d hidden (summed over shards) and d/d weight_shard against
+    autograd through the full-vocabulary oracle gradient."""
+    n, K, V = 11, 24, 264
+    g = torch.Generator().manual_seed(2)
+    H = torch.randn(n, K, generator=g, dtype=torch.float64)
+    W = torch.randn(V, K, generator=g, dtype=torch.float64) * 0.5
+    t, _, lab = synthetic.logit_batch(n, V, seed=5)
+    t = t.double()
+    logits = H @ W.t()
+    ref = O.loca_kl(t, logits, lab, T, ALPHA, mode="reference")
+    dH_ref, dW_ref = ref.grad @ W, ref.grad.t() @ H
+    cuts = [0, 96, 200, V]
+    world = len(cuts) - 1
+    coll = ThreadCollectives(world)
+    out, err = [None] * world, []
+
+    def work(rank):
+        try:
+            lo, hi = cuts[rank], cuts[rank + 1]
+            h = H.clone().requires_grad_(True)
+            w = W[lo:hi].clone().requires_grad_(True)
+            loss = sharded.lm_head_kd_vocab_sharded(h, w, t[:, lo:hi].contiguous(), lab, lo, V, T, alpha=ALPHA,
+                                                    phases=TorchVocabPhases(), collectives=coll.bind(rank))
+            loss.backward()
+            out[rank] = (loss.item(), h.grad, w.grad)
+        except Exception as exc:  # noqa: BLE001
+            err.append(exc)
+            coll.barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [th.start() for th in threads]
+    [th.join() for th in threads]
+    assert not err, err
+    for rank, (loss, dH, dW) in enumerate(out):
+        lo, hi = cuts[rank], cuts[rank + 1]
+        assert abs(loss - ref.loss.item()) <= 2e-6 * abs(ref.loss.item())
+        assert ((dH - dH_ref).norm() / dH_ref.norm()).item() <= 1e-6
+        assert ((dW - dW_ref[lo:hi]).norm() / dW_ref[lo:hi].norm()).item() <= 1e-6
