@@ -420,9 +420,16 @@ def main() -> None:
             cpu = {"value": CPU_SAMPLE_ROWS / best, "unit": "tokens/s", "cores": threads, "kind": "port",
                    "sample": f"oracle/reference_port.py eager LoCa fwd+bwd, fp32, B=1,S={CPU_SAMPLE_ROWS},V={V} "
                              f"(BASELINE configs[0]), best of 3 after 1 warm-up = {best:.3f} s on {cpu_model_name()}"}
-        # status_clear, teacher_stats, owner_init, owner_scatter, table_fill, table_consts, queue_init, cluster emit,
-        # streaming helper emit, loss_finalize, regrad (early exit)
-        launches_per_step = 11 if mode == "reference" else 6
+        # our kernels per step (the helper-stream pair queue_init + streaming emit only runs with clusters of 8):
+        #   1 GPU, as-written: status_clear, teacher_stats, owner_init, owner_scatter, table_fill, table_consts, fused emit,
+        #                      loss_finalize, regrad (early exit)                                                    = 9
+        #   1 GPU, per-row   : status_clear, teacher_stats, fused emit, loss_finalize, regrad                       = 5
+        #   N GPUs, as-written (phase-split ABI): teacher_stats[_peers], owner_init, owner_scatter, table_fill, table_consts,
+        #                      fused emit, loss_finalize                                                             = 7
+        if mode == "reference":
+            launches_per_step = 9 if world == 1 else 7
+        else:
+            launches_per_step = 5
         out = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
