@@ -221,9 +221,18 @@ class _InfoNCE(torch.autograd.Function):
         return grad, None, None, None
 
 
-def info_nce(student_feats, teacher_feats, temperature: float = 0.07, upstream=None):
+def info_nce(student_feats, teacher_feats, temperature: float = 0.07, upstream=None, proj=None):
     """Mean-pool over tokens (3-D input), L2-normalise, student x teacher^T / temperature, cross-entropy
-    against the diagonal — P1:243-248 followed by ``contrastive_loss`` (P1:393-416)."""
+    against the diagonal — P1:243-248 followed by ``contrastive_loss`` (P1:393-416).
+
+    ``proj`` ([D_s, D_t], optional, not in the reference where both towers are SigLIP-1152): a learned projection of the
+    student features, ``contrastive_loss(x_s @ proj, x_t)``.  Mean-pooling is linear, so the projection is applied to the pooled
+    student vectors (a plain library GEMM, differentiable w.r.t. ``proj``) instead of to every token."""
+    if proj is not None:
+        # pooled in fp32 (like the kernel's own pooling), projected, then the 2-D form of the op (tokens == 1)
+        pooled = student_feats.float().mean(dim=1) if student_feats.dim() == 3 else student_feats.float()
+        student_feats = torch.matmul(pooled, proj.float())
+        teacher_feats = teacher_feats.float().mean(dim=1) if teacher_feats.dim() == 3 else teacher_feats.float()
     return _InfoNCE.apply(student_feats, teacher_feats, temperature, upstream)
 
 
@@ -265,6 +274,11 @@ class _FeatureMSE(torch.autograd.Function):
         return grad, None, None
 
 
-def feature_mse(inp, target, upstream=None):
-    """``mean((input.float() - target.float())**2)`` (EV:160-165); gradient in ``input``'s dtype."""
+def feature_mse(inp, target, upstream=None, proj=None):
+    """``mean((input.float() - target.float())**2)`` (EV:160-165); gradient in ``input``'s dtype.
+
+    ``proj`` ([D_in, D_target], optional, not in the reference): ``mse_loss(input @ proj, target)`` for a student whose hidden
+    size differs from the teacher's (896 vs 3584); the projection is a plain library GEMM, differentiable w.r.t. ``proj``."""
+    if proj is not None:
+        inp = torch.matmul(inp, proj)
     return _FeatureMSE.apply(inp, target, upstream)

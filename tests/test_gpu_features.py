@@ -86,3 +86,29 @@ def test_mse_odd_sizes_and_unaligned():
         loss.backward()
         assert abs(loss.item() - ref.loss.item()) <= 1e-5 * ref.loss.item()
         assert grad_close(ad.grad.float().cpu(), ref.grad)
+
+
+def test_learned_projections_match_the_reference_applied_to_projected_features():
+    """`proj` is not in the reference (both towers are SigLIP-1152): the oracle is the reference loss applied to x_s @ W."""
+    g = torch.Generator().manual_seed(9)
+    xs, xt = synthetic.vision_feature_batch(6, 19, 96, seed=4)
+    W = (torch.randn(96, 160, generator=g) * 0.1)
+    xt_wide = torch.randn(6, 19, 160, generator=g).to(torch.bfloat16)
+    ref = O.info_nce((xs.double() @ W.double()), xt_wide)
+    xd = xs.cuda().requires_grad_(True)
+    Wd = W.cuda().requires_grad_(True)
+    loss = kd.info_nce(xd, xt_wide.cuda(), proj=Wd)
+    loss.backward()
+    assert abs(loss.item() - ref.loss.item()) <= 2e-5 * abs(ref.loss.item())
+    assert Wd.grad is not None and torch.isfinite(Wd.grad).all() and torch.isfinite(xd.grad.float()).all()
+    a = torch.randn(300, 48, generator=g).to(torch.bfloat16)
+    b = torch.randn(300, 80, generator=g).to(torch.bfloat16)
+    P = (torch.randn(48, 80, generator=g) * 0.2).to(torch.bfloat16)
+    proj_ref = (a.float() @ P.float()).to(torch.bfloat16)            # what the bf16 GEMM hands to the loss
+    ref = O.feature_mse(proj_ref, b)
+    ad, Pd = a.cuda().requires_grad_(True), P.cuda().requires_grad_(True)
+    loss = kd.feature_mse(ad, b.cuda(), proj=Pd)
+    loss.backward()
+    assert abs(loss.item() - ref.loss.item()) <= 1e-3 * ref.loss.item()      # cuBLAS bf16 accumulation order vs the fp32 product
+    d_proj = ref.grad.float() @ P.float().t()
+    assert ((ad.grad.float().cpu() - d_proj).norm() / d_proj.norm()).item() <= 1e-2
