@@ -450,18 +450,15 @@ row_emit_fused_kernel(const FusedParams cp) {
             else st_async_v4(dst + 16, 0u, (uint32_t)claimed, __float_as_uint(mt_w), 0u, rbar);
         }
         // xlogy(v, v) of the row's own override cells (log2 units); a bad label poisons the row like the reference's gather would raise
-        auto own_xlogy_of = [&]() -> float {
-            float x = 0.f;
-            if constexpr (PER_ROW) {
-                if (rec_r.label >= 0) {
-                    if (rec_r.k != rec_r.label && rec_r.v1 != 0.f) x += rec_r.v1 * log2f(rec_r.v1);
-                    if (rec_r.v2 != 0.f) x += rec_r.v2 * log2f(rec_r.v2);
-                } else {
-                    x = NaN;
-                }
+        float own_xlogy = 0.f;                  // computed before the reduction wait: it depends on the token record only
+        if constexpr (PER_ROW) {
+            if (rec_r.label >= 0) {
+                if (rec_r.k != rec_r.label && rec_r.v1 != 0.f) own_xlogy += rec_r.v1 * __log2f(rec_r.v1);
+                if (rec_r.v2 != 0.f) own_xlogy += rec_r.v2 * __log2f(rec_r.v2);
+            } else {
+                own_xlogy = NaN;
             }
-            return x;
-        };
+        }
         // one warp per pipeline folds the NSLOT partials and broadcasts the row statistics through shared memory
         if (pw == 0) {
             mbar_wait_cta(bar_red1, ph1);
@@ -529,7 +526,6 @@ row_emit_fused_kernel(const FusedParams cp) {
                     row += __shfl_xor_sync(0xffffffffu, row, o);
                 }
             }
-            const float own_xlogy = own_xlogy_of();
             int claim_all = 0;
             if (DYN) claim_all = __shfl_sync(0xffffffffu, __float_as_int(sb[0].y), 0);     // slot 0 = (rank 0, warp 0)
             bool all_kept = true;
@@ -633,7 +629,7 @@ row_emit_fused_kernel(const FusedParams cp) {
                     qq = warp_sum(qq);
                     if (lane == 0) {
                         bcast[2] = qq;
-                        if (rank == 0) p.rowaux[r] = make_float4(lse2_t, lse2_s, qq, rr + own_xlogy_of());
+                        if (rank == 0) p.rowaux[r] = make_float4(lse2_t, lse2_s, qq, rr + own_xlogy);
                     }
                 }
                 named_bar_sync(bar2, WPP * 32);
