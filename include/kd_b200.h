@@ -146,7 +146,8 @@ int kd_logit_kd_regrad(const void* teacher, int64_t ld_t, const void* student, i
  *   unit = ln2 (1 for KD_KL_LOG_TARGET).  `table` is the full V_total-entry table (the kernels index it at col0 + c).
  * ---------------------------------------------------------------------------------------------------- */
 #define KD_VSHARD_STAT_WORDS 12
-int kd_vshard_stats(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* labels /* may be NULL */,
+int kd_vshard_stats(const void* teacher, int64_t ld_t, const void* student /* NULL: teacher half only */, int64_t ld_s,
+                    const int64_t* labels /* may be NULL */,
                     int64_t col0, float* stats, int64_t n_rows, int64_t V_local, int dtype, float T, void* stream);
 int kd_vshard_combine(const float* stats_all, int n_shards, int64_t n_rows, const int64_t* labels, int64_t V_total, float T,
                       float alpha, int variant, kd_token_record* records, float* lse2, float* rowconst, uint32_t* status,
@@ -158,6 +159,23 @@ int kd_vshard_emit(const void* teacher, int64_t ld_t, const void* student, int64
                    const kd_token_record* records, const float* table, int64_t col0, void* grad_student, int64_t ld_g,
                    int64_t n_rows, int64_t V_local, int dtype, float T, float eps, int variant, double inv_norm,
                    const float* upstream, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Student lm_head feeding the vocabulary-sharded KD — the producer of `student_outputs.logits` (P1:228-240; in the
+ * reference the HF Qwen2 lm_head, 896 x 151 936), as a hand-written tcgen05 / tensor-memory GEMM:
+ *   logits[n_rows, V_local] = hidden[n_rows, H] . weight[V_local, H]^T     (bf16 / fp16, fp32 accumulation, row-major,
+ *                                                                          pitches ld_* in elements)
+ * When `stat_partials` is not NULL ([kd_lm_head_stat_tiles(V_local)][n_rows][2] floats) the epilogue also leaves each
+ * row's (max, sum 2^((x - max) log2e / T)) over every 256-column tile of the ROUNDED logits; kd_lm_head_stats_merge folds
+ * them into words 7, 8 of the rows' kd_vshard_stats blocks, and kd_vshard_stats may then be called with student == NULL
+ * (teacher half only) — the student logits are not read again for their statistics.
+ * KD_ERR_UNSUPPORTED: fp32 operands, or bases / pitches / V_local that are not multiples of 16 bytes (use a library GEMM).
+ * ---------------------------------------------------------------------------------------------------- */
+int kd_lm_head_stat_tiles(int64_t V_local);
+int kd_lm_head_fwd(const void* hidden, int64_t ld_h, const void* weight, int64_t ld_w, void* logits, int64_t ld_c,
+                   float* stat_partials /* may be NULL */, int64_t n_rows, int64_t V_local, int64_t H, int dtype, float T,
+                   void* stream);
+int kd_lm_head_stats_merge(const float* stat_partials, int64_t n_tiles, float* stats, int64_t n_rows, float T, void* stream);
 
 /* grad *= (*factor) in place, skipped on device when *factor == 1 (kept for callers that accept double rounding). */
 int kd_scale_rows(void* grad, int64_t ld_g, int64_t n_rows, int64_t V, int dtype, const float* factor, void* stream);

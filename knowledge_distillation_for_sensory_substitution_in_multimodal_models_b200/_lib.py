@@ -44,6 +44,9 @@ SIGNATURES = {
     "kd_vshard_combine": (_i, [_p, _i, _i64, _p, _i64, _f, _f, _i, _p, _p, _p, _p, _p]),
     "kd_vshard_accum": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i, _f, _f, _i, _p]),
     "kd_vshard_emit": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i, _f, _f, _i, _d, _p, _p]),
+    "kd_lm_head_stat_tiles": (_i, [_i64]),
+    "kd_lm_head_fwd": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i, _f, _p]),
+    "kd_lm_head_stats_merge": (_i, [_p, _i64, _p, _i64, _f, _p]),
     "kd_info_nce_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "kd_info_nce_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i64, _i64, _i64, _i, _f, _p, _u, _p]),
     "kd_info_nce_regrad": (_i, [_p, _sz, _p, _i64, _i64, _i64, _i, _p, _p]),

@@ -106,9 +106,9 @@ vshard_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __rest
         MaxSum mt, msd;
         Top2 top;
         shard_row_stats<T>(teacher + r * ld_t, V_local, k2, mt, &top, col0);
-        shard_row_stats<T>(student + r * ld_s, V_local, k2, msd, nullptr, col0);
+        if (student) shard_row_stats<T>(student + r * ld_s, V_local, k2, msd, nullptr, col0);
         mt = block_merge_ms(mt, k2, smf);
-        msd = block_merge_ms(msd, k2, smf);
+        if (student) msd = block_merge_ms(msd, k2, smf);
         top = block_merge_top(top, smf, smi);
         if (threadIdx.x == 0) {
             float* o = stats + r * kStatWords;
@@ -120,7 +120,7 @@ vshard_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __rest
             o[0] = mt.m; o[1] = mt.s;
             o[2] = top.a1; o[3] = __int_as_float(top.i1); o[4] = top.a2; o[5] = __int_as_float(top.i2);
             o[6] = x_label;
-            o[7] = msd.m; o[8] = msd.s;
+            if (student) { o[7] = msd.m; o[8] = msd.s; }      // else: kd_lm_head_stats_merge fills them from the GEMM's partials
             o[9] = o[10] = o[11] = 0.f;
         }
         __syncthreads();
@@ -371,8 +371,8 @@ extern "C" {
 int kd_vshard_stats(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* labels, int64_t col0,
                     float* stats, int64_t n_rows, int64_t V_local, int dtype, float T, void* stream) {
     if (int rc = vs_check(n_rows, V_local, dtype, T)) return rc;
-    KD_CHECK_ARG(teacher && student && stats, "kd_vshard_stats: null pointer");
-    KD_CHECK_ARG(ld_t >= V_local && ld_s >= V_local && col0 >= 0, "kd_vshard_stats: bad shape");
+    KD_CHECK_ARG(teacher && stats, "kd_vshard_stats: null pointer");
+    KD_CHECK_ARG(ld_t >= V_local && (!student || ld_s >= V_local) && col0 >= 0, "kd_vshard_stats: bad shape");
     if (n_rows == 0) return KD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float k2 = kLog2e / T;
