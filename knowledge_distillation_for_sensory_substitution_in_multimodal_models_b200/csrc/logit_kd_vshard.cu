@@ -32,8 +32,10 @@ __device__ __forceinline__ bool vec_ok(const T* row, int n) {        // 16-byte 
     return (reinterpret_cast<uintptr_t>(row) & 15u) == 0 && n % Elem<T>::kPack == 0;
 }
 
+// `lane` of `stride` cooperating threads (a warp or the whole block) walks the row
 template <typename T>
-__device__ __forceinline__ void shard_row_stats(const T* __restrict__ row, int n, float k2, MaxSum& ms, Top2* top, int col0) {
+__device__ __forceinline__ void shard_row_stats(const T* __restrict__ row, int n, float k2, MaxSum& ms, Top2* top, int col0, int lane,
+                                                int stride) {
     constexpr int P = Elem<T>::kPack;
     ms.init();
     if (top) top->init();
@@ -47,9 +49,9 @@ __device__ __forceinline__ void shard_row_stats(const T* __restrict__ row, int n
     };
     if (vec_ok(row, n)) {
         const uint4* rv = reinterpret_cast<const uint4*>(row);
-        for (int v = threadIdx.x; v < n / P; v += kVsThreads) {
+        auto vec = [&](const uint4& raw, int v) {
             float x[P];
-            Elem<T>::unpack(ldg_stream(rv + v), x);
+            Elem<T>::unpack(raw, x);
             float vm = x[0];
 #pragma unroll
             for (int i = 1; i < P; ++i) vm = fmaxf(vm, x[i]);
@@ -57,15 +59,27 @@ __device__ __forceinline__ void shard_row_stats(const T* __restrict__ row, int n
                 ms.s = (ms.m == -INFINITY) ? 0.f : ms.s * ex2((ms.m - vm) * k2);
                 ms.m = vm;
             }
+            const float mk = ms.m * k2;
 #pragma unroll
-            for (int i = 0; i < P; ++i) ms.s += ex2((x[i] - ms.m) * k2);
+            for (int i = 0; i < P; ++i) ms.s += ex2(fmaf(x[i], k2, -mk));
             if (top && vm >= top->a2) {
 #pragma unroll
                 for (int i = 0; i < P; ++i) top->push(x[i], col0 + v * P + i);
             }
+        };
+        const int nv = n / P;
+        int v = lane;
+        for (; v + 3 * stride < nv; v += 4 * stride) {      // four loads in flight per thread
+            const uint4 a0 = ldg_stream(rv + v), a1 = ldg_stream(rv + v + stride), a2 = ldg_stream(rv + v + 2 * stride),
+                        a3 = ldg_stream(rv + v + 3 * stride);
+            vec(a0, v);
+            vec(a1, v + stride);
+            vec(a2, v + 2 * stride);
+            vec(a3, v + 3 * stride);
         }
+        for (; v < nv; v += stride) vec(ldg_stream(rv + v), v);
     } else {
-        for (int c = threadIdx.x; c < n; c += kVsThreads) one(Elem<T>::to_float(row[c]), c);
+        for (int c = lane; c < n; c += stride) one(Elem<T>::to_float(row[c]), c);
     }
 }
 
@@ -96,21 +110,33 @@ __device__ __forceinline__ Top2 block_merge_top(Top2 t, float* smf, int* smi) {
 }
 
 // ---- 1. local statistics ------------------------------------------------------------------------------
-template <typename T>
+// G threads per row: 32 (a warp per row, shuffle-only reductions: many short rows) or the whole block (few long rows)
+template <typename T, int G>
 __global__ void __launch_bounds__(kVsThreads)
 vshard_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __restrict__ student, int64_t ld_s,
                     const int64_t* __restrict__ labels, int col0, int64_t n_rows, int V_local, float k2, float* __restrict__ stats) {
     __shared__ float smf[2 * kVsWarps];
     __shared__ int smi[2 * kVsWarps];
-    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    constexpr int RPB = kVsThreads / G;
+    const int sub = threadIdx.x / G, gl = threadIdx.x % G;
+    for (int64_t r0 = (int64_t)blockIdx.x * RPB; r0 < n_rows; r0 += (int64_t)gridDim.x * RPB) {
+        const int64_t r = r0 + sub;
+        if (r >= n_rows) continue;      // G == 32 only (warp-uniform); RPB == 1 otherwise
         MaxSum mt, msd;
         Top2 top;
-        shard_row_stats<T>(teacher + r * ld_t, V_local, k2, mt, &top, col0);
-        if (student) shard_row_stats<T>(student + r * ld_s, V_local, k2, msd, nullptr, col0);
-        mt = block_merge_ms(mt, k2, smf);
-        if (student) msd = block_merge_ms(msd, k2, smf);
-        top = block_merge_top(top, smf, smi);
-        if (threadIdx.x == 0) {
+        msd.init();
+        shard_row_stats<T>(teacher + r * ld_t, V_local, k2, mt, &top, col0, gl, G);
+        if (student) shard_row_stats<T>(student + r * ld_s, V_local, k2, msd, nullptr, col0, gl, G);
+        if constexpr (G == 32) {
+            warp_merge(mt, k2);
+            if (student) warp_merge(msd, k2);
+            warp_merge(top);
+        } else {
+            mt = block_merge_ms(mt, k2, smf);
+            if (student) msd = block_merge_ms(msd, k2, smf);
+            top = block_merge_top(top, smf, smi);
+        }
+        if (gl == 0) {
             float* o = stats + r * kStatWords;
             float x_label = -INFINITY;
             if (labels) {
@@ -123,7 +149,7 @@ vshard_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __rest
             if (student) { o[7] = msd.m; o[8] = msd.s; }      // else: kd_lm_head_stats_merge fills them from the GEMM's partials
             o[9] = o[10] = o[11] = 0.f;
         }
-        __syncthreads();
+        if constexpr (G != 32) __syncthreads();
     }
 }
 
@@ -207,15 +233,19 @@ __device__ __forceinline__ ShardOverride<VARIANT> make_override(const float* tab
 }
 
 // ---- 3. local part of the row sum and of Q_r ----------------------------------------------------------
-template <int VARIANT, typename T>
+template <int VARIANT, typename T, int G>
 __global__ void __launch_bounds__(kVsThreads)
 vshard_accum_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __restrict__ student, int64_t ld_s,
                     const float2* __restrict__ lse2, const kd_token_record* __restrict__ rec, const float* __restrict__ table,
                     int col0, int64_t n_rows, int V_local, float k2, float thr2, float2* __restrict__ partial) {
     __shared__ float sm[2 * kVsWarps];
     constexpr bool LOCA = (VARIANT == KD_LOCA_REFERENCE || VARIANT == KD_LOCA_PER_ROW);
+    constexpr int RPB = kVsThreads / G;
     const float NaN = __int_as_float(0x7fc00000);
-    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    const int sub = threadIdx.x / G, gl = threadIdx.x % G;
+    for (int64_t r0 = (int64_t)blockIdx.x * RPB; r0 < n_rows; r0 += (int64_t)gridDim.x * RPB) {
+        const int64_t r = r0 + sub;
+        if (r >= n_rows) continue;      // G == 32 only (warp-uniform)
         const float2 l2 = lse2[r];
         const ShardOverride<VARIANT> ov = make_override<VARIANT>(table, rec, r, col0);
         const T* trow = teacher + r * ld_t;
@@ -225,8 +255,8 @@ vshard_accum_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __rest
             constexpr int P = Elem<T>::kPack;
             const uint4* tv = reinterpret_cast<const uint4*>(trow);
             const uint4* sv = reinterpret_cast<const uint4*>(srow);
-#pragma unroll 2
-            for (int v = threadIdx.x; v < V_local / P; v += kVsThreads) {
+#pragma unroll 4
+            for (int v = gl; v < V_local / P; v += G) {
                 float xt[P], xs[P];
                 Elem<T>::unpack(ldg_stream(tv + v), xt);
                 Elem<T>::unpack(ldg_stream(sv + v), xs);
@@ -235,21 +265,25 @@ vshard_accum_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __rest
                     PointTerm<VARIANT>::accum(xt[i], xs[i], LOCA ? ov.of(v * P + i) : NaN, k2, l2.x, l2.y, thr2, row, Q);
             }
         } else {
-            for (int c = threadIdx.x; c < V_local; c += kVsThreads)
+            for (int c = gl; c < V_local; c += G)
                 PointTerm<VARIANT>::accum(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]), LOCA ? ov.of(c) : NaN, k2, l2.x, l2.y,
                                           thr2, row, Q);
         }
         row = warp_sum(row);
         Q = warp_sum(Q);
-        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-        __syncthreads();
-        if (l == 0) { sm[w] = row; sm[kVsWarps + w] = Q; }
-        __syncthreads();
-        if (w == 0) {
-            float a = (l < kVsWarps) ? sm[l] : 0.f, b = (l < kVsWarps) ? sm[kVsWarps + l] : 0.f;
-            a = warp_sum(a);
-            b = warp_sum(b);
-            if (l == 0) partial[r] = make_float2(a, b);
+        if constexpr (G == 32) {
+            if (gl == 0) partial[r] = make_float2(row, Q);
+        } else {
+            const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+            __syncthreads();
+            if (l == 0) { sm[w] = row; sm[kVsWarps + w] = Q; }
+            __syncthreads();
+            if (w == 0) {
+                float a = (l < kVsWarps) ? sm[l] : 0.f, b = (l < kVsWarps) ? sm[kVsWarps + l] : 0.f;
+                a = warp_sum(a);
+                b = warp_sum(b);
+                if (l == 0) partial[r] = make_float2(a, b);
+            }
         }
     }
 }
@@ -294,6 +328,51 @@ vshard_emit_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __restr
     }
 }
 
+// warp-per-row form of the gradient kernel (many short rows): the row's scalars are loaded once per ~V_local cells and
+// every lane keeps four teacher + four student loads in flight
+template <int VARIANT, typename T>
+__global__ void __launch_bounds__(kVsThreads)
+vshard_emit_rows_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __restrict__ student, int64_t ld_s,
+                        const float2* __restrict__ lse2, const float* __restrict__ Q_rows, const kd_token_record* __restrict__ rec,
+                        const float* __restrict__ table, int col0, T* __restrict__ grad, int64_t ld_g, int64_t n_rows, int V_local,
+                        float k2, float thr2, float gscale, const float* __restrict__ upstream) {
+    constexpr bool LOCA = (VARIANT == KD_LOCA_REFERENCE || VARIANT == KD_LOCA_PER_ROW);
+    const float NaN = __int_as_float(0x7fc00000);
+    const float g = gscale * (upstream ? *upstream : 1.f);
+    const int sub = threadIdx.x >> 5, gl = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * kVsWarps + sub; r < n_rows; r += (int64_t)gridDim.x * kVsWarps) {
+        const float2 l2 = lse2[r];
+        const float gQ = g * Q_rows[r];
+        const ShardOverride<VARIANT> ov = make_override<VARIANT>(table, rec, r, col0);
+        const T* trow = teacher + r * ld_t;
+        const T* srow = student + r * ld_s;
+        T* grow = grad + r * ld_g;
+        if (vec_ok(trow, V_local) && vec_ok(srow, V_local) && vec_ok(grow, V_local)) {
+            constexpr int P = Elem<T>::kPack;
+            const uint4* tv = reinterpret_cast<const uint4*>(trow);
+            const uint4* sv = reinterpret_cast<const uint4*>(srow);
+            uint4* gv = reinterpret_cast<uint4*>(grow);
+#pragma unroll 4
+            for (int v = gl; v < V_local / P; v += 32) {
+                float xt[P], xs[P], o[P];
+                Elem<T>::unpack(ldg_stream(tv + v), xt);
+                Elem<T>::unpack(ldg_stream(sv + v), xs);
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+                    o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? ov.of(v * P + i) : NaN, k2, l2.x, l2.y, thr2, g, gQ);
+                stg_stream(gv + v, Elem<T>::pack(o));
+            }
+        } else {
+            for (int c = gl; c < V_local; c += 32)
+                grow[c] = Elem<T>::from_float(PointTerm<VARIANT>::grad(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]),
+                                                                       LOCA ? ov.of(c) : NaN, k2, l2.x, l2.y, thr2, g, gQ));
+        }
+    }
+}
+
+// a warp per row once every resident warp has a row of its own; the whole block per row below that
+bool vs_warp_rows(int64_t n_rows);
+
 int vs_sm_count() {
     static int n = 0;
     if (!n) {
@@ -304,6 +383,8 @@ int vs_sm_count() {
     }
     return n;
 }
+
+bool vs_warp_rows(int64_t n_rows) { return n_rows >= (int64_t)vs_sm_count() * 64; }
 
 int vs_check(int64_t n_rows, int64_t V_local, int dtype, float T) {
     KD_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "n_rows out of range (%lld)", (long long)n_rows);
@@ -317,8 +398,14 @@ template <int VARIANT, typename T>
 int launch_accum(const void* t, int64_t ld_t, const void* s, int64_t ld_s, const float2* lse2, const kd_token_record* rec,
                  const float* table, int col0, int64_t n_rows, int V_local, float k2, float thr2, float2* partial, cudaStream_t st) {
     const int64_t cap = (int64_t)vs_sm_count() * 8;
-    vshard_accum_kernel<VARIANT, T><<<(int)(n_rows < cap ? n_rows : cap), kVsThreads, 0, st>>>(
-        static_cast<const T*>(t), ld_t, static_cast<const T*>(s), ld_s, lse2, rec, table, col0, n_rows, V_local, k2, thr2, partial);
+    if (vs_warp_rows(n_rows)) {
+        const int64_t blocks = (n_rows + kVsWarps - 1) / kVsWarps;
+        vshard_accum_kernel<VARIANT, T, 32><<<(int)(blocks < cap ? blocks : cap), kVsThreads, 0, st>>>(
+            static_cast<const T*>(t), ld_t, static_cast<const T*>(s), ld_s, lse2, rec, table, col0, n_rows, V_local, k2, thr2, partial);
+    } else {
+        vshard_accum_kernel<VARIANT, T, kVsThreads><<<(int)(n_rows < cap ? n_rows : cap), kVsThreads, 0, st>>>(
+            static_cast<const T*>(t), ld_t, static_cast<const T*>(s), ld_s, lse2, rec, table, col0, n_rows, V_local, k2, thr2, partial);
+    }
     KD_CHECK_LAUNCH("vshard_accum_kernel");
     return KD_OK;
 }
@@ -327,6 +414,14 @@ template <int VARIANT, typename T>
 int launch_emit(const void* t, int64_t ld_t, const void* s, int64_t ld_s, const float2* lse2, const float* Q, const kd_token_record* rec,
                 const float* table, int col0, void* grad, int64_t ld_g, int64_t n_rows, int V_local, float k2, float thr2, float gscale,
                 const float* upstream, cudaStream_t st) {
+    if (vs_warp_rows(n_rows)) {
+        const int64_t cap = (int64_t)vs_sm_count() * 8, blocks = (n_rows + kVsWarps - 1) / kVsWarps;
+        vshard_emit_rows_kernel<VARIANT, T><<<(int)(blocks < cap ? blocks : cap), kVsThreads, 0, st>>>(
+            static_cast<const T*>(t), ld_t, static_cast<const T*>(s), ld_s, lse2, Q, rec, table, col0, static_cast<T*>(grad), ld_g,
+            n_rows, V_local, k2, thr2, gscale, upstream);
+        KD_CHECK_LAUNCH("vshard_emit_rows_kernel");
+        return KD_OK;
+    }
     int64_t gx = (V_local + kVsThreads - 1) / kVsThreads;
     gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
     int64_t gy = (int64_t)vs_sm_count() * 16 / gx;
@@ -377,20 +472,24 @@ int kd_vshard_stats(const void* teacher, int64_t ld_t, const void* student, int6
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float k2 = kLog2e / T;
     const int64_t cap = (int64_t)vs_sm_count() * 8;
-    const int grid = (int)(n_rows < cap ? n_rows : cap);
+    const bool warp_rows = vs_warp_rows(n_rows);
+    const int64_t blocks = warp_rows ? (n_rows + kVsWarps - 1) / kVsWarps : n_rows;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+#define KD_VS_STATS(TT)                                                                                                           \
+    do {                                                                                                                          \
+        if (warp_rows)                                                                                                            \
+            vshard_stats_kernel<TT, 32><<<grid, kVsThreads, 0, st>>>(static_cast<const TT*>(teacher), ld_t,                        \
+                static_cast<const TT*>(student), ld_s, labels, (int)col0, n_rows, (int)V_local, k2, stats);                       \
+        else                                                                                                                      \
+            vshard_stats_kernel<TT, kVsThreads><<<grid, kVsThreads, 0, st>>>(static_cast<const TT*>(teacher), ld_t,                \
+                static_cast<const TT*>(student), ld_s, labels, (int)col0, n_rows, (int)V_local, k2, stats);                       \
+    } while (0)
     switch (dtype) {
-        case KD_DTYPE_BF16:
-            vshard_stats_kernel<__nv_bfloat16><<<grid, kVsThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(teacher), ld_t,
-                static_cast<const __nv_bfloat16*>(student), ld_s, labels, (int)col0, n_rows, (int)V_local, k2, stats);
-            break;
-        case KD_DTYPE_F16:
-            vshard_stats_kernel<__half><<<grid, kVsThreads, 0, st>>>(static_cast<const __half*>(teacher), ld_t,
-                static_cast<const __half*>(student), ld_s, labels, (int)col0, n_rows, (int)V_local, k2, stats);
-            break;
-        default:
-            vshard_stats_kernel<float><<<grid, kVsThreads, 0, st>>>(static_cast<const float*>(teacher), ld_t,
-                static_cast<const float*>(student), ld_s, labels, (int)col0, n_rows, (int)V_local, k2, stats);
+        case KD_DTYPE_BF16: KD_VS_STATS(__nv_bfloat16); break;
+        case KD_DTYPE_F16: KD_VS_STATS(__half); break;
+        default: KD_VS_STATS(float);
     }
+#undef KD_VS_STATS
     KD_CHECK_LAUNCH("vshard_stats_kernel");
     return KD_OK;
 }

@@ -104,7 +104,9 @@ def test_vocab_sharded_world_size_2_gloo():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["reference", "per_row", "kl", "kl_log_target"])
-@pytest.mark.parametrize("n,V,cuts,Tk", [(24, 8192, [0, 4096, 8192], 2.0), (9, 5000, [0, 1237, 5000], 0.8)])
+@pytest.mark.parametrize("n,V,cuts,Tk", [(24, 8192, [0, 4096, 8192], 2.0), (9, 5000, [0, 1237, 5000], 0.8),
+                                         # >= 64 rows per SM: the warp-per-row kernels (vector and ragged scalar walks)
+                                         (9600, 1040, [0, 520, 1040], 2.0), (9500, 777, [0, 301, 777], 0.8)])
 def test_cuda_phases_two_simulated_shards(mode, n, V, cuts, Tk):
     t, s, lab = synthetic.logit_batch(n, V, seed=21, peaked=(Tk < 1.0))
     res = _run_shards(mode, t, s, lab, cuts, Tk, sharded.CudaVocabPhases, device="cuda", dtype=torch.bfloat16)
