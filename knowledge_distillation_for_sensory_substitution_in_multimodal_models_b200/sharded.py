@@ -410,14 +410,27 @@ class _LmHeadVocabShardedKD(torch.autograd.Function):
         loss, grad_logits = logit_kd_vocab_sharded(teacher_shard, logits, labels, col0, V_total, T, mode=mode, alpha=alpha, eps=eps,
                                                    n_rows_norm=n_rows_norm, reduction=reduction, group=group, phases=phases,
                                                    collectives=collectives, student_partials=partials)
-        ctx.save_for_backward(hidden, weight_shard, grad_logits)
+        ctx.save_for_backward(hidden, weight_shard)
+        ctx.grad_logits = grad_logits                                               # ours: rescaled in place by the backward
         ctx.collectives = collectives if collectives is not None else DistCollectives(group)
         return loss
 
     @staticmethod
     def backward(ctx, grad_output):
-        hidden, weight_shard, grad_logits = ctx.saved_tensors
-        g = grad_logits.to(hidden.dtype) * grad_output.to(hidden.dtype)
+        hidden, weight_shard = ctx.saved_tensors
+        grad_logits, ctx.grad_logits = ctx.grad_logits, None
+        if grad_logits is None:
+            raise RuntimeError("lm_head_kd_vocab_sharded: backward through the same graph twice")
+        if grad_logits.is_cuda and grad_logits.dtype == hidden.dtype and grad_logits.stride(1) == 1:
+            # d loss / d logits *= grad_output on the device, skipped there when it is 1 (the usual loss.backward())
+            dev = grad_logits.device
+            go = grad_output.detach().to(device=dev, dtype=torch.float32).reshape(()).contiguous()
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().kd_scale_rows(grad_logits.data_ptr(), grad_logits.stride(0), grad_logits.shape[0],
+                                                     grad_logits.shape[1], _dtype_code(grad_logits), go.data_ptr(), _stream_ptr(dev)))
+            g = grad_logits
+        else:
+            g = grad_logits.to(hidden.dtype) * grad_output.to(hidden.dtype)
         d_hidden = torch.matmul(g, weight_shard.detach())                           # partial over this rank's columns
         d_hidden = ctx.collectives.sum_(d_hidden.contiguous())                      # sum over the vocabulary shards
         d_weight = torch.matmul(g.t(), hidden.detach())

@@ -104,3 +104,17 @@ def test_lm_head_kd_against_single_gpu_op():
     ref = kd.loca_kl(teacher, logits.clone().requires_grad_(True), labels, T=T, alpha=0.8)
     got = sharded.lm_head_kd_vocab_sharded(hidden, weight, teacher, labels, 0, v, T, alpha=0.8)
     assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item())
+
+
+def test_lm_head_kd_backward_scales_with_grad_output():
+    n, v, h, T = 256, 1024, 128, 2.0
+    hidden, weight = _operands(n, v, h, torch.bfloat16, seed=23)
+    teacher = (torch.randn(n, v, device="cuda") * 2).to(torch.bfloat16)
+    labels = torch.randint(0, v, (n,), device="cuda")
+    grads = []
+    for scale in (1.0, 4.0):          # a power of two: the bf16 gradients must scale exactly
+        hd, wd = hidden.clone().requires_grad_(True), weight.clone().requires_grad_(True)
+        (sharded.lm_head_kd_vocab_sharded(hd, wd, teacher, labels, 0, v, T) * scale).backward()
+        grads.append((hd.grad.float(), wd.grad.float()))
+    assert float((grads[1][0] - 4.0 * grads[0][0]).norm() / grads[1][0].norm()) <= 2e-3
+    assert float((grads[1][1] - 4.0 * grads[0][1]).norm() / grads[1][1].norm()) <= 2e-3
