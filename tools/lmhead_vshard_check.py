@@ -1,5 +1,5 @@
-"""2+ GPU check of BASELINE configs[4] (library-GEMM form): vocabulary-parallel student lm_head (896 x 151 936) feeding the
-vocabulary-sharded LoCa KD.  Correctness at 64 rows against the fp64 oracle, then the 64k-token step time.
+"""2+ GPU check of BASELINE configs[4]: vocabulary-parallel student lm_head (896 x 151 936; the tcgen05 kernel, or the
+library GEMM with `library` as the first argument) feeding the vocabulary-sharded LoCa KD.  Correctness at 64 rows against the fp64 oracle, then the 64k-token step time.
    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/lmhead_vshard_check.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,6 +13,7 @@ dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
 torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
 K, V, T = 896, 151936, 2.0
+GEMM = sys.argv[1] if len(sys.argv) > 1 else "tcgen05"
 lo, hi = rank * (V // world), (rank + 1) * (V // world) if rank < world - 1 else V
 g = torch.Generator().manual_seed(11)
 n = 64
@@ -25,7 +26,7 @@ dH_ref = ref.grad @ W.double()
 dW_ref = ref.grad.t() @ H.double()
 h = H.to(dev).requires_grad_(True)
 w = W[lo:hi].to(dev).requires_grad_(True)
-loss = sharded.lm_head_kd_vocab_sharded(h, w, t[:, lo:hi].contiguous().to(dev), lab.to(dev), lo, V, T)
+loss = sharded.lm_head_kd_vocab_sharded(h, w, t[:, lo:hi].contiguous().to(dev), lab.to(dev), lo, V, T, gemm=GEMM)
 loss.backward()
 e_loss = abs(loss.item() - ref.loss.item()) / abs(ref.loss.item())
 e_dh = ((h.grad.double().cpu() - dH_ref).norm() / dH_ref.norm()).item()
@@ -41,7 +42,7 @@ lab = torch.randint(0, V, (n,), device=dev)
 dist.broadcast(lab, 0)
 def step():
     H.grad = None; Ws.grad = None
-    sharded.lm_head_kd_vocab_sharded(H, Ws, ts, lab, lo, V, T).backward()
+    sharded.lm_head_kd_vocab_sharded(H, Ws, ts, lab, lo, V, T, gemm=GEMM).backward()
 for _ in range(2): step()
 torch.cuda.synchronize(); dist.barrier()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -51,6 +52,6 @@ b.record(); torch.cuda.synchronize()
 ms = torch.tensor([a.elapsed_time(b) / 3], device=dev)
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print(f"lm_head (896 x {V}) + LoCa KD, {n} tokens over {world} GPUs: {ms.item():.1f} ms/step = {n / ms.item() * 1e3:.0f} tokens/s", flush=True)
+    print(f"[{GEMM}] lm_head (896 x {V}) + LoCa KD, {n} tokens over {world} GPUs: {ms.item():.1f} ms/step = {n / ms.item() * 1e3:.0f} tokens/s", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
