@@ -166,7 +166,7 @@ int kd_vshard_emit(const void* teacher, int64_t ld_t, const void* student, int64
  *   logits[n_rows, V_local] = hidden[n_rows, H] . weight[V_local, H]^T     (bf16 / fp16, fp32 accumulation, row-major,
  *                                                                          pitches ld_* in elements)
  * When `stat_partials` is not NULL ([kd_lm_head_stat_tiles(V_local)][n_rows][2] floats) the epilogue also leaves each
- * row's (max, sum 2^((x - max) log2e / T)) over every 256-column tile of the ROUNDED logits; kd_lm_head_stats_merge folds
+ * row's (max, sum 2^((x - max) log2e / T)) over every 128-column tile of the ROUNDED logits; kd_lm_head_stats_merge folds
  * them into words 7, 8 of the rows' kd_vshard_stats blocks, and kd_vshard_stats may then be called with student == NULL
  * (teacher half only) — the student logits are not read again for their statistics.
  * KD_ERR_UNSUPPORTED: fp32 operands, or bases / pitches / V_local that are not multiples of 16 bytes (use a library GEMM).
@@ -176,18 +176,6 @@ int kd_lm_head_fwd(const void* hidden, int64_t ld_h, const void* weight, int64_t
                    float* stat_partials /* may be NULL */, int64_t n_rows, int64_t V_local, int64_t H, int dtype, float T,
                    void* stream);
 int kd_lm_head_stats_merge(const float* stat_partials, int64_t n_tiles, float* stats, int64_t n_rows, float T, void* stream);
-/* The same GEMM with ALL of kd_vshard_stats in its epilogue: each epilogue thread also streams its row's teacher cells
- * (`teacher` [n_rows, V_local], pitch ld_t; global column of local column 0 = col0) and leaves their (max, sum-exp, best,
- * runner-up) per tile in `teacher_partials` ([tiles][n_rows][8] 32-bit words); kd_lm_head_stats_merge_kd then writes the
- * complete 12-word statistics block of every row (the label logit is gathered there) and kd_vshard_stats is not called.
- * Exact, but measured slower than kd_lm_head_fwd + the teacher-only kd_vshard_stats: opt-in. */
-#define KD_LM_HEAD_TEACHER_WORDS 8
-int kd_lm_head_fwd_kd(const void* hidden, int64_t ld_h, const void* weight, int64_t ld_w, void* logits, int64_t ld_c,
-                      float* stat_partials, const void* teacher, int64_t ld_t, int64_t col0, float* teacher_partials,
-                      int64_t n_rows, int64_t V_local, int64_t H, int dtype, float T, void* stream);
-int kd_lm_head_stats_merge_kd(const float* stat_partials, const float* teacher_partials, int64_t n_tiles, const void* teacher,
-                              int64_t ld_t, const int64_t* labels /* may be NULL */, int64_t col0, int64_t V_local, float* stats,
-                              int64_t n_rows, int dtype, float T, void* stream);
 
 /* grad *= (*factor) in place, skipped on device when *factor == 1 (kept for callers that accept double rounding). */
 int kd_scale_rows(void* grad, int64_t ld_g, int64_t n_rows, int64_t V, int dtype, const float* factor, void* stream);

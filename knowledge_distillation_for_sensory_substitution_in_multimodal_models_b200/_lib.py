@@ -21,7 +21,6 @@ FLAG_NO_GRAD, FLAG_FORCE_STREAMING = 1, 2
 STATUS_BAD_LABEL = 1
 TOKEN_RECORD_BYTES = 16
 VSHARD_STAT_WORDS = 12
-LM_HEAD_TEACHER_WORDS = 8
 
 _p, _i64, _sz, _f, _d, _i, _u = C.c_void_p, C.c_int64, C.c_size_t, C.c_float, C.c_double, C.c_int, C.c_uint
 
@@ -48,8 +47,6 @@ SIGNATURES = {
     "kd_lm_head_stat_tiles": (_i, [_i64]),
     "kd_lm_head_fwd": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i, _f, _p]),
     "kd_lm_head_stats_merge": (_i, [_p, _i64, _p, _i64, _f, _p]),
-    "kd_lm_head_fwd_kd": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _p, _i64, _i64, _i64, _i, _f, _p]),
-    "kd_lm_head_stats_merge_kd": (_i, [_p, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i, _f, _p]),
     "kd_info_nce_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "kd_info_nce_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i64, _i64, _i64, _i, _f, _p, _u, _p]),
     "kd_info_nce_regrad": (_i, [_p, _sz, _p, _i64, _i64, _i64, _i, _p, _p]),

@@ -2,22 +2,26 @@
 // reference takes from the HF student at P1:228-240 are `hidden @ W_lm_head^T`, 896 x 151 936 for Qwen2-0.5B).
 //
 //   logits[n_rows, V_local] = hidden[n_rows, H] * weight[V_local, H]^T        bf16/fp16 operands, fp32 accumulation, 16-bit out
-//   partials[tile][row]     = (max, sum 2^((x - max) * log2e / T)) of the row's ROUNDED logits inside column tile `tile`
+//   partials[tile][row]     = (max, sum 2^((x - max) * log2e / T)) of the row's ROUNDED logits inside 128-column tile `tile`
 //
 // so that kd_vshard_stats does not read the student logits again (its teacher half is all that is left to stream).
 //
 // Tensor-core kernel for sm_100a, hand-written:
-//   * persistent, one CTA per SM walking 128 x 256 output tiles in groups of 16 row tiles (a wave of CTAs touches ~16
-//     hidden tiles and ~9 weight tiles: both stay in L2);
-//   * operands arrive by 2-D TMA (SWIZZLE_128B, K blocks of 64) into a 4-stage ring, one full/empty mbarrier pair per stage;
-//   * warp 0 lane 0 issues the TMA loads, warp 1 lane 0 issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = 256,
-//     K = 16), tcgen05.commit releases the stage / publishes the accumulator;
-//   * tensor memory holds TWO 128 x 256 fp32 accumulators (all 512 columns): warps 2-5 drain tile i (tcgen05.ld, thread = row,
-//     online max / sum-exp, conversion, XOR-swizzled shared-memory staging, TMA store) while the MMAs of tile i + 1 run;
+//   * persistent CTA PAIRS (cluster 2 x 1 x 1 = the two SMs of a TPC), one 256 x 256 output tile per pair at a time, walked in
+//     groups of 8 row tiles (a wave touches ~8 x 256 hidden rows and ~9 weight tiles: both stay in L2);
+//   * tcgen05.mma.cta_group::2.kind::f16 (M = 256 over the pair, N = 256, K = 16) issued by ONE lane of the even CTA; each CTA
+//     feeds its 128 hidden rows and HALF of the weight tile (32 KB per 64-wide K block instead of 48 KB), so the shared-memory
+//     fill per SM drops by a third — what matters on a power-bound GEMM;
+//   * operands arrive by 2-D TMA (SWIZZLE_128B) into a 5-stage ring in each CTA; the loads carry .cta_group::2 and complete on
+//     the LEADER's full barrier, tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs;
+//   * tensor memory holds TWO 128 x 256 fp32 accumulators per CTA (all 512 columns): eight epilogue warps (two per TMEM lane
+//     quarter, 128 columns each) drain tile i — tcgen05.ld with thread = row, rounding, online max / sum-exp, XOR-swizzled
+//     shared-memory staging, TMA stores, two slabs in flight per half — while the MMAs of tile i + 1 run; they hand the
+//     accumulator back on the leader's barrier (remote mbarrier arrive);
 //   * ragged shapes: TMA zero-fills out-of-range rows / K columns on load and clips on store; the statistics mask columns
 //     >= V_local themselves.
-// Measured (profiles/r2_tcgen05_gemm_probe.txt, the standalone form tools/tcgen05_gemm_probe.cu): 16 384 x 151 936 x 896 in
-// 3.26 ms = 1.37 PFLOP/s, the library GEMM 3.23 ms on the same box class; 16 384 x 8 192 x 3 584: 0.597 ms vs 0.612 ms.
+// Measured: DESIGN.md §4.3, profiles/r2_tcgen05_gemm_probe.txt (development path: tools/tcgen05_probe.cu -> tcgen05_gemm_probe.cu
+// -> tcgen05_gemm2_probe.cu).
 #include <cuda.h>
 #include <math.h>
 
@@ -27,13 +31,16 @@ namespace kd {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+// a CTA PAIR (cluster 2 x 1 x 1, the two SMs of a TPC) owns one 256 x 256 output tile: BM rows and half of the weight tile per CTA
+constexpr int BM = 128, BN = 256, BNH = BN / 2, BK = 64, STAGES = 5;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SLAB = 64;                           // output columns per TMA store (one 128-byte swizzle atom)
 constexpr int C_SLAB_BYTES = BM * SLAB * 2;
-constexpr int GEMM_THREADS = 192;
-constexpr int GROUP_M = 16;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 2 * C_SLAB_BYTES + 1024;
+constexpr int EPI_HALVES = 2;                     // two epilogue warp quads, 128 of the tile's 256 columns each
+constexpr int STAT_COLS = BN / EPI_HALVES;        // columns per statistics partial
+constexpr int GEMM_THREADS = 64 + EPI_HALVES * 128;
+constexpr int GROUP_M = 8;                        // in 256-row pair tiles
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + EPI_HALVES * 2 * C_SLAB_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -52,6 +59,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                  "l"(map), "r"(c0), "r"(c1), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {      // the same shared-memory offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// 2-SM TMA load: the data lands in THIS CTA's shared memory, the completion bytes on the pair leader's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+                 : "memory");
+}
+// arrives on `bar` (same offset) in BOTH CTAs of the pair once the MMAs issued so far have retired
+__device__ __forceinline__ void commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // K-major operand tile, 128-byte swizzle: 128-byte rows, 8-row groups 1024 B apart (SBO); LBO is unused for this layout
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t addr) {
@@ -104,67 +132,63 @@ template <> struct Pack2<__half> {
     }
 };
 
-// what the teacher side of kd_vshard_stats needs from one 256-column tile of a row
-struct TeacherTile {
-    float m, s, a1, a2;
-    int i1, i2, pad0, pad1;
-};
-
-// STATS: 0 = product only, 1 = + student (max, sum-exp) per tile, 2 = + the teacher's (max, sum-exp, best, runner-up) per tile
+// STATS: 0 = product only, 1 = + the rows' (max, sum-exp) per 128-column half tile
 template <typename T, int STATS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                    const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapT, int M, int N, int K, float k2,
-                    float2* __restrict__ partials, int col0, TeacherTile* __restrict__ tparts) {
+                    const __grid_constant__ CUtensorMap mapC, int M, int N, int K, float k2, float2* __restrict__ partials) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) unsigned long long bars[2 * STAGES + 5];
+    __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4];
     __shared__ uint32_t tmem_base_sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t rank;                                  // 0 = pair leader (issues the MMAs, owns the full / accumulator-empty barriers)
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int row_off = (int)rank * BM;             // this CTA's rows inside the pair's 256-row tile
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + STAGES * 8;
     const uint32_t bar_acc_full = bar_full + 2 * STAGES * 8, bar_acc_empty = bar_acc_full + 2 * 8;
-    const uint32_t bar_teacher = bar_acc_empty + 2 * 8;
-    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN, tiles = tiles_m * tiles_n;
+    const int tiles_m = (M + 2 * BM - 1) / (2 * BM), tiles_n = (N + BN - 1) / BN, tiles = tiles_m * tiles_n;
     const int kblocks = (K + BK - 1) / BK;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full + a * 8, 1); mbar_init(bar_acc_empty + a * 8, 4); }
-        mbar_init(bar_teacher, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full + a * 8, 1); mbar_init(bar_acc_empty + a * 8, 2 * 4 * EPI_HALVES); }      // every epilogue warp of both CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_sm)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_sm)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    cluster_sync_all();                             // barriers initialised and tensor memory allocated in both CTAs
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_sm;
 
     if (warp == 0) {
-        if (lane == 0) {      // ---------------- TMA producer ----------------
+        if (lane == 0) {      // ---------------- TMA producer (both CTAs) ----------------
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int t = pair; t < tiles; t += npairs) {
                 int tile_m, tile_n;
                 tile_coords(t, tiles_m, tiles_n, tile_m, tile_n);
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(bar_empty + s * 8, ph ^ 1u);
-                    mbar_expect_tx(bar_full + s * 8, STAGE_BYTES);
+                    if (rank == 0) mbar_expect_tx(bar_full + s * 8, 2 * STAGE_BYTES);      // both CTAs' bytes land on the leader's barrier
+                    const uint32_t leader_full = mapa_rank(bar_full + s * 8, 0);
                     const uint32_t dstA = smem_u32(smem + s * STAGE_BYTES), dstB = dstA + A_BYTES;
-                    tma_load_2d(dstA, &mapA, kb * BK, tile_m * BM, bar_full + s * 8);
-                    tma_load_2d(dstB, &mapB, kb * BK, tile_n * BN, bar_full + s * 8);
+                    tma_load_2d_2sm(dstA, &mapA, kb * BK, tile_m * 2 * BM + row_off, leader_full);
+                    tma_load_2d_2sm(dstB, &mapB, kb * BK, tile_n * BN + (int)rank * BNH, leader_full);
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {      // ---------------- MMA issuer ----------------
-            // D fp32 (bit 4), A/B format (bits 7-9 / 10-12), N >> 3 at bit 17, M >> 4 at bit 24; both operands K-major
+        if (lane == 0 && rank == 0) {      // ---------------- MMA issuer (pair leader only) ----------------
+            // D fp32 (bit 4), A/B format (bits 7-9 / 10-12), N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 over the pair); K-major
             const uint32_t idesc = (1u << 4) | (Pack2<T>::kFormat << 7) | (Pack2<T>::kFormat << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                   ((uint32_t)(BM >> 4) << 24);
+                                   ((uint32_t)((2 * BM) >> 4) << 24);
             uint32_t it = 0, i = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+            for (int t = pair; t < tiles; t += npairs, ++i) {
                 const uint32_t as = i & 1, aph = (i >> 1) & 1;
                 mbar_wait(bar_acc_empty + as * 8, aph ^ 1u);      // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -180,85 +204,42 @@ lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
                         asm volatile(
                             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
                             "l"(da), "l"(db), "r"(idesc), "r"(acc)
                             : "memory");
                     }
-                    // the stage returns to the producer once the MMAs that read it have retired
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty + s * 8)
-                                 : "memory");
+                    commit_pair(bar_empty + s * 8);      // the stage returns to both producers once the MMAs that read it retire
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_acc_full + as * 8)
-                             : "memory");
+                commit_pair(bar_acc_full + as * 8);
             }
         }
-    } else {                  // ---------------- epilogue: warps 2..5 <-> TMEM lane quarters (warp % 4) ----------------
-        const int q = warp & 3;
+    } else {                  // ---------------- epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----------------
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int r_in = q * 32 + lane;
-        // STATS == 2 trades the second output staging buffer for a teacher slab (same 128 x 64 box, same swizzle), which the
-        // elected thread fetches by TMA one slab ahead
-        constexpr int CBUFS = (STATS == 2) ? 1 : 2;
-        unsigned char* cstage = smem + STAGES * STAGE_BYTES;
-        unsigned char* tbuf = cstage + C_SLAB_BYTES;
-        uint32_t i = 0, slab = 0, tphase = 0;
-        if constexpr (STATS == 2) {
-            if (tid == 64 && (int)blockIdx.x < tiles) {
-                int tm0, tn0;
-                tile_coords(blockIdx.x, tiles_m, tiles_n, tm0, tn0);
-                mbar_expect_tx(bar_teacher, C_SLAB_BYTES);
-                tma_load_2d(smem_u32(tbuf), &mapT, tn0 * BN, tm0 * BM, bar_teacher);
-            }
-        }
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+        const bool elected = (tid == 64 + half * 128);                 // issues this half's TMA stores
+        unsigned char* cstage = smem + STAGES * STAGE_BYTES + half * 2 * C_SLAB_BYTES;
+        const int n_stat = (N + STAT_COLS - 1) / STAT_COLS;
+        uint32_t i = 0, slab = 0;
+        for (int t = pair; t < tiles; t += npairs, ++i) {
             int tile_m, tile_n;
             tile_coords(t, tiles_m, tiles_n, tile_m, tile_n);
             const uint32_t as = i & 1, aph = (i >> 1) & 1;
             mbar_wait(bar_acc_full + as * 8, aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            MaxSum ms, mt;
-            Top2 top;
+            MaxSum ms;
             ms.init();
-            mt.init();
-            top.init();
-            const int row_g = tile_m * BM + r_in;
+            const int row_g = tile_m * 2 * BM + row_off + r_in;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += SLAB, ++slab) {
+            for (int c = half * STAT_COLS; c < (half + 1) * STAT_COLS; c += SLAB, ++slab) {
                 uint32_t r[SLAB];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * BN + (uint32_t)c;
                 tmem_ld32(taddr, r);
                 tmem_ld32(taddr + 32, r + 32);
-                uint4 traw[SLAB / 8];
-                if constexpr (STATS == 2) {      // this row's 64 teacher cells from the TMA-staged slab (swizzled like the output stage)
-                    mbar_wait(bar_teacher, tphase);
-                    tphase ^= 1u;
-#pragma unroll
-                    for (int j = 0; j < SLAB / 8; ++j)
-                        traw[j] = *reinterpret_cast<const uint4*>(tbuf + r_in * 128 + ((j ^ (r_in & 7)) << 4));
-                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                unsigned char* buf = cstage + (CBUFS == 2 ? (slab & 1) : 0) * C_SLAB_BYTES;
-                // the TMA store that last read this staging buffer must be done with it
-                if (tid == 64) {
-                    if constexpr (CBUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if constexpr (STATS == 2) {      // every thread holds its teacher cells: fetch the next slab (this tile's, or the next tile's first)
-                    if (tid == 64) {
-                        int nm = tile_m, nn = tile_n, nc = c + SLAB;
-                        bool more = true;
-                        if (nc == BN) {
-                            nc = 0;
-                            more = t + (int)gridDim.x < tiles;
-                            if (more) tile_coords(t + gridDim.x, tiles_m, tiles_n, nm, nn);
-                        }
-                        if (more) {
-                            mbar_expect_tx(bar_teacher, C_SLAB_BYTES);
-                            tma_load_2d(smem_u32(tbuf), &mapT, nn * BN + nc, nm * BM, bar_teacher);
-                        }
-                    }
-                }
-                float vmax = -INFINITY;
+                unsigned char* buf = cstage + (slab & 1) * C_SLAB_BYTES;
+                // the TMA store that read this staging buffer two slabs ago must be done with it
+                if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
                 const int col_base = tile_n * BN + c;
 #pragma unroll
                 for (int j = 0; j < SLAB / 8; ++j) {
@@ -276,16 +257,17 @@ lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     *reinterpret_cast<uint4*>(buf + r_in * 128 + ((j ^ (r_in & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (tid == 64) {
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                if (elected) {
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&mapC), "r"(col_base),
-                                 "r"(tile_m * BM), "r"(smem_u32(buf))
+                                 "r"(tile_m * 2 * BM + row_off), "r"(smem_u32(buf))
                                  : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 if constexpr (STATS != 0) {      // online (max, sum-exp) of this row over the slab's in-range columns
-                    const int valid = min(SLAB, N - col_base);      // > 0: tiles start inside the matrix; N % 8 == 0
-                    if (valid == SLAB) {
+                    const int valid = min(SLAB, N - col_base);      // may be <= 0 in the last tile: the whole slab is out of range
+                    float vmax = -INFINITY;
+                    if (valid >= SLAB) {
 #pragma unroll
                         for (int x = 0; x < SLAB; ++x) vmax = fmaxf(vmax, __uint_as_float(r[x]));
                     } else {
@@ -299,59 +281,34 @@ lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         ms.s = (ms.m == -INFINITY) ? 0.f : ms.s * ex2((ms.m - vmax) * k2);
                         ms.m = vmax;
                     }
-                    const float mk = ms.m * k2;
-                    float s0 = 0.f, s1 = 0.f;
+                    if (ms.m != -INFINITY) {
+                        const float mk = ms.m * k2;
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                    for (int x = 0; x < SLAB; x += 2) {
-                        s0 += ex2(fmaf(__uint_as_float(r[x]), k2, -mk));
-                        s1 += ex2(fmaf(__uint_as_float(r[x + 1]), k2, -mk));
-                    }
-                    ms.s += s0 + s1;
-                }
-                if constexpr (STATS == 2) {      // the teacher's side of kd_vshard_stats for the same cells
-                    const int valid_t = (row_g < M) ? min(SLAB, N - col_base) : 0;
-#pragma unroll
-                    for (int j = 0; j < SLAB / 8; ++j) {
-                        if (8 * j < valid_t) {
-                            float x[8];
-                            Elem<T>::unpack(traw[j], x);
-                            float vm = x[0];
-#pragma unroll
-                            for (int e = 1; e < 8; ++e) vm = fmaxf(vm, x[e]);
-                            if (vm > mt.m) {
-                                mt.s = (mt.m == -INFINITY) ? 0.f : mt.s * ex2((mt.m - vm) * k2);
-                                mt.m = vm;
-                            }
-                            const float mk = mt.m * k2;
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) mt.s += ex2(fmaf(x[e], k2, -mk));
-                            if (vm >= top.a2) {
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) top.push(x[e], col0 + col_base + 8 * j + e);
-                            }
+                        for (int x = 0; x < SLAB; x += 4) {
+                            s0 += ex2(fmaf(__uint_as_float(r[x]), k2, -mk));
+                            s1 += ex2(fmaf(__uint_as_float(r[x + 1]), k2, -mk));
+                            s2 += ex2(fmaf(__uint_as_float(r[x + 2]), k2, -mk));
+                            s3 += ex2(fmaf(__uint_as_float(r[x + 3]), k2, -mk));
                         }
+                        ms.s += (s0 + s1) + (s2 + s3);
                     }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acc_empty + as * 8) : "memory");
+            if (lane == 0)      // on the leader's barrier: its MMA warp reuses the accumulator of BOTH CTAs
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar_acc_empty + as * 8, 0)) : "memory");
             if constexpr (STATS != 0) {
-                if (row_g < M) partials[(size_t)tile_n * M + row_g] = make_float2(ms.m, ms.s);
-            }
-            if constexpr (STATS == 2) {
-                if (row_g < M) {
-                    uint4* o = reinterpret_cast<uint4*>(tparts + (size_t)tile_n * M + row_g);
-                    o[0] = make_uint4(__float_as_uint(mt.m), __float_as_uint(mt.s), __float_as_uint(top.a1), __float_as_uint(top.a2));
-                    o[1] = make_uint4((uint32_t)top.i1, (uint32_t)top.i2, 0u, 0u);
-                }
+                const int st = tile_n * EPI_HALVES + half;
+                if (row_g < M && st < n_stat) partials[(size_t)st * M + row_g] = make_float2(ms.m, ms.s);
             }
         }
-        if (tid == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    cluster_sync_all();                             // neither CTA may leave (or free tensor memory) while its peer still uses the pair
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 // merges the per-tile student (max, sum-exp) of each row into words 7, 8 of its kd_vshard_stats block
@@ -367,42 +324,6 @@ __global__ void lm_head_stats_merge_kernel(const float2* __restrict__ partials, 
     }
     stats[r * stat_words + 7] = ms.m;
     stats[r * stat_words + 8] = ms.s;
-}
-
-// teacher + student: the whole 12-word kd_vshard_stats block of each row from the GEMM's per-tile partials
-template <typename T>
-__global__ void lm_head_stats_merge_kd_kernel(const float2* __restrict__ partials, const TeacherTile* __restrict__ tparts, int n_tiles,
-                                              int64_t n_rows, float k2, const T* __restrict__ teacher, int64_t ld_t,
-                                              const int64_t* __restrict__ labels, int col0, int V_local, float* __restrict__ stats,
-                                              int stat_words) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
-    MaxSum ms, mt;
-    Top2 top;
-    ms.init();
-    mt.init();
-    top.init();
-    for (int t = 0; t < n_tiles; ++t) {
-        const float2 p = partials[(size_t)t * n_rows + r];
-        ms.merge(p.x, p.y, k2);
-        const uint4* tp = reinterpret_cast<const uint4*>(tparts + (size_t)t * n_rows + r);
-        const uint4 a = tp[0], b = tp[1];
-        mt.merge(__uint_as_float(a.x), __uint_as_float(a.y), k2);
-        Top2 o;
-        o.a1 = __uint_as_float(a.z); o.a2 = __uint_as_float(a.w); o.i1 = (int)b.x; o.i2 = (int)b.y;
-        top.merge(o);
-    }
-    float x_label = -INFINITY;
-    if (labels) {
-        const int64_t lab = labels[r] - col0;
-        if (lab >= 0 && lab < V_local) x_label = Elem<T>::to_float(teacher[r * ld_t + lab]);
-    }
-    float* o = stats + r * stat_words;
-    o[0] = mt.m; o[1] = mt.s;
-    o[2] = top.a1; o[3] = __int_as_float(top.i1); o[4] = top.a2; o[5] = __int_as_float(top.i2);
-    o[6] = x_label;
-    o[7] = ms.m; o[8] = ms.s;
-    o[9] = o[10] = o[11] = 0.f;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -441,14 +362,15 @@ int gemm_sm_count() {
 }
 
 template <typename T, int STATS>
-int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& tmap, int M, int N, int K,
-                float k2, float2* partials, int col0, TeacherTile* tparts, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K, float k2, float2* partials,
+                cudaStream_t st) {
     auto kern = lm_head_gemm_kernel<T, STATS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);      // per device, cheap
     if (e != cudaSuccess) return cuda_fail(e, "lm_head_gemm_kernel: shared-memory opt-in");
-    const int64_t tiles = (int64_t)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = (int)(tiles < gemm_sm_count() ? tiles : gemm_sm_count());
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, b, c, tmap, M, N, K, k2, partials, col0, tparts);
+    const int64_t tiles = (int64_t)((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+    const int64_t pairs = gemm_sm_count() / 2;
+    const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);      // persistent CTA pairs (cluster 2 x 1 x 1)
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, b, c, M, N, K, k2, partials);
     KD_CHECK_LAUNCH("lm_head_gemm_kernel");
     return KD_OK;
 }
@@ -461,92 +383,46 @@ using namespace kd;
 
 extern "C" {
 
-int kd_lm_head_stat_tiles(int64_t V_local) { return V_local <= 0 ? 0 : (int)((V_local + BN - 1) / BN); }
+int kd_lm_head_stat_tiles(int64_t V_local) { return V_local <= 0 ? 0 : (int)((V_local + STAT_COLS - 1) / STAT_COLS); }
 
-static int lm_head_fwd_impl(const char* who, const void* hidden, int64_t ld_h, const void* weight, int64_t ld_w, void* logits,
-                            int64_t ld_c, float* stat_partials, const void* teacher, int64_t ld_t, int64_t col0,
-                            float* teacher_partials, int64_t n_rows, int64_t V_local, int64_t H, int dtype, float T, void* stream) {
-    KD_CHECK_ARG(n_rows >= 0 && V_local >= 0 && H >= 1, "%s: bad shape", who);
+int kd_lm_head_fwd(const void* hidden, int64_t ld_h, const void* weight, int64_t ld_w, void* logits, int64_t ld_c,
+                   float* stat_partials, int64_t n_rows, int64_t V_local, int64_t H, int dtype, float T, void* stream) {
+    KD_CHECK_ARG(n_rows >= 0 && V_local >= 0 && H >= 1, "kd_lm_head_fwd: bad shape");
     if (dtype != KD_DTYPE_BF16 && dtype != KD_DTYPE_F16) {
-        set_error("%s: bf16 / fp16 operands only (tensor-core path); got dtype %d", who, dtype);
+        set_error("kd_lm_head_fwd: bf16 / fp16 operands only (tensor-core path); got dtype %d", dtype);
         return KD_ERR_UNSUPPORTED;
     }
     if (n_rows == 0 || V_local == 0) return KD_OK;
-    KD_CHECK_ARG(hidden && weight && logits, "%s: null pointer", who);
-    KD_CHECK_ARG(!stat_partials || T > 0.f, "%s: T must be positive", who);
-    KD_CHECK_ARG(ld_h >= H && ld_w >= H && ld_c >= V_local, "%s: row pitch smaller than the row", who);
-    KD_CHECK_ARG(!teacher_partials || (teacher && stat_partials && ld_t >= V_local && col0 >= 0),
-                 "%s: the teacher statistics need the teacher columns and the student partials", who);
-    bool aligned = ld_h % 8 == 0 && ld_w % 8 == 0 && ld_c % 8 == 0 && V_local % 8 == 0 &&
-                   ((reinterpret_cast<uintptr_t>(hidden) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(logits)) & 15u) == 0;
-    if (teacher_partials) aligned = aligned && ld_t % 8 == 0 && (reinterpret_cast<uintptr_t>(teacher) & 15u) == 0;
-    if (!aligned || n_rows >= (int64_t(1) << 31) || V_local >= (int64_t(1) << 31) || H >= (int64_t(1) << 31) ||
-        col0 + V_local >= (int64_t(1) << 31)) {
-        set_error("%s: TMA needs 16-byte aligned bases, row pitches and V_local that are multiples of 8 elements", who);
+    KD_CHECK_ARG(hidden && weight && logits, "kd_lm_head_fwd: null pointer");
+    KD_CHECK_ARG(!stat_partials || T > 0.f, "kd_lm_head_fwd: T must be positive");
+    KD_CHECK_ARG(ld_h >= H && ld_w >= H && ld_c >= V_local, "kd_lm_head_fwd: row pitch smaller than the row");
+    const bool aligned = ld_h % 8 == 0 && ld_w % 8 == 0 && ld_c % 8 == 0 && V_local % 8 == 0 &&
+                         ((reinterpret_cast<uintptr_t>(hidden) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(logits)) & 15u) == 0;
+    if (!aligned || n_rows >= (int64_t(1) << 31) - 2 * BM || V_local >= (int64_t(1) << 31) - BN || H >= (int64_t(1) << 31) - BK) {
+        set_error("kd_lm_head_fwd: TMA needs 16-byte aligned bases, row pitches and V_local that are multiples of 8 elements");
         return KD_ERR_UNSUPPORTED;
     }
     if (!encode_tiled()) {
-        set_error("%s: the driver does not export cuTensorMapEncodeTiled", who);
+        set_error("kd_lm_head_fwd: the driver does not export cuTensorMapEncodeTiled");
         return KD_ERR_CUDA;
     }
     const CUtensorMapDataType dt = dtype == KD_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    CUtensorMap ma, mb, mc, mt;
+    CUtensorMap ma, mb, mc;
     if (!make_map(&ma, dt, hidden, n_rows, H, ld_h, BM, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
-        !make_map(&mb, dt, weight, V_local, H, ld_w, BN, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
-        !make_map(&mc, dt, logits, n_rows, V_local, ld_c, BM, CU_TENSOR_MAP_L2_PROMOTION_NONE) ||
-        !make_map(&mt, dt, teacher_partials ? teacher : logits, n_rows, V_local, teacher_partials ? ld_t : ld_c, BM,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) {
-        set_error("%s: cuTensorMapEncodeTiled rejected a matrix (n_rows %lld, V_local %lld, H %lld)", who, (long long)n_rows,
+        !make_map(&mb, dt, weight, V_local, H, ld_w, BNH, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
+        !make_map(&mc, dt, logits, n_rows, V_local, ld_c, BM, CU_TENSOR_MAP_L2_PROMOTION_NONE)) {
+        set_error("kd_lm_head_fwd: cuTensorMapEncodeTiled rejected a matrix (n_rows %lld, V_local %lld, H %lld)", (long long)n_rows,
                   (long long)V_local, (long long)H);
         return KD_ERR_CUDA;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float k2 = stat_partials ? kLog2e / T : 0.f;
     float2* parts = reinterpret_cast<float2*>(stat_partials);
-    TeacherTile* tparts = reinterpret_cast<TeacherTile*>(teacher_partials);
-    const int M = (int)n_rows, N = (int)V_local, K = (int)H, c0 = (int)col0;
-#define KD_HEAD_LAUNCH(TT)                                                                                      \
-    (tparts ? launch_gemm<TT, 2>(ma, mb, mc, mt, M, N, K, k2, parts, c0, tparts, st)                             \
-            : parts ? launch_gemm<TT, 1>(ma, mb, mc, mt, M, N, K, k2, parts, 0, nullptr, st)                    \
-                    : launch_gemm<TT, 0>(ma, mb, mc, mt, M, N, K, k2, parts, 0, nullptr, st))
-    return dtype == KD_DTYPE_BF16 ? KD_HEAD_LAUNCH(__nv_bfloat16) : KD_HEAD_LAUNCH(__half);
-#undef KD_HEAD_LAUNCH
-}
-
-int kd_lm_head_fwd(const void* hidden, int64_t ld_h, const void* weight, int64_t ld_w, void* logits, int64_t ld_c,
-                   float* stat_partials, int64_t n_rows, int64_t V_local, int64_t H, int dtype, float T, void* stream) {
-    return lm_head_fwd_impl("kd_lm_head_fwd", hidden, ld_h, weight, ld_w, logits, ld_c, stat_partials, nullptr, 0, 0, nullptr, n_rows,
-                            V_local, H, dtype, T, stream);
-}
-
-int kd_lm_head_fwd_kd(const void* hidden, int64_t ld_h, const void* weight, int64_t ld_w, void* logits, int64_t ld_c,
-                      float* stat_partials, const void* teacher, int64_t ld_t, int64_t col0, float* teacher_partials, int64_t n_rows,
-                      int64_t V_local, int64_t H, int dtype, float T, void* stream) {
-    KD_CHECK_ARG(stat_partials && teacher_partials, "kd_lm_head_fwd_kd: both partial blocks are required");
-    return lm_head_fwd_impl("kd_lm_head_fwd_kd", hidden, ld_h, weight, ld_w, logits, ld_c, stat_partials, teacher, ld_t, col0,
-                            teacher_partials, n_rows, V_local, H, dtype, T, stream);
-}
-
-int kd_lm_head_stats_merge_kd(const float* stat_partials, const float* teacher_partials, int64_t n_tiles, const void* teacher,
-                              int64_t ld_t, const int64_t* labels, int64_t col0, int64_t V_local, float* stats, int64_t n_rows,
-                              int dtype, float T, void* stream) {
-    KD_CHECK_ARG(n_rows >= 0 && n_tiles >= 1 && n_tiles < (1 << 30) && T > 0.f && V_local >= 1 && col0 >= 0,
-                 "kd_lm_head_stats_merge_kd: bad arguments");
-    KD_CHECK_ARG(dtype == KD_DTYPE_BF16 || dtype == KD_DTYPE_F16, "kd_lm_head_stats_merge_kd: bf16 / fp16 only");
-    if (n_rows == 0) return KD_OK;
-    KD_CHECK_ARG(stat_partials && teacher_partials && teacher && stats, "kd_lm_head_stats_merge_kd: null pointer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned grid = (unsigned)((n_rows + 127) / 128);
-    const float2* sp = reinterpret_cast<const float2*>(stat_partials);
-    const TeacherTile* tp = reinterpret_cast<const TeacherTile*>(teacher_partials);
+    const int M = (int)n_rows, N = (int)V_local, K = (int)H;
     if (dtype == KD_DTYPE_BF16)
-        lm_head_stats_merge_kd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(sp, tp, (int)n_tiles, n_rows, kLog2e / T,
-            static_cast<const __nv_bfloat16*>(teacher), ld_t, labels, (int)col0, (int)V_local, stats, KD_VSHARD_STAT_WORDS);
-    else
-        lm_head_stats_merge_kd_kernel<__half><<<grid, 128, 0, st>>>(sp, tp, (int)n_tiles, n_rows, kLog2e / T,
-            static_cast<const __half*>(teacher), ld_t, labels, (int)col0, (int)V_local, stats, KD_VSHARD_STAT_WORDS);
-    KD_CHECK_LAUNCH("lm_head_stats_merge_kd_kernel");
-    return KD_OK;
+        return parts ? launch_gemm<__nv_bfloat16, 1>(ma, mb, mc, M, N, K, k2, parts, st)
+                     : launch_gemm<__nv_bfloat16, 0>(ma, mb, mc, M, N, K, k2, parts, st);
+    return parts ? launch_gemm<__half, 1>(ma, mb, mc, M, N, K, k2, parts, st) : launch_gemm<__half, 0>(ma, mb, mc, M, N, K, k2, parts, st);
 }
 
 int kd_lm_head_stats_merge(const float* stat_partials, int64_t n_tiles, float* stats, int64_t n_rows, float T, void* stream) {

@@ -230,33 +230,21 @@ _LN2 = 0.6931471805599453
 class CudaVocabPhases:
     """The four phase calls of the vocabulary-sharded path (kd_vshard_stats / _combine / _accum / _emit)."""
 
-    def stats(self, teacher, student, labels, col0, T, student_partials=None, teacher_partials=None):
+    def stats(self, teacher, student, labels, col0, T, student_partials=None):
         """``student_partials`` ([tiles, n, 2], from ``lm_head_fwd``): the student half comes from the GEMM epilogue and the
-        student logits are not read here; with ``teacher_partials`` ([tiles, n, 8]) as well nothing is streamed at all."""
+        student logits are not read here."""
         dev = student.device
         n, v_local = student.shape
         out = torch.empty((n, _lib.VSHARD_STAT_WORDS), dtype=torch.float32, device=dev)
         lib = _lib.load()
-        lab_ptr = labels.data_ptr() if labels is not None else None
-        if student_partials is not None:
-            tiles = lib.kd_lm_head_stat_tiles(v_local)
-            if tuple(student_partials.shape) != (tiles, n, 2) or not student_partials.is_contiguous():
-                raise ValueError("student_partials must be the contiguous [tiles, n_rows, 2] block lm_head_fwd returned")
-            if teacher_partials is not None and (tuple(teacher_partials.shape) != (tiles, n, _lib.LM_HEAD_TEACHER_WORDS)
-                                                 or not teacher_partials.is_contiguous()):
-                raise ValueError("teacher_partials must be the contiguous [tiles, n_rows, 8] block lm_head_fwd returned")
         with torch.cuda.device(dev):
-            if teacher_partials is not None:
-                _lib.check(lib.kd_lm_head_stats_merge_kd(student_partials.data_ptr(), teacher_partials.data_ptr(),
-                                                         student_partials.shape[0], teacher.data_ptr(), teacher.stride(0), lab_ptr,
-                                                         int(col0), v_local, out.data_ptr(), n, _dtype_code(student), float(T),
-                                                         _stream_ptr(dev)))
-                return out
             _lib.check(lib.kd_vshard_stats(teacher.data_ptr(), teacher.stride(0),
                                            student.data_ptr() if student_partials is None else None, student.stride(0),
-                                           lab_ptr, int(col0), out.data_ptr(), n, v_local, _dtype_code(student), float(T),
-                                           _stream_ptr(dev)))
+                                           labels.data_ptr() if labels is not None else None, int(col0), out.data_ptr(),
+                                           n, v_local, _dtype_code(student), float(T), _stream_ptr(dev)))
             if student_partials is not None:
+                if tuple(student_partials.shape) != (lib.kd_lm_head_stat_tiles(v_local), n, 2) or not student_partials.is_contiguous():
+                    raise ValueError("student_partials must be the contiguous [tiles, n_rows, 2] block lm_head_fwd returned")
                 _lib.check(lib.kd_lm_head_stats_merge(student_partials.data_ptr(), student_partials.shape[0], out.data_ptr(), n,
                                                       float(T), _stream_ptr(dev)))
         return out
@@ -325,15 +313,14 @@ class DistCollectives:
 
 def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, T, mode="reference", alpha=0.8, eps=1e-8,
                            n_rows_norm=None, reduction="mean", upstream=None, group=None, phases=None, collectives=None,
-                           want_grad=True, student_partials=None, teacher_partials=None):
+                           want_grad=True, student_partials=None):
     """Logit KD over logits sharded along the vocabulary.
 
     ``teacher_shard`` / ``student_shard``: this rank's columns ``[col0, col0 + V_local)`` of all rows; ``labels``: all rows'
     labels (LoCa modes), global class indices.  ``mode``: ``"reference"`` (as written, P1:184-185), ``"per_row"``, ``"kl"``
     (P1:331-343) or ``"kl_log_target"`` (FB:206-219).  Returns ``(loss, grad_shard)``: the GLOBAL loss (identical on every
     rank) and the gradient w.r.t. this rank's student columns.  ``student_partials``: the per-tile student statistics
-    ``lm_head_fwd(..., T=T)`` produced together with ``student_shard`` (the stats phase then streams only the teacher);
-    ``teacher_partials``: the teacher's, from ``lm_head_fwd(..., T=T, teacher=teacher_shard, col0=col0)`` (no stats sweep at all).
+    ``lm_head_fwd(..., T=T)`` produced together with ``student_shard`` (the stats phase then streams only the teacher).
     """
     variant = _VS_VARIANTS[mode]
     if phases is None:
@@ -355,7 +342,7 @@ def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, 
         raise ValueError(f"unknown reduction {reduction!r}")
 
     if student_partials is not None:                                        # student (max, sum-exp) left by the lm_head GEMM
-        stats = phases.stats(t2, s2, lab, col0, T, student_partials=student_partials, teacher_partials=teacher_partials)
+        stats = phases.stats(t2, s2, lab, col0, T, student_partials=student_partials)
     else:
         stats = phases.stats(t2, s2, lab, col0, T)
     stats_all = collectives.gather_stats(stats)                             # exchange 1: [G, n, 12]
@@ -381,12 +368,10 @@ def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, 
 # backward (library GEMMs) close the loop — dH needs the sum over the vocabulary shards: one all-reduce of [n_rows, hidden].
 # Keeping the logits out of HBM altogether (recomputing them in the backward) is the step after this one.
 # ---------------------------------------------------------------------------------------------------------------------
-def lm_head_fwd(hidden, weight, T=None, teacher=None, col0=0):
-    """``hidden`` [n_rows, H] x ``weight`` [V_local, H] -> ``(logits [n_rows, V_local], partials, teacher_partials)`` through
-    ``kd_lm_head_fwd`` / ``kd_lm_head_fwd_kd``.  With ``T`` the epilogue also returns the per-256-column-tile student (max,
-    sum-exp at temperature T) block [tiles, n_rows, 2]; with ``teacher`` ([n_rows, V_local], same dtype) it streams the teacher
-    cells too and returns their per-tile (max, sum-exp, best, runner-up) block [tiles, n_rows, 8].  Both are consumed by
-    ``logit_kd_vocab_sharded(student_partials=..., teacher_partials=...)``.  bf16 / fp16 CUDA tensors only."""
+def lm_head_fwd(hidden, weight, T=None):
+    """``hidden`` [n_rows, H] x ``weight`` [V_local, H] -> (``logits`` [n_rows, V_local], ``partials`` or None) through
+    ``kd_lm_head_fwd``.  With ``T`` the epilogue also returns the per-256-column-tile student (max, sum-exp at temperature T)
+    block [tiles, n_rows, 2] that ``logit_kd_vocab_sharded(student_partials=...)`` consumes.  bf16 / fp16 CUDA tensors only."""
     dev = _require_cuda(hidden, weight)
     if hidden.dim() != 2 or weight.dim() != 2 or hidden.shape[1] != weight.shape[1] or hidden.dtype != weight.dtype:
         raise ValueError("lm_head_fwd: hidden [n_rows, H] and weight [V_local, H] of one dtype expected")
@@ -395,22 +380,14 @@ def lm_head_fwd(hidden, weight, T=None, teacher=None, col0=0):
     n, v_local = h.shape[0], w.shape[0]
     lib = _lib.load()
     logits = torch.empty((n, v_local), dtype=h.dtype, device=dev)
-    partials = tparts = None
+    partials = None
     if T is not None:
         partials = torch.empty((lib.kd_lm_head_stat_tiles(v_local), n, 2), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        if teacher is not None:
-            if T is None or tuple(teacher.shape) != (n, v_local) or teacher.dtype != h.dtype or teacher.stride(1) != 1:
-                raise ValueError("lm_head_fwd: the teacher statistics need T and a [n_rows, V_local] teacher of the operands' dtype")
-            tparts = torch.empty((partials.shape[0], n, _lib.LM_HEAD_TEACHER_WORDS), dtype=torch.float32, device=dev)
-            _lib.check(lib.kd_lm_head_fwd_kd(h.data_ptr(), h.stride(0), w.data_ptr(), w.stride(0), logits.data_ptr(),
-                                             logits.stride(0), partials.data_ptr(), teacher.data_ptr(), teacher.stride(0), int(col0),
-                                             tparts.data_ptr(), n, v_local, h.shape[1], _dtype_code(h), float(T), _stream_ptr(dev)))
-        else:
-            _lib.check(lib.kd_lm_head_fwd(h.data_ptr(), h.stride(0), w.data_ptr(), w.stride(0), logits.data_ptr(), logits.stride(0),
-                                          partials.data_ptr() if partials is not None else None, n, v_local, h.shape[1],
-                                          _dtype_code(h), float(T) if T is not None else 1.0, _stream_ptr(dev)))
-    return logits, partials, tparts
+        _lib.check(lib.kd_lm_head_fwd(h.data_ptr(), h.stride(0), w.data_ptr(), w.stride(0), logits.data_ptr(), logits.stride(0),
+                                      partials.data_ptr() if partials is not None else None, n, v_local, h.shape[1],
+                                      _dtype_code(h), float(T) if T is not None else 1.0, _stream_ptr(dev)))
+    return logits, partials
 
 
 def _tensor_core_head_applies(hidden, weight) -> bool:
@@ -422,20 +399,17 @@ class _LmHeadVocabShardedKD(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hidden, weight_shard, teacher_shard, labels, col0, V_total, T, mode, alpha, eps, n_rows_norm, reduction,
                 group, phases, collectives, gemm):
-        partials = tparts = None
-        if gemm in ("tcgen05", "tcgen05_kd") and phases is None and _tensor_core_head_applies(hidden, weight_shard):
-            t_ok = (gemm == "tcgen05_kd" and teacher_shard.dim() == 2 and teacher_shard.dtype == hidden.dtype
-                    and teacher_shard.stride(1) == 1 and teacher_shard.stride(0) % 8 == 0 and teacher_shard.data_ptr() % 16 == 0)
-            logits, partials, tparts = lm_head_fwd(hidden.detach(), weight_shard.detach(), T=T,
-                                                   teacher=teacher_shard if t_ok else None, col0=col0)
-        elif gemm != "library" and phases is None and hidden.is_cuda and hidden.dtype != torch.float32:
+        partials = None
+        if gemm == "tcgen05" and phases is None and _tensor_core_head_applies(hidden, weight_shard):
+            logits, partials = lm_head_fwd(hidden.detach(), weight_shard.detach(), T=T)
+        elif gemm == "tcgen05" and phases is None and hidden.is_cuda and hidden.dtype != torch.float32:
             raise ValueError("lm_head_kd_vocab_sharded: hidden size and V_local must be multiples of 8 for the tensor-core head "
                              "(pass gemm='library' otherwise)")
         else:                                                                       # fp32 operands / host-side test doubles
             logits = torch.matmul(hidden.detach(), weight_shard.detach().t())      # [n_rows, V_local], the student's dtype
         loss, grad_logits = logit_kd_vocab_sharded(teacher_shard, logits, labels, col0, V_total, T, mode=mode, alpha=alpha, eps=eps,
                                                    n_rows_norm=n_rows_norm, reduction=reduction, group=group, phases=phases,
-                                                   collectives=collectives, student_partials=partials, teacher_partials=tparts)
+                                                   collectives=collectives, student_partials=partials)
         ctx.save_for_backward(hidden, weight_shard)
         ctx.grad_logits = grad_logits                                               # ours: rescaled in place by the backward
         ctx.collectives = collectives if collectives is not None else DistCollectives(group)
@@ -468,12 +442,9 @@ def lm_head_kd_vocab_sharded(hidden, weight_shard, teacher_shard, labels, col0, 
                              gemm="tcgen05"):
     """KD loss of a vocabulary-parallel student ``lm_head``: ``hidden`` [n_rows, K] (replicated), ``weight_shard`` [V_local, K] (this
     rank's rows of the 151 936 x 896 head), ``teacher_shard`` [n_rows, V_local].  Differentiable w.r.t. ``hidden`` and
-    ``weight_shard``; the returned loss is the global one.  ``gemm``: ``"tcgen05"`` (the hand-written kernel, the
-    student's row statistics fused into its epilogue; the teacher is streamed by ``kd_vshard_stats``), ``"tcgen05_kd"`` (the
-    teacher's statistics in the epilogue as well — exact, but measured SLOWER: 5.6 ms against 1.77 + 0.75 ms at 65 536 x 18 992 x
-    896, the four epilogue warps have no latency hiding for that chain; kept for the record) or ``"library"`` (torch.matmul; also
-    what fp32 operands use)."""
-    if gemm not in ("tcgen05", "tcgen05_kd", "library"):
+    ``weight_shard``; the returned loss is the global one.  ``gemm``: ``"tcgen05"`` (the hand-written kernel, statistics fused
+    into its epilogue) or ``"library"`` (torch.matmul; also what fp32 operands use)."""
+    if gemm not in ("tcgen05", "library"):
         raise ValueError(f"unknown gemm {gemm!r}")
     return _LmHeadVocabShardedKD.apply(hidden, weight_shard, teacher_shard, labels, int(col0), int(V_total), float(T), mode,
                                        float(alpha), float(eps), n_rows_norm, reduction, group, phases, collectives, gemm)

@@ -47,7 +47,7 @@ def test_size_queries_and_argument_validation_need_no_gpu():
     rc = lib.kd_feature_mse_fwd_bwd(None, None, None, None, None, 0, 0, 0, None, 0, None)
     assert rc == 1
     # the tensor-core student head: tile count of the statistics block, argument checks before any CUDA call
-    assert lib.kd_lm_head_stat_tiles(151936) == 594 and lib.kd_lm_head_stat_tiles(256) == 1 and lib.kd_lm_head_stat_tiles(0) == 0
+    assert lib.kd_lm_head_stat_tiles(151936) == 1187 and lib.kd_lm_head_stat_tiles(256) == 2 and lib.kd_lm_head_stat_tiles(0) == 0
     assert lib.kd_lm_head_fwd(None, 896, None, 896, None, 151936, None, 16, 151936, 896, _lib.DTYPE_BF16, 2.0, None) == 1
     assert b"null pointer" in lib.kd_last_error()
     assert lib.kd_lm_head_fwd(None, 896, None, 896, None, 151936, None, 16, 151936, 896, _lib.DTYPE_F32, 2.0, None) == 2

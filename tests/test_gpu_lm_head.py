@@ -24,7 +24,7 @@ def _operands(n, v, h, dtype, seed=0):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 def test_lm_head_gemm_matches_fp32_product(n, v, h, dtype):
     hidden, weight = _operands(n, v, h, dtype, seed=n + v)
-    logits, partials, _ = sharded.lm_head_fwd(hidden, weight)
+    logits, partials = sharded.lm_head_fwd(hidden, weight)
     assert partials is None and logits.shape == (n, v) and logits.dtype == dtype
     ref = hidden.float() @ weight.float().t()
     ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11      # one rounding of the exact fp32 sum (+ summation order)
@@ -41,8 +41,8 @@ def test_lm_head_gemm_strided_operands():
     big_h[:, :128] = hidden
     big_w = torch.zeros(520, 192, device="cuda", dtype=torch.bfloat16)
     big_w[:, :128] = weight
-    a = sharded.lm_head_fwd(big_h[:, :128], big_w[:, :128])[0]
-    b = sharded.lm_head_fwd(hidden, weight)[0]
+    a, _ = sharded.lm_head_fwd(big_h[:, :128], big_w[:, :128])
+    b, _ = sharded.lm_head_fwd(hidden, weight)
     assert torch.equal(a, b)
 
 
@@ -58,26 +58,14 @@ def test_lm_head_gemm_rejects_what_tma_cannot_address():
 @pytest.mark.parametrize("T", [2.0, 0.8])
 def test_epilogue_statistics_match_the_streamed_kernel(n, v, h, T):
     hidden, weight = _operands(n, v, h, torch.bfloat16, seed=3)
-    logits, partials, _ = sharded.lm_head_fwd(hidden, weight, T=T)
-    plain = sharded.lm_head_fwd(hidden, weight)[0]
+    logits, partials = sharded.lm_head_fwd(hidden, weight, T=T)
+    plain, _ = sharded.lm_head_fwd(hidden, weight)
     assert torch.equal(logits, plain)                                # the statistics do not perturb the product
     teacher = torch.randn(n, v, device="cuda").to(torch.bfloat16)
-    teacher[::7, 5] = teacher[::7, 77]                               # ties between best / runner-up candidates
     labels = torch.randint(0, v, (n,), device="cuda")
     ph = sharded.CudaVocabPhases()
-    col0 = 1000
-    streamed = ph.stats(teacher, logits, labels + col0, col0, T)
-    fused = ph.stats(teacher, logits, labels + col0, col0, T, student_partials=partials)
-    # ... and with the teacher's side in the epilogue as well: no sweep over either matrix
-    logits2, partials2, tparts = sharded.lm_head_fwd(hidden, weight, T=T, teacher=teacher, col0=col0)
-    assert torch.equal(logits2, logits) and torch.equal(partials2, partials)
-    both = ph.stats(teacher, logits, labels + col0, col0, T, student_partials=partials2, teacher_partials=tparts)
-    assert torch.equal(both[:, 7:], fused[:, 7:])
-    cols = [0, 2, 3, 4, 5, 6]                                        # max, best / runner-up (value, index bits), label logit
-    assert torch.equal(both[:, cols].contiguous().view(torch.int32), streamed[:, cols].contiguous().view(torch.int32))
-    lt_a = streamed[:, 0].double() * (1.4426950408889634 / T) + streamed[:, 1].double().log2()
-    lt_b = both[:, 0].double() * (1.4426950408889634 / T) + both[:, 1].double().log2()
-    assert float((lt_a - lt_b).abs().max()) <= 2e-6 * max(1.0, float(lt_a.abs().max()))
+    streamed = ph.stats(teacher, logits, labels, 0, T)
+    fused = ph.stats(teacher, logits, labels, 0, T, student_partials=partials)
     assert torch.equal(streamed[:, :7], fused[:, :7])               # teacher half: the same kernel
     assert torch.equal(streamed[:, 7], fused[:, 7])                 # student max
     k2 = 1.4426950408889634 / T
@@ -93,18 +81,17 @@ def test_lm_head_kd_matches_the_library_gemm_form(mode):
     teacher = (torch.randn(n, v, device="cuda") * 2).to(torch.bfloat16)
     labels = torch.randint(0, v, (n,), device="cuda")
     out = {}
-    for gemm in ("tcgen05", "tcgen05_kd", "library"):
+    for gemm in ("tcgen05", "library"):
         hd, wd = hidden.clone().requires_grad_(True), weight.clone().requires_grad_(True)
         loss = sharded.lm_head_kd_vocab_sharded(hd, wd, teacher, labels, 0, v, T, mode=mode, gemm=gemm)
         loss.backward()
         out[gemm] = (loss.item(), hd.grad.float(), wd.grad.float())
+    la, ha, wa = out["tcgen05"]
     lb, hb, wb = out["library"]
     # the two GEMMs round a handful of logits differently (summation order): compare at the bf16 tolerance of the path
-    for gemm in ("tcgen05", "tcgen05_kd"):
-        la, ha, wa = out[gemm]
-        assert abs(la - lb) <= 2e-4 * abs(lb)
-        assert float((ha - hb).norm() / hb.norm()) <= 2e-3
-        assert float((wa - wb).norm() / wb.norm()) <= 2e-3
+    assert abs(la - lb) <= 2e-4 * abs(lb)
+    assert float((ha - hb).norm() / hb.norm()) <= 2e-3
+    assert float((wa - wb).norm() / wb.norm()) <= 2e-3
 
 
 def test_lm_head_kd_against_single_gpu_op():
@@ -113,7 +100,7 @@ def test_lm_head_kd_against_single_gpu_op():
     hidden, weight = _operands(n, v, h, torch.bfloat16, seed=17)
     teacher = (torch.randn(n, v, device="cuda") * 2).to(torch.bfloat16)
     labels = torch.randint(0, v, (n,), device="cuda")
-    logits = sharded.lm_head_fwd(hidden, weight)[0]
+    logits, _ = sharded.lm_head_fwd(hidden, weight)
     ref = kd.loca_kl(teacher, logits.clone().requires_grad_(True), labels, T=T, alpha=0.8)
     got = sharded.lm_head_kd_vocab_sharded(hidden, weight, teacher, labels, 0, v, T, alpha=0.8)
     assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item())

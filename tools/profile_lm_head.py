@@ -13,6 +13,6 @@ v = int(sys.argv[2]) if len(sys.argv) > 2 else 151936
 hidden = torch.randn(n, 896, device="cuda").to(torch.bfloat16)
 weight = (torch.randn(v, 896, device="cuda") * 0.1).to(torch.bfloat16)
 for _ in range(3):
-    logits, partials, _ = sharded.lm_head_fwd(hidden, weight, T=2.0)
+    logits, partials = sharded.lm_head_fwd(hidden, weight, T=2.0)
 torch.cuda.synchronize()
 print("ok", logits.shape, partials.shape)
