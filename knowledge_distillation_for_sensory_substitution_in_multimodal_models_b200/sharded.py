@@ -370,7 +370,7 @@ def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, 
 # ---------------------------------------------------------------------------------------------------------------------
 def lm_head_fwd(hidden, weight, T=None):
     """``hidden`` [n_rows, H] x ``weight`` [V_local, H] -> (``logits`` [n_rows, V_local], ``partials`` or None) through
-    ``kd_lm_head_fwd``.  With ``T`` the epilogue also returns the per-256-column-tile student (max, sum-exp at temperature T)
+    ``kd_lm_head_fwd``.  With ``T`` the epilogue also returns the per-128-column-tile student (max, sum-exp at temperature T)
     block [tiles, n_rows, 2] that ``logit_kd_vocab_sharded(student_partials=...)`` consumes.  bf16 / fp16 CUDA tensors only."""
     dev = _require_cuda(hidden, weight)
     if hidden.dim() != 2 or weight.dim() != 2 or hidden.shape[1] != weight.shape[1] or hidden.dtype != weight.dtype:
