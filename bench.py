@@ -388,6 +388,29 @@ def main() -> None:
                                           "frac": 6 * ha.numel() / (ms / 1e3) / 1e9 / peak_gbs}
         del ha, hb
         torch.cuda.empty_cache()
+        # the student lm_head (896 x 151 936) on the tensor cores with its fused row statistics, next to the library GEMM on the
+        # same operands; bound: tensor pipe, against the measured sustained bf16 peak
+        try:
+            hd = torch.randn(N, 896, device=dev, dtype=torch.bfloat16)
+            wt = (torch.randn(V, 896, device=dev) * 0.05).to(torch.bfloat16)
+            out = torch.empty(N, V, device=dev, dtype=torch.bfloat16)
+            ms_own = timeit(lambda: sharded.lm_head_fwd(hd, wt, T=T_KD), k=5, w=2)
+            ms_lib = timeit(lambda: torch.matmul(hd, wt.t(), out=out), k=5, w=2)
+            tf_peak, tf_src = 1401.6, "fallback"
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    tf_peak, tf_src = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+            except Exception:
+                pass
+            tf = 2.0 * N * V * 896 / (ms_own / 1e3) / 1e12
+            side[f"lm_head_gemm_{N}x{V}x896"] = {"ms": ms_own, "tflops": tf, "bound": "tensor", "peak_tflops": tf_peak,
+                                                "frac": tf / tf_peak, "peak_source": tf_src, "library_gemm_ms": ms_lib,
+                                                "note": "hand-written tcgen05 cta_group::2 kernel incl. fused row statistics and "
+                                                        "output allocation; library = torch.matmul into a preallocated output"}
+            del hd, wt, out
+        except Exception as exc:  # noqa: BLE001 - a side measurement must not take the headline down
+            side["lm_head_gemm"] = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
 
     # ---- end-to-end through the public API with HOST buffers ----------------------------------------------
     e2e = None

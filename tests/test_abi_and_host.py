@@ -60,7 +60,8 @@ def test_cpu_tensors_are_rejected_loudly():
     t = torch.zeros(2, 16)
     lab = torch.zeros(2, dtype=torch.long)
     for call in (lambda: kd.loca_kl(t, t, lab, 2.0), lambda: kd.temperature_kl(t, t, 2.0),
-                 lambda: kd.info_nce(t, t), lambda: kd.feature_mse(t, t)):
+                 lambda: kd.info_nce(t, t), lambda: kd.feature_mse(t, t),
+                 lambda: sharded.lm_head_fwd(t.to(torch.bfloat16), t.to(torch.bfloat16))):
         with pytest.raises(RuntimeError, match="CUDA-only"):
             call()
 
