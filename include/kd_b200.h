@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KD_B200_ABI_VERSION 1
+#define KD_B200_ABI_VERSION 2
 
 /* element types of logits / features (gradients are written in the same type as the student tensor) */
 enum { KD_DTYPE_BF16 = 0, KD_DTYPE_F16 = 1, KD_DTYPE_F32 = 2 };
@@ -115,7 +115,9 @@ int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t
                  const float* table, const double* table_consts, void* grad_student, int64_t ld_g,
                  float* loss_out, void* rowaux /* float4[n_rows + 1]; the extra entry is scratch (row queue) */,
                  int64_t n_rows, int64_t V, int dtype,
-                 float T, float eps, double inv_norm, const float* upstream, unsigned flags, void* stream);
+                 float T, float eps, double inv_norm, const float* upstream,
+                 const uint32_t* status /* phase A's status word (may be NULL): a bad label NaN-poisons the loss like P1:166 raises */,
+                 unsigned flags, void* stream);
 
 /* Re-emission of the gradient for autograd's backward when the incoming grad_output differs from the scale that
  * was folded into the forward launch: grad = (*upstream) * T * inv_norm * (sp * Q_r - w) recomputed from the row
@@ -190,9 +192,10 @@ int kd_info_nce_fwd_bwd(const void* student, const void* teacher, void* grad_stu
                         void* workspace, size_t workspace_bytes, int64_t M, int64_t tokens, int64_t D,
                         int dtype, float temperature, const float* upstream, unsigned flags, void* stream);
 /* backward re-emission from the fp32 pooled gradient kept in `workspace`: grad = (*ratio) * d(mean)/tokens broadcast
- * over tokens, skipped when *ratio == 1 (ratio = grad_output / the upstream folded in at forward time). */
+ * over tokens (ratio = grad_output / the upstream folded in at forward time), skipped when *skip_if_one == 1 (may be
+ * NULL = never skip: a repeated backward that writes a fresh buffer). */
 int kd_info_nce_regrad(const void* workspace, size_t workspace_bytes, void* grad_student, int64_t M, int64_t tokens,
-                       int64_t D, int dtype, const float* ratio, void* stream);
+                       int64_t D, int dtype, const float* ratio, const float* skip_if_one, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Feature MSE — replaces mse_loss (EV:160-165): mean((input.float() - target.float())^2) and

@@ -15,6 +15,7 @@ _lock = threading.Lock()
 _lib: C.CDLL | None = None
 
 # mirrors of the header enums
+ABI_VERSION = 2
 DTYPE_BF16, DTYPE_F16, DTYPE_F32 = 0, 1, 2
 LOCA_REFERENCE, LOCA_PER_ROW, KL_PLAIN, KL_LOG_TARGET = 0, 1, 2, 3
 FLAG_NO_GRAD, FLAG_FORCE_STREAMING = 1, 2
@@ -37,7 +38,7 @@ SIGNATURES = {
     "kd_loca_teacher_stats_peers": (_i, [_p, _i64, _p, _p, _i, _i64, _p, _p, _i64, _i64, _i, _f, _f, _p]),
     "kd_loca_table_workspace_bytes": (_i, [_i64, C.POINTER(_sz)]),
     "kd_loca_build_table": (_i, [_p, _i64, _i64, _p, _p, _p, _sz, _p]),
-    "kd_loca_emit": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i, _f, _f, _d, _p, _u, _p]),
+    "kd_loca_emit": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i, _f, _f, _d, _p, _p, _u, _p]),
     "kd_logit_kd_regrad": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _sz, _i64, _i64, _i, _f, _f, _i, _d, _p, _p, _p]),
     "kd_scale_rows": (_i, [_p, _i64, _i64, _i64, _i, _p, _p]),
     "kd_vshard_stats": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i, _f, _p]),
@@ -49,7 +50,7 @@ SIGNATURES = {
     "kd_lm_head_stats_merge": (_i, [_p, _i64, _p, _i64, _f, _p]),
     "kd_info_nce_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "kd_info_nce_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i64, _i64, _i64, _i, _f, _p, _u, _p]),
-    "kd_info_nce_regrad": (_i, [_p, _sz, _p, _i64, _i64, _i64, _i, _p, _p]),
+    "kd_info_nce_regrad": (_i, [_p, _sz, _p, _i64, _i64, _i64, _i, _p, _p, _p]),
     "kd_feature_mse_workspace_bytes": (_i, [_i64, C.POINTER(_sz)]),
     "kd_feature_mse_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i64, _i, _p, _u, _p]),
     "kd_feature_mse_regrad": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p]),
@@ -85,8 +86,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.kd_abi_version() != 1:
-            raise KDError(f"ABI version mismatch: library {lib.kd_abi_version()}, binding 1")
+        if lib.kd_abi_version() != ABI_VERSION:
+            raise KDError(f"ABI version mismatch: library {lib.kd_abi_version()}, binding {ABI_VERSION}")
         _lib = lib
         return lib
 

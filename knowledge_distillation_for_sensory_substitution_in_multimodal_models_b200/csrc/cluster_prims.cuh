@@ -47,6 +47,9 @@ __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, u
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {     // sub-CTA barrier: one row pipeline's warps
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {   // non-blocking side of a producer/consumer pair
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
 }

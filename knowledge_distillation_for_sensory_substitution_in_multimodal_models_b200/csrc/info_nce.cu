@@ -198,13 +198,11 @@ __global__ void nce_finalize_kernel(const float* __restrict__ rowloss, int M, fl
 // token (the previous version recomputed idx % ncol and re-read the source for every store: 1.8 TB/s).
 template <typename T>
 __global__ void __launch_bounds__(256)
-broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P, int D, bool vec, const float* ratio) {
+broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P, int D, bool vec, const float* ratio,
+                      const float* skip_if_one) {
     constexpr int E = Elem<T>::kPack;
-    float f = 1.f;
-    if (ratio) {            // backward re-emission: skip when grad_output is what forward assumed
-        f = *ratio;
-        if (f == 1.f) return;
-    }
+    if (skip_if_one && *skip_if_one == 1.f) return;      // backward re-emission: grad_output is what forward assumed
+    const float f = ratio ? *ratio : 1.f;
     const int m = blockIdx.y;
     const float* src = dmean + (int64_t)m * D;
     T* dst = dx + (int64_t)m * P * D;
@@ -294,19 +292,19 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
         int bx = vec_out ? (P + 15) / 16 : (int)(((int64_t)P * D + 255) / 256);      // >= 16 tokens per CTA and row
         if (bx > 32) bx = 32;
         if (bx < 1) bx = 1;
-        broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, nullptr);
+        broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, nullptr, nullptr);
         KD_CHECK_LAUNCH("broadcast_rows_kernel");
     }
     return KD_OK;
 }
 
 template <typename T>
-int run_regrad(const float* dmean, void* dx, int M, int P, int D, const float* ratio, cudaStream_t st) {
+int run_regrad(const float* dmean, void* dx, int M, int P, int D, const float* ratio, const float* skip, cudaStream_t st) {
     constexpr int E = Elem<T>::kPack;
     const bool vec_out = (D % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
     int bx = vec_out ? (P + 15) / 16 : (int)(((int64_t)P * D + 255) / 256);
     bx = bx > 32 ? 32 : (bx < 1 ? 1 : bx);
-    broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, ratio);
+    broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, ratio, skip);
     KD_CHECK_LAUNCH("broadcast_rows_kernel");
     return KD_OK;
 }
@@ -345,7 +343,7 @@ int kd_info_nce_fwd_bwd(const void* student, const void* teacher, void* grad_stu
 }
 
 int kd_info_nce_regrad(const void* workspace, size_t workspace_bytes, void* grad_student, int64_t M, int64_t tokens,
-                       int64_t D, int dtype, const float* ratio, void* stream) {
+                       int64_t D, int dtype, const float* ratio, const float* skip_if_one, void* stream) {
     KD_CHECK_ARG(workspace && grad_student && ratio, "kd_info_nce_regrad: null pointer");
     KD_CHECK_ARG(M >= 1 && tokens >= 1 && D >= 1, "kd_info_nce_regrad: bad shape");
     KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
@@ -357,9 +355,9 @@ int kd_info_nce_regrad(const void* workspace, size_t workspace_bytes, void* grad
     const float* dmean = reinterpret_cast<const float*>(static_cast<const char*>(workspace) + w.dmean);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (dtype) {
-        case KD_DTYPE_BF16: return kd::run_regrad<__nv_bfloat16>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, st);
-        case KD_DTYPE_F16: return kd::run_regrad<__half>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, st);
-        default: return kd::run_regrad<float>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, st);
+        case KD_DTYPE_BF16: return kd::run_regrad<__nv_bfloat16>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, skip_if_one, st);
+        case KD_DTYPE_F16: return kd::run_regrad<__half>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, skip_if_one, st);
+        default: return kd::run_regrad<float>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, skip_if_one, st);
     }
 }
 

@@ -260,6 +260,10 @@ template <> struct Pair<__nv_bfloat16> {
         __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
         return *reinterpret_cast<uint32_t*>(&h);
     }
+    static __device__ __forceinline__ bool any_ge(uint32_t a, uint32_t b) {      // either half of a >= the same half of b
+        __nv_bfloat162 r = __hge2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r) != 0u;
+    }
 };
 template <> struct Pair<__half> {
     static constexpr uint32_t kPosInf2 = 0x7c007c00u;
@@ -279,6 +283,10 @@ template <> struct Pair<__half> {
     static __device__ __forceinline__ uint32_t narrow(float lo, float hi) {
         __half2 h = __floats2half2_rn(lo, hi);
         return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ bool any_ge(uint32_t a, uint32_t b) {
+        __half2 r = __hge2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r) != 0u;
     }
 };
 

@@ -1159,7 +1159,7 @@ int kd_loca_build_table(const kd_token_record* records_all, int64_t n_tokens_all
 int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const float* lse2_t,
                  const float* table, const double* table_consts, void* grad_student, int64_t ld_g, float* loss_out,
                  void* rowaux, int64_t n_rows, int64_t V, int dtype, float T, float eps, double inv_norm,
-                 const float* upstream, unsigned flags, void* stream) {
+                 const float* upstream, const uint32_t* status, unsigned flags, void* stream) {
     if (int rc = check_common(n_rows, V, dtype, T)) return rc;
     KD_CHECK_ARG(teacher && student && lse2_t && table && table_consts && loss_out && rowaux, "kd_loca_emit: null pointer");
     KD_CHECK_ARG((flags & KD_FLAG_NO_GRAD) || grad_student, "kd_loca_emit: grad_student is null");
@@ -1175,7 +1175,7 @@ int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t
         if (int rc = launch_emit(p, KD_LOCA_REFERENCE, dtype, st, reinterpret_cast<int*>(p.rowaux + n_rows))) return rc;
     }
     loss_finalize_kernel<<<1, kFinalThreads, 0, st>>>(p.rowaux, n_rows, (double)kLn2, (double)T * T * inv_norm, table_consts,
-                                                      nullptr, loss_out);
+                                                      status, loss_out);
     KD_CHECK_LAUNCH("loss_finalize_kernel");
     return KD_OK;
 }
@@ -1212,28 +1212,18 @@ int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, 
     p.gscale = static_cast<float>(T * inv_norm); p.flags = flags;
     p.records = reinterpret_cast<kd_token_record*>(ws + w.records);
 
-    // per-row LoCa on the fused kernel: phase A supplies lse2_t and the token records {label, v1, k, v2}, the emit patches
-    // the row's own override cells after its sweep (8V bytes/token instead of 6V, but half the arithmetic of the 3-sweep kernel)
-    bool per_row_two_phase = false;
-    if (variant == KD_LOCA_PER_ROW && n_rows > 0 && !(flags & KD_FLAG_FORCE_STREAMING)) {
-        EmitParams probe = p;
-        probe.lse2_t_in = reinterpret_cast<float*>(ws + w.lse2_t);
-        int nc = 0, cpc = 0, pipes = 0, srows = 0;
-        per_row_two_phase = fused_applies(probe, variant, dtype) &&
-                            cluster_launch_shape(probe, variant, dtype, &nc, &cpc, &pipes, &srows) == KD_OK;
-    }
-    if (variant == KD_LOCA_REFERENCE || per_row_two_phase) {
+    // the as-written mode needs every row's record before any row's q is known: phase A + table build, then the emit.
+    // Per-row LoCa derives its teacher statistics inside the emit kernel's single sweep (6V bytes per token).
+    if (variant == KD_LOCA_REFERENCE) {
         kd_token_record* rec = reinterpret_cast<kd_token_record*>(ws + w.records);
         float* lse2_t = reinterpret_cast<float*>(ws + w.lse2_t);
         if (n_rows > 0) {
             if (int rc = kd_loca_teacher_stats(teacher, ld_t, labels, rec, lse2_t, status, n_rows, V, dtype, T, alpha, stream)) return rc;
         }
         p.lse2_t_in = lse2_t;
-        if (variant == KD_LOCA_REFERENCE) {
-            float* table = reinterpret_cast<float*>(ws + w.table);
-            if (int rc = kd_loca_build_table(rec, n_rows, V, table, consts, ws + w.table_ws, w.table_ws_bytes, stream)) return rc;
-            p.table = table;
-        }
+        float* table = reinterpret_cast<float*>(ws + w.table);
+        if (int rc = kd_loca_build_table(rec, n_rows, V, table, consts, ws + w.table_ws, w.table_ws_bytes, stream)) return rc;
+        p.table = table;
     }
     if (n_rows > 0) {
         if (int rc = launch_emit(p, variant, dtype, st, reinterpret_cast<int*>(ws + w.queue))) return rc;

@@ -123,6 +123,7 @@ class _LogitKD(torch.autograd.Function):
                 ws.data_ptr(), ws_bytes, n_rows, V, _dtype_code(student), float(T), float(alpha), float(eps),
                 int(variant), _inv_norm(reduction, n_rows, V, batch, n_total), up_ptr, int(flags), _stream_ptr(dev)))
         ctx.grad = grad
+        ctx.need_grad = need_grad
         ctx.student_shape = student.shape
         ctx.dev = dev
         ctx.upstream = up_t
@@ -135,20 +136,24 @@ class _LogitKD(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
-        grad = ctx.grad
-        if grad is None:
+        if not ctx.need_grad:
             return (None,) * 11
-        ctx.grad = None
+        # First backward: the gradient the forward launch produced, re-emitted in place only if grad_output differs from the
+        # scale folded in there.  A later backward through the same graph (retain_graph=True, two losses sharing the node)
+        # must not touch that buffer — autograd may have handed it out as ``student.grad`` — so the gradient is recomputed
+        # from the saved row statistics into a fresh one (skip pointer NULL = never skip).
+        first = ctx.grad is not None
         go, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
         t2, s2 = ctx.rows
         n_rows, V, dt, T, eps, variant, inv_norm = ctx.call
         ws = ctx.workspace
         with torch.cuda.device(ctx.dev):
+            grad = ctx.grad if first else torch.empty((n_rows, V), dtype=s2.dtype, device=ctx.dev)
+            ctx.grad = None
             _lib.check(_lib.load().kd_logit_kd_regrad(t2.data_ptr(), t2.stride(0), s2.data_ptr(), s2.stride(0),
                                                       grad.data_ptr(), grad.stride(0), ws.data_ptr(), ws.numel(),
                                                       n_rows, V, dt, T, eps, variant, inv_norm, go.data_ptr(),
-                                                      ratio.data_ptr(), _stream_ptr(ctx.dev)))
-        ctx.rows = ctx.workspace = None
+                                                      ratio.data_ptr() if first else None, _stream_ptr(ctx.dev)))
         return (None, grad.view(ctx.student_shape), None, None, None, None, None, None, None, None, None)
 
 
@@ -201,23 +206,24 @@ class _InfoNCE(torch.autograd.Function):
                                                loss.data_ptr(), ws.data_ptr(), ws_bytes, M, P, D, _dtype_code(xs),
                                                float(temperature), up_ptr, 0 if need_grad else _lib.FLAG_NO_GRAD,
                                                _stream_ptr(dev)))
-        ctx.grad, ctx.dev, ctx.upstream = grad, dev, up_t
-        ctx.workspace, ctx.shape3 = ws, (M, P, D)
+        ctx.grad, ctx.dev, ctx.upstream, ctx.need_grad = grad, dev, up_t, need_grad
+        ctx.workspace, ctx.shape3, ctx.gdtype, ctx.gshape = ws, (M, P, D), xs.dtype, xs.shape
         return loss
 
     @staticmethod
     def backward(ctx, grad_output):
-        grad = ctx.grad
-        if grad is None:
+        if not ctx.need_grad:
             return None, None, None, None
-        ctx.grad = None
+        first = ctx.grad is not None           # see _LogitKD.backward: a repeated backward re-emits into a fresh buffer
         _, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
         M, P, D = ctx.shape3
         ws = ctx.workspace
         with torch.cuda.device(ctx.dev):
+            grad = ctx.grad if first else torch.empty(ctx.gshape, dtype=ctx.gdtype, device=ctx.dev)
+            ctx.grad = None
             _lib.check(_lib.load().kd_info_nce_regrad(ws.data_ptr(), ws.numel(), grad.data_ptr(), M, P, D,
-                                                      _dtype_code(grad), ratio.data_ptr(), _stream_ptr(ctx.dev)))
-        ctx.workspace = None
+                                                      _dtype_code(grad), ratio.data_ptr(), ratio.data_ptr() if first else None,
+                                                      _stream_ptr(ctx.dev)))
         return grad, None, None, None
 
 
@@ -254,23 +260,23 @@ class _FeatureMSE(torch.autograd.Function):
             _lib.check(lib.kd_feature_mse_fwd_bwd(a.data_ptr(), b.data_ptr(), grad.data_ptr() if need_grad else None,
                                                   loss.data_ptr(), ws.data_ptr(), ws_bytes, a.numel(), _dtype_code(a),
                                                   up_ptr, 0 if need_grad else _lib.FLAG_NO_GRAD, _stream_ptr(dev)))
-        ctx.grad, ctx.dev, ctx.upstream = grad, dev, up_t
+        ctx.grad, ctx.dev, ctx.upstream, ctx.need_grad = grad, dev, up_t, need_grad
         ctx.inputs = (a, b) if need_grad else None
         return loss
 
     @staticmethod
     def backward(ctx, grad_output):
-        grad = ctx.grad
-        if grad is None:
+        if not ctx.need_grad:
             return None, None, None
-        ctx.grad = None
+        first = ctx.grad is not None           # see _LogitKD.backward: a repeated backward re-emits into a fresh buffer
         go, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
         a, b = ctx.inputs
         with torch.cuda.device(ctx.dev):
+            grad = ctx.grad if first else torch.empty_like(a)
+            ctx.grad = None
             _lib.check(_lib.load().kd_feature_mse_regrad(a.data_ptr(), b.data_ptr(), grad.data_ptr(), a.numel(),
-                                                         _dtype_code(a), go.data_ptr(), ratio.data_ptr(),
+                                                         _dtype_code(a), go.data_ptr(), ratio.data_ptr() if first else None,
                                                          _stream_ptr(ctx.dev)))
-        ctx.inputs = None
         return grad, None, None
 
 

@@ -60,7 +60,7 @@ class CudaPhases:
         return table, consts
 
     def emit(self, teacher, student, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad=True,
-             force_streaming=False):
+             force_streaming=False, status=None):
         dev = student.device
         n, V = student.shape
         loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -73,7 +73,8 @@ class CudaPhases:
                                                 lse2_t.data_ptr(), table.data_ptr(), consts.data_ptr(),
                                                 grad.data_ptr() if want_grad else None, V, loss.data_ptr(),
                                                 rowaux.data_ptr(), n, V, _dtype_code(student), float(T), float(eps),
-                                                float(inv_norm), up_ptr, flags, _stream_ptr(dev)))
+                                                float(inv_norm), up_ptr, status.data_ptr() if status is not None else None,
+                                                flags, _stream_ptr(dev)))
         return loss, grad
 
 
@@ -84,28 +85,32 @@ def shard_rows(n_total: int, world_size: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
-_shard_counts: dict = {}     # (group id, local rows) -> rows of every rank; shard sizes are exchanged once, not per step
+def exchange_counts(n_local: int, device, group=None) -> list[int]:
+    """Row count of every rank, in rank order.  One small all-gather plus a host read-back: call it once when the shard
+    sizes are fixed, or pass ``counts=`` explicitly every step when they vary (each rank then knows them from the data
+    pipeline).  Nothing is cached here: ranks that resize independently must not diverge in the collectives they issue."""
+    world = dist.get_world_size(group)
+    n = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
+    out = torch.empty((world,), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, n, group=group)
+    return [int(c) for c in out.tolist()]
 
 
 def gather_records(records: torch.Tensor, group=None, counts=None) -> torch.Tensor:
     """All-gather ragged [n_i, 4] int32 record blocks in rank order (global flattened token order).
 
-    The per-rank row counts need a host read-back, so they are exchanged only the first time a given local
-    shard size is seen for ``group`` (pass ``counts`` explicitly when ranks resize independently)."""
+    ``counts`` = rows of every rank; when omitted they are exchanged on every call (:func:`exchange_counts`, one host
+    read-back) — never cached, so shards may change size from step to step on any subset of ranks."""
     if group is None and not (dist.is_available() and dist.is_initialized()):
         return records
     world = dist.get_world_size(group)
     if world == 1:
         return records
-    key = (id(group), int(records.shape[0]))
     if counts is None:
-        counts = _shard_counts.get(key)
-    if counts is None:
-        n_local = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
-        gathered = [torch.zeros_like(n_local) for _ in range(world)]
-        dist.all_gather(gathered, n_local, group=group)
-        counts = [int(c.item()) for c in gathered]
-        _shard_counts[key] = counts
+        counts = exchange_counts(records.shape[0], records.device, group)
+    counts = [int(c) for c in counts]
+    if len(counts) != world or counts[dist.get_rank(group)] != records.shape[0]:
+        raise ValueError(f"counts {counts} do not describe this rank's {records.shape[0]} rows / a world of {world}")
     if len(set(counts)) == 1:            # even shards: one contiguous all-gather, no padding or concatenation
         out = torch.empty((world * counts[0], 4), dtype=records.dtype, device=records.device)
         dist.all_gather_into_tensor(out, records.contiguous(), group=group)
@@ -128,15 +133,14 @@ class PeerRecordExchange:
     step i has read that buffer.
     """
 
-    def __init__(self, n_local: int, device, group=None):
+    def __init__(self, counts, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        counts = torch.zeros(self.world, dtype=torch.int64, device=device)
-        counts[self.rank] = n_local
-        dist.all_reduce(counts, group=self.group)
-        self.counts = [int(c) for c in counts.tolist()]
+        self.counts = [int(c) for c in counts]
+        if len(self.counts) != self.world:
+            raise ValueError(f"counts {self.counts} do not describe a world of {self.world}")
         self.offset, self.n_total = sum(self.counts[: self.rank]), sum(self.counts)
         self.bufs, self.handles = [], []
         for _ in range(2):
@@ -150,23 +154,35 @@ class PeerRecordExchange:
         i = self.step & 1
         self.step += 1
         hdl = self.handles[i]
-        lse2_t, _status = phases.teacher_stats_peers(teacher, labels, T, alpha, V, hdl.buffer_ptrs_dev, self.world, self.offset)
+        if teacher.shape[0] != self.counts[self.rank]:
+            raise ValueError(f"this exchange was built for {self.counts[self.rank]} local rows, got {teacher.shape[0]}")
+        lse2_t, status = phases.teacher_stats_peers(teacher, labels, T, alpha, V, hdl.buffer_ptrs_dev, self.world, self.offset)
         hdl.barrier(channel=0)
-        return self.bufs[i], lse2_t
+        return self.bufs[i], lse2_t, status
 
 
-_peer_exchanges: dict = {}
+_peer_exchanges: dict = {}       # (group, device, counts of every rank) -> PeerRecordExchange; keyed by ALL ranks' counts
+
+
+def _sum_status(status, group, multi):
+    """A bad label on any rank must poison every rank's loss (the reference raises, P1:166): OR = max of the status words."""
+    if status is not None and multi:
+        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)
+    return status
 
 
 def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, group=None, upstream=None,
-                          phases=None, reduce_loss=True, want_grad=True, n_total=None, exchange="nccl"):
+                          phases=None, reduce_loss=True, want_grad=True, n_total=None, exchange="nccl", counts=None):
     """As-written LoCa over tokens sharded across the ranks of ``group``.
 
     ``teacher``/``student``/``labels`` hold this rank's rows.  Returns ``(loss, grad_local)`` where
     ``loss`` is the GLOBAL loss (identical on every rank) when ``reduce_loss`` and the local partial otherwise.
+    ``counts``: rows of every rank in rank order; pass it when shard sizes vary from step to step (sequence lengths do) —
+    without it the counts are exchanged on every call (one host read-back), nothing is cached across calls.
     ``phases`` injects the three phase implementations (tests run the host logic on CPU with an
     oracle-backed stand-in; the product default is :class:`CudaPhases`).  ``exchange="peer"`` replaces the NCCL
     all-gather of the records by peer stores issued from the phase-A kernel itself (:class:`PeerRecordExchange`).
+    A label outside ``[0, V)`` on ANY rank NaN-poisons the loss on every rank (the reference raises at P1:166).
     """
     if phases is None:
         phases = CudaPhases()
@@ -175,41 +191,44 @@ def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, grou
     V = s2.shape[1]
     lab = labels.reshape(-1).to(torch.int64).contiguous()
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if multi and counts is None:
+        counts = exchange_counts(t2.shape[0], t2.device, group)
     if exchange == "peer" and multi:
         # phase A + all-gather in one kernel: records go straight into every rank's buffer over NVLink
-        key = (id(group), int(t2.shape[0]), t2.device.index)
+        key = (id(group), t2.device.index, tuple(int(c) for c in counts))
         ex = _peer_exchanges.get(key)
         if ex is None:
-            ex = _peer_exchanges[key] = PeerRecordExchange(int(t2.shape[0]), t2.device, group)
-        rec_all, lse2_t = ex.run(phases, t2, lab, T, alpha, V)
+            ex = _peer_exchanges[key] = PeerRecordExchange(counts, t2.device, group)
+        rec_all, lse2_t, status = ex.run(phases, t2, lab, T, alpha, V)
     else:
-        rec, lse2_t, _status = phases.teacher_stats(t2, lab, T, alpha, V)
-        rec_all = gather_records(rec, group)
+        rec, lse2_t, status = phases.teacher_stats(t2, lab, T, alpha, V)
+        rec_all = gather_records(rec, group, counts) if multi else rec
+    status = _sum_status(status, group, multi)
     if n_total is None:
         n_total = rec_all.shape[0]
     table, consts = phases.build_table(rec_all, V)
     inv_norm = 1.0 / (float(n_total) * float(V))
-    loss, grad = phases.emit(t2, s2, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad=want_grad)
-    if reduce_loss and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    loss, grad = phases.emit(t2, s2, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad=want_grad, status=status)
+    if reduce_loss and multi:
         loss = loss.clone()
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
     return loss, grad
 
 
-def per_row_token_sharded(fn, teacher, student, *args, group=None, reduce_loss=True, **kw):
+def per_row_token_sharded(fn, teacher, student, *args, group=None, reduce_loss=True, n_total=None, **kw):
     """Row-independent variants: run ``fn`` (``loca_kl(mode='per_row')`` / ``temperature_kl``) on the local rows
-    normalised by the global token count; the only collective is the scalar loss sum."""
+    normalised by the global token count; the only data-path collective is the scalar loss sum.  ``n_total`` = global
+    token count; when omitted it is all-reduced on every call (one host read-back, nothing cached)."""
     n_local = _rows(student).shape[0]
-    n_total = n_local
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        key = ("n_total", id(group), n_local)
-        n_total = _shard_counts.get(key)
-        if n_total is None:      # the global token count needs a host read-back: exchanged once per shard size, not per step
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if n_total is None:
+        n_total = n_local
+        if multi:
             t = torch.tensor([n_local], dtype=torch.int64, device=student.device)
             dist.all_reduce(t, group=group)
-            n_total = _shard_counts[key] = int(t.item())
-    loss = fn(teacher, student, *args, n_total=n_total, **kw)
-    if reduce_loss and n_total != n_local:
+            n_total = int(t.item())
+    loss = fn(teacher, student, *args, n_total=int(n_total), **kw)
+    if reduce_loss and multi:
         red = loss.detach().clone()
         dist.all_reduce(red, group=group)
         loss = loss + (red - loss.detach())       # value = global sum, gradient = local path
@@ -346,7 +365,7 @@ def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, 
     else:
         stats = phases.stats(t2, s2, lab, col0, T)
     stats_all = collectives.gather_stats(stats)                             # exchange 1: [G, n, 12]
-    rec, lse2, rowconst, _status = phases.combine(stats_all, lab, V_total, T, alpha, variant)
+    rec, lse2, rowconst, status = phases.combine(stats_all, lab, V_total, T, alpha, variant)
     table, table_const = None, 0.0
     if variant == _lib.LOCA_REFERENCE:
         table, consts = phases.build_table(rec, V_total)
@@ -357,6 +376,8 @@ def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, 
     unit = 1.0 if variant == _lib.KL_LOG_TARGET else _LN2
     rows = collectives.sum_(partial[:, 0].double().sum().reshape(1) * unit)[0]
     loss = (rows + rowconst.double().sum() * _LN2 + float(n) * table_const) * (float(T) * float(T) * inv_norm)
+    if loca and status is not None:          # a label outside [0, V_total): the reference raises (P1:166) — NaN, no host sync
+        loss = torch.where(status.reshape(()) != 0, torch.full_like(loss, float("nan")), loss)
     return loss.float(), grad
 
 

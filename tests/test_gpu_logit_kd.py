@@ -88,6 +88,40 @@ def test_loca_against_oracle(N, V, T, peaked, boost, mode, force_streaming):
     assert row_err.max().item() <= 2.0 ** -8
 
 
+@pytest.mark.parametrize("V,T,boost", [(151936, 2.0, 1.0), (151936, 0.8, 4.0), (18440, 1.0, 1.0)])
+def test_per_row_label_and_runner_up_positions(V, T, boost):
+    """Single-pass per-row LoCa: the fold patches the row's own two cells analytically and the owning lanes re-write the
+    two gradient elements.  Rows where the label IS the runner-up (one cell, v2 wins — P1:185 after P1:184), is the best
+    cell, sits in the first / last column, or where best and runner-up share a 16-byte vector or straddle CTA slices."""
+    N = 24
+    t, s, lab = synthetic.logit_batch(N, V, seed=300 + V % 11)
+    s = (s.float() * boost).to(torch.bfloat16)
+    t = t.float()
+    top = t.topk(2, dim=-1)
+    lab[0] = top.indices[0, 1]                  # label == runner-up
+    lab[1] = top.indices[1, 0]                  # label == best
+    lab[2], lab[3] = 0, V - 1                   # first / last column
+    t[4, 8], t[4, 9] = 30.0, 29.0               # best and runner-up in one vector
+    t[5, V - 1], t[5, 0] = 30.0, 29.0           # ... at the two ends of the row
+    t[6, V // 9 * 4 - 1], t[6, V // 9 * 4] = 31.0, 30.5
+    lab[6] = V // 9 * 4
+    # teacher confident of the label, p_gt ~ 0.9 (p_gt -> 1 itself is outside the parity domain: DESIGN.md section 3)
+    t[7, 5], lab[7] = T * (torch.logsumexp(t[7] / T, dim=0).item() + 2.2), 5
+    t = t.to(torch.bfloat16)
+    ref = O.loca_kl(t, s, lab, T, 0.8, mode="per_row", chunk_rows=4)
+    loss, grad = run_loca(t, s, lab, T, 0.8, "per_row", torch.bfloat16)
+    assert abs(loss - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
+    assert grad_close(grad, ref.grad)
+    row_err = (grad.double() - ref.grad).norm(dim=1) / ref.grad.norm(dim=1)
+    assert row_err.max().item() <= 2.0 ** -8
+    # the override cells themselves (a wrong patch would hide in the norm of 151 936 cells)
+    rows = torch.arange(N)
+    k = ref.aux["stats"]["k"]
+    for cols in (lab, k):
+        ours, want = grad[rows, cols].double(), ref.grad[rows, cols]
+        assert ((ours - want).abs() <= 2.0 ** -7 * want.abs() + 1e-30).all()
+
+
 @pytest.mark.parametrize("force_streaming", PATHS)
 def test_teacher_wider_than_student_and_strided_rows(force_streaming):
     """P1:155 slices the teacher to the student's vocabulary: we take a row stride instead of a copy."""

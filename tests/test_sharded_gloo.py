@@ -19,13 +19,15 @@ class OraclePhases:
     """CPU stand-in for sharded.CudaPhases with the same record layout ([n,4] int32: label, v1 bits, k, v2 bits)."""
 
     def teacher_stats(self, teacher, labels, T, alpha, V):
-        st = O.loca_row_stats(teacher, labels, T, alpha, V, dtype=torch.float64)
+        bad = (labels < 0) | (labels >= V)
+        status = torch.tensor([1 if bool(bad.any()) else 0], dtype=torch.int32)      # KD_STATUS_BAD_LABEL, like phase A
+        st = O.loca_row_stats(teacher, labels.clamp(0, V - 1), T, alpha, V, dtype=torch.float64)
         rec = torch.empty((labels.numel(), 4), dtype=torch.int32)
         rec[:, 0] = st["labels"].int()
         rec[:, 1] = st["v1"].float().view(torch.int32)
         rec[:, 2] = st["k"].int()
         rec[:, 3] = st["v2"].float().view(torch.int32)
-        return rec, None, None
+        return rec, None, status
 
     def build_table(self, records_all, V):
         lab, k = records_all[:, 0].long(), records_all[:, 2].long()
@@ -34,11 +36,15 @@ class OraclePhases:
         self.stats_all = {"labels": lab, "k": k, "v1": v1, "v2": v2}
         return O.build_override_table(lab, k, v1, v2, V), None
 
-    def emit(self, teacher, student, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad=True, force_streaming=False):
+    def emit(self, teacher, student, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad=True, force_streaming=False,
+             status=None):
         lab_local = torch.zeros(student.shape[0], dtype=torch.long)     # labels only matter through the table here
         res = O.loca_kl(teacher, student, lab_local, T, ALPHA, eps, mode=O.LOCA_REFERENCE, inv_norm=inv_norm,
                         stats_override=self.stats_all)
-        return res.loss.float(), res.grad
+        loss = res.loss.float()
+        if status is not None and int(status.item()) != 0:               # what loss_finalize_kernel does with the status word
+            loss = torch.full_like(loss, float("nan"))
+        return loss, res.grad
 
 
 def _free_port():
@@ -66,6 +72,47 @@ def _worker(rank, world, port, n_total, out):
         out[rank] = (ok_loss, ok_grad, ok_kl)
     finally:
         dist.destroy_process_group()
+
+
+def _worker_resizing(rank, world, port, out):
+    """Shard sizes change from step to step, on one rank only at first: nothing may be cached across calls (a stale count
+    made one rank skip the count collective the other issued — gloo 'collective mismatch', a hang on NCCL)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = []
+        # (rows of rank 0, rows of rank 1): rank 1 keeps 2 rows while rank 0 goes 2 -> 3, then both change, then explicit counts
+        for step, (n0, n1, explicit) in enumerate([(2, 2, False), (3, 2, False), (3, 5, False), (4, 1, True), (2, 2, True)]):
+            n_total = n0 + n1
+            t, s, lab = synthetic.logit_batch(n_total, V, seed=50 + step)
+            lo, hi = (0, n0) if rank == 0 else (n0, n_total)
+            counts = [n0, n1] if explicit else None
+            loss, grad = sharded.loca_kl_token_sharded(t[lo:hi], s[lo:hi], lab[lo:hi], T, ALPHA, phases=OraclePhases(), counts=counts)
+            full = O.loca_kl(t, s, lab, T, ALPHA)
+            ok.append(abs(loss.item() - full.loss.item()) <= 1e-6 * abs(full.loss.item())
+                      and ((grad - full.grad[lo:hi]).norm() / full.grad[lo:hi].norm()).item() <= 1e-6)
+            part = sharded.per_row_token_sharded(
+                lambda a, b, n_total=None: O.temperature_kl(a, b, T, inv_norm=1.0 / (n_total * V)).loss.float(), t[lo:hi], s[lo:hi],
+                n_total=n_total if explicit else None)
+            ok.append(abs(part.item() - O.temperature_kl(t, s, T).loss.item()) <= 1e-6 * abs(part.item()))
+        # a label outside [0, V) on ONE rank poisons the loss on BOTH (the reference raises, P1:166)
+        t, s, lab = synthetic.logit_batch(6, V, seed=70)
+        lab[4] = -100
+        lo, hi = (0, 3) if rank == 0 else (3, 6)
+        loss, _ = sharded.loca_kl_token_sharded(t[lo:hi], s[lo:hi], lab[lo:hi], T, ALPHA, phases=OraclePhases())
+        ok.append(bool(torch.isnan(loss).item()))
+        out[rank] = all(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_token_sharded_shards_that_resize_between_steps():
+    world, port = 2, _free_port()
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_resizing, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
 
 
 @pytest.mark.timeout(180)

@@ -1,0 +1,6 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT
+echo "== default"; python tools/r2/time_modes.py per_row kl per_row_T0.8p reference_T0.8p reference
+echo "== nocand"; KD_B200_LIB=$PWD/tools/variants/nocand/libkd_b200.so python tools/r2/time_modes.py per_row per_row_T0.8p
+echo "== trace"; KD_TRACE_DUMP=$PWD/gpurun_out/trace_pr.bin KD_B200_LIB=$PWD/tools/variants/trace/libkd_b200.so ROWS=8192 python tools/r2/time_modes.py per_row
+python tools/trace_fused.py gpurun_out/trace_pr.bin; rm -f gpurun_out/trace_pr.bin
