@@ -61,14 +61,22 @@ def top2_lowest_index(p: torch.Tensor):
 
 
 def loca_row_stats(teacher: torch.Tensor, labels: torch.Tensor, T: float, alpha: float, V: int,
-                   dtype=torch.float64):
+                   dtype=torch.float64, chunk_rows: int | None = None):
     """Per-token calibration scalars of P1:155-180.
 
     Returns dict of [N] tensors: p_gt (P1:166), k (P1:170-171), p_k (P1:174),
     v1 = 1 - s*(sum tp - p_gt) (P1:184 rhs), v2 = s*p_k (P1:185 rhs), tsum.
+    Runs on the device of ``teacher`` (the tests run it in fp64 on the GPU for the full benchmark shape), row chunk by
+    row chunk when ``chunk_rows`` is given.
     """
-    t = _as_rows(teacher)[:, :V].to(dtype)                      # P1:155 (vocab slice)
-    lab = labels.reshape(-1).long()
+    rows_all = _as_rows(teacher)
+    if chunk_rows is not None and rows_all.shape[0] > chunk_rows:
+        lab_all = labels.reshape(-1)
+        parts = [loca_row_stats(rows_all[r0:r0 + chunk_rows], lab_all[r0:r0 + chunk_rows], T, alpha, V, dtype)
+                 for r0 in range(0, rows_all.shape[0], chunk_rows)]
+        return {k: torch.cat([p_[k] for p_ in parts]) for k in parts[0]}
+    t = rows_all[:, :V].to(dtype)                               # P1:155 (vocab slice)
+    lab = labels.reshape(-1).long().to(t.device)
     if lab.numel() and (lab.min() < 0 or lab.max() >= V):
         raise IndexError("labels must lie in [0, V) — the reference raises on -100 (SURVEY §8a)")
     tp = torch.softmax(t / T, dim=-1)                             # P1:158
@@ -88,11 +96,12 @@ def build_override_table(labels: torch.Tensor, k: torch.Tensor, v1: torch.Tensor
     For every row the SAME columns are overwritten: column labels[r] <- v1[r]
     (row order, last wins), then column k[r] <- v2[r] (row order, last wins).
     """
-    ov = torch.full((V,), math.nan, dtype=v1.dtype)
+    dev = v1.device
+    ov = torch.full((V,), math.nan, dtype=v1.dtype, device=dev)
     n = labels.numel()
-    order = torch.arange(n)
-    own_l = torch.full((V,), -1, dtype=torch.long).scatter_reduce(0, labels, order, "amax", include_self=True)
-    own_k = torch.full((V,), -1, dtype=torch.long).scatter_reduce(0, k, order, "amax", include_self=True)
+    order = torch.arange(n, device=dev)
+    own_l = torch.full((V,), -1, dtype=torch.long, device=dev).scatter_reduce(0, labels, order, "amax", include_self=True)
+    own_k = torch.full((V,), -1, dtype=torch.long, device=dev).scatter_reduce(0, k, order, "amax", include_self=True)
     sel = own_l >= 0
     ov[sel] = v1[own_l[sel]]
     sel = own_k >= 0
@@ -102,7 +111,7 @@ def build_override_table(labels: torch.Tensor, k: torch.Tensor, v1: torch.Tensor
 
 def loca_kl(teacher, student, labels, T: float, alpha: float = 0.8, eps: float = 1e-8,
             mode: str = LOCA_REFERENCE, inv_norm: float | None = None, dtype=torch.float64,
-            want_grad: bool = True, chunk_rows: int = 64, stats_override=None) -> KDResult:
+            want_grad: bool = True, chunk_rows: int = 64, stats_override=None, grad_stride: int | None = None) -> KDResult:
     """LoCa KL (without the ``+ student_loss`` term of P1:194) and d loss / d student.
 
     loss = T^2 * inv_norm * sum_{r,v} [ xlogy(q,q) - q*log(max(sp,eps)) ]      (P1:188-192)
@@ -112,24 +121,32 @@ def loca_kl(teacher, student, labels, T: float, alpha: float = 0.8, eps: float =
     ``stats_override`` (dict with labels,k,v1,v2 of ALL tokens in global order) lets a caller
     emulate token-sharded execution: the table is built from the global list while
     ``teacher``/``student`` hold only the local rows.
+    ``grad_stride``: keep only every ``grad_stride``-th column of the gradient (``grad`` is then [N, ceil(V/stride)]) plus,
+    in ``aux``, the gradient at each row's label / runner-up cell and the per-row gradient norm — the full fp64 gradient
+    of the benchmark shape (16 384 x 151 936) would be 20 GB.  Device-agnostic: runs where ``student`` lives.
     """
     s_rows = _as_rows(student)
     t_rows = _as_rows(teacher)
     N, V = s_rows.shape
+    dev = s_rows.device
     if inv_norm is None:
         inv_norm = 1.0 / (N * V)
-    st = loca_row_stats(t_rows, labels, T, alpha, V, dtype=dtype)
+    st = loca_row_stats(t_rows, labels, T, alpha, V, dtype=dtype, chunk_rows=chunk_rows)
     ov = None
     if mode == LOCA_REFERENCE:
         src = st if stats_override is None else stats_override
-        ov = build_override_table(src["labels"].reshape(-1).long(), src["k"].reshape(-1).long(),
-                                  src["v1"].to(dtype), src["v2"].to(dtype), V)
+        ov = build_override_table(src["labels"].reshape(-1).long().to(dev), src["k"].reshape(-1).long().to(dev),
+                                  src["v1"].to(dev, dtype), src["v2"].to(dev, dtype), V)
     elif mode != LOCA_PER_ROW:
         raise ValueError(mode)
 
-    total = torch.zeros((), dtype=dtype)
-    grad = torch.empty((N, V), dtype=dtype) if want_grad else None
-    Q_all = torch.empty(N, dtype=dtype)
+    total = torch.zeros((), dtype=dtype, device=dev)
+    n_keep = V if grad_stride is None else (V + grad_stride - 1) // grad_stride
+    grad = torch.empty((N, n_keep), dtype=dtype, device=dev) if want_grad else None
+    g_lab = torch.empty(N, dtype=dtype, device=dev)
+    g_k = torch.empty(N, dtype=dtype, device=dev)
+    g_norm = torch.empty(N, dtype=dtype, device=dev)
+    Q_all = torch.empty(N, dtype=dtype, device=dev)
     for r0 in range(0, N, chunk_rows):
         r1 = min(N, r0 + chunk_rows)
         t = t_rows[r0:r1, :V].to(dtype)
@@ -140,7 +157,7 @@ def loca_kl(teacher, student, labels, T: float, alpha: float = 0.8, eps: float =
         if mode == LOCA_REFERENCE:
             q = torch.where(torch.isnan(ov)[None, :], q, ov[None, :].expand_as(q))
         else:
-            rows = torch.arange(r1 - r0)
+            rows = torch.arange(r1 - r0, device=dev)
             q[rows, st["labels"][r0:r1]] = st["v1"][r0:r1]
             q[rows, st["k"][r0:r1]] = st["v2"][r0:r1]
         keep = sp >= eps                                          # clamp(min=eps) passes grad where sp >= eps (P1:161-162)
@@ -149,10 +166,17 @@ def loca_kl(teacher, student, labels, T: float, alpha: float = 0.8, eps: float =
         Q = (q * keep).sum(dim=-1)
         Q_all[r0:r1] = Q
         if want_grad:
-            grad[r0:r1] = (T * inv_norm) * (sp * Q[:, None] - q * keep)
+            gchunk = (T * inv_norm) * (sp * Q[:, None] - q * keep)
+            rows = torch.arange(r1 - r0, device=dev)
+            g_lab[r0:r1] = gchunk[rows, st["labels"][r0:r1]]
+            g_k[r0:r1] = gchunk[rows, st["k"][r0:r1]]
+            g_norm[r0:r1] = gchunk.norm(dim=1)
+            grad[r0:r1] = gchunk if grad_stride is None else gchunk[:, ::grad_stride]
     loss = total * (T * T * inv_norm)
-    aux = {"stats": st, "override": ov, "Q": Q_all}
-    return KDResult(loss, grad.reshape(student.shape) if want_grad else None, aux)
+    aux = {"stats": st, "override": ov, "Q": Q_all, "grad_at_label": g_lab, "grad_at_k": g_k, "grad_row_norm": g_norm}
+    if want_grad and grad_stride is None:
+        grad = grad.reshape(student.shape)
+    return KDResult(loss, grad if want_grad else None, aux)
 
 
 # --------------------------------------------------------------------------------------
@@ -169,10 +193,11 @@ def temperature_kl(teacher, student, T: float, inv_norm: float | None = None, lo
     s_rows = _as_rows(student)
     t_rows = _as_rows(teacher)
     N, V = s_rows.shape
+    dev = s_rows.device
     if inv_norm is None:
         inv_norm = 1.0 / (N * V)
-    total = torch.zeros((), dtype=dtype)
-    grad = torch.empty((N, V), dtype=dtype) if want_grad else None
+    total = torch.zeros((), dtype=dtype, device=dev)
+    grad = torch.empty((N, V), dtype=dtype, device=dev) if want_grad else None
     for r0 in range(0, N, chunk_rows):
         r1 = min(N, r0 + chunk_rows)
         t = t_rows[r0:r1, :V].to(dtype)

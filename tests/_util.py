@@ -31,19 +31,19 @@ def rel_err(a, b) -> float:
     return (a - b).norm().item() / (den if den > 0 else 1.0)
 
 
-def grad_close(ours, ref, dtype=torch.bfloat16, tol=2e-3) -> bool:
-    """Gradient parity for a 16-bit output.
+GRAD_ERRORS: list = []      # (test id, relative error) of every grad_close call, summarised at the end of the run (conftest.py)
 
-    BASELINE.json's gate is 2e-3 relative "for bf16", i.e. the level of ONE rounding to bf16 (max 2^-8 per
-    element; ~1.7e-3 on the norm for smoothly distributed values, up to 2^-8 when a few cells dominate the norm).
-    A kernel cannot beat the output rounding, so the check is: (i) within `tol` of the exact oracle, or —
-    when the cells that dominate the norm happen to round badly — (ii) within 2^-8 of the exact oracle AND
-    within 1e-3 of the oracle rounded to the output dtype (only cells sitting on a rounding boundary may differ).
+
+def grad_close(ours, ref, dtype=torch.bfloat16, tol=2e-3) -> bool:
+    """Gradient parity for a 16-bit output: BASELINE.json's gate, 2e-3 relative on the L2 norm — no looser fallback.
+
+    One exact rounding to bf16 costs at most 2^-9 = 1.95e-3 per element (about 1.1e-3 on the norm of smoothly distributed
+    values), so the gate leaves the kernels ~1e-4 of their own.  Every measured error is recorded and the worst cases are
+    printed in the terminal summary, so the margin is visible in GPUTEST logs.
     """
+    import os
     ours = torch.as_tensor(ours, dtype=torch.float64)
     ref = torch.as_tensor(ref, dtype=torch.float64)
     e = rel_err(ours, ref)
-    if e <= tol:
-        return True
-    rounded = ref.to(torch.float32).to(dtype).to(torch.float64)
-    return e <= 2.0 ** -8 and rel_err(ours, rounded) <= 1e-3
+    GRAD_ERRORS.append((os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0], e))
+    return e <= tol

@@ -31,3 +31,17 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN_DIR
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Worst gradient errors seen by tests/_util.grad_close (gate: 2e-3 relative on the norm)."""
+    try:
+        from _util import GRAD_ERRORS
+    except Exception:
+        return
+    if not GRAD_ERRORS:
+        return
+    worst = sorted(GRAD_ERRORS, key=lambda x: -x[1])[:8]
+    terminalreporter.write_line(f"grad_close: {len(GRAD_ERRORS)} checks, gate 2e-3; worst:")
+    for name, e in worst:
+        terminalreporter.write_line(f"  {e:.3e}  {name}")
