@@ -11,6 +11,11 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller unless stated;
  *   - the library never allocates or frees device memory and never synchronises the device;
+ *   - process-wide state is limited to: the thread-local error string, per-device launch configuration cached on first use
+ *     (occupancy of the cluster kernels, opt-in shared-memory size), tuning switches read ONCE from the environment
+ *     (KD_FUSED, KD_CLUSTER_SIZE, KD_SPARE_SMS, KD_HELPER_RESERVE — A/B experiments, never needed in production) and one
+ *     internal non-blocking helper stream + event pair per device, used only where clusters of 8 would leave >= 20 SMs idle;
+ *     nothing of it changes results;
  *   - every call takes the CUDA stream (a cudaStream_t passed as void*) and is graph-capture safe;
  *   - return value 0 = success, otherwise a KD_ERR_* code; kd_last_error() gives a thread-local message;
  *   - row-major 2-D tensors are described by (pointer, leading dimension in ELEMENTS).

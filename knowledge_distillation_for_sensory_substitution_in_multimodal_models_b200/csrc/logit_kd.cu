@@ -286,209 +286,6 @@ teacher_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const int64_t*
 }
 
 // ------------------------------------------------------------------------------------------------
-// Phase A, TMA-fed: the same statistics, but the teacher row is streamed through a ring of shared-memory stages by a
-// producer warp (1-D bulk copies, one mbarrier pair per stage) while 8 consumer warps compute from shared memory.
-// The register-staged kernel above alternates "issue 8 loads / wait / compute" per thread (long-scoreboard stalls,
-// 56 % of DRAM peak in ncu); here the copies of the next chunks — and of the next row — are in flight during the
-// arithmetic and during the end-of-row merges.  Opt-in (KD_STATS_TMA=1): it measured slower, see launch_teacher_stats.
-// ------------------------------------------------------------------------------------------------
-#ifndef KD_TMA_CONSUMERS
-#define KD_TMA_CONSUMERS 256
-#endif
-#ifndef KD_TMA_STAGES
-#define KD_TMA_STAGES 6
-#endif
-#ifndef KD_TMA_CTAS_PER_SM
-#define KD_TMA_CTAS_PER_SM 2
-#endif
-constexpr int kTmaConsumers = KD_TMA_CONSUMERS;      // consumer threads
-constexpr int kTmaThreads = kTmaConsumers + 32;      // + one producer warp
-constexpr int kTmaStages = KD_TMA_STAGES;
-constexpr int kTmaVecPerThread = 4;
-constexpr int kTmaChunkVec = kTmaConsumers * kTmaVecPerThread;      // 16-byte vectors per stage
-
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kTmaConsumers) : "memory"); }
-
-template <typename T>
-__global__ void __launch_bounds__(kTmaThreads)
-teacher_stats_tma_kernel(const T* __restrict__ teacher, int64_t ld_t, const int64_t* __restrict__ labels,
-                         kd_token_record* __restrict__ rec, float* __restrict__ lse2_t, uint32_t* status,
-                         int64_t n_rows, int V, float k2, float alpha) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ float smf[4 * kMaxWarps];
-    __shared__ int smi[2 * kMaxWarps];
-    __shared__ int thr_shared[2];        // CTA-wide runner-up bound, one slot per row parity
-    __shared__ __align__(8) unsigned long long bars[2 * kTmaStages];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t s_stage0 = smem_u32(smem);
-    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + kTmaStages * 8;
-    if (tid == 0) {
-        for (int i = 0; i < kTmaStages; ++i) {
-            mbar_init(bar_full + i * 8, 1);
-            mbar_init(bar_empty + i * 8, kTmaConsumers / 32);
-        }
-        fence_mbar_init();
-        thr_shared[0] = thr_shared[1] = float_key(-INFINITY);
-    }
-    __syncthreads();
-    const int nvec = V / 8;
-    const int n_chunks = (nvec + kTmaChunkVec - 1) / kTmaChunkVec;
-
-    if (warp == kTmaConsumers / 32) {
-        // ---------------- producer: one lane walks (row, chunk) in the consumers' order ----------------
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
-                const T* row = teacher + r * ld_t;
-                for (int c = 0; c < n_chunks; ++c) {
-                    mbar_wait_cta(bar_empty + stage * 8, phase ^ 1u);       // passes at once on a fresh barrier
-                    const int nv = min(kTmaChunkVec, nvec - c * kTmaChunkVec);
-                    mbar_expect_tx(bar_full + stage * 8, (uint32_t)nv * 16u);
-                    tma_load_1d(s_stage0 + stage * (kTmaChunkVec * 16), row + (int64_t)c * kTmaChunkVec * 8, (uint32_t)nv * 16u,
-                                bar_full + stage * 8);
-                    if (++stage == kTmaStages) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumers ----------------
-    const u64 k2p = pk(k2, k2);
-    const float slack = 64.f / k2;          // logits may exceed the reference by this much before a rescale
-    int stage = 0, parity = 0;
-    uint32_t phase = 0;
-    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x, parity ^= 1) {
-        if (tid == 0) thr_shared[parity ^ 1] = float_key(-INFINITY);       // next row's slot (rows are separated by the merges' barriers)
-        Top2 top;
-        top.init();
-        float ref = -INFINITY, lane_max = -INFINITY, thr_top = -INFINITY;
-        u64 mkp = pk(0.f, 0.f), acc0 = pk(0.f, 0.f), acc1 = pk(0.f, 0.f);
-        auto vec_max = [&](const uint4& raw) -> float {
-            const uint32_t m2 = Pair<T>::vmax(Pair<T>::vmax(raw.x, raw.y), Pair<T>::vmax(raw.z, raw.w));
-            float m_lo, m_hi;
-            upk(Pair<T>::widen(m2), m_lo, m_hi);
-            return fmaxf(m_lo, m_hi);
-        };
-        auto consume = [&](const uint4& raw, int v) {
-            const float vm = vec_max(raw);
-            lane_max = fmaxf(lane_max, vm);
-            if (vm > ref + slack || ref == -INFINITY) {     // rare: first vector, or a cell far above the reference
-                const float sc = (ref == -INFINITY) ? 0.f : ex2((ref - vm) * k2);
-                acc0 = mul2(acc0, pk(sc, sc));
-                acc1 = mul2(acc1, pk(sc, sc));
-                ref = vm;
-                mkp = pk(-vm * k2, -vm * k2);
-            }
-            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float e0, e1;
-                upk(fma2(Pair<T>::widen(w[i]), k2p, mkp), e0, e1);
-                if (i & 1) acc1 = add2(acc1, pk(ex2(e0), ex2(e1)));
-                else acc0 = add2(acc0, pk(ex2(e0), ex2(e1)));
-            }
-            if (vm >= thr_top) {                             // rare: a cell that may be best or runner-up
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float x0, x1;
-                    upk(Pair<T>::widen(w[i]), x0, x1);
-                    top.push(x0, v * 8 + 2 * i);
-                    top.push(x1, v * 8 + 2 * i + 1);
-                }
-                if (top.a2 > thr_top) {
-                    thr_top = top.a2;
-                    atomicMax(thr_shared + parity, float_key(thr_top));
-                }
-            }
-        };
-        for (int c = 0; c < n_chunks; ++c) {
-            mbar_wait_cta(bar_full + stage * 8, phase);
-            const int nv = min(kTmaChunkVec, nvec - c * kTmaChunkVec);
-            const uint32_t s_chunk = s_stage0 + stage * (kTmaChunkVec * 16);
-            uint4 raw[kTmaVecPerThread];
-#pragma unroll
-            for (int u = 0; u < kTmaVecPerThread; ++u) {
-                const int v = tid + u * kTmaConsumers;
-                raw[u] = make_uint4(Pair<T>::kNegInf2, Pair<T>::kNegInf2, Pair<T>::kNegInf2, Pair<T>::kNegInf2);
-                if (v < nv) raw[u] = lds128(s_chunk + v * 16);
-            }
-            // the stage can be refilled as soon as every lane of the warp holds its vectors in registers
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cta(bar_empty + stage * 8);
-            if (++stage == kTmaStages) { stage = 0; phase ^= 1u; }
-            if (c == 0) {      // first chunk: the 2nd largest lane maximum of the warp is a valid lower bound of the runner-up
-                float bm = vec_max(raw[0]);
-#pragma unroll
-                for (int u = 1; u < kTmaVecPerThread; ++u) bm = fmaxf(bm, vec_max(raw[u]));
-                const float wm = warp_max(bm);
-                const unsigned holders = __ballot_sync(0xffffffffu, bm == wm);
-                thr_top = warp_max((lane == __ffs(holders) - 1) ? -INFINITY : bm);
-                if (lane == 0) atomicMax(thr_shared + parity, float_key(thr_top));
-            }
-            thr_top = fmaxf(thr_top, key_float(*reinterpret_cast<volatile int*>(thr_shared + parity)));
-#pragma unroll
-            for (int u = 0; u < kTmaVecPerThread; ++u) {
-                const int v = tid + u * kTmaConsumers;
-                if (v < nv) consume(raw[u], c * kTmaChunkVec + v);
-            }
-        }
-        // ---- merge the 256 consumer threads (named barrier: the producer warp is not part of it) ----
-        MaxSum ms;
-        {
-            float a0, a1;
-            upk(add2(acc0, acc1), a0, a1);
-            ms.m = lane_max;      // partial relative to the lane's true maximum (<= ref + slack, so the factor is finite)
-            ms.s = (lane_max == -INFINITY) ? 0.f : (a0 + a1) * ex2((ref - lane_max) * k2);
-        }
-        warp_merge(ms, k2);
-        warp_merge(top);
-        if (lane == 0) {
-            smf[warp] = ms.m; smf[kMaxWarps + warp] = ms.s;
-            smf[2 * kMaxWarps + warp] = top.a1; smf[3 * kMaxWarps + warp] = top.a2;
-            smi[warp] = top.i1; smi[kMaxWarps + warp] = top.i2;
-        }
-        consumer_sync();
-        if (warp == 0) {
-            MaxSum rm;
-            rm.init();
-            Top2 rt;
-            rt.init();
-            if (lane < kTmaConsumers / 32) {
-                rm.m = smf[lane]; rm.s = smf[kMaxWarps + lane];
-                rt.a1 = smf[2 * kMaxWarps + lane]; rt.a2 = smf[3 * kMaxWarps + lane];
-                rt.i1 = smi[lane]; rt.i2 = smi[kMaxWarps + lane];
-            }
-            warp_merge(rm, k2);
-            warp_merge(rt);
-            if (lane == 0) {
-                const float l2 = lse2_of(rm, k2);
-                const int64_t lab = labels[r];
-                kd_token_record out;
-                if (lab < 0 || lab >= V) {
-                    atomicOr(status, KD_STATUS_BAD_LABEL);
-                    out.label = -1;
-                    out.v1 = __int_as_float(0x7fc00000);
-                    out.k = rt.i2;
-                    out.v2 = __int_as_float(0x7fc00000);
-                } else {
-                    float v1, v2;
-                    loca_scalars(Elem<T>::to_float(teacher[r * ld_t + lab]), rt.a2, l2, k2, alpha, v1, v2);
-                    out.label = static_cast<int>(lab);
-                    out.v1 = v1;
-                    out.k = (V > 1) ? rt.i2 : 0;
-                    out.v2 = v2;
-                }
-                rec[r] = out;
-                lse2_t[r] = l2;
-            }
-        }
-        consumer_sync();      // smf / smi and the parity slot are reused by the next row
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // override table (P1:184-185): last token in flattened order wins; the k pass runs after the label pass
 // ------------------------------------------------------------------------------------------------
 __global__ void owner_init_kernel(int* own, int n) {
@@ -872,28 +669,8 @@ template <typename T>
 int launch_teacher_stats(const void* teacher, int64_t ld_t, const int64_t* labels, kd_token_record* rec, float* lse2_t,
                          uint32_t* status, int64_t n_rows, int V, float k2, float alpha, cudaStream_t st,
                          kd_token_record* const* peers = nullptr, int n_peers = 0, int64_t row_offset = 0) {
-    if constexpr (sizeof(T) == 2) {
-        // KD_STATS_TMA=1 selects the TMA-fed kernel.  Measured on B200 (16 384 x 151 936 bf16): 1.046 ms at best (512 consumers,
-        // 3 stages, 2 CTAs/SM) against 0.998 ms for the register-staged kernel — phase A is bound by issue slots + the XU pipe at
-        // limited occupancy, not by load latency — so the register-staged kernel stays the default.
-        static int use_tma = -1;
-        if (use_tma < 0) { const char* e = getenv("KD_STATS_TMA"); use_tma = e ? atoi(e) : 0; }
-        if (use_tma && !peers && rows_vectorizable<T>(teacher, ld_t) && V % 8 == 0 && V >= 8 * kTmaConsumers) {
-            auto kfn = teacher_stats_tma_kernel<T>;
-            const int smem = kTmaStages * kTmaChunkVec * 16;
-            static bool configured = false;
-            if (!configured) {
-                cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(teacher_stats_tma_kernel)");
-                configured = true;
-            }
-            const int64_t cap = (int64_t)sm_count() * KD_TMA_CTAS_PER_SM;
-            const int g = static_cast<int>(n_rows < cap ? n_rows : cap);
-            kfn<<<g, kTmaThreads, smem, st>>>(static_cast<const T*>(teacher), ld_t, labels, rec, lse2_t, status, n_rows, V, k2, alpha);
-            KD_CHECK_LAUNCH("teacher_stats_tma_kernel");
-            return KD_OK;
-        }
-    }
+    // (A TMA-fed producer/consumer form of this kernel measured 1.05-1.40 ms against 1.00 ms: phase A is bound by issue slots + the
+    // XU pipe at its occupancy, not by load latency; it lives in the history of this file, commit 8d7f217.)
     const int grid = static_cast<int>(n_rows < (int64_t)sm_count() * 8 ? n_rows : (int64_t)sm_count() * 8);
     if (rows_vectorizable<T>(teacher, ld_t))
         teacher_stats_kernel<T, true><<<grid, kStatsThreads, 0, st>>>(static_cast<const T*>(teacher), ld_t, labels, rec,
@@ -951,14 +728,23 @@ HelperStream* helper_stream() {
     return &h;
 }
 
-int spare_sm_mode() {       // KD_SPARE_SMS=0 disables the helper launch
-    static int v = -1;
-    if (v < 0) {
+// Tuning switches, read from the environment ONCE (first use) and never again: KD_SPARE_SMS (0 = no helper launch, 1 = force it,
+// 2 = dynamic row queue without the helper), KD_HELPER_RESERVE (rows per cluster pipeline the helper leaves alone).
+struct Tunables {
+    int spare_sms, spare_forced, helper_reserve;
+    Tunables() {
         const char* e = getenv("KD_SPARE_SMS");
-        v = e ? atoi(e) : 1;
+        spare_sms = e ? atoi(e) : 1;
+        spare_forced = e != nullptr;
+        const char* r = getenv("KD_HELPER_RESERVE");
+        helper_reserve = r ? atoi(r) : 10;
     }
-    return v;
+};
+const Tunables& tunables() {
+    static const Tunables t;
+    return t;
 }
+int spare_sm_mode() { return tunables().spare_sms; }
 
 int launch_emit_stream_any(const EmitParams& p, int variant, int dtype, cudaStream_t st) {
     switch (dtype) {
@@ -992,7 +778,7 @@ int launch_emit(const EmitParams& p_in, int variant, int dtype, cudaStream_t st,
     // The helper pays off when a fifth of the machine would otherwise idle (clusters of 8: 28 spare SMs, emit 3.07 -> 3.00 ms); with
     // clusters of 9 only 13 SMs are spare and the extra stream / event traffic costs as much as their rows bring (measured: step
     // 3.79-3.85 ms without against 3.86-3.91 ms with, CUDA-graph replay).  KD_SPARE_SMS=1 forces it on, 0 off, default: automatic.
-    const int min_spare = (spare_sm_mode() == 1 && getenv("KD_SPARE_SMS")) ? 8 : 20;
+    const int min_spare = (spare_sm_mode() == 1 && tunables().spare_forced) ? 8 : 20;
     if (queue && spare_sm_mode() && spare >= min_spare && p.n_rows >= (int64_t)n_clusters * pipes * 8) hs = helper_stream();
     if (hs) {
         queue_init_kernel<<<1, 1, 0, st>>>(queue, n_clusters * static_rows);   // the first rows of every cluster are static
@@ -1007,9 +793,7 @@ int launch_emit(const EmitParams& p_in, int variant, int dtype, cudaStream_t st,
         EmitParams h = p;
         // the helper stops claiming near the end: one of its rows takes far longer than a cluster row, and a late claim would leave the
         // cluster SMs idle behind it (KD_HELPER_RESERVE = rows per cluster pipeline that stay with the cluster kernel)
-        static int reserve = -1;
-        if (reserve < 0) { const char* e = getenv("KD_HELPER_RESERVE"); reserve = e ? atoi(e) : 10; }
-        h.queue_tail_reserve = n_clusters * pipes * reserve;
+        h.queue_tail_reserve = n_clusters * pipes * tunables().helper_reserve;
         h.helper_ctas = spare * 2;
         rc = launch_emit_stream_any(h, variant, dtype, hs->stream);
         if (rc != KD_OK) return rc;

@@ -336,15 +336,20 @@ def test_benchmark_shape_against_oracle(mode, T, peaked, boost):
     assert abs(loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item())
     g = sd.grad
     assert grad_close(g[:, ::stride].double(), ref.grad)                                   # strided sample, whole batch
-    # per row: the sampled columns against the oracle's, scaled by the row's full gradient norm
+    # Per row.  A row whose exact gradient all but vanishes (one kept cell with sp -> 1: g*q*(sp - 1)) has no meaningful
+    # RELATIVE error in fp32 — the reference's own fp32 arithmetic cancels there too — so rows are measured against
+    # max(their own norm, 1e-3 of the median row norm).
+    ref_norm = ref.aux["grad_row_norm"]
+    scale = torch.maximum(ref_norm, 1e-3 * ref_norm.median())
     ours_rows = g.double().norm(dim=1)
-    assert ((ours_rows - ref.aux["grad_row_norm"]).abs() / ref.aux["grad_row_norm"]).max().item() <= GRAD_RTOL_BF16
-    row_err = (g[:, ::stride].double() - ref.grad).norm(dim=1) / ref.grad.norm(dim=1)
+    assert ((ours_rows - ref_norm).abs() / scale).max().item() <= 2.0 ** -8        # one cell can carry a row: the format's bound
+    frac = (ref.grad.norm(dim=1) / ref_norm).clamp_min(1e-3)          # share of the row norm the sampled columns carry
+    row_err = (g[:, ::stride].double() - ref.grad).norm(dim=1) / (scale * frac)
     assert row_err.max().item() <= 2.0 ** -7
-    # the override cells themselves
+    # the override cells themselves: one bf16 rounding of the cell plus the cancellation in g*(sp*Q - q*m), bounded by the row
     rows = torch.arange(N, device="cuda")
     for cols, want in ((lab, ref.aux["grad_at_label"]), (ref.aux["stats"]["k"], ref.aux["grad_at_k"])):
         got = g[rows, cols].double()
-        assert ((got - want).abs() <= 2.0 ** -7 * want.abs() + 1e-30).all()
+        assert ((got - want).abs() <= 2.0 ** -7 * want.abs() + GRAD_RTOL_BF16 * scale).all()
     del ref, g, sd, t, s
     torch.cuda.empty_cache()
