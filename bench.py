@@ -189,6 +189,62 @@ def run_reference_arm(args) -> None:
 
 
 # --------------------------------------------------------------------------------------------------------
+# parity of the timed configuration itself (outside the timed region; oracle = checker only)
+# --------------------------------------------------------------------------------------------------------
+def parity_block(kd, sharded, dist, teacher, student, labels, mode, world, rank, dev, loss_value, step, exchange, phases):
+    """Loss and a strided gradient sample of THE BENCHMARKED BATCH against oracle/kd_oracle.py run chunked in fp64 on the GPU.
+    N > 1: every rank runs the oracle on its rows with the GLOBAL table (its fp64 token records are all-gathered), the partial
+    losses are summed, and — on 256 rows per rank — the sharded loss is compared with the one-GPU op on the concatenated batch."""
+    from oracle import kd_oracle as O
+    N = teacher.shape[0]
+    n_total = N * world
+    stride = 97
+    step()                                              # leaves the gradient of the benchmarked batch in student.grad
+    grad = student.grad
+    override = None
+    if world > 1 and mode == "reference":
+        st = O.loca_row_stats(teacher, labels, T_KD, ALPHA, V, chunk_rows=128)
+        override = {}
+        for key in ("labels", "k", "v1", "v2"):
+            part = st[key].contiguous()
+            full = torch.empty((n_total,), dtype=part.dtype, device=dev)
+            dist.all_gather_into_tensor(full, part)
+            override[key] = full
+    ref = O.loca_kl(teacher, student.detach(), labels, T_KD, ALPHA, mode=mode, inv_norm=1.0 / (float(n_total) * V), chunk_rows=128,
+                    grad_stride=stride, stats_override=override)
+    ref_loss = ref.loss.reshape(1).clone()
+    num = (grad[:, ::stride].double() - ref.grad).pow(2).sum().reshape(1)
+    den = ref.grad.pow(2).sum().reshape(1)
+    if world > 1:
+        for x in (ref_loss, num, den):
+            dist.all_reduce(x)
+    out = {"oracle": "oracle/kd_oracle.py, fp64 on the GPU, chunked; every 97th gradient column", "rows_checked": n_total,
+           "loss": loss_value, "oracle_loss": ref_loss.item(), "loss_rel_err": abs(loss_value - ref_loss.item()) / abs(ref_loss.item()),
+           "grad_rel_err": (num.sqrt() / den.sqrt()).item(), "gates": {"loss": 1e-5, "grad": 2e-3}}
+    del ref
+    if world > 1:
+        m = 256
+        tt, ss, ll = teacher[:m].contiguous(), student.detach()[:m].contiguous(), labels[:m].contiguous()
+        if mode == "reference":
+            sl, _ = sharded.loca_kl_token_sharded(tt, ss, ll, T_KD, ALPHA, phases=phases, exchange="nccl", counts=[m] * world)
+        else:
+            sl = sharded.per_row_token_sharded(kd.loca_kl, tt, ss, ll, T_KD, alpha=ALPHA, mode="per_row", n_total=m * world)
+        gt = torch.empty((world * m, tt.shape[1]), dtype=tt.dtype, device=dev)
+        gs = torch.empty((world * m, ss.shape[1]), dtype=ss.dtype, device=dev)
+        gl = torch.empty((world * m,), dtype=ll.dtype, device=dev)
+        dist.all_gather_into_tensor(gt, tt)
+        dist.all_gather_into_tensor(gs, ss)
+        dist.all_gather_into_tensor(gl, ll)
+        one = kd.loca_kl(gt, gs, gl, T_KD, alpha=ALPHA, mode=mode)
+        out["sharded_vs_one_gpu"] = {"rows": world * m, "sharded_loss": sl.item(), "one_gpu_loss_of_concatenated_batch": one.item(),
+                                     "rel_diff": abs(sl.item() - one.item()) / abs(one.item())}
+        del gt, gs, gl
+    out["ok"] = bool(out["loss_rel_err"] <= 1e-5 and out["grad_rel_err"] <= 2e-3 and
+                     out.get("sharded_vs_one_gpu", {}).get("rel_diff", 0.0) <= 1e-5)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
 def main() -> None:
@@ -202,6 +258,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the per_row / KL / InfoNCE / MSE side measurements")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the benchmarked batch")
     ap.add_argument("--force-streaming", action="store_true", help="time the general streaming emit kernel instead of the cluster kernel")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1, as-written mode: record all-gather by peer stores from the phase-A kernel (NVLink symmetric memory) or by NCCL")
@@ -234,6 +291,7 @@ def main() -> None:
     teacher, student, labels = synthetic.logit_batch(N, V, seed=1234 + rank, device=dev)
     student.requires_grad_(True)
     n_total = N * world
+    counts = [N] * world                  # fixed, equal shards: passed explicitly so no step pays a count exchange
     phases = sharded.CudaPhases()
     exchange = args.exchange if world > 1 else "none"
     if world > 1 and mode == "reference" and exchange == "peer":
@@ -255,10 +313,11 @@ def main() -> None:
             loss = kd.loca_kl(teacher, student, labels, T_KD, alpha=ALPHA, mode=mode)
             loss.backward()
         elif mode == "reference":
-            loss, grad = sharded.loca_kl_token_sharded(teacher, student.detach(), labels, T_KD, ALPHA, phases=phases, exchange=exchange)
+            loss, grad = sharded.loca_kl_token_sharded(teacher, student.detach(), labels, T_KD, ALPHA, phases=phases, exchange=exchange,
+                                                       counts=counts)
             student.grad = grad
         else:
-            loss = sharded.per_row_token_sharded(kd.loca_kl, teacher, student, labels, T_KD, alpha=ALPHA, mode="per_row")
+            loss = sharded.per_row_token_sharded(kd.loca_kl, teacher, student, labels, T_KD, alpha=ALPHA, mode="per_row", n_total=n_total)
             loss.backward()
         return loss
 
@@ -284,6 +343,13 @@ def main() -> None:
     ms_step = ms_total.item() / args.steps
     value = n_total / (ms_step / 1e3)
     loss_value = float(loss.item())
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_block(kd, sharded, dist, teacher, student, labels, mode, world, rank, dev, loss_value, step, exchange, phases)
+        except Exception as exc:  # noqa: BLE001 - report, do not hide the headline
+            parity = {"ok": False, "error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
 
     # ---- dominant kernel (phase C / emit) timed alone with CUDA events on its launch stream ------------
     roof = None
@@ -317,14 +383,19 @@ def main() -> None:
             emit_ms, stats_ms = a.elapsed_time(b) / k, b.elapsed_time(c) / k
             emit_bytes = 3 * esize * V * N            # read teacher + read student + write grad
             achieved = emit_bytes / (emit_ms / 1e3) / 1e9
-            traffic = None
-            try:      # dram__bytes_read+write per row from the committed ncu --set full capture (profiles/)
-                with open(os.path.join(ROOT, "profiles", "emit_traffic.json")) as f:
-                    traffic = json.load(f)["dram_bytes_per_row"] * N
-            except Exception:  # noqa: BLE001
-                pass
+            traffic, traffic_src = None, None
+            if not args.force_streaming and N == ROWS_PER_GPU:
+                try:      # dram__bytes_read+write per row from the committed ncu --set full capture of THIS kernel and shape
+                    with open(os.path.join(ROOT, "profiles", "emit_traffic.json")) as f:
+                        tj = json.load(f)
+                    traffic = tj["dram_bytes_per_row"] * N
+                    traffic_src = (f"NOT measured in this run: static ncu --set full capture ({tj.get('rows', '?')} rows, "
+                                   f"{tj.get('source', 'profiles/')}, commit {tj.get('commit', '?')}) x {N} rows")
+                except Exception:  # noqa: BLE001
+                    pass
             roof = {"bound": "hbm", "kernel": "LoCa emit (phase C: q/Q_r/loss/grad)", "achieved": achieved, "peak": peak_gbs,
-                    "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "algorithmic_bytes": emit_bytes,
+                    "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes": emit_bytes,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_token": 3 * esize * V, "kernel_ms": emit_ms}
             side["teacher_stats"] = {"kernel_ms": stats_ms, "achieved_gbs": esize * V * N / (stats_ms / 1e3) / 1e9,
@@ -368,6 +439,27 @@ def main() -> None:
             ms = timeit(f, k=5, w=2)
             side[name] = {"ms": ms, "tokens_per_s": N / (ms / 1e3), "achieved_gbs": byt / (ms / 1e3) / 1e9,
                           "frac": byt / (ms / 1e3) / 1e9 / peak_gbs}
+        # the reference's own temperatures (P1:71 T = 0.8, LG:75 T = 1) on peaked logits (label = teacher's best class on ~70 % of
+        # the rows, student 4x sharper): every row takes the sp >= eps clamp path (pass B' + second reduction), the slow case
+        tpk, spk, lpk = synthetic.logit_batch(N, V, seed=4321, device=dev, peaked=True)
+        spk = (spk.float() * 4.0).to(torch.bfloat16).requires_grad_(True)
+
+        def fbp(f):
+            def run():
+                spk.grad = None
+                f().backward()
+            return run
+        for name, f, byt in (
+            ("loca_reference_T0.8_peaked", fbp(lambda: kd.loca_kl(tpk, spk, lpk, 0.8, alpha=ALPHA)), 8 * V * N),
+            ("loca_reference_T1_peaked", fbp(lambda: kd.loca_kl(tpk, spk, lpk, 1.0, alpha=ALPHA)), 8 * V * N),
+            ("loca_per_row_T0.8_peaked", fbp(lambda: kd.loca_kl(tpk, spk, lpk, 0.8, alpha=ALPHA, mode="per_row")), 6 * V * N),
+            ("kl_log_target_T0.8", fb(lambda: kd.temperature_kl(teacher, student, 0.8, log_target_quirk=True)), 6 * V * N),
+        ):
+            ms = timeit(f, k=5, w=2)
+            side[name] = {"ms": ms, "tokens_per_s": N / (ms / 1e3), "achieved_gbs": byt / (ms / 1e3) / 1e9,
+                          "frac": byt / (ms / 1e3) / 1e9 / peak_gbs, "algorithmic_bytes_per_token": byt // N}
+        del tpk, spk, lpk
+        torch.cuda.empty_cache()
         xs, xt = synthetic.vision_feature_batch(64, 729, 1152, device=dev)
         xs.requires_grad_(True)
 
@@ -434,7 +526,7 @@ def main() -> None:
                 l_ = kd.loca_kl(dt_, ds_, dl_, T_KD, alpha=ALPHA, mode=mode, n_total=n_total)
                 l_.backward()
             else:
-                l_, g_ = sharded.loca_kl_token_sharded(dt_, ds_.detach(), dl_, T_KD, ALPHA, phases=phases, exchange=exchange)
+                l_, g_ = sharded.loca_kl_token_sharded(dt_, ds_.detach(), dl_, T_KD, ALPHA, phases=phases, exchange=exchange, counts=counts)
             return float(l_.item())          # device -> host read of the step's result
 
         ke = max(2, min(args.steps, 5))
@@ -481,7 +573,7 @@ def main() -> None:
                        **({"exchange": "phase A stores records into every rank's buffer over NVLink (symmetric memory) + device barrier"
                            if exchange == "peer" else "NCCL all-gather of 16 B/token records"} if (world > 1 and mode == "reference") else {}),
                        "l2": "inputs (2 x 4.98 GB/GPU) exceed the 126 MB L2; no flush needed"},
-            "loss": loss_value, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "loss": loss_value, "parity": parity, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary(), "secondary": side,
         }
         print(json.dumps(out))

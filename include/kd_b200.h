@@ -184,6 +184,33 @@ int kd_lm_head_fwd(const void* hidden, int64_t ld_h, const void* weight, int64_t
                    void* stream);
 int kd_lm_head_stats_merge(const float* stat_partials, int64_t n_tiles, float* stats, int64_t n_rows, float T, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * The same tcgen05 kernel as a general product, for the two BACKWARD GEMMs of the lm_head (the reference gets them from autograd
+ * through the HF lm_head, P1:228-240) and for the learned projections of BASELINE configs[2] / [3]:
+ *   C[M, N] = A[M, K] . B[N, K]^T        bf16 / fp16 operands, fp32 accumulation; C in the operand type or fp32 (c_is_f32)
+ * a_mn_major / b_mn_major = 1: the operand is stored TRANSPOSED (A as [K, M] with pitch ld_a, B as [K, N] with pitch ld_b) and is read
+ * through an MN-major shared-memory descriptor — nothing is transposed in HBM:
+ *   dH[n, H]  = g[n, V] . W[V, H]          -> A = g (K-major), B = W with b_mn_major = 1, c_is_f32 = 1 (summed over vocabulary shards in fp32)
+ *   dW[V, H]  = g[n, V]^T . hidden[n, H]   -> A = g with a_mn_major = 1, B = hidden with b_mn_major = 1
+ * KD_ERR_UNSUPPORTED: fp32 operands, a_mn_major without b_mn_major, pointers / pitches that are not multiples of 16 bytes.
+ * ---------------------------------------------------------------------------------------------------- */
+int kd_gemm(const void* A, int64_t ld_a, int a_mn_major, const void* B, int64_t ld_b, int b_mn_major, void* C, int64_t ld_c,
+            int c_is_f32, int64_t M, int64_t N, int64_t K, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Projected feature MSE (BASELINE configs[3]; mse_loss EV:160-165 applied to `input @ proj`, the intended use at EV:304 / P1:375
+ * for a student whose width differs from the teacher's): the projection GEMM with the MSE as its epilogue — the [M, N] projected
+ * tensor never reaches HBM.
+ *   loss = mean( (round(input . proj) .float() - target.float())^2 )        (the product rounded to the operand type, as a library GEMM hands it on)
+ *   grad_projected[M, N] = upstream * 2 (projected - target) / (M N)        in the operand type; the caller forms
+ *   d input = grad_projected . proj^T (kd_gemm, both K-major) and d proj = input^T . grad_projected (kd_gemm, both MN-major).
+ * input [M, K], proj [K, N], target [M, N] row-major; bf16 / fp16.
+ * ---------------------------------------------------------------------------------------------------- */
+int kd_proj_mse_workspace_bytes(int64_t M, int64_t N, size_t* bytes);
+int kd_proj_mse_fwd_bwd(const void* input, int64_t ld_x, const void* proj, int64_t ld_w, const void* target, int64_t ld_t,
+                        void* grad_projected, int64_t ld_g, float* loss_out, void* workspace, size_t workspace_bytes, int64_t M,
+                        int64_t N, int64_t K, int dtype, const float* upstream, void* stream);
+
 /* grad *= (*factor) in place, skipped on device when *factor == 1 (kept for callers that accept double rounding). */
 int kd_scale_rows(void* grad, int64_t ld_g, int64_t n_rows, int64_t V, int dtype, const float* factor, void* stream);
 

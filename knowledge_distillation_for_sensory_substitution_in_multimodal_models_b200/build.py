@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkd_b200.so")
-SOURCES = ["kd_core.cu", "logit_kd.cu", "logit_kd_cluster.cu", "logit_kd_fused.cu", "logit_kd_vshard.cu", "lm_head_gemm.cu", "feature_mse.cu", "info_nce.cu"]
+SOURCES = ["kd_core.cu", "logit_kd.cu", "logit_kd_cluster.cu", "logit_kd_fused.cu", "logit_kd_vshard.cu", "kd_gemm.cu", "feature_mse.cu", "info_nce.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

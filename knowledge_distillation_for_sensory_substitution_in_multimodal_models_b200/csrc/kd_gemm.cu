@@ -1,10 +1,17 @@
-// lm_head_gemm.cu — the student lm_head feeding the vocabulary-sharded logit KD (BASELINE configs[4]; the logits the
-// reference takes from the HF student at P1:228-240 are `hidden @ W_lm_head^T`, 896 x 151 936 for Qwen2-0.5B).
+// kd_gemm.cu — the tensor-core GEMMs of the path: the student lm_head feeding the vocabulary-sharded logit KD (BASELINE
+// configs[4]; the logits the reference takes from the HF student at P1:228-240 are `hidden @ W_lm_head^T`, 896 x 151 936 for
+// Qwen2-0.5B), its two backward products, and the learned projections of BASELINE configs[2] / [3].
 //
-//   logits[n_rows, V_local] = hidden[n_rows, H] * weight[V_local, H]^T        bf16/fp16 operands, fp32 accumulation, 16-bit out
-//   partials[tile][row]     = (max, sum 2^((x - max) * log2e / T)) of the row's ROUNDED logits inside 128-column tile `tile`
+//   C[M, N] = A[M, K] * B[N, K]^T        bf16/fp16 operands, fp32 accumulation, 16-bit or fp32 out
 //
-// so that kd_vshard_stats does not read the student logits again (its teacher half is all that is left to stream).
+// Either operand may be K-major (its K index contiguous in memory: A stored [M, K], B stored [N, K]) or MN-major (stored
+// transposed: A as [K, M], B as [K, N]) — the tensor core reads both through its shared-memory descriptor, so no operand is
+// ever transposed in HBM:   forward   logits = hidden * W^T                 A K-major, B K-major
+//                           dH        = g * W           (B = W  as [K=V, N=H])   A K-major, B MN-major
+//                           dW        = g^T * hidden    (A = g as [K=n, M=V], B = hidden as [K=n, N=H])   both MN-major
+// Epilogues: plain store; + per-row (max, sum-exp) partials of the ROUNDED logits (so that kd_vshard_stats does not read the
+// student logits again); or the feature-MSE epilogue (EV:160-165 on a projected tensor): the product is rounded like the
+// library GEMM would, compared with the target tile, and what is stored is the GRADIENT w.r.t. the product.
 //
 // Tensor-core kernel for sm_100a, hand-written:
 //   * persistent CTA PAIRS (cluster 2 x 1 x 1 = the two SMs of a TPC), one 256 x 256 output tile per pair at a time, walked in
@@ -34,8 +41,9 @@ namespace {
 // a CTA PAIR (cluster 2 x 1 x 1, the two SMs of a TPC) owns one 256 x 256 output tile: BM rows and half of the weight tile per CTA
 constexpr int BM = 128, BN = 256, BNH = BN / 2, BK = 64, STAGES = 5;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SLAB = 64;                           // output columns per TMA store (one 128-byte swizzle atom)
-constexpr int C_SLAB_BYTES = BM * SLAB * 2;
+constexpr int SLAB = 64;                           // 16-bit output columns per TMA store (one 128-byte swizzle atom; fp32: 32)
+constexpr int C_SLAB_BYTES = BM * 128;
+constexpr int MN_GROUP_BYTES = BK * 128;           // MN-major operand: one 64-element MN group = BK rows of 128 bytes
 constexpr int EPI_HALVES = 2;                     // two epilogue warp quads, 128 of the tile's 256 columns each
 constexpr int STAT_COLS = BN / EPI_HALVES;        // columns per statistics partial
 constexpr int GEMM_THREADS = 64 + EPI_HALVES * 128;
@@ -86,6 +94,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t addr) {
     d |= (uint64_t)2 << 61;      // SWIZZLE_128B
     return d;
 }
+// MN-major operand tile, 128-byte swizzle (canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): a 128-byte row holds 64
+// consecutive M (or N) elements of ONE k; 8 k-rows form the 1024-byte swizzle atom (SBO = 1024 B to the next 8 k), the next 64
+// M / N elements start MN_GROUP_BYTES further (LBO).  One K = 16 MMA reads two atoms: its descriptor starts 2048 B after the last.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(MN_GROUP_BYTES >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tile_m, int& tile_n) {
     const int per_group = GROUP_M * tiles_n;
     const int g = t / per_group, first_m = g * GROUP_M;
@@ -127,11 +147,34 @@ template <> struct Pack2<__half> {
     }
 };
 
-// STATS: 0 = product only, 1 = + the rows' (max, sum-exp) per 128-column half tile
-template <typename T, int STATS>
+// epilogues
+constexpr int EPI_STORE = 0;      // C = round(acc)
+constexpr int EPI_STATS = 1;      // + the rows' (max, sum-exp) per 128-column half tile (student lm_head)
+constexpr int EPI_MSE = 2;        // C = upstream * 2 (round(acc) - target) / numel; partial sums of (round(acc) - target)^2
+
+struct GemmExtra {                // what the non-plain epilogues need
+    float2* partials;             // EPI_STATS: [stat tiles][M] (max, sum-exp)
+    float k2;                     // EPI_STATS: log2(e) / T
+    const void* target;           // EPI_MSE: [M, N] in the operand type, pitch ld_t elements
+    int64_t ld_t;
+    float gscale;                 // EPI_MSE: 2 / numel
+    const float* upstream;        // EPI_MSE: device scalar or nullptr
+    float* sq_partials;           // EPI_MSE: [tiles * 2 CTAs * EPI_HALVES * 4 warps] sums of squared differences
+};
+
+template <typename OutT> struct OutPack;          // accumulator values -> the 16-byte chunks of a 128-byte staging row
+template <> struct OutPack<float> { static constexpr int kCols = 32; };
+template <> struct OutPack<__nv_bfloat16> { static constexpr int kCols = 64; };
+template <> struct OutPack<__half> { static constexpr int kCols = 64; };
+
+// T: operand type; EPI: epilogue; A_MN / B_MN: operand stored MN-major (transposed in memory); OutT: T or float
+template <typename T, int EPI, bool A_MN, bool B_MN, typename OutT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                    const __grid_constant__ CUtensorMap mapC, int M, int N, int K, float k2, float2* __restrict__ partials) {
+kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapC, int M, int N, int K, const GemmExtra ex) {
+    constexpr int SLABC = OutPack<OutT>::kCols;     // output columns per 128-byte staging row
+    constexpr bool OUT32 = sizeof(OutT) == 4;
+    static_assert(EPI == EPI_STORE || !OUT32, "the statistics / MSE epilogues write the operand type");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4];
@@ -166,22 +209,33 @@ lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int t = pair; t < tiles; t += npairs) {
                 int tile_m, tile_n;
                 tile_coords(t, tiles_m, tiles_n, tile_m, tile_n);
+                const int m0 = tile_m * 2 * BM + row_off, n0 = tile_n * BN + (int)rank * BNH;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(bar_empty + s * 8, ph ^ 1u);
                     if (rank == 0) mbar_expect_tx(bar_full + s * 8, 2 * STAGE_BYTES);      // both CTAs' bytes land on the leader's barrier
                     const uint32_t leader_full = mapa_rank(bar_full + s * 8, 0);
                     const uint32_t dstA = smem_u32(smem + s * STAGE_BYTES), dstB = dstA + A_BYTES;
-                    tma_load_2d_2sm(dstA, &mapA, kb * BK, tile_m * 2 * BM + row_off, leader_full);
-                    tma_load_2d_2sm(dstB, &mapB, kb * BK, tile_n * BN + (int)rank * BNH, leader_full);
+                    if constexpr (A_MN) {       // two boxes of {64 M elements, BK k-rows}: coordinates (m, k)
+                        tma_load_2d_2sm(dstA, &mapA, m0, kb * BK, leader_full);
+                        tma_load_2d_2sm(dstA + MN_GROUP_BYTES, &mapA, m0 + 64, kb * BK, leader_full);
+                    } else {
+                        tma_load_2d_2sm(dstA, &mapA, kb * BK, m0, leader_full);
+                    }
+                    if constexpr (B_MN) {
+                        tma_load_2d_2sm(dstB, &mapB, n0, kb * BK, leader_full);
+                        tma_load_2d_2sm(dstB + MN_GROUP_BYTES, &mapB, n0 + 64, kb * BK, leader_full);
+                    } else {
+                        tma_load_2d_2sm(dstB, &mapB, kb * BK, n0, leader_full);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {      // ---------------- MMA issuer (pair leader only) ----------------
-            // D fp32 (bit 4), A/B format (bits 7-9 / 10-12), N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 over the pair); K-major
-            const uint32_t idesc = (1u << 4) | (Pack2<T>::kFormat << 7) | (Pack2<T>::kFormat << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                   ((uint32_t)((2 * BM) >> 4) << 24);
+            // D fp32 (bit 4), A/B format (bits 7-9 / 10-12), A / B MN-major (bits 15 / 16), N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | (Pack2<T>::kFormat << 7) | (Pack2<T>::kFormat << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
             uint32_t it = 0, i = 0;
             for (int t = pair; t < tiles; t += npairs, ++i) {
                 const uint32_t as = i & 1, aph = (i >> 1) & 1;
@@ -195,7 +249,8 @@ lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), b0 = a0 + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = umma_desc_sw128(a0 + k * 32), db = umma_desc_sw128(b0 + k * 32);
+                        const uint64_t da = A_MN ? umma_desc_sw128_mn(a0 + k * 2048) : umma_desc_sw128(a0 + k * 32);
+                        const uint64_t db = B_MN ? umma_desc_sw128_mn(b0 + k * 2048) : umma_desc_sw128(b0 + k * 32);
                         const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
                         asm volatile(
                             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -214,6 +269,8 @@ lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const bool elected = (tid == 64 + half * 128);                 // issues this half's TMA stores
         unsigned char* cstage = smem + STAGES * STAGE_BYTES + half * 2 * C_SLAB_BYTES;
         const int n_stat = (N + STAT_COLS - 1) / STAT_COLS;
+        float mse_g = 0.f;
+        if constexpr (EPI == EPI_MSE) mse_g = ex.gscale * (ex.upstream ? *ex.upstream : 1.f);
         uint32_t i = 0, slab = 0;
         for (int t = pair; t < tiles; t += npairs, ++i) {
             int tile_m, tile_n;
@@ -223,33 +280,61 @@ lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             MaxSum ms;
             ms.init();
+            float sq = 0.f;
             const int row_g = tile_m * 2 * BM + row_off + r_in;
 #pragma unroll 1
-            for (int c = half * STAT_COLS; c < (half + 1) * STAT_COLS; c += SLAB, ++slab) {
-                uint32_t r[SLAB];
+            for (int c = half * STAT_COLS; c < (half + 1) * STAT_COLS; c += SLABC, ++slab) {
+                uint32_t r[SLABC];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + as * BN + (uint32_t)c;
                 tmem_ld32(taddr, r);
-                tmem_ld32(taddr + 32, r + 32);
+                if constexpr (SLABC == 64) tmem_ld32(taddr + 32, r + 32);
+                const int col_base = tile_n * BN + c;
+                uint4 tg[EPI == EPI_MSE ? SLABC / 8 : 1];
+                if constexpr (EPI == EPI_MSE) {      // the target row's 128 bytes of this slab (zero outside the matrix)
+                    const T* trow = static_cast<const T*>(ex.target) + (int64_t)row_g * ex.ld_t + col_base;
+#pragma unroll
+                    for (int j = 0; j < SLABC / 8; ++j) {
+                        tg[j] = make_uint4(0, 0, 0, 0);
+                        if (row_g < M && col_base + 8 * j < N) tg[j] = ldg_stream(trow + 8 * j);      // N % 8 == 0: whole chunks
+                    }
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 unsigned char* buf = cstage + (slab & 1) * C_SLAB_BYTES;
                 // the TMA store that read this staging buffer two slabs ago must be done with it
                 if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-                const int col_base = tile_n * BN + c;
+                if constexpr (OUT32) {
 #pragma unroll
-                for (int j = 0; j < SLAB / 8; ++j) {
-                    uint32_t w[4];
+                    for (int j = 0; j < SLABC / 4; ++j)
+                        *reinterpret_cast<uint4*>(buf + r_in * 128 + ((j ^ (r_in & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                } else {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float a = __uint_as_float(r[8 * j + 2 * u]), b = __uint_as_float(r[8 * j + 2 * u + 1]);
-                        w[u] = Pack2<T>::pack(a, b);
-                        if constexpr (STATS != 0) {
-                            r[8 * j + 2 * u] = __float_as_uint(a);
-                            r[8 * j + 2 * u + 1] = __float_as_uint(b);
+                    for (int j = 0; j < SLABC / 8; ++j) {
+                        uint32_t w[4];
+                        [[maybe_unused]] const uint32_t tw[4] = {tg[EPI == EPI_MSE ? j : 0].x, tg[EPI == EPI_MSE ? j : 0].y,
+                                                                 tg[EPI == EPI_MSE ? j : 0].z, tg[EPI == EPI_MSE ? j : 0].w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float a = __uint_as_float(r[8 * j + 2 * u]), b = __uint_as_float(r[8 * j + 2 * u + 1]);
+                            w[u] = Pack2<T>::pack(a, b);             // a, b come back rounded to the operand type
+                            if constexpr (EPI == EPI_STATS) {
+                                r[8 * j + 2 * u] = __float_as_uint(a);
+                                r[8 * j + 2 * u + 1] = __float_as_uint(b);
+                            }
+                            if constexpr (EPI == EPI_MSE) {           // (input.float() - target.float())^2 on the ROUNDED product
+                                float ta, tb;
+                                upk(Pair<T>::widen(tw[u]), ta, tb);
+                                float da = a - ta, db = b - tb;
+                                sq = fmaf(da, da, sq);
+                                sq = fmaf(db, db, sq);
+                                da *= mse_g;
+                                db *= mse_g;
+                                w[u] = Pack2<T>::pack(da, db);
+                            }
                         }
+                        // 16-byte chunk j of row r_in lands at chunk j ^ (r_in % 8): conflict-free, and what SWIZZLE_128B expects
+                        *reinterpret_cast<uint4*>(buf + r_in * 128 + ((j ^ (r_in & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
-                    // 16-byte chunk j of row r_in lands at chunk j ^ (r_in % 8): conflict-free, and what SWIZZLE_128B expects
-                    *reinterpret_cast<uint4*>(buf + r_in * 128 + ((j ^ (r_in & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
@@ -259,15 +344,16 @@ lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                                  : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                if constexpr (STATS != 0) {      // online (max, sum-exp) of this row over the slab's in-range columns
-                    const int valid = min(SLAB, N - col_base);      // may be <= 0 in the last tile: the whole slab is out of range
+                if constexpr (EPI == EPI_STATS) {      // online (max, sum-exp) of this row over the slab's in-range columns
+                    const float k2 = ex.k2;
+                    const int valid = min(SLABC, N - col_base);      // may be <= 0 in the last tile: the whole slab is out of range
                     float vmax = -INFINITY;
-                    if (valid >= SLAB) {
+                    if (valid >= SLABC) {
 #pragma unroll
-                        for (int x = 0; x < SLAB; ++x) vmax = fmaxf(vmax, __uint_as_float(r[x]));
+                        for (int x = 0; x < SLABC; ++x) vmax = fmaxf(vmax, __uint_as_float(r[x]));
                     } else {
 #pragma unroll
-                        for (int x = 0; x < SLAB; ++x) {
+                        for (int x = 0; x < SLABC; ++x) {
                             if (x >= valid) r[x] = 0xff800000u;      // -inf
                             vmax = fmaxf(vmax, __uint_as_float(r[x]));
                         }
@@ -280,7 +366,7 @@ lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         const float mk = ms.m * k2;
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                        for (int x = 0; x < SLAB; x += 4) {
+                        for (int x = 0; x < SLABC; x += 4) {
                             s0 += ex2(fmaf(__uint_as_float(r[x]), k2, -mk));
                             s1 += ex2(fmaf(__uint_as_float(r[x + 1]), k2, -mk));
                             s2 += ex2(fmaf(__uint_as_float(r[x + 2]), k2, -mk));
@@ -294,9 +380,13 @@ lm_head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             __syncwarp();
             if (lane == 0)      // on the leader's barrier: its MMA warp reuses the accumulator of BOTH CTAs
                 asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar_acc_empty + as * 8, 0)) : "memory");
-            if constexpr (STATS != 0) {
+            if constexpr (EPI == EPI_STATS) {
                 const int st = tile_n * EPI_HALVES + half;
-                if (row_g < M && st < n_stat) partials[(size_t)st * M + row_g] = make_float2(ms.m, ms.s);
+                if (row_g < M && st < n_stat) ex.partials[(size_t)st * M + row_g] = make_float2(ms.m, ms.s);
+            }
+            if constexpr (EPI == EPI_MSE) {          // out-of-range rows / columns contributed (0 - 0)^2
+                sq = warp_sum(sq);
+                if (lane == 0) ex.sq_partials[((size_t)t * 2 + rank) * (EPI_HALVES * 4) + (warp - 2)] = sq;
             }
         }
         if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -335,12 +425,13 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// row-major [rows, cols] 16-bit matrix with row pitch `ld` elements; boxes of 64 columns x box_rows rows, 128-byte swizzle
-bool make_map(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-              CUtensorMapL2promotion promo) {
+// row-major [rows, cols] matrix of `esize`-byte elements with row pitch `ld` elements; boxes of box_cols x box_rows, 128-byte
+// swizzle (box_cols * esize == 128)
+bool make_map(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+              int box_rows, CUtensorMapL2promotion promo) {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)esize};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return encode_tiled()(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -356,19 +447,88 @@ int gemm_sm_count() {
     return sms;
 }
 
-template <typename T, int STATS>
-int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K, float k2, float2* partials,
+template <typename T, int EPI, bool A_MN, bool B_MN, typename OutT>
+int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K, const GemmExtra& ex,
                 cudaStream_t st) {
-    auto kern = lm_head_gemm_kernel<T, STATS>;
+    auto kern = kd_gemm_kernel<T, EPI, A_MN, B_MN, OutT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);      // per device, cheap
-    if (e != cudaSuccess) return cuda_fail(e, "lm_head_gemm_kernel: shared-memory opt-in");
+    if (e != cudaSuccess) return cuda_fail(e, "kd_gemm_kernel: shared-memory opt-in");
     const int64_t tiles = (int64_t)((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     const int64_t pairs = gemm_sm_count() / 2;
     const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);      // persistent CTA pairs (cluster 2 x 1 x 1)
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, b, c, M, N, K, k2, partials);
-    KD_CHECK_LAUNCH("lm_head_gemm_kernel");
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, b, c, M, N, K, ex);
+    KD_CHECK_LAUNCH("kd_gemm_kernel");
     return KD_OK;
 }
+
+template <typename T>
+int dispatch_gemm(int epi, bool a_mn, bool b_mn, bool out32, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M,
+                  int N, int K, const GemmExtra& ex, cudaStream_t st) {
+    if (epi == EPI_STATS) return launch_gemm<T, EPI_STATS, false, false, T>(a, b, c, M, N, K, ex, st);
+    if (epi == EPI_MSE) return launch_gemm<T, EPI_MSE, false, true, T>(a, b, c, M, N, K, ex, st);
+    if (!a_mn && !b_mn) return out32 ? launch_gemm<T, EPI_STORE, false, false, float>(a, b, c, M, N, K, ex, st)
+                                     : launch_gemm<T, EPI_STORE, false, false, T>(a, b, c, M, N, K, ex, st);
+    if (!a_mn && b_mn) return out32 ? launch_gemm<T, EPI_STORE, false, true, float>(a, b, c, M, N, K, ex, st)
+                                    : launch_gemm<T, EPI_STORE, false, true, T>(a, b, c, M, N, K, ex, st);
+    if (a_mn && b_mn) return out32 ? launch_gemm<T, EPI_STORE, true, true, float>(a, b, c, M, N, K, ex, st)
+                                   : launch_gemm<T, EPI_STORE, true, true, T>(a, b, c, M, N, K, ex, st);
+    set_error("kd_gemm: A MN-major with B K-major is not built (transpose the roles: C^T = B A^T)");
+    return KD_ERR_UNSUPPORTED;
+}
+
+// Shared front end: argument checks, tensor maps, dispatch.  A: logical [M, K]; B: logical [N, K]; *_mn = stored transposed.
+int run_gemm(const char* who, int epi, const void* A, int64_t ld_a, bool a_mn, const void* B, int64_t ld_b, bool b_mn, void* C, int64_t ld_c,
+             bool out32, int64_t M, int64_t N, int64_t K, int dtype, const GemmExtra& ex, cudaStream_t st) {
+    if (dtype != KD_DTYPE_BF16 && dtype != KD_DTYPE_F16) {
+        set_error("%s: bf16 / fp16 operands only (tensor-core path); got dtype %d", who, dtype);
+        return KD_ERR_UNSUPPORTED;
+    }
+    if (M == 0 || N == 0) return KD_OK;
+    KD_CHECK_ARG(A && B && C, "%s: null pointer", who);
+    KD_CHECK_ARG(ld_a >= (a_mn ? M : K) && ld_b >= (b_mn ? N : K) && ld_c >= N, "%s: row pitch smaller than the row", who);
+    const int64_t c_mult = out32 ? 4 : 8;
+    const bool aligned = ld_a % 8 == 0 && ld_b % 8 == 0 && ld_c % c_mult == 0 && N % 8 == 0 && (!a_mn || M % 8 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15u) == 0;
+    if (!aligned || M >= (int64_t(1) << 31) - 2 * BM || N >= (int64_t(1) << 31) - BN || K >= (int64_t(1) << 31) - BK) {
+        set_error("%s: TMA needs 16-byte aligned bases and row pitches, and N (and M of an MN-major A) a multiple of 8 elements", who);
+        return KD_ERR_UNSUPPORTED;
+    }
+    if (!encode_tiled()) {
+        set_error("%s: the driver does not export cuTensorMapEncodeTiled", who);
+        return KD_ERR_CUDA;
+    }
+    const CUtensorMapDataType dt = dtype == KD_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const auto promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    CUtensorMap ma, mb, mc;
+    const bool ok_a = a_mn ? make_map(&ma, dt, 2, A, K, M, ld_a, 64, BK, promo) : make_map(&ma, dt, 2, A, M, K, ld_a, BK, BM, promo);
+    const bool ok_b = b_mn ? make_map(&mb, dt, 2, B, K, N, ld_b, 64, BK, promo) : make_map(&mb, dt, 2, B, N, K, ld_b, BK, BNH, promo);
+    const bool ok_c = out32 ? make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, M, N, ld_c, 32, BM, CU_TENSOR_MAP_L2_PROMOTION_NONE)
+                            : make_map(&mc, dt, 2, C, M, N, ld_c, 64, BM, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (!ok_a || !ok_b || !ok_c) {
+        set_error("%s: cuTensorMapEncodeTiled rejected a matrix (M %lld, N %lld, K %lld)", who, (long long)M, (long long)N, (long long)K);
+        return KD_ERR_CUDA;
+    }
+    if (dtype == KD_DTYPE_BF16) return dispatch_gemm<__nv_bfloat16>(epi, a_mn, b_mn, out32, ma, mb, mc, (int)M, (int)N, (int)K, ex, st);
+    return dispatch_gemm<__half>(epi, a_mn, b_mn, out32, ma, mb, mc, (int)M, (int)N, (int)K, ex, st);
+}
+
+// loss = sum of the epilogue's partial sums / numel, in a fixed order
+__global__ void proj_mse_finalize_kernel(const float* __restrict__ partials, int n, double inv_numel, float* __restrict__ loss_out) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partials[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += sh[i];
+        *loss_out = (float)(tot * inv_numel);
+    }
+}
+
+int64_t gemm_tiles(int64_t M, int64_t N) { return ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN); }
 
 }  // namespace
 
@@ -383,41 +543,55 @@ int kd_lm_head_stat_tiles(int64_t V_local) { return V_local <= 0 ? 0 : (int)((V_
 int kd_lm_head_fwd(const void* hidden, int64_t ld_h, const void* weight, int64_t ld_w, void* logits, int64_t ld_c,
                    float* stat_partials, int64_t n_rows, int64_t V_local, int64_t H, int dtype, float T, void* stream) {
     KD_CHECK_ARG(n_rows >= 0 && V_local >= 0 && H >= 1, "kd_lm_head_fwd: bad shape");
-    if (dtype != KD_DTYPE_BF16 && dtype != KD_DTYPE_F16) {
-        set_error("kd_lm_head_fwd: bf16 / fp16 operands only (tensor-core path); got dtype %d", dtype);
-        return KD_ERR_UNSUPPORTED;
-    }
-    if (n_rows == 0 || V_local == 0) return KD_OK;
-    KD_CHECK_ARG(hidden && weight && logits, "kd_lm_head_fwd: null pointer");
     KD_CHECK_ARG(!stat_partials || T > 0.f, "kd_lm_head_fwd: T must be positive");
-    KD_CHECK_ARG(ld_h >= H && ld_w >= H && ld_c >= V_local, "kd_lm_head_fwd: row pitch smaller than the row");
-    const bool aligned = ld_h % 8 == 0 && ld_w % 8 == 0 && ld_c % 8 == 0 && V_local % 8 == 0 &&
-                         ((reinterpret_cast<uintptr_t>(hidden) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(logits)) & 15u) == 0;
-    if (!aligned || n_rows >= (int64_t(1) << 31) - 2 * BM || V_local >= (int64_t(1) << 31) - BN || H >= (int64_t(1) << 31) - BK) {
-        set_error("kd_lm_head_fwd: TMA needs 16-byte aligned bases, row pitches and V_local that are multiples of 8 elements");
-        return KD_ERR_UNSUPPORTED;
-    }
-    if (!encode_tiled()) {
-        set_error("kd_lm_head_fwd: the driver does not export cuTensorMapEncodeTiled");
-        return KD_ERR_CUDA;
-    }
-    const CUtensorMapDataType dt = dtype == KD_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    CUtensorMap ma, mb, mc;
-    if (!make_map(&ma, dt, hidden, n_rows, H, ld_h, BM, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
-        !make_map(&mb, dt, weight, V_local, H, ld_w, BNH, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
-        !make_map(&mc, dt, logits, n_rows, V_local, ld_c, BM, CU_TENSOR_MAP_L2_PROMOTION_NONE)) {
-        set_error("kd_lm_head_fwd: cuTensorMapEncodeTiled rejected a matrix (n_rows %lld, V_local %lld, H %lld)", (long long)n_rows,
-                  (long long)V_local, (long long)H);
-        return KD_ERR_CUDA;
+    GemmExtra ex{};
+    ex.partials = reinterpret_cast<float2*>(stat_partials);
+    ex.k2 = stat_partials ? kLog2e / T : 0.f;
+    return run_gemm("kd_lm_head_fwd", stat_partials ? EPI_STATS : EPI_STORE, hidden, ld_h, false, weight, ld_w, false, logits, ld_c, false,
+                    n_rows, V_local, H, dtype, ex, static_cast<cudaStream_t>(stream));
+}
+
+int kd_gemm(const void* A, int64_t ld_a, int a_mn_major, const void* B, int64_t ld_b, int b_mn_major, void* C, int64_t ld_c, int c_is_f32,
+            int64_t M, int64_t N, int64_t K, int dtype, void* stream) {
+    KD_CHECK_ARG(M >= 0 && N >= 0 && K >= 1, "kd_gemm: bad shape");
+    GemmExtra ex{};
+    return run_gemm("kd_gemm", EPI_STORE, A, ld_a, a_mn_major != 0, B, ld_b, b_mn_major != 0, C, ld_c, c_is_f32 != 0, M, N, K, dtype, ex,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int kd_proj_mse_workspace_bytes(int64_t M, int64_t N, size_t* bytes) {
+    KD_CHECK_ARG(bytes != nullptr && M >= 0 && N >= 0, "kd_proj_mse_workspace_bytes: bad arguments");
+    *bytes = (size_t)gemm_tiles(M, N) * 2 * EPI_HALVES * 4 * sizeof(float) + 256;
+    return KD_OK;
+}
+
+int kd_proj_mse_fwd_bwd(const void* input, int64_t ld_x, const void* proj, int64_t ld_w, const void* target, int64_t ld_t,
+                        void* grad_projected, int64_t ld_g, float* loss_out, void* workspace, size_t workspace_bytes, int64_t M,
+                        int64_t N, int64_t K, int dtype, const float* upstream, void* stream) {
+    KD_CHECK_ARG(M >= 1 && N >= 1 && K >= 1, "kd_proj_mse_fwd_bwd: bad shape");
+    KD_CHECK_ARG(target && loss_out && workspace, "kd_proj_mse_fwd_bwd: null pointer");
+    KD_CHECK_ARG(ld_t >= N && ld_t % 8 == 0 && (reinterpret_cast<uintptr_t>(target) & 15u) == 0, "kd_proj_mse_fwd_bwd: target rows must be 16-byte aligned");
+    size_t need = 0;
+    kd_proj_mse_workspace_bytes(M, N, &need);
+    if (workspace_bytes < need) {
+        set_error("kd_proj_mse_fwd_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
+        return KD_ERR_WORKSPACE_TOO_SMALL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const float k2 = stat_partials ? kLog2e / T : 0.f;
-    float2* parts = reinterpret_cast<float2*>(stat_partials);
-    const int M = (int)n_rows, N = (int)V_local, K = (int)H;
-    if (dtype == KD_DTYPE_BF16)
-        return parts ? launch_gemm<__nv_bfloat16, 1>(ma, mb, mc, M, N, K, k2, parts, st)
-                     : launch_gemm<__nv_bfloat16, 0>(ma, mb, mc, M, N, K, k2, parts, st);
-    return parts ? launch_gemm<__half, 1>(ma, mb, mc, M, N, K, k2, parts, st) : launch_gemm<__half, 0>(ma, mb, mc, M, N, K, k2, parts, st);
+    GemmExtra ex{};
+    ex.target = target;
+    ex.ld_t = ld_t;
+    ex.gscale = (float)(2.0 / ((double)M * (double)N));
+    ex.upstream = upstream;
+    ex.sq_partials = static_cast<float*>(workspace);
+    // projected[M, N] = input[M, K] * proj[K, N]: B = proj^T is stored MN-major
+    if (int rc = run_gemm("kd_proj_mse_fwd_bwd", EPI_MSE, input, ld_x, false, proj, ld_w, true, grad_projected, ld_g, false, M, N, K, dtype,
+                          ex, st))
+        return rc;
+    const int n_part = (int)(gemm_tiles(M, N) * 2 * EPI_HALVES * 4);
+    proj_mse_finalize_kernel<<<1, 1024, 0, st>>>(ex.sq_partials, n_part, 1.0 / ((double)M * (double)N), loss_out);
+    KD_CHECK_LAUNCH("proj_mse_finalize_kernel");
+    return KD_OK;
 }
 
 int kd_lm_head_stats_merge(const float* stat_partials, int64_t n_tiles, float* stats, int64_t n_rows, float T, void* stream) {

@@ -280,11 +280,84 @@ class _FeatureMSE(torch.autograd.Function):
         return grad, None, None
 
 
+def gemm(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False, b_mn_major: bool = False, out_dtype=None, out=None):
+    """``C[M, N] = A[M, K] . B[N, K]^T`` on the tcgen05 kernel (``kd_gemm``).  ``a`` is ``[M, K]`` (or ``[K, M]`` with
+    ``a_mn_major``: the operand is stored transposed and read through an MN-major descriptor, nothing is transposed in HBM),
+    ``b`` is ``[N, K]`` (or ``[K, N]`` with ``b_mn_major``).  bf16 / fp16 CUDA operands; ``out_dtype``: theirs or float32."""
+    dev = _require_cuda(a, b)
+    if a.dim() != 2 or b.dim() != 2 or a.dtype != b.dtype:
+        raise ValueError("gemm: two 2-D operands of one dtype expected")
+    a = a if a.stride(1) == 1 else a.contiguous()
+    b = b if b.stride(1) == 1 else b.contiguous()
+    M, K = (a.shape[1], a.shape[0]) if a_mn_major else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn_major else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise ValueError(f"gemm: contraction lengths differ ({K} vs {Kb})")
+    out_dtype = out_dtype or a.dtype
+    if out_dtype not in (a.dtype, torch.float32):
+        raise TypeError("gemm: the output is the operand type or float32")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=dev)
+    elif out.shape != (M, N) or out.dtype != out_dtype or out.stride(1) != 1:
+        raise ValueError("gemm: `out` must be a row-major [M, N] tensor of the output dtype")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().kd_gemm(a.data_ptr(), a.stride(0), int(a_mn_major), b.data_ptr(), b.stride(0), int(b_mn_major),
+                                       out.data_ptr(), out.stride(0), int(out_dtype == torch.float32), M, N, K, _dtype_code(a),
+                                       _stream_ptr(dev)))
+    return out
+
+
+class _ProjectedMSE(torch.autograd.Function):
+    """``mse_loss(input @ proj, target)`` (EV:160-165 on a projected tensor) with the MSE as the projection GEMM's epilogue."""
+
+    @staticmethod
+    def forward(ctx, inp, proj, target, upstream):
+        dev = _require_cuda(inp, proj, target)
+        x = inp.detach().reshape(-1, inp.shape[-1])
+        tgt = target.detach().reshape(-1, target.shape[-1])
+        x = x if x.stride(1) == 1 else x.contiguous()
+        tgt = tgt if tgt.stride(1) == 1 else tgt.contiguous()
+        w = proj.detach() if proj.stride(1) == 1 else proj.detach().contiguous()
+        M, K = x.shape
+        N = w.shape[1]
+        if w.shape[0] != K or tgt.shape != (M, N) or not (x.dtype == w.dtype == tgt.dtype):
+            raise ValueError("feature_mse(proj=...): input [.., K], proj [K, N], target [.., N] of one 16-bit dtype expected")
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            ws_bytes = _lib.size_query("kd_proj_mse_workspace_bytes", M, N)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            gp = torch.empty((M, N), dtype=x.dtype, device=dev)          # d loss / d (input @ proj); the product itself is never stored
+            up_t, up_ptr = _upstream_ptr(upstream, dev)
+            _lib.check(lib.kd_proj_mse_fwd_bwd(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), tgt.data_ptr(), tgt.stride(0),
+                                               gp.data_ptr(), gp.stride(0), loss.data_ptr(), ws.data_ptr(), ws_bytes, M, N, K,
+                                               _dtype_code(x), up_ptr, _stream_ptr(dev)))
+        ctx.saved = (x, w, gp)
+        ctx.dev, ctx.upstream, ctx.in_shape = dev, up_t, inp.shape
+        ctx.needs = (inp.requires_grad, proj.requires_grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, w, gp = ctx.saved
+        _, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
+        with torch.cuda.device(ctx.dev):
+            g = torch.empty_like(gp)                       # rescaled copy (skipped on the device when the ratio is 1)
+            g.copy_(gp)
+            _lib.check(_lib.load().kd_scale_rows(g.data_ptr(), g.stride(0), g.shape[0], g.shape[1], _dtype_code(g), ratio.data_ptr(),
+                                                 _stream_ptr(ctx.dev)))
+        d_in = gemm(g, w).view(ctx.in_shape) if ctx.needs[0] else None                       # [M, N] . [K, N]^T
+        d_proj = gemm(x, g, a_mn_major=True, b_mn_major=True) if ctx.needs[1] else None     # [M, K]^T . [M, N]
+        return d_in, d_proj, None, None
+
+
 def feature_mse(inp, target, upstream=None, proj=None):
     """``mean((input.float() - target.float())**2)`` (EV:160-165); gradient in ``input``'s dtype.
 
     ``proj`` ([D_in, D_target], optional, not in the reference): ``mse_loss(input @ proj, target)`` for a student whose hidden
-    size differs from the teacher's (896 vs 3584); the projection is a plain library GEMM, differentiable w.r.t. ``proj``."""
+    size differs from the teacher's (896 vs 3584; BASELINE configs[3]).  The projection runs on the tcgen05 kernel with the MSE
+    as its epilogue — the projected tensor never reaches HBM — and is differentiable w.r.t. ``input`` and ``proj`` (two more
+    products on the same kernel).  16-bit operands, dimensions multiples of 8."""
     if proj is not None:
-        inp = torch.matmul(inp, proj)
+        return _ProjectedMSE.apply(inp, proj, target, upstream)
     return _FeatureMSE.apply(inp, target, upstream)

@@ -18,6 +18,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .functional import _dtype_code, _require_cuda, _rows, _stream_ptr, _upstream_ptr
+from .functional import gemm as tc_gemm
 
 
 class CudaPhases:
@@ -389,7 +390,7 @@ def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, 
 # backward (library GEMMs) close the loop — dH needs the sum over the vocabulary shards: one all-reduce of [n_rows, hidden].
 # Keeping the logits out of HBM altogether (recomputing them in the backward) is the step after this one.
 # ---------------------------------------------------------------------------------------------------------------------
-def lm_head_fwd(hidden, weight, T=None):
+def lm_head_fwd(hidden, weight, T=None, out=None):
     """``hidden`` [n_rows, H] x ``weight`` [V_local, H] -> (``logits`` [n_rows, V_local], ``partials`` or None) through
     ``kd_lm_head_fwd``.  With ``T`` the epilogue also returns the per-128-column-tile student (max, sum-exp at temperature T)
     block [tiles, n_rows, 2] that ``logit_kd_vocab_sharded(student_partials=...)`` consumes.  bf16 / fp16 CUDA tensors only."""
@@ -400,7 +401,9 @@ def lm_head_fwd(hidden, weight, T=None):
     w = weight if weight.stride(1) == 1 else weight.contiguous()
     n, v_local = h.shape[0], w.shape[0]
     lib = _lib.load()
-    logits = torch.empty((n, v_local), dtype=h.dtype, device=dev)
+    logits = out if out is not None else torch.empty((n, v_local), dtype=h.dtype, device=dev)
+    if logits.shape != (n, v_local) or logits.dtype != h.dtype or logits.stride(1) != 1:
+        raise ValueError("lm_head_fwd: `out` must be a row-major [n_rows, V_local] tensor of the operand dtype")
     partials = None
     if T is not None:
         partials = torch.empty((lib.kd_lm_head_stat_tiles(v_local), n, 2), dtype=torch.float32, device=dev)
@@ -421,7 +424,9 @@ class _LmHeadVocabShardedKD(torch.autograd.Function):
     def forward(ctx, hidden, weight_shard, teacher_shard, labels, col0, V_total, T, mode, alpha, eps, n_rows_norm, reduction,
                 group, phases, collectives, gemm):
         partials = None
+        ctx.gemm = "library"
         if gemm == "tcgen05" and phases is None and _tensor_core_head_applies(hidden, weight_shard):
+            ctx.gemm = "tcgen05"
             logits, partials = lm_head_fwd(hidden.detach(), weight_shard.detach(), T=T)
         elif gemm == "tcgen05" and phases is None and hidden.is_cuda and hidden.dtype != torch.float32:
             raise ValueError("lm_head_kd_vocab_sharded: hidden size and V_local must be multiples of 8 for the tensor-core head "
@@ -452,9 +457,16 @@ class _LmHeadVocabShardedKD(torch.autograd.Function):
             g = grad_logits
         else:
             g = grad_logits.to(hidden.dtype) * grad_output.to(hidden.dtype)
-        d_hidden = torch.matmul(g, weight_shard.detach())                           # partial over this rank's columns
-        d_hidden = ctx.collectives.sum_(d_hidden.contiguous())                      # sum over the vocabulary shards
-        d_weight = torch.matmul(g.t(), hidden.detach())
+        if ctx.gemm == "tcgen05":
+            # both backward products on the tcgen05 kernel, operands read in place through MN-major descriptors (kd_gemm):
+            # the partial dH leaves the kernel in fp32 and is summed over the vocabulary shards in fp32, rounded ONCE
+            d_hidden = tc_gemm(g, weight_shard.detach(), b_mn_major=True, out_dtype=torch.float32)       # [n, V_l] . [V_l, H]
+            d_hidden = ctx.collectives.sum_(d_hidden).to(hidden.dtype)
+            d_weight = tc_gemm(g, hidden.detach(), a_mn_major=True, b_mn_major=True)                     # [n, V_l]^T . [n, H]
+        else:
+            d_hidden = torch.matmul(g.float(), weight_shard.detach().float()) if g.dtype != torch.float32 else torch.matmul(g, weight_shard.detach())
+            d_hidden = ctx.collectives.sum_(d_hidden.contiguous()).to(hidden.dtype)                   # fp32 partials, one rounding
+            d_weight = torch.matmul(g.t(), hidden.detach())
         return (d_hidden, d_weight) + (None,) * 14
 
 
