@@ -171,13 +171,13 @@ template <> struct OutPack<__half> { static constexpr int kCols = 64; };
 template <typename T, int EPI, bool A_MN, bool B_MN, typename OutT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapC, int M, int N, int K, const GemmExtra ex) {
+               const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapT, int M, int N, int K, const GemmExtra ex) {
     constexpr int SLABC = OutPack<OutT>::kCols;     // output columns per 128-byte staging row
     constexpr bool OUT32 = sizeof(OutT) == 4;
     static_assert(EPI == EPI_STORE || !OUT32, "the statistics / MSE epilogues write the operand type");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4];
+    __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4 + EPI_HALVES];
     __shared__ uint32_t tmem_base_sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t rank;                                  // 0 = pair leader (issues the MMAs, owns the full / accumulator-empty barriers)
@@ -186,12 +186,14 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int row_off = (int)rank * BM;             // this CTA's rows inside the pair's 256-row tile
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + STAGES * 8;
     const uint32_t bar_acc_full = bar_full + 2 * STAGES * 8, bar_acc_empty = bar_acc_full + 2 * 8;
+    const uint32_t bar_tgt = bar_acc_empty + 2 * 8;            // EPI_MSE: "the target slab has landed in the staging buffer", one per column half
     const int tiles_m = (M + 2 * BM - 1) / (2 * BM), tiles_n = (N + BN - 1) / BN, tiles = tiles_m * tiles_n;
     const int kblocks = (K + BK - 1) / BK;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full + a * 8, 1); mbar_init(bar_acc_empty + a * 8, 2 * 4 * EPI_HALVES); }      // every epilogue warp of both CTAs
+        for (int h = 0; h < EPI_HALVES; ++h) mbar_init(bar_tgt + h * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -272,6 +274,21 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float mse_g = 0.f;
         if constexpr (EPI == EPI_MSE) mse_g = ex.gscale * (ex.upstream ? *ex.upstream : 1.f);
         uint32_t i = 0, slab = 0;
+        // EPI_MSE: the target slab of step `slab` is brought by TMA into the staging buffer the step will overwrite with its
+        // output (same 128-byte swizzle: a thread finds its row's chunk j at j ^ (row % 8)), one step ahead
+        auto fetch_target = [&](int tt, int c, uint32_t sl) {
+            int tm, tn;
+            tile_coords(tt, tiles_m, tiles_n, tm, tn);
+            const uint32_t dst = smem_u32(cstage + (sl & 1) * C_SLAB_BYTES);
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");       // the store that last read this buffer is done with it
+            mbar_expect_tx(bar_tgt + half * 8, C_SLAB_BYTES);
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                         "l"(&mapT), "r"(tn * BN + c), "r"(tm * 2 * BM + row_off), "r"(bar_tgt + half * 8)
+                         : "memory");
+        };
+        if constexpr (EPI == EPI_MSE) {
+            if (elected && pair < tiles) fetch_target(pair, half * STAT_COLS, 0);
+        }
         for (int t = pair; t < tiles; t += npairs, ++i) {
             int tile_m, tile_n;
             tile_coords(t, tiles_m, tiles_n, tile_m, tile_n);
@@ -290,19 +307,19 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if constexpr (SLABC == 64) tmem_ld32(taddr + 32, r + 32);
                 const int col_base = tile_n * BN + c;
                 uint4 tg[EPI == EPI_MSE ? SLABC / 8 : 1];
-                if constexpr (EPI == EPI_MSE) {      // the target row's 128 bytes of this slab (zero outside the matrix)
-                    const T* trow = static_cast<const T*>(ex.target) + (int64_t)row_g * ex.ld_t + col_base;
-#pragma unroll
-                    for (int j = 0; j < SLABC / 8; ++j) {
-                        tg[j] = make_uint4(0, 0, 0, 0);
-                        if (row_g < M && col_base + 8 * j < N) tg[j] = ldg_stream(trow + 8 * j);      // N % 8 == 0: whole chunks
-                    }
-                }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 unsigned char* buf = cstage + (slab & 1) * C_SLAB_BYTES;
-                // the TMA store that read this staging buffer two slabs ago must be done with it
-                if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                if constexpr (EPI == EPI_MSE) {      // the target row's 128 bytes of this slab (TMA zero-fills outside the matrix)
+                    mbar_wait(bar_tgt + half * 8, slab & 1);
+#pragma unroll
+                    for (int j = 0; j < SLABC / 8; ++j) tg[j] = *reinterpret_cast<const uint4*>(buf + r_in * 128 + ((j ^ (r_in & 7)) << 4));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");      // every thread holds its target chunks: the buffer may be overwritten
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // the TMA store that read this staging buffer two slabs ago must be done with it
+                    if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                }
                 if constexpr (OUT32) {
 #pragma unroll
                     for (int j = 0; j < SLABC / 4; ++j)
@@ -343,6 +360,11 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                  "r"(tile_m * 2 * BM + row_off), "r"(smem_u32(buf))
                                  : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if constexpr (EPI == EPI_MSE) {      // next step's target slab -> the other staging buffer
+                        int nt = t, nc = c + SLABC;
+                        if (nc >= (half + 1) * STAT_COLS) { nt = t + npairs; nc = half * STAT_COLS; }
+                        if (nt < tiles) fetch_target(nt, nc, slab + 1);
+                    }
                 }
                 if constexpr (EPI == EPI_STATS) {      // online (max, sum-exp) of this row over the slab's in-range columns
                     const float k2 = ex.k2;
@@ -448,30 +470,30 @@ int gemm_sm_count() {
 }
 
 template <typename T, int EPI, bool A_MN, bool B_MN, typename OutT>
-int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K, const GemmExtra& ex,
-                cudaStream_t st) {
+int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& tg, int M, int N, int K,
+                const GemmExtra& ex, cudaStream_t st) {
     auto kern = kd_gemm_kernel<T, EPI, A_MN, B_MN, OutT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);      // per device, cheap
     if (e != cudaSuccess) return cuda_fail(e, "kd_gemm_kernel: shared-memory opt-in");
     const int64_t tiles = (int64_t)((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     const int64_t pairs = gemm_sm_count() / 2;
     const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);      // persistent CTA pairs (cluster 2 x 1 x 1)
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, b, c, M, N, K, ex);
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, b, c, tg, M, N, K, ex);
     KD_CHECK_LAUNCH("kd_gemm_kernel");
     return KD_OK;
 }
 
 template <typename T>
-int dispatch_gemm(int epi, bool a_mn, bool b_mn, bool out32, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M,
-                  int N, int K, const GemmExtra& ex, cudaStream_t st) {
-    if (epi == EPI_STATS) return launch_gemm<T, EPI_STATS, false, false, T>(a, b, c, M, N, K, ex, st);
-    if (epi == EPI_MSE) return launch_gemm<T, EPI_MSE, false, true, T>(a, b, c, M, N, K, ex, st);
-    if (!a_mn && !b_mn) return out32 ? launch_gemm<T, EPI_STORE, false, false, float>(a, b, c, M, N, K, ex, st)
-                                     : launch_gemm<T, EPI_STORE, false, false, T>(a, b, c, M, N, K, ex, st);
-    if (!a_mn && b_mn) return out32 ? launch_gemm<T, EPI_STORE, false, true, float>(a, b, c, M, N, K, ex, st)
-                                    : launch_gemm<T, EPI_STORE, false, true, T>(a, b, c, M, N, K, ex, st);
-    if (a_mn && b_mn) return out32 ? launch_gemm<T, EPI_STORE, true, true, float>(a, b, c, M, N, K, ex, st)
-                                   : launch_gemm<T, EPI_STORE, true, true, T>(a, b, c, M, N, K, ex, st);
+int dispatch_gemm(int epi, bool a_mn, bool b_mn, bool out32, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                  const CUtensorMap& tg, int M, int N, int K, const GemmExtra& ex, cudaStream_t st) {
+    if (epi == EPI_STATS) return launch_gemm<T, EPI_STATS, false, false, T>(a, b, c, tg, M, N, K, ex, st);
+    if (epi == EPI_MSE) return launch_gemm<T, EPI_MSE, false, true, T>(a, b, c, tg, M, N, K, ex, st);
+    if (!a_mn && !b_mn) return out32 ? launch_gemm<T, EPI_STORE, false, false, float>(a, b, c, tg, M, N, K, ex, st)
+                                     : launch_gemm<T, EPI_STORE, false, false, T>(a, b, c, tg, M, N, K, ex, st);
+    if (!a_mn && b_mn) return out32 ? launch_gemm<T, EPI_STORE, false, true, float>(a, b, c, tg, M, N, K, ex, st)
+                                    : launch_gemm<T, EPI_STORE, false, true, T>(a, b, c, tg, M, N, K, ex, st);
+    if (a_mn && b_mn) return out32 ? launch_gemm<T, EPI_STORE, true, true, float>(a, b, c, tg, M, N, K, ex, st)
+                                   : launch_gemm<T, EPI_STORE, true, true, T>(a, b, c, tg, M, N, K, ex, st);
     set_error("kd_gemm: A MN-major with B K-major is not built (transpose the roles: C^T = B A^T)");
     return KD_ERR_UNSUPPORTED;
 }
@@ -504,12 +526,14 @@ int run_gemm(const char* who, int epi, const void* A, int64_t ld_a, bool a_mn, c
     const bool ok_b = b_mn ? make_map(&mb, dt, 2, B, K, N, ld_b, 64, BK, promo) : make_map(&mb, dt, 2, B, N, K, ld_b, BK, BNH, promo);
     const bool ok_c = out32 ? make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, M, N, ld_c, 32, BM, CU_TENSOR_MAP_L2_PROMOTION_NONE)
                             : make_map(&mc, dt, 2, C, M, N, ld_c, 64, BM, CU_TENSOR_MAP_L2_PROMOTION_NONE);
-    if (!ok_a || !ok_b || !ok_c) {
+    CUtensorMap mt = mc;                      // EPI_MSE: the target, tiled like the output
+    const bool ok_t = epi != EPI_MSE || make_map(&mt, dt, 2, ex.target, M, N, ex.ld_t, 64, BM, promo);
+    if (!ok_a || !ok_b || !ok_c || !ok_t) {
         set_error("%s: cuTensorMapEncodeTiled rejected a matrix (M %lld, N %lld, K %lld)", who, (long long)M, (long long)N, (long long)K);
         return KD_ERR_CUDA;
     }
-    if (dtype == KD_DTYPE_BF16) return dispatch_gemm<__nv_bfloat16>(epi, a_mn, b_mn, out32, ma, mb, mc, (int)M, (int)N, (int)K, ex, st);
-    return dispatch_gemm<__half>(epi, a_mn, b_mn, out32, ma, mb, mc, (int)M, (int)N, (int)K, ex, st);
+    if (dtype == KD_DTYPE_BF16) return dispatch_gemm<__nv_bfloat16>(epi, a_mn, b_mn, out32, ma, mb, mc, mt, (int)M, (int)N, (int)K, ex, st);
+    return dispatch_gemm<__half>(epi, a_mn, b_mn, out32, ma, mb, mc, mt, (int)M, (int)N, (int)K, ex, st);
 }
 
 // loss = sum of the epilogue's partial sums / numel, in a fixed order

@@ -339,11 +339,12 @@ class _ProjectedMSE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
-        x, w, gp = ctx.saved
+        if ctx.saved is None:
+            raise RuntimeError("feature_mse(proj=...): backward through the same graph twice (the projected gradient is rescaled in place)")
+        x, w, g = ctx.saved
+        ctx.saved = None
         _, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
-        with torch.cuda.device(ctx.dev):
-            g = torch.empty_like(gp)                       # rescaled copy (skipped on the device when the ratio is 1)
-            g.copy_(gp)
+        with torch.cuda.device(ctx.dev):         # d loss / d projected *= grad_output / upstream, skipped on the device when that is 1
             _lib.check(_lib.load().kd_scale_rows(g.data_ptr(), g.stride(0), g.shape[0], g.shape[1], _dtype_code(g), ratio.data_ptr(),
                                                  _stream_ptr(ctx.dev)))
         d_in = gemm(g, w).view(ctx.in_shape) if ctx.needs[0] else None                       # [M, N] . [K, N]^T

@@ -464,7 +464,10 @@ class _LmHeadVocabShardedKD(torch.autograd.Function):
             d_hidden = ctx.collectives.sum_(d_hidden).to(hidden.dtype)
             d_weight = tc_gemm(g, hidden.detach(), a_mn_major=True, b_mn_major=True)                     # [n, V_l]^T . [n, H]
         else:
-            d_hidden = torch.matmul(g.float(), weight_shard.detach().float()) if g.dtype != torch.float32 else torch.matmul(g, weight_shard.detach())
+            try:                                    # library GEMM with an fp32 result
+                d_hidden = torch.mm(g, weight_shard.detach(), out_dtype=torch.float32)
+            except (TypeError, RuntimeError):
+                d_hidden = torch.matmul(g.float(), weight_shard.detach().float())
             d_hidden = ctx.collectives.sum_(d_hidden.contiguous()).to(hidden.dtype)                   # fp32 partials, one rounding
             d_weight = torch.matmul(g.t(), hidden.detach())
         return (d_hidden, d_weight) + (None,) * 14
