@@ -245,6 +245,85 @@ def parity_block(kd, sharded, dist, teacher, student, labels, mode, world, rank,
 
 
 # --------------------------------------------------------------------------------------------------------
+# BASELINE configs[4] (N >= 2): fused student lm_head (896 x 151 936) + LoCa-KL, vocabulary sharded, 64k tokens
+# --------------------------------------------------------------------------------------------------------
+def vshard_line(sharded, synthetic, dist, world, rank, dev):
+    """Every rank holds all 65 536 hidden rows and V / world columns of the head and of the teacher logits; per step: tcgen05 head
+    GEMM (+ fused student statistics) -> stats -> all-gather -> combine -> table -> accum -> all-reduce(Q_r) -> emit -> dH (fp32 partial,
+    all-reduced) and dW on the tcgen05 kernel.  Parity at 64 rows against the fp64 oracle first; then the timed 64k-token step."""
+    from oracle import kd_oracle as O
+    K, n_tok = 896, 65_536
+    lo = rank * (V // world)
+    hi = (rank + 1) * (V // world) if rank < world - 1 else V
+    out = {"tokens": n_tok, "head": f"{K} x {V}", "columns_per_gpu": hi - lo, "mode": "reference (as written)", "T": T_KD}
+    # ---- parity, 64 rows, identical operands on every rank (CPU generator) ----
+    g = torch.Generator().manual_seed(11)
+    n = 64
+    Hs = torch.randn(n, K, generator=g).to(torch.bfloat16)
+    Wf = (torch.randn(V, K, generator=g) * 0.02).to(torch.bfloat16)
+    t, _, lab = synthetic.logit_batch(n, V, seed=12)
+    Hd, Wd, td = Hs.to(dev), Wf.to(dev), t.to(dev)
+    logits = torch.matmul(Hd.float(), Wd.float().t()).to(torch.bfloat16)           # what a bf16 GEMM hands to the loss
+    ref = O.loca_kl(td, logits, lab.to(dev), T_KD, ALPHA, chunk_rows=16)
+    dH_ref = ref.grad @ Wd.double()
+    dW_ref = ref.grad.t() @ Hd.double()
+    h = Hd.clone().requires_grad_(True)
+    w = Wd[lo:hi].clone().requires_grad_(True)
+    loss = sharded.lm_head_kd_vocab_sharded(h, w, td[:, lo:hi].contiguous(), lab.to(dev), lo, V, T_KD)
+    loss.backward()
+    errs = torch.tensor([abs(loss.item() - ref.loss.item()) / abs(ref.loss.item()),
+                         ((h.grad.double() - dH_ref).norm() / dH_ref.norm()).item(),
+                         ((w.grad.double() - dW_ref[lo:hi]).norm() / dW_ref[lo:hi].norm()).item()], device=dev, dtype=torch.float64)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    out["parity_64_rows"] = {"loss_rel_err": errs[0].item(), "dH_rel_err": errs[1].item(), "dW_rel_err": errs[2].item(),
+                             "gates": {"loss": 1e-5, "dH": 2e-3, "dW": 2e-3},
+                             "ok": bool(errs[0].item() <= 1e-5 and errs[1].item() <= 2e-3 and errs[2].item() <= 2e-3)}
+    del Hd, Wd, td, logits, ref, dH_ref, dW_ref, h, w, loss
+    torch.cuda.empty_cache()
+    # ---- timed step ----
+    gd = torch.Generator(device=dev).manual_seed(5)
+    H = torch.randn(n_tok, K, device=dev, generator=gd).to(torch.bfloat16).requires_grad_(True)           # same seed: replicated
+    Ws = (torch.randn(hi - lo, K, device=dev) * 0.02).to(torch.bfloat16).requires_grad_(True)
+    ts = torch.empty(n_tok, hi - lo, device=dev, dtype=torch.bfloat16)
+    for r0 in range(0, n_tok, 8192):
+        ts[r0:r0 + 8192] = (torch.randn(8192, hi - lo, device=dev) * 2.0).to(torch.bfloat16)
+    labs = torch.randint(0, V, (n_tok,), device=dev, generator=gd)
+
+    def step():
+        H.grad = None
+        Ws.grad = None
+        sharded.lm_head_kd_vocab_sharded(H, Ws, ts, labs, lo, V, T_KD).backward()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = 5
+    a.record()
+    for _ in range(k):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b) / k], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    tf_peak = 1401.6
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tf_peak = float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:  # noqa: BLE001
+        pass
+    flops = 3 * 2.0 * n_tok * K * V                      # forward product + dH + dW, whole job
+    out.update({"ms_per_step": ms.item(), "tokens_per_s": n_tok / (ms.item() / 1e3), "tflops_whole_job": flops / (ms.item() / 1e3) / 1e12,
+                "bound": "tensor", "peak_tflops_per_gpu": tf_peak, "frac": flops / (ms.item() / 1e3) / 1e12 / (world * tf_peak),
+                "scaling": "strong (65 536 tokens, head sharded over the GPUs)",
+                "note": "frac = achieved whole-job TFLOP/s / (n_gpus x measured sustained bf16 peak); the streaming KD phases "
+                        "(3 teacher reads, 2 student reads, 1 gradient write per shard) are HBM-bound and sit inside the same step"})
+    del H, Ws, ts, labs
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
 def main() -> None:
@@ -480,29 +559,73 @@ def main() -> None:
                                           "frac": 6 * ha.numel() / (ms / 1e3) / 1e9 / peak_gbs}
         del ha, hb
         torch.cuda.empty_cache()
+        tf_peak, tf_src = 1401.6, "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                tf_peak, tf_src = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        except Exception:  # noqa: BLE001
+            pass
+        # BASELINE configs[3]: feature MSE on PROJECTED hidden states (student 896-d -> teacher 3584-d), B=16, S=4096: the projection
+        # on the tcgen05 kernel with the MSE as its epilogue, fwd + bwd (d input, d proj on the same kernel); bound: tensor pipe
+        try:
+            hs_, ht_, wp_ = synthetic.hidden_state_batch(65_536, 896, 3584, device=dev)
+            hs_.requires_grad_(True)
+            wp_.requires_grad_(True)
+
+            def pmse():
+                hs_.grad = None
+                wp_.grad = None
+                kd.feature_mse(hs_, ht_, proj=wp_).backward()
+
+            def pmse_fwd():
+                with torch.no_grad():
+                    kd.feature_mse(hs_, ht_, proj=wp_)
+
+            def pmse_lib():
+                hs_.grad = None
+                wp_.grad = None
+                kd.feature_mse(torch.matmul(hs_, wp_), ht_).backward()
+            ms, ms_f, ms_l = timeit(pmse), timeit(pmse_fwd), timeit(pmse_lib)
+            fl = 2.0 * 65_536 * 896 * 3584 / 1e12
+            side["projected_feature_mse_65536x896to3584"] = {
+                "ms": ms, "forward_ms": ms_f, "tflops": 3 * fl / (ms / 1e3), "forward_tflops": fl / (ms_f / 1e3), "bound": "tensor",
+                "peak_tflops": tf_peak, "frac": 3 * fl / (ms / 1e3) / tf_peak, "forward_frac": fl / (ms_f / 1e3) / tf_peak,
+                "peak_source": tf_src, "library_gemm_plus_mse_kernel_ms": ms_l,
+                "note": "tokens/s = 65536 / (ms / 1e3); the [65536, 3584] projected tensor never reaches HBM (MSE in the GEMM epilogue)"}
+            del hs_, ht_, wp_
+        except Exception as exc:  # noqa: BLE001
+            side["projected_feature_mse"] = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
         # the student lm_head (896 x 151 936) on the tensor cores with its fused row statistics, next to the library GEMM on the
         # same operands; bound: tensor pipe, against the measured sustained bf16 peak
         try:
             hd = torch.randn(N, 896, device=dev, dtype=torch.bfloat16)
             wt = (torch.randn(V, 896, device=dev) * 0.05).to(torch.bfloat16)
             out = torch.empty(N, V, device=dev, dtype=torch.bfloat16)
-            ms_own = timeit(lambda: sharded.lm_head_fwd(hd, wt, T=T_KD), k=5, w=2)
+            out2 = torch.empty(N, V, device=dev, dtype=torch.bfloat16)
+            ms_own = timeit(lambda: sharded.lm_head_fwd(hd, wt, T=T_KD, out=out2), k=5, w=2)
             ms_lib = timeit(lambda: torch.matmul(hd, wt.t(), out=out), k=5, w=2)
-            tf_peak, tf_src = 1401.6, "fallback"
-            try:
-                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                    tf_peak, tf_src = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
-            except Exception:
-                pass
+            del out2
             tf = 2.0 * N * V * 896 / (ms_own / 1e3) / 1e12
             side[f"lm_head_gemm_{N}x{V}x896"] = {"ms": ms_own, "tflops": tf, "bound": "tensor", "peak_tflops": tf_peak,
                                                 "frac": tf / tf_peak, "peak_source": tf_src, "library_gemm_ms": ms_lib,
-                                                "note": "hand-written tcgen05 cta_group::2 kernel incl. fused row statistics and "
-                                                        "output allocation; library = torch.matmul into a preallocated output"}
+                                                "note": "hand-written tcgen05 cta_group::2 kernel incl. fused row statistics; both it and "
+                                                        "the library GEMM (torch.matmul) write a preallocated output"}
             del hd, wt, out
         except Exception as exc:  # noqa: BLE001 - a side measurement must not take the headline down
             side["lm_head_gemm"] = {"error": f"{type(exc).__name__}: {exc}"}
         torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4] at N >= 2 (all ranks take part) ----------------------------------------------
+    vshard = None
+    if world > 1 and not args.no_secondary:
+        try:
+            vshard = vshard_line(sharded, synthetic, dist, world, rank, dev)
+        except Exception as exc:  # noqa: BLE001
+            vshard = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
+        if rank == 0:
+            side["lm_head_kd_vshard"] = vshard
 
     # ---- end-to-end through the public API with HOST buffers ----------------------------------------------
     e2e = None
