@@ -19,11 +19,26 @@ class KDLossMethods:
     ``loca_mode`` ("reference" | "per_row") selects the LoCa semantics; the default is the as-written one."""
 
     loca_mode = "reference"
+    kd_group = None          # torch.distributed group the tokens are sharded over (None = this process holds the whole batch)
+    kd_exchange = "nccl"     # record exchange of the as-written mode: "nccl" (all-gather) or "peer" (stores from phase A over NVLink)
 
     # P1:141-194 / LG:208-261 — returns loca + student_loss like the reference (P1:194)
     def compute_loca_loss(self, teacher_logits, student_logits, student_loss, labels, alpha=0.8):
-        loca = F_kd.loca_kl(teacher_logits, student_logits, labels, self.T, alpha=alpha,
-                            mode=getattr(self, "loca_mode", "reference"))
+        mode = getattr(self, "loca_mode", "reference")
+        group = getattr(self, "kd_group", None)
+        if group is not None:
+            # tokens sharded over the ranks of `group`: the loss is the one of the CONCATENATED batch (one 16 B/token exchange in
+            # the as-written mode, none otherwise), the gradient is this rank's rows'
+            from . import sharded
+            if mode == "reference":
+                loca = sharded.loca_kl_token_sharded_autograd(teacher_logits, student_logits, labels, self.T, alpha=alpha, group=group,
+                                                              exchange=getattr(self, "kd_exchange", "nccl"),
+                                                              phases=getattr(self, "kd_phases", None))
+            else:
+                loca = sharded.per_row_token_sharded(F_kd.loca_kl, teacher_logits, student_logits, labels, self.T, alpha=alpha,
+                                                     mode="per_row", group=group)
+        else:
+            loca = F_kd.loca_kl(teacher_logits, student_logits, labels, self.T, alpha=alpha, mode=mode)
         return loca + student_loss
 
     # P1:316-354 / EV:246-283 — features arrive pooled + normalised (P1:243-248)
@@ -80,11 +95,14 @@ _PATCHABLE = ("compute_loca_loss", "compute_vision_loss", "compute_loss", "compu
               "contrastive_loss", "mse_loss")
 
 
-def patch_reference(target, loca_mode: str = "reference", only_existing: bool = True):
+def patch_reference(target, loca_mode: str = "reference", only_existing: bool = True, group=None, exchange: str = "nccl"):
     """Rebind the reference's loss methods on ``target`` (a class or an instance) to the CUDA-backed ones.
 
     Only methods the target already defines are replaced unless ``only_existing=False``.  Returns the
     list of patched names.  The reference's call sites (P1:251/254/258, LG:165, FB:162/165, EV:236) stay untouched.
+    ``group``: a ``torch.distributed`` process group over which the TOKENS of a step are sharded (one process per GPU):
+    ``compute_loca_loss`` then returns the loss of the concatenated batch and differentiates w.r.t. the local rows
+    (``sharded.loca_kl_token_sharded_autograd``); ``exchange`` picks the record exchange of the as-written mode.
     """
     import types
 
@@ -100,4 +118,6 @@ def patch_reference(target, loca_mode: str = "reference", only_existing: bool = 
             setattr(target, name, types.MethodType(fn, target))
         patched.append(name)
     setattr(target, "loca_mode", loca_mode)
+    setattr(target, "kd_group", group)
+    setattr(target, "kd_exchange", exchange)
     return patched

@@ -216,6 +216,45 @@ def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, grou
     return loss, grad
 
 
+class _TokenShardedLoCa(torch.autograd.Function):
+    """Differentiable front of :func:`loca_kl_token_sharded` (what ``patch_reference(..., group=...)`` binds): the gradient of
+    the local rows is produced in the forward launch with ``upstream`` folded in; ``backward`` multiplies it in place by
+    ``grad_output / upstream`` on the device — a no-op kernel exit when that is 1, the usual ``loss.backward()``."""
+
+    @staticmethod
+    def forward(ctx, teacher, student, labels, T, alpha, eps, group, upstream, phases, exchange, counts):
+        need_grad = student.requires_grad
+        loss, grad = loca_kl_token_sharded(teacher.detach(), student.detach(), labels, T, alpha, eps, group=group, upstream=upstream,
+                                           phases=phases, want_grad=need_grad, exchange=exchange, counts=counts)
+        ctx.grad, ctx.shape, ctx.need_grad = grad, student.shape, need_grad
+        ctx.upstream = None if upstream is None else torch.as_tensor(upstream, dtype=torch.float32, device=student.device).reshape(())
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if not ctx.need_grad:
+            return (None,) * 11
+        if ctx.grad is None:
+            raise RuntimeError("loca_kl_token_sharded_autograd: backward through the same graph twice (the gradient is rescaled in place)")
+        g, ctx.grad = ctx.grad, None
+        go = grad_output.detach().to(device=g.device, dtype=torch.float32).reshape(())
+        ratio = (go if ctx.upstream is None else go / ctx.upstream).contiguous()
+        if g.is_cuda:
+            with torch.cuda.device(g.device):
+                _lib.check(_lib.load().kd_scale_rows(g.data_ptr(), g.stride(0), g.shape[0], g.shape[1], _dtype_code(g), ratio.data_ptr(),
+                                                     _stream_ptr(g.device)))
+        else:                                     # host-side test doubles only (the product path is CUDA)
+            g = (g * ratio.to(g.dtype)).to(g.dtype)
+        return (None, g.reshape(ctx.shape)) + (None,) * 9
+
+
+def loca_kl_token_sharded_autograd(teacher, student, labels, T, alpha=0.8, eps=1e-8, group=None, upstream=None, phases=None,
+                                   exchange="nccl", counts=None):
+    """As-written LoCa over token shards as a differentiable loss: the GLOBAL loss value on every rank, the gradient w.r.t. this
+    rank's student rows through autograd.  Same arguments as :func:`loca_kl_token_sharded`."""
+    return _TokenShardedLoCa.apply(teacher, student, labels, float(T), float(alpha), float(eps), group, upstream, phases, exchange, counts)
+
+
 def per_row_token_sharded(fn, teacher, student, *args, group=None, reduce_loss=True, n_total=None, **kw):
     """Row-independent variants: run ``fn`` (``loca_kl(mode='per_row')`` / ``temperature_kl``) on the local rows
     normalised by the global token count; the only data-path collective is the scalar loss sum.  ``n_total`` = global

@@ -106,6 +106,41 @@ def _worker_resizing(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _worker_autograd(rank, world, port, out):
+    """patch_reference(..., group=...) -> compute_loca_loss on token shards: global loss value, local gradient through autograd,
+    grad_output != 1 handled in backward (P1:260 multiplies the loss by gamma)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import types
+        from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import patch_reference
+        n_total, cut = 11, 4
+        t, s, lab = synthetic.logit_batch(n_total, V, seed=9)
+        lo, hi = (0, cut) if rank == 0 else (cut, n_total)
+        mod = types.SimpleNamespace(T=T, compute_loca_loss=None)
+        patch_reference(mod, group=dist.group.WORLD)
+        mod.kd_phases = OraclePhases()
+        sl = s[lo:hi].double().requires_grad_(True)
+        ce = torch.tensor(0.25, dtype=torch.float64, requires_grad=True)
+        total = mod.compute_loca_loss(t[lo:hi].double(), sl, ce, lab[lo:hi], ALPHA)
+        (0.8 * total).backward()
+        full = O.loca_kl(t, s, lab, T, ALPHA)
+        ok_loss = abs(total.item() - (full.loss.item() + 0.25)) <= 1e-6 * abs(total.item())
+        ok_grad = ((sl.grad - 0.8 * full.grad[lo:hi]).norm() / (0.8 * full.grad[lo:hi]).norm()).item() <= 1e-6
+        out[rank] = (ok_loss, ok_grad, abs(ce.grad.item() - 0.8) <= 1e-12)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_patched_compute_loca_loss_on_token_shards_is_differentiable():
+    world, port = 2, _free_port()
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_autograd, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: (True, True, True), 1: (True, True, True)}
+
+
 @pytest.mark.timeout(180)
 def test_token_sharded_shards_that_resize_between_steps():
     world, port = 2, _free_port()
