@@ -1,0 +1,49 @@
+"""The Lightning-compatible module on stand-in models: every phase runs, trains, and handles the padded
+labels (-100, DM:145-146) the reference's compute_loca_loss cannot (P1:166)."""
+import pytest
+import torch
+
+import train_online_kd
+from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200.module import OnlineKnowledgeDistillationModule, TinyCausalLM
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(bs, pad):
+    return next(train_online_kd.synthetic_batches(1, bs, 64, 2048, 9, 64, torch.device("cuda"), pad_last=pad))
+
+
+@pytest.mark.parametrize("phase", [1, 2, 3])
+@pytest.mark.parametrize("mode", ["reference", "per_row"])
+def test_every_phase_gives_a_finite_loss_and_student_gradients(phase, mode):
+    student, teacher = TinyCausalLM(2048, 64, seed=1).cuda(), TinyCausalLM(2048, 128, seed=2).cuda()
+    m = OnlineKnowledgeDistillationModule(student, teacher, phase=phase, loca_mode=mode)
+    loss = m.training_step(_batch(2, pad=True), 0)
+    assert torch.isfinite(loss).item()
+    loss.backward()
+    grads = [p.grad for p in student.parameters() if p.grad is not None]
+    assert grads and all(torch.isfinite(g).all().item() for g in grads)
+    assert all(p.grad is None for p in teacher.parameters())
+
+
+def test_padded_labels_equal_the_unpadded_rows_alone():
+    """Dropping the -100 rows == running the reference's loss on the valid rows only."""
+    import knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 as kd
+    student, teacher = TinyCausalLM(2048, 64, seed=1).cuda(), TinyCausalLM(2048, 128, seed=2).cuda()
+    m = OnlineKnowledgeDistillationModule(student, teacher, phase=2)
+    b = _batch(2, pad=True)
+    with torch.no_grad():
+        total = m(b)
+        so = student(b["depth_input_ids"], b["depth_pixel_values"], labels=b["labels"])
+        to = teacher(b["rgb_input_ids"], b["rgb_pixel_values"], labels=b["labels"])
+        ok = b["labels"].reshape(-1) >= 0
+        want = kd.loca_kl(to.logits.reshape(-1, 2048)[ok], so.logits.reshape(-1, 2048)[ok], b["labels"].reshape(-1)[ok], 0.8) + so.loss
+    assert abs(total.item() - want.item()) <= 1e-6 * abs(want.item())
+    m2 = OnlineKnowledgeDistillationModule(student, teacher, phase=2, sanitize_labels=False)
+    assert torch.isnan(m2(b)).item()                    # what the reference does here is raise (P1:166): we poison, never accept
+
+
+def test_training_loop_reduces_the_loss():
+    hist = train_online_kd.main(["--synthetic", "--phase", "2", "--batch_size", "2", "--max_epochs", "6", "--accumulate_grad_batches", "2",
+                                 "--learning_rate", "3e-3", "--steps_per_epoch", "4"])
+    assert hist[-1] < hist[0]
