@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KD_B200_ABI_VERSION 2
+#define KD_B200_ABI_VERSION 3
 
 /* element types of logits / features (gradients are written in the same type as the student tensor) */
 enum { KD_DTYPE_BF16 = 0, KD_DTYPE_F16 = 1, KD_DTYPE_F32 = 2 };
@@ -134,6 +134,29 @@ int kd_logit_kd_regrad(const void* teacher, int64_t ld_t, const void* student, i
                        int dtype, float T, float eps, int variant, double inv_norm, const float* upstream,
                        const float* skip_if_one, void* stream);
 
+/* As-written LoCa KL + the student's cross-entropy in ONE pass over the logits — SURVEY.md §8(f) rank 1.  The reference adds
+ * `student_outputs.loss` (P1:194; again at P1:260 in phase 3), which the HF student computes at P1:238-240 from the SAME student
+ * logits: shifted labels, ignore_index -100 (the datamodule pads with it, dataset/.../CustomSUNRGBDOneVisionDataModule.py:145-146),
+ * mean over the valid positions, temperature 1.  Here the row the fused kernel already holds in shared memory yields it too:
+ *   loss_out    = KD + ce_weight * CE            ce_loss_out (may be NULL) = CE = sum_valid (lse(xs) - xs[c]) * (*ce_inv_count)
+ *   grad_student = upstream * ( dKD + ce_weight * (softmax(xs) - onehot(c)) * (*ce_inv_count) )   (rows with c == -100: dKD only)
+ * ce_labels[r] = id of the token FOLLOWING row r (the caller shifts: labels[b, s + 1], -100 at the last position of a sequence
+ * and wherever the target is masked); ce_inv_count = device scalar 1 / (number of valid ce_labels in the whole batch) — the host
+ * never reads it.  A ce_label outside [0, V) other than -100 sets KD_STATUS_BAD_LABEL and NaN-poisons the losses
+ * (F.cross_entropy raises).  Needs the fused kernel's shape (bf16 / fp16 logits, V % 8 == 0, alpha in [0, 1], 16-byte aligned
+ * rows): KD_ERR_UNSUPPORTED otherwise — the caller then adds a separately computed CE.  With T == 1 the CE is free (its
+ * exponentials are the KD's); otherwise valid rows pay one more ex2 per cell in each sweep, ignored rows nothing. */
+int kd_logit_kd_ce_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* labels,
+                           const int64_t* ce_labels, const float* ce_inv_count, float ce_weight, void* grad_student,
+                           int64_t ld_g, float* loss_out, float* ce_loss_out, void* workspace, size_t workspace_bytes,
+                           int64_t n_rows, int64_t V, int dtype, float T, float alpha, float eps, double inv_norm,
+                           const float* upstream, unsigned flags, void* stream);
+/* kd_logit_kd_regrad for a forward made by kd_logit_kd_ce_fwd_bwd (same workspace) */
+int kd_logit_kd_ce_regrad(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* ce_labels,
+                          const float* ce_inv_count, float ce_weight, void* grad_student, int64_t ld_g, const void* workspace,
+                          size_t workspace_bytes, int64_t n_rows, int64_t V, int dtype, float T, float eps, double inv_norm,
+                          const float* upstream, const float* skip_if_one, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------------------
  * Vocabulary-sharded logit KD (BASELINE.json configs[4]): every rank holds all n_rows rows but only
@@ -219,6 +242,11 @@ int kd_scale_rows(void* grad, int64_t ld_g, int64_t n_rows, int64_t V, int dtype
  *   pooled[m,:] = normalize(mean_p x[m,p,:])   (tokens == 1 treats x as already [M, D])
  *   loss = mean_m( logsumexp_j(us[m].ut[j]/temp) - us[m].ut[m]/temp )
  * ---------------------------------------------------------------------------------------------------- */
+/* Token-level calls (M >= 1024, M and D multiples of 8 — e.g. the 46 656 x 1152 un-pooled SigLIP tokens; contrastive_loss accepts
+ * any [M, D]) run `student @ teacher.T` (P1:410) on the tcgen05 kernel: fp16 unit vectors, the rows' online log-sum-exp and the
+ * diagonal in the GEMM epilogue, softmax - I from a recomputation, G . u_t as a third product; the M x M similarity matrix is
+ * never stored (the fp16 gradient matrix is, in the workspace: 2 M^2 bytes).  KD_FLAG_FORCE_STREAMING selects the exact fp32
+ * CUDA-core row kernel instead. */
 int kd_info_nce_workspace_bytes(int64_t M, int64_t tokens, int64_t D, size_t* bytes);
 int kd_info_nce_fwd_bwd(const void* student, const void* teacher, void* grad_student, float* loss_out,
                         void* workspace, size_t workspace_bytes, int64_t M, int64_t tokens, int64_t D,

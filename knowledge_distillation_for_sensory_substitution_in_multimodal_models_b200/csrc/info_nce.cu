@@ -7,6 +7,11 @@
 //
 // Three launches: pool+normalise (HBM-bound, the only pass that touches the [M,P,D] tensors), one CTA per
 // similarity row for logits -> log-softmax -> gradient row, and the broadcast write of dx.
+//
+// Token-level M (>= 1024 rows, M and D multiples of 8): the similarity matrix runs on the TENSOR CORES and never reaches HBM —
+// kd_gemm.cu's tcgen05 kernel with (1) an epilogue that folds the rows' online (max, sum-exp) and picks up the diagonal,
+// (2) a recomputation whose epilogue writes softmax - I as fp16, (3) G . u_t with an fp32 result; the unit vectors are fp16
+// operands (|x| <= 1 keeps 11 mantissa bits), everything else (pooling, norms, the projection off u_s) stays fp32.
 #include "kd_common.cuh"
 
 namespace kd {
@@ -23,7 +28,7 @@ pool_partial_kernel(const T* __restrict__ xs, const T* __restrict__ xt, float* _
                     int nsplit, bool vec) {
     extern __shared__ float sm[];        // [groups][D] partial sums
     constexpr int E = Elem<T>::kPack;
-    const int mt = blockIdx.y, split = blockIdx.x;
+    const int mt = blockIdx.x / nsplit, split = blockIdx.x % nsplit;      // x only: 2 M can exceed the 65 535 limit of y
     const int m = mt % M;
     const T* x = (mt >= M ? xt : xs) + (int64_t)m * P * D;
     const int p0 = (int)(((int64_t)P * split) / nsplit), p1 = (int)(((int64_t)P * (split + 1)) / nsplit);
@@ -68,7 +73,7 @@ pool_partial_kernel(const T* __restrict__ xs, const T* __restrict__ xt, float* _
 // ---- finish: add the partials, take the mean, L2-normalise (F.normalize eps) -------------------------------------
 __global__ void __launch_bounds__(256)
 pool_finish_kernel(const float* __restrict__ partials, float* __restrict__ us, float* __restrict__ ut, float* __restrict__ norm_s,
-                   int M, int P, int D, int nsplit) {
+                   int M, int P, int D, int nsplit, __half* __restrict__ us16 = nullptr, __half* __restrict__ ut16 = nullptr) {
     extern __shared__ float sm[];        // [D] pooled vector
     __shared__ float red[8];
     const int mt = blockIdx.x, m = mt % M;
@@ -91,6 +96,10 @@ pool_finish_kernel(const float* __restrict__ partials, float* __restrict__ us, f
     const float nrm = sqrtf(tot);
     const float inv = 1.f / fmaxf(nrm, kNormEps);
     for (int d = threadIdx.x; d < D; d += 256) u[d] = sm[d] * inv;
+    if (us16) {          // tensor-core similarity: the unit vectors as fp16 operands (|x| <= 1: 11 mantissa bits)
+        __half* h = (is_teacher ? ut16 : us16) + (int64_t)m * D;
+        for (int d = threadIdx.x; d < D; d += 256) h[d] = __float2half_rn(sm[d] * inv);
+    }
     if (!is_teacher && threadIdx.x == 0) norm_s[m] = nrm;
 }
 
@@ -185,12 +194,19 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
     }
 }
 
-__global__ void nce_finalize_kernel(const float* __restrict__ rowloss, int M, float* __restrict__ loss) {
+__global__ void __launch_bounds__(1024) nce_finalize_kernel(const float* __restrict__ rowloss, int M, float* __restrict__ loss) {
+    __shared__ double sh[32];
     double a = 0.0;
-    for (int i = threadIdx.x; i < M; i += 32) a += (double)rowloss[i];
+    for (int i = threadIdx.x; i < M; i += blockDim.x) a += (double)rowloss[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (threadIdx.x == 0) *loss = static_cast<float>(a / (double)M);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += sh[k];      // fixed order: deterministic
+        *loss = static_cast<float>(tot / (double)M);
+    }
 }
 
 // ---- dx[m,p,:] = dmean[m,:] -----------------------------------------------------------------------
@@ -203,7 +219,7 @@ broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P
     constexpr int E = Elem<T>::kPack;
     if (skip_if_one && *skip_if_one == 1.f) return;      // backward re-emission: grad_output is what forward assumed
     const float f = ratio ? *ratio : 1.f;
-    const int m = blockIdx.y;
+    const int m = blockIdx.x;                              // rows on x (no 65 535 limit), token chunks on y
     const float* src = dmean + (int64_t)m * D;
     T* dst = dx + (int64_t)m * P * D;
     if (vec) {
@@ -219,13 +235,110 @@ broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P
             const uint4 packed = Elem<T>::pack(v);
             uint4* col = reinterpret_cast<uint4*>(dst) + c;
 #pragma unroll 4
-            for (int p = blockIdx.x * slots + slot; p < P; p += gridDim.x * slots) stg_stream(col + (int64_t)p * ncol, packed);
+            for (int p = blockIdx.y * slots + slot; p < P; p += gridDim.y * slots) stg_stream(col + (int64_t)p * ncol, packed);
         }
     } else {
         const int64_t total = (int64_t)P * D;
-        for (int64_t idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256)
+        for (int64_t idx = blockIdx.y * 256ll + threadIdx.x; idx < total; idx += (int64_t)gridDim.y * 256)
             dst[idx] = Elem<T>::from_float(src[idx % D] * f);
     }
+}
+
+
+// ---- tensor-core similarity (token-level M) ------------------------------------------------------------------------
+// P == 1 (features are already [M, D]): one warp normalises student row i AND teacher row i (fp32 math; fp32 + fp16 copies out)
+// and takes their exact fp32 dot product — the diagonal similarity the loss subtracts.
+template <typename T>
+__global__ void __launch_bounds__(256)
+nce_normalize_pair_kernel(const T* __restrict__ xs, const T* __restrict__ xt, float* __restrict__ us, float* __restrict__ ut,
+                          __half* __restrict__ us16, __half* __restrict__ ut16, float* __restrict__ norm_s,
+                          float* __restrict__ diag_exact, int M, int D) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), l = threadIdx.x & 31;
+    if (i >= M) return;
+    const T* a = xs + (int64_t)i * D;
+    const T* b = xt + (int64_t)i * D;
+    float ss = 0.f, tt = 0.f, st = 0.f;
+    for (int d = l; d < D; d += 32) {
+        const float x = Elem<T>::to_float(a[d]), y = Elem<T>::to_float(b[d]);
+        ss = fmaf(x, x, ss);
+        tt = fmaf(y, y, tt);
+        st = fmaf(x, y, st);
+    }
+    ss = warp_sum(ss);
+    tt = warp_sum(tt);
+    st = warp_sum(st);
+    const float ns = sqrtf(ss), nt = sqrtf(tt);
+    const float is = 1.f / fmaxf(ns, kNormEps), it = 1.f / fmaxf(nt, kNormEps);
+    for (int d = l; d < D; d += 32) {
+        const float x = Elem<T>::to_float(a[d]) * is, y = Elem<T>::to_float(b[d]) * it;
+        us[(int64_t)i * D + d] = x;
+        ut[(int64_t)i * D + d] = y;
+        us16[(int64_t)i * D + d] = __float2half_rn(x);
+        ut16[(int64_t)i * D + d] = __float2half_rn(y);
+    }
+    if (l == 0) {
+        norm_s[i] = ns;
+        diag_exact[i] = st * is * it;
+    }
+}
+// pooled features (P > 1): the exact diagonal from the fp32 unit vectors, one warp per row
+__global__ void __launch_bounds__(256)
+nce_diag_kernel(const float* __restrict__ us, const float* __restrict__ ut, float* __restrict__ diag_exact, int M, int D) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), l = threadIdx.x & 31;
+    if (i >= M) return;
+    float st = 0.f;
+    for (int d = l; d < D; d += 32) st = fmaf(us[(int64_t)i * D + d], ut[(int64_t)i * D + d], st);
+    st = warp_sum(st);
+    if (l == 0) diag_exact[i] = st;
+}
+
+// Rows' log-sum-exp and loss terms from the GEMM epilogue's partials.  L[i, j] = acc[i, j] / temp (log2 units: acc * k2).
+//   lse2[i] = log2 sum_j 2^(acc k2)  — from the tensor-core values only, so that the gradient epilogue's softmax is consistent;
+//   loss_i  = log1p( sum_{j != i} 2^((acc_ij - d_i) k2) ),  d_i = the EXACT fp32 diagonal similarity.
+// The tensor core accumulates in fp32 with truncation: a sum of 1152 same-sign terms (the diagonal of related features) comes
+// out ~4e-6 low, which shifts lse - L_ii by 5e-5 relative when the off-diagonal entries (mixed signs, unbiased) are measured
+// against it.  Measuring them against the exact diagonal removes the bias.  The tiles are merged in double and the part of the
+// sum away from the maximum is kept apart: with a dominant diagonal the sum is 1 + r, r ~ 1e-2 ... 1e-6, and r's digits matter.
+__global__ void __launch_bounds__(256)
+nce_tc_rows_kernel(const float2* __restrict__ partials, int n_tiles, const float* __restrict__ diag_tc,
+                   const float* __restrict__ diag_exact, int M, float k2, float* __restrict__ lse2, float* __restrict__ rowloss) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= M) return;
+    float mx = -INFINITY;
+    for (int t = 0; t < n_tiles; ++t) mx = fmaxf(mx, partials[(size_t)t * M + i].x);
+    double main_s = 0.0, rest = 0.0;          // tiles sitting at the maximum / all others, relative to mx
+    for (int t = 0; t < n_tiles; ++t) {
+        const float2 p = partials[(size_t)t * M + i];
+        if (p.x == -INFINITY) continue;
+        if (p.x == mx) main_s += (double)p.y;
+        else rest += (double)(p.y * exp2f((p.x - mx) * k2));
+    }
+    lse2[i] = (float)((double)mx * (double)k2 + log2(main_s + rest));
+    // off-diagonal sum relative to mx: take the tensor core's own diagonal term out of the tile it sits in
+    const double dterm = exp2((double)(diag_tc[i] - mx) * (double)k2);
+    const double off = (main_s - dterm) + rest;
+    rowloss[i] = (float)log1p(fmax(off, 0.0) * exp2((double)(mx - diag_exact[i]) * (double)k2));
+}
+
+// dmean[i, :] = (du - (du . u_s) u_s) * upstream / (P * max(|mean|, eps)),  du = dU[i, :] * (1 / (2^14 * temp * M))
+__global__ void __launch_bounds__(256)
+nce_tc_finish_kernel(const float* __restrict__ dU, const float* __restrict__ us, const float* __restrict__ norm_s,
+                     float* __restrict__ dmean, int D, float du_scale, float inv_tokens, const float* upstream) {
+    __shared__ float red[8];
+    const int i = blockIdx.x;
+    const float* du = dU + (int64_t)i * D;
+    const float* u = us + (int64_t)i * D;
+    float dots = 0.f;
+    for (int d = threadIdx.x; d < D; d += 256) dots = fmaf(du[d] * du_scale, u[d], dots);
+    dots = warp_sum(dots);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dots;
+    __syncthreads();
+    float tot = 0.f;
+    for (int k = 0; k < 8; ++k) tot += red[k];
+    const float nrm = norm_s[i];
+    const float dot = (nrm > kNormEps) ? tot : 0.f;
+    const float sc = inv_tokens * (upstream ? *upstream : 1.f) / fmaxf(nrm, kNormEps);
+    for (int d = threadIdx.x; d < D; d += 256) dmean[(int64_t)i * D + d] = (du[d] * du_scale - dot * u[d]) * sc;
 }
 
 constexpr int kMaxPoolSplit = 8;
@@ -243,10 +356,32 @@ NceWorkspace nce_layout(int64_t M, int64_t D) {
     w.total = off;
     return w;
 }
+// Tensor-core form: the same leading blocks (kd_info_nce_regrad finds dmean at the same offset), pooling partials for the one
+// split large M gets, then the fp16 operands, the epilogue's statistics, the [M, M] gradient matrix and the fp32 product G . ut
+struct NceTcWorkspace { NceWorkspace base; size_t us16, ut16, stat, diag, diag_exact, lse2, g16, du, total; };
+NceTcWorkspace nce_tc_layout(int64_t M, int64_t D) {
+    NceTcWorkspace w{};
+    w.base = nce_layout(M, D);
+    size_t off = w.base.partials;
+    auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
+    take(sizeof(float) * 2 * M * D);                       // pooling partials, nsplit = 1
+    w.us16 = take(sizeof(__half) * M * D);
+    w.ut16 = take(sizeof(__half) * M * D);
+    w.stat = take(sizeof(float2) * (size_t)nce_stat_tiles(M) * M);
+    w.diag = take(sizeof(float) * M);
+    w.diag_exact = take(sizeof(float) * M);
+    w.lse2 = take(sizeof(float) * M);
+    w.g16 = take(sizeof(__half) * M * M);
+    w.du = take(sizeof(float) * M * D);
+    w.total = off;
+    return w;
+}
+constexpr int kTcMinRows = 1024;        // below this the CUDA-core row kernel (exact fp32 similarities) is the better tool
+bool nce_tc_applies(int64_t M, int64_t D) { return M >= kTcMinRows && M % 8 == 0 && D % 8 == 0; }
 
 template <typename T>
 int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const NceWorkspace& w, int M, int P, int D,
-        float temperature, const float* upstream, unsigned flags, cudaStream_t st) {
+        float temperature, const float* upstream, unsigned flags, cudaStream_t st, const NceTcWorkspace* tc = nullptr) {
     constexpr int E = Elem<T>::kPack;
     const bool want_grad = !(flags & KD_FLAG_NO_GRAD);
     float* us = reinterpret_cast<float*>(ws + w.us);
@@ -255,7 +390,12 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
     float* dmean = reinterpret_cast<float*>(ws + w.dmean);
     float* rowloss = reinterpret_cast<float*>(ws + w.rowloss);
     const bool vec_in = (D % E == 0) && ((reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(xt)) & 15u) == 0;
-    {
+    if (tc && P == 1) {
+        nce_normalize_pair_kernel<T><<<(M + 7) / 8, 256, 0, st>>>(static_cast<const T*>(xs), static_cast<const T*>(xt), us, ut,
+                                                                 reinterpret_cast<__half*>(ws + tc->us16), reinterpret_cast<__half*>(ws + tc->ut16),
+                                                                 norm_s, reinterpret_cast<float*>(ws + tc->diag_exact), M, D);
+        KD_CHECK_LAUNCH("nce_normalize_pair_kernel");
+    } else {
         float* partials = reinterpret_cast<float*>(ws + w.partials);
         const int ncol = vec_in ? D / E : D;
         const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
@@ -266,33 +406,61 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
         int nsplit = (148 * 4) / (2 * M);
         if (nsplit > kMaxPoolSplit) nsplit = kMaxPoolSplit;
         if (nsplit > (P + 63) / 64) nsplit = (P + 63) / 64;
-        if (nsplit < 1) nsplit = 1;
+        if (nsplit < 1 || tc) nsplit = 1;
         auto kfn = pool_partial_kernel<T>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kfn<<<dim3(nsplit, 2 * M), kPoolThreads, smem, st>>>(static_cast<const T*>(xs), static_cast<const T*>(xt), partials, M, P, D, nsplit, vec_in);
+        kfn<<<(unsigned)(nsplit * 2 * (int64_t)M), kPoolThreads, smem, st>>>(static_cast<const T*>(xs), static_cast<const T*>(xt), partials, M, P, D, nsplit, vec_in);
         KD_CHECK_LAUNCH("pool_partial_kernel");
         KD_CHECK_ARG(sizeof(float) * (size_t)D <= 200 * 1024, "info_nce: feature dimension %d too large", D);
         if (sizeof(float) * (size_t)D > 48 * 1024)
             cudaFuncSetAttribute(pool_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * D));
-        pool_finish_kernel<<<2 * M, 256, sizeof(float) * (size_t)D, st>>>(partials, us, ut, norm_s, M, P, D, nsplit);
+        pool_finish_kernel<<<2 * M, 256, sizeof(float) * (size_t)D, st>>>(partials, us, ut, norm_s, M, P, D, nsplit,
+                                                                          tc ? reinterpret_cast<__half*>(ws + tc->us16) : nullptr,
+                                                                          tc ? reinterpret_cast<__half*>(ws + tc->ut16) : nullptr);
         KD_CHECK_LAUNCH("pool_finish_kernel");
     }
-    {
+    if (tc) {
+        // Similarities on the tensor cores (P1:410 `torch.mm(student_features, teacher_features.T)`), never stored: one product
+        // for the rows' log-sum-exp + diagonal, one recomputation whose epilogue writes softmax - I, one product with u_t.
+        const float k2 = kLog2e / temperature;
+        const __half* us16 = reinterpret_cast<const __half*>(ws + tc->us16);
+        const __half* ut16 = reinterpret_cast<const __half*>(ws + tc->ut16);
+        float* stat = reinterpret_cast<float*>(ws + tc->stat);
+        float* diag = reinterpret_cast<float*>(ws + tc->diag);
+        float* lse2 = reinterpret_cast<float*>(ws + tc->lse2);
+        float* diag_exact = reinterpret_cast<float*>(ws + tc->diag_exact);
+        if (P != 1) {
+            nce_diag_kernel<<<(M + 7) / 8, 256, 0, st>>>(us, ut, diag_exact, M, D);
+            KD_CHECK_LAUNCH("nce_diag_kernel");
+        }
+        if (int rc = nce_gemm_stats(us16, ut16, M, D, k2, stat, diag, st)) return rc;
+        nce_tc_rows_kernel<<<(M + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(stat), nce_stat_tiles(M), diag, diag_exact, M, k2, lse2, rowloss);
+        KD_CHECK_LAUNCH("nce_tc_rows_kernel");
+        if (want_grad) {
+            __half* g16 = reinterpret_cast<__half*>(ws + tc->g16);
+            float* du = reinterpret_cast<float*>(ws + tc->du);
+            if (int rc = nce_gemm_grad(us16, ut16, M, D, k2, lse2, g16, st)) return rc;
+            if (int rc = nce_gemm_du(g16, ut16, du, M, D, st)) return rc;
+            nce_tc_finish_kernel<<<M, 256, 0, st>>>(du, us, norm_s, dmean, D, 1.f / (nce_grad_scale() * temperature * (float)M),
+                                                    1.f / (float)P, upstream);
+            KD_CHECK_LAUNCH("nce_tc_finish_kernel");
+        }
+    } else {
         const size_t smem = sizeof(float) * ((size_t)D + M);
-        KD_CHECK_ARG(smem <= 220 * 1024, "info_nce: M + D = %d floats exceed shared memory (tensor-core path not built yet)", M + D);
+        KD_CHECK_ARG(smem <= 220 * 1024, "info_nce: M + D = %d floats exceed the row kernel's shared memory; the tensor-core form needs M and D to be multiples of 8", M + D);
         if (smem > 48 * 1024) cudaFuncSetAttribute(similarity_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         similarity_row_kernel<<<M, kRowThreads, smem, st>>>(us, ut, norm_s, dmean, rowloss, M, D, 1.f / temperature,
                                                             1.f / (float)P, upstream, want_grad);
         KD_CHECK_LAUNCH("similarity_row_kernel");
     }
-    nce_finalize_kernel<<<1, 32, 0, st>>>(rowloss, M, loss);
+    nce_finalize_kernel<<<1, M >= 1024 ? 1024 : 32, 0, st>>>(rowloss, M, loss);
     KD_CHECK_LAUNCH("nce_finalize_kernel");
     if (want_grad) {
         const bool vec_out = (D % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
         int bx = vec_out ? (P + 15) / 16 : (int)(((int64_t)P * D + 255) / 256);      // >= 16 tokens per CTA and row
         if (bx > 32) bx = 32;
         if (bx < 1) bx = 1;
-        broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, nullptr, nullptr);
+        broadcast_rows_kernel<T><<<dim3(M, bx), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, nullptr, nullptr);
         KD_CHECK_LAUNCH("broadcast_rows_kernel");
     }
     return KD_OK;
@@ -304,7 +472,7 @@ int run_regrad(const float* dmean, void* dx, int M, int P, int D, const float* r
     const bool vec_out = (D % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
     int bx = vec_out ? (P + 15) / 16 : (int)(((int64_t)P * D + 255) / 256);
     bx = bx > 32 ? 32 : (bx < 1 ? 1 : bx);
-    broadcast_rows_kernel<T><<<dim3(bx, M), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, ratio, skip);
+    broadcast_rows_kernel<T><<<dim3(M, bx), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, ratio, skip);
     KD_CHECK_LAUNCH("broadcast_rows_kernel");
     return KD_OK;
 }
@@ -317,6 +485,10 @@ extern "C" {
 int kd_info_nce_workspace_bytes(int64_t M, int64_t tokens, int64_t D, size_t* bytes) {
     KD_CHECK_ARG(bytes != nullptr && M >= 1 && tokens >= 1 && D >= 1, "kd_info_nce_workspace_bytes: bad arguments");
     *bytes = kd::nce_layout(M, D).total;
+    if (kd::nce_tc_applies(M, D)) {        // either form may run (KD_FLAG_FORCE_STREAMING picks the row kernel): room for both
+        const size_t tc = kd::nce_tc_layout(M, D).total;
+        if (tc > *bytes) *bytes = tc;
+    }
     return KD_OK;
 }
 
@@ -329,16 +501,21 @@ int kd_info_nce_fwd_bwd(const void* student, const void* teacher, void* grad_stu
     KD_CHECK_ARG(temperature > 0.f, "temperature must be positive");
     KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
     const kd::NceWorkspace w = kd::nce_layout(M, D);
-    if (workspace_bytes < w.total) {
-        kd::set_error("kd_info_nce_fwd_bwd: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    // token-level M: similarities on the tensor cores; small M (the pooled 64 x 64 case): one CTA per row on the CUDA cores
+    const bool use_tc = kd::nce_tc_applies(M, D) && !(flags & KD_FLAG_FORCE_STREAMING);
+    const kd::NceTcWorkspace wtc = use_tc ? kd::nce_tc_layout(M, D) : kd::NceTcWorkspace{};
+    const size_t need = use_tc ? wtc.total : w.total;
+    if (workspace_bytes < need) {
+        kd::set_error("kd_info_nce_fwd_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
         return KD_ERR_WORKSPACE_TOO_SMALL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(workspace);
+    const kd::NceTcWorkspace* tc = use_tc ? &wtc : nullptr;
     switch (dtype) {
-        case KD_DTYPE_BF16: return kd::run<__nv_bfloat16>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st);
-        case KD_DTYPE_F16: return kd::run<__half>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st);
-        default: return kd::run<float>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st);
+        case KD_DTYPE_BF16: return kd::run<__nv_bfloat16>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st, tc);
+        case KD_DTYPE_F16: return kd::run<__half>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st, tc);
+        default: return kd::run<float>(student, teacher, grad_student, loss_out, ws, w, (int)M, (int)tokens, (int)D, temperature, upstream, flags, st, tc);
     }
 }
 
@@ -348,8 +525,8 @@ int kd_info_nce_regrad(const void* workspace, size_t workspace_bytes, void* grad
     KD_CHECK_ARG(M >= 1 && tokens >= 1 && D >= 1, "kd_info_nce_regrad: bad shape");
     KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
     const kd::NceWorkspace w = kd::nce_layout(M, D);
-    if (workspace_bytes < w.total) {
-        kd::set_error("kd_info_nce_regrad: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    if (workspace_bytes < w.partials) {          // only the leading blocks (pooled gradient) are read; both forms share them
+        kd::set_error("kd_info_nce_regrad: workspace %zu < %zu bytes", workspace_bytes, w.partials);
         return KD_ERR_WORKSPACE_TOO_SMALL;
     }
     const float* dmean = reinterpret_cast<const float*>(static_cast<const char*>(workspace) + w.dmean);

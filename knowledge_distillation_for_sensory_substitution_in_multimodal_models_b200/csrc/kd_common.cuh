@@ -19,6 +19,12 @@ constexpr int kWarp = 32;
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+// kd_gemm.cu: the tensor-core products of contrastive_loss (fp16 unit vectors), driven by info_nce.cu
+int nce_stat_tiles(int64_t M);
+int nce_gemm_stats(const void* us16, const void* ut16, int64_t M, int64_t D, float k2, float* partials, float* diag, cudaStream_t st);
+int nce_gemm_grad(const void* us16, const void* ut16, int64_t M, int64_t D, float k2, const float* lse2, void* G16, cudaStream_t st);
+int nce_gemm_du(const void* G16, const void* ut16, float* dU, int64_t M, int64_t D, cudaStream_t st);
+float nce_grad_scale();
 
 #define KD_CHECK_ARG(cond, ...)                      \
     do {                                             \

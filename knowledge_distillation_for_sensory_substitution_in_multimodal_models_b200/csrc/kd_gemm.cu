@@ -32,6 +32,8 @@
 #include <cuda.h>
 #include <math.h>
 
+#include <type_traits>
+
 #include "kd_common.cuh"
 
 namespace kd {
@@ -151,6 +153,10 @@ template <> struct Pack2<__half> {
 constexpr int EPI_STORE = 0;      // C = round(acc)
 constexpr int EPI_STATS = 1;      // + the rows' (max, sum-exp) per 128-column half tile (student lm_head)
 constexpr int EPI_MSE = 2;        // C = upstream * 2 (round(acc) - target) / numel; partial sums of (round(acc) - target)^2
+// contrastive_loss on the tensor cores (P1:406-414: logits = fs @ ft^T / temperature; cross_entropy against the diagonal)
+constexpr int EPI_NCE_STATS = 3;  // nothing stored: the rows' (max, sum-exp) of the UNROUNDED similarities + the diagonal
+constexpr int EPI_NCE_GRAD = 4;   // C = (softmax(acc / temperature) - I) * 2^14 from the rows' log-sum-exp (recomputed product)
+constexpr float kNceGradScale = 16384.f;      // keeps softmax entries down to 4e-9 out of fp16's subnormal range; |C| <= 2^14
 
 struct GemmExtra {                // what the non-plain epilogues need
     float2* partials;             // EPI_STATS: [stat tiles][M] (max, sum-exp)
@@ -160,6 +166,8 @@ struct GemmExtra {                // what the non-plain epilogues need
     float gscale;                 // EPI_MSE: 2 / numel
     const float* upstream;        // EPI_MSE: device scalar or nullptr
     float* sq_partials;           // EPI_MSE: [tiles * 2 CTAs * EPI_HALVES * 4 warps] sums of squared differences
+    float* diag;                  // EPI_NCE_STATS: [M] acc[i, i]
+    const float* lse2;            // EPI_NCE_GRAD: [M] log2-sum-exp2 of the rows' acc * k2
 };
 
 template <typename OutT> struct OutPack;          // accumulator values -> the 16-byte chunks of a 128-byte staging row
@@ -175,6 +183,8 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr int SLABC = OutPack<OutT>::kCols;     // output columns per 128-byte staging row
     constexpr bool OUT32 = sizeof(OutT) == 4;
     static_assert(EPI == EPI_STORE || !OUT32, "the statistics / MSE epilogues write the operand type");
+    constexpr bool STATS = (EPI == EPI_STATS || EPI == EPI_NCE_STATS);
+    constexpr bool STORE = (EPI != EPI_NCE_STATS);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) unsigned long long bars[2 * STAGES + 4 + EPI_HALVES];
@@ -299,6 +309,8 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             ms.init();
             float sq = 0.f;
             const int row_g = tile_m * 2 * BM + row_off + r_in;
+            [[maybe_unused]] float nce_nl = 0.f;      // EPI_NCE_GRAD: -log2-sum-exp2 of this thread's row
+            if constexpr (EPI == EPI_NCE_GRAD) nce_nl = (row_g < M) ? -ex.lse2[row_g] : 0.f;
 #pragma unroll 1
             for (int c = half * STAT_COLS; c < (half + 1) * STAT_COLS; c += SLABC, ++slab) {
                 uint32_t r[SLABC];
@@ -314,13 +326,23 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int j = 0; j < SLABC / 8; ++j) tg[j] = *reinterpret_cast<const uint4*>(buf + r_in * 128 + ((j ^ (r_in & 7)) << 4));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");      // every thread holds its target chunks: the buffer may be overwritten
+                } else if constexpr (!STORE) {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 } else {
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     // the TMA store that read this staging buffer two slabs ago must be done with it
                     if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
                 }
-                if constexpr (OUT32) {
+                if constexpr (EPI == EPI_NCE_STATS) {      // the diagonal entry of this thread's row, if the slab holds it
+                    const int dcol = row_g - col_base;
+                    if (dcol >= 0 && dcol < SLABC && row_g < M) {
+                        float dv = 0.f;
+#pragma unroll
+                        for (int x = 0; x < SLABC; ++x) dv = (x == dcol) ? __uint_as_float(r[x]) : dv;
+                        ex.diag[row_g] = dv;
+                    }
+                } else if constexpr (OUT32) {
 #pragma unroll
                     for (int j = 0; j < SLABC / 4; ++j)
                         *reinterpret_cast<uint4*>(buf + r_in * 128 + ((j ^ (r_in & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
@@ -333,6 +355,15 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             float a = __uint_as_float(r[8 * j + 2 * u]), b = __uint_as_float(r[8 * j + 2 * u + 1]);
+                            if constexpr (EPI == EPI_NCE_GRAD) {      // softmax from the row's log-sum-exp, minus the identity
+                                const int cg = col_base + 8 * j + 2 * u;
+                                a = ex2(fmaf(a, ex.k2, nce_nl));
+                                b = ex2(fmaf(b, ex.k2, nce_nl));
+                                if (cg == row_g) a -= 1.f;
+                                if (cg + 1 == row_g) b -= 1.f;
+                                a *= kNceGradScale;
+                                b *= kNceGradScale;
+                            }
                             w[u] = Pack2<T>::pack(a, b);             // a, b come back rounded to the operand type
                             if constexpr (EPI == EPI_STATS) {
                                 r[8 * j + 2 * u] = __float_as_uint(a);
@@ -353,9 +384,11 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         *reinterpret_cast<uint4*>(buf + r_in * 128 + ((j ^ (r_in & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-                if (elected) {
+                if constexpr (STORE) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                }
+                if (STORE && elected) {
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&mapC), "r"(col_base),
                                  "r"(tile_m * 2 * BM + row_off), "r"(smem_u32(buf))
                                  : "memory");
@@ -366,7 +399,7 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (nt < tiles) fetch_target(nt, nc, slab + 1);
                     }
                 }
-                if constexpr (EPI == EPI_STATS) {      // online (max, sum-exp) of this row over the slab's in-range columns
+                if constexpr (STATS) {      // online (max, sum-exp) of this row over the slab's in-range columns
                     const float k2 = ex.k2;
                     const int valid = min(SLABC, N - col_base);      // may be <= 0 in the last tile: the whole slab is out of range
                     float vmax = -INFINITY;
@@ -402,7 +435,7 @@ kd_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             __syncwarp();
             if (lane == 0)      // on the leader's barrier: its MMA warp reuses the accumulator of BOTH CTAs
                 asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(bar_acc_empty + as * 8, 0)) : "memory");
-            if constexpr (EPI == EPI_STATS) {
+            if constexpr (STATS) {
                 const int st = tile_n * EPI_HALVES + half;
                 if (row_g < M && st < n_stat) ex.partials[(size_t)st * M + row_g] = make_float2(ms.m, ms.s);
             }
@@ -488,6 +521,15 @@ int dispatch_gemm(int epi, bool a_mn, bool b_mn, bool out32, const CUtensorMap& 
                   const CUtensorMap& tg, int M, int N, int K, const GemmExtra& ex, cudaStream_t st) {
     if (epi == EPI_STATS) return launch_gemm<T, EPI_STATS, false, false, T>(a, b, c, tg, M, N, K, ex, st);
     if (epi == EPI_MSE) return launch_gemm<T, EPI_MSE, false, true, T>(a, b, c, tg, M, N, K, ex, st);
+    if (epi == EPI_NCE_STATS || epi == EPI_NCE_GRAD) {      // fp16 operands only: unit vectors keep 11 mantissa bits there
+        if constexpr (std::is_same<T, __half>::value) {
+            if (epi == EPI_NCE_STATS) return launch_gemm<T, EPI_NCE_STATS, false, false, T>(a, b, c, tg, M, N, K, ex, st);
+            return launch_gemm<T, EPI_NCE_GRAD, false, false, T>(a, b, c, tg, M, N, K, ex, st);
+        } else {
+            set_error("kd_gemm: the contrastive epilogues take fp16 operands");
+            return KD_ERR_UNSUPPORTED;
+        }
+    }
     if (!a_mn && !b_mn) return out32 ? launch_gemm<T, EPI_STORE, false, false, float>(a, b, c, tg, M, N, K, ex, st)
                                      : launch_gemm<T, EPI_STORE, false, false, T>(a, b, c, tg, M, N, K, ex, st);
     if (!a_mn && b_mn) return out32 ? launch_gemm<T, EPI_STORE, false, true, float>(a, b, c, tg, M, N, K, ex, st)
@@ -555,6 +597,36 @@ __global__ void proj_mse_finalize_kernel(const float* __restrict__ partials, int
 int64_t gemm_tiles(int64_t M, int64_t N) { return ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN); }
 
 }  // namespace
+
+// ---- contrastive_loss on the tensor cores (info_nce.cu drives these; fp16 unit vectors us, ut: [M, D]) ----------------------
+int nce_stat_tiles(int64_t M) { return (int)((M + STAT_COLS - 1) / STAT_COLS); }
+
+// rows' (max, sum 2^((x - max) k2)) partials per 128-column half tile of us . ut^T (never stored) + its diagonal
+int nce_gemm_stats(const void* us16, const void* ut16, int64_t M, int64_t D, float k2, float* partials, float* diag, cudaStream_t st) {
+    GemmExtra ex{};
+    ex.partials = reinterpret_cast<float2*>(partials);
+    ex.k2 = k2;
+    ex.diag = diag;
+    // C is never written by this epilogue: any aligned address makes a valid (unused) tensor map
+    return run_gemm("kd_info_nce (similarity statistics)", EPI_NCE_STATS, us16, D, false, ut16, D, false, partials, M, false, M, M, D,
+                    KD_DTYPE_F16, ex, st);
+}
+
+// G16[M, M] = fp16( (2^(us . ut^T k2 - lse2[row]) - I) * 2^14 ): the product is recomputed, only the gradient matrix is stored
+int nce_gemm_grad(const void* us16, const void* ut16, int64_t M, int64_t D, float k2, const float* lse2, void* G16, cudaStream_t st) {
+    GemmExtra ex{};
+    ex.k2 = k2;
+    ex.lse2 = lse2;
+    return run_gemm("kd_info_nce (softmax - I)", EPI_NCE_GRAD, us16, D, false, ut16, D, false, G16, M, false, M, M, D, KD_DTYPE_F16, ex, st);
+}
+
+// dU[M, D] (fp32) = G16[M, M] . ut16[M, D]   (B = ut^T is stored MN-major)
+int nce_gemm_du(const void* G16, const void* ut16, float* dU, int64_t M, int64_t D, cudaStream_t st) {
+    GemmExtra ex{};
+    return run_gemm("kd_info_nce (G . ut)", EPI_STORE, G16, M, false, ut16, D, true, dU, D, true, M, D, M, KD_DTYPE_F16, ex, st);
+}
+
+float nce_grad_scale() { return kNceGradScale; }
 
 }  // namespace kd
 

@@ -515,10 +515,12 @@ row_emit_stream_kernel(const EmitParams p) {
 // ------------------------------------------------------------------------------------------------
 // backward re-emission: one streaming sweep that recomputes the gradient from saved row statistics
 // ------------------------------------------------------------------------------------------------
-template <int VARIANT, typename T, bool VEC>
+template <int VARIANT, typename T, bool VEC, bool CE = false>
 __global__ void __launch_bounds__(256)
 regrad_kernel(const EmitParams p, const float* skip_if_one) {
     if (skip_if_one && *skip_if_one == 1.f) return;
+    [[maybe_unused]] float g_ce_all = 0.f;
+    if constexpr (CE) g_ce_all = (p.upstream ? *p.upstream : 1.f) * p.ce_weight * *p.ce_inv_count;
     constexpr int P = Elem<T>::kPack;
     constexpr bool LOCA = (VARIANT == KD_LOCA_REFERENCE || VARIANT == KD_LOCA_PER_ROW);
     const float NaN = __int_as_float(0x7fc00000);
@@ -528,6 +530,22 @@ regrad_kernel(const EmitParams p, const float* skip_if_one) {
     for (int64_t r = blockIdx.y; r < p.n_rows; r += gridDim.y) {
         const float4 aux = p.rowaux[r];
         const float lse2_t = aux.x, lse2_s = aux.y, gQ = g * aux.z;
+        // fused cross-entropy: + g_ce * (2^(xs log2 e - lse1) - [c == next-token id]) on rows whose label is not ignored
+        [[maybe_unused]] float g_ce = 0.f, lse1 = 0.f;
+        [[maybe_unused]] int ce_c = -1;
+        if constexpr (CE) {
+            const int64_t c64 = p.ce_labels[r];
+            if (c64 != kCeIgnore) {
+                const bool ok = c64 >= 0 && c64 < (int64_t)V;
+                g_ce = ok ? g_ce_all : NaN;
+                ce_c = ok ? (int)c64 : -1;
+                lse1 = p.ceaux[r].x;
+            }
+        }
+        auto ce_term = [&](float xs, int c) -> float {
+            if constexpr (CE) return g_ce == 0.f ? 0.f : g_ce * (ex2(fmaf(xs, kLog2e, -lse1)) - (c == ce_c ? 1.f : 0.f));
+            return 0.f;
+        };
         int ov_label = -1, ov_k = -1;
         float v1 = NaN, v2 = NaN;
         if constexpr (VARIANT == KD_LOCA_PER_ROW) {
@@ -554,13 +572,15 @@ regrad_kernel(const EmitParams p, const float* skip_if_one) {
                 Elem<T>::unpack(ldg_stream(sv + v), xs);
 #pragma unroll
                 for (int i = 0; i < P; ++i)
-                    o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? override_of(v * P + i) : NaN, p.k2, lse2_t, lse2_s, p.thr2, g, gQ);
+                    o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? override_of(v * P + i) : NaN, p.k2, lse2_t, lse2_s, p.thr2, g, gQ) +
+                           ce_term(xs[i], v * P + i);
                 stg_stream(gv + v, Elem<T>::pack(o));
             }
         }
         for (int c = nvec * P + t0; c < V; c += stride)
             grow[c] = Elem<T>::from_float(PointTerm<VARIANT>::grad(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]),
-                                                                   LOCA ? override_of(c) : NaN, p.k2, lse2_t, lse2_s, p.thr2, g, gQ));
+                                                                   LOCA ? override_of(c) : NaN, p.k2, lse2_t, lse2_s, p.thr2, g, gQ) +
+                                          ce_term(Elem<T>::to_float(srow[c]), c));
     }
 }
 
@@ -571,10 +591,19 @@ regrad_kernel(const EmitParams p, const float* skip_if_one) {
 constexpr int kFinalThreads = 1024;
 __global__ void __launch_bounds__(kFinalThreads)
 loss_finalize_kernel(const float4* __restrict__ rowaux, int64_t n_rows, double unit, double scale,
-                     const double* __restrict__ table_consts, const uint32_t* __restrict__ status, float* __restrict__ loss_out) {
+                     const double* __restrict__ table_consts, const uint32_t* __restrict__ status, float* __restrict__ loss_out,
+                     const float2* __restrict__ ceaux = nullptr, const float* __restrict__ ce_inv_count = nullptr, float ce_weight = 0.f,
+                     float* __restrict__ ce_out = nullptr) {
     __shared__ double sh[kFinalThreads / 32];
-    double acc = 0.0;
+    __shared__ double sh_ce[kFinalThreads / 32];
+    double acc = 0.0, ce = 0.0;
     for (int64_t r = threadIdx.x; r < n_rows; r += kFinalThreads) acc += static_cast<double>(rowaux[r].w);
+    if (ceaux) {      // fused cross-entropy: sum of the rows' terms (0 on ignored rows), fixed order
+        for (int64_t r = threadIdx.x; r < n_rows; r += kFinalThreads) ce += static_cast<double>(ceaux[r].y);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ce += __shfl_xor_sync(0xffffffffu, ce, o);
+        if ((threadIdx.x & 31) == 0) sh_ce[threadIdx.x >> 5] = ce;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
@@ -584,8 +613,19 @@ loss_finalize_kernel(const float4* __restrict__ rowaux, int64_t n_rows, double u
         for (int i = 0; i < kFinalThreads / 32; ++i) tot += sh[i];
         tot *= unit;
         if (table_consts) tot += static_cast<double>(n_rows) * table_consts[0];
-        float out = static_cast<float>(tot * scale);
-        if (status && (*status & KD_STATUS_BAD_LABEL)) out = __int_as_float(0x7fc00000);
+        double total = tot * scale;
+        if (ceaux) {          // mean over the valid labels (0 valid labels -> 0 * inf = NaN, like F.cross_entropy)
+            double ce_tot = 0.0;
+            for (int i = 0; i < kFinalThreads / 32; ++i) ce_tot += sh_ce[i];
+            ce_tot *= static_cast<double>(*ce_inv_count);
+            if (ce_out) *ce_out = static_cast<float>(ce_tot);
+            total += static_cast<double>(ce_weight) * ce_tot;
+        }
+        float out = static_cast<float>(total);
+        if (status && (*status & KD_STATUS_BAD_LABEL)) {
+            out = __int_as_float(0x7fc00000);
+            if (ceaux && ce_out) *ce_out = out;
+        }
         *loss_out = out;
     }
 }
@@ -635,7 +675,7 @@ int sm_count() {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {   // layout of the caller-provided logit-KD workspace
-    size_t rowaux, records, lse2_t, table_ws, table_ws_bytes, table, consts, status, queue, total;
+    size_t rowaux, records, lse2_t, table_ws, table_ws_bytes, table, consts, status, queue, ceaux, total;
 };
 
 size_t table_workspace_bytes(int64_t V) {   // owner arrays (labels pass, k pass) + per-block partial sums
@@ -656,6 +696,7 @@ Workspace workspace_layout(int64_t n_rows, int64_t V) {
     w.consts = take(sizeof(double) * 2);
     w.status = take(sizeof(uint32_t));
     w.queue = take(sizeof(int));
+    w.ceaux = take(sizeof(float2) * n_rows);      // fused cross-entropy: per-row {lse at temperature 1, CE term}
     w.total = off;
     return w;
 }
@@ -766,6 +807,15 @@ int launch_emit(const EmitParams& p_in, int variant, int dtype, cudaStream_t st,
     p.row_queue = nullptr;
     p.queue_tail_reserve = 0;
     p.helper_ctas = 0;
+    if (p.ce_labels) {
+        // the fused cross-entropy exists in the fused cluster kernel only: no streaming fallback, no helper sharing its rows
+        const char* why = "the fused cross-entropy needs the fused kernel's shape: as-written LoCa, alpha in [0, 1], bf16 / fp16 logits, "
+                          "V a multiple of 8 that fits the cluster, 16-byte aligned rows";
+        if ((p.flags & KD_FLAG_FORCE_STREAMING) || !fused_applies(p, variant, dtype)) { set_error("%s", why); return KD_ERR_UNSUPPORTED; }
+        const int rc = launch_emit_cluster(p, variant, dtype, st, nullptr, nullptr, nullptr);
+        if (rc == KD_ERR_UNSUPPORTED) set_error("%s", why);
+        return rc;
+    }
     if (p.flags & KD_FLAG_FORCE_STREAMING) return launch_emit_stream_any(p, variant, dtype, st);
 
     int n_clusters = 0, cta_per = 8, pipes = 2, static_rows = 4;
@@ -812,6 +862,14 @@ int launch_regrad_t(const EmitParams& p, const float* skip, cudaStream_t st) {
     int64_t gy = (int64_t)sm_count() * 16 / gx;
     gy = gy < 1 ? 1 : (gy > p.n_rows ? p.n_rows : gy);
     dim3 grid((unsigned)gx, (unsigned)gy);
+    if constexpr (VARIANT == KD_LOCA_REFERENCE) {
+        if (p.ce_labels) {
+            if (vec) regrad_kernel<VARIANT, T, true, true><<<grid, 256, 0, st>>>(p, skip);
+            else regrad_kernel<VARIANT, T, false, true><<<grid, 256, 0, st>>>(p, skip);
+            KD_CHECK_LAUNCH("regrad_kernel");
+            return KD_OK;
+        }
+    }
     if (vec) regrad_kernel<VARIANT, T, true><<<grid, 256, 0, st>>>(p, skip);
     else regrad_kernel<VARIANT, T, false><<<grid, 256, 0, st>>>(p, skip);
     KD_CHECK_LAUNCH("regrad_kernel");
@@ -964,10 +1022,11 @@ int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t
     return KD_OK;
 }
 
-int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* labels,
-                        void* grad_student, int64_t ld_g, float* loss_out, void* workspace, size_t workspace_bytes,
-                        int64_t n_rows, int64_t V, int dtype, float T, float alpha, float eps, int variant,
-                        double inv_norm, const float* upstream, unsigned flags, void* stream) {
+static int logit_kd_fwd_bwd_impl(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* labels,
+                                 void* grad_student, int64_t ld_g, float* loss_out, void* workspace, size_t workspace_bytes,
+                                 int64_t n_rows, int64_t V, int dtype, float T, float alpha, float eps, int variant,
+                                 double inv_norm, const float* upstream, unsigned flags, void* stream,
+                                 const int64_t* ce_labels, const float* ce_inv_count, float ce_weight, float* ce_loss_out) {
     if (int rc = check_common(n_rows, V, dtype, T)) return rc;
     KD_CHECK_ARG(variant >= KD_LOCA_REFERENCE && variant <= KD_KL_LOG_TARGET, "unknown logit-KD variant %d", variant);
     const bool loca = (variant == KD_LOCA_REFERENCE || variant == KD_LOCA_PER_ROW);
@@ -995,6 +1054,13 @@ int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, 
     p.n_rows = n_rows; p.V = (int)V; p.k2 = kLog2e / T; p.alpha = alpha; p.thr2 = loca ? log2f(eps) : -INFINITY;
     p.gscale = static_cast<float>(T * inv_norm); p.flags = flags;
     p.records = reinterpret_cast<kd_token_record*>(ws + w.records);
+    float2* ceaux = nullptr;
+    if (ce_labels) {
+        KD_CHECK_ARG(variant == KD_LOCA_REFERENCE, "the fused cross-entropy rides the as-written LoCa mode (variant 0)");
+        KD_CHECK_ARG(ce_inv_count != nullptr, "kd_logit_kd_ce_fwd_bwd: ce_inv_count is null");
+        ceaux = reinterpret_cast<float2*>(ws + w.ceaux);
+        p.ce_labels = ce_labels; p.ce_inv_count = ce_inv_count; p.ce_weight = ce_weight; p.ceaux = ceaux;
+    }
 
     // the as-written mode needs every row's record before any row's q is known: phase A + table build, then the emit.
     // Per-row LoCa derives its teacher statistics inside the emit kernel's single sweep (6V bytes per token).
@@ -1014,15 +1080,35 @@ int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, 
     }
     const double unit = (variant == KD_KL_LOG_TARGET) ? 1.0 : (double)kLn2;
     loss_finalize_kernel<<<1, kFinalThreads, 0, st>>>(rowaux, n_rows, unit, (double)T * T * inv_norm,
-                                                      variant == KD_LOCA_REFERENCE ? consts : nullptr, status, loss_out);
+                                                      variant == KD_LOCA_REFERENCE ? consts : nullptr, status, loss_out,
+                                                      ceaux, ce_inv_count, ce_weight, ce_loss_out);
     KD_CHECK_LAUNCH("loss_finalize_kernel");
     return KD_OK;
 }
 
-int kd_logit_kd_regrad(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, void* grad_student,
-                       int64_t ld_g, const void* workspace, size_t workspace_bytes, int64_t n_rows, int64_t V, int dtype,
-                       float T, float eps, int variant, double inv_norm, const float* upstream, const float* skip_if_one,
-                       void* stream) {
+int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* labels,
+                        void* grad_student, int64_t ld_g, float* loss_out, void* workspace, size_t workspace_bytes,
+                        int64_t n_rows, int64_t V, int dtype, float T, float alpha, float eps, int variant,
+                        double inv_norm, const float* upstream, unsigned flags, void* stream) {
+    return logit_kd_fwd_bwd_impl(teacher, ld_t, student, ld_s, labels, grad_student, ld_g, loss_out, workspace, workspace_bytes, n_rows, V,
+                                 dtype, T, alpha, eps, variant, inv_norm, upstream, flags, stream, nullptr, nullptr, 0.f, nullptr);
+}
+
+int kd_logit_kd_ce_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* labels,
+                           const int64_t* ce_labels, const float* ce_inv_count, float ce_weight, void* grad_student, int64_t ld_g,
+                           float* loss_out, float* ce_loss_out, void* workspace, size_t workspace_bytes, int64_t n_rows, int64_t V,
+                           int dtype, float T, float alpha, float eps, double inv_norm, const float* upstream, unsigned flags,
+                           void* stream) {
+    KD_CHECK_ARG(ce_labels && ce_inv_count, "kd_logit_kd_ce_fwd_bwd: null pointer");
+    return logit_kd_fwd_bwd_impl(teacher, ld_t, student, ld_s, labels, grad_student, ld_g, loss_out, workspace, workspace_bytes, n_rows, V,
+                                 dtype, T, alpha, eps, KD_LOCA_REFERENCE, inv_norm, upstream, flags, stream, ce_labels, ce_inv_count,
+                                 ce_weight, ce_loss_out);
+}
+
+static int logit_kd_regrad_impl(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, void* grad_student,
+                                int64_t ld_g, const void* workspace, size_t workspace_bytes, int64_t n_rows, int64_t V, int dtype,
+                                float T, float eps, int variant, double inv_norm, const float* upstream, const float* skip_if_one,
+                                void* stream, const int64_t* ce_labels, const float* ce_inv_count, float ce_weight) {
     if (int rc = check_common(n_rows, V, dtype, T)) return rc;
     KD_CHECK_ARG(variant >= KD_LOCA_REFERENCE && variant <= KD_KL_LOG_TARGET, "unknown logit-KD variant %d", variant);
     KD_CHECK_ARG(teacher && student && grad_student && workspace, "kd_logit_kd_regrad: null pointer");
@@ -1042,12 +1128,33 @@ int kd_logit_kd_regrad(const void* teacher, int64_t ld_t, const void* student, i
     p.table = reinterpret_cast<const float*>(ws + w.table);
     p.upstream = upstream; p.n_rows = n_rows; p.V = (int)V; p.k2 = kLog2e / T;
     p.thr2 = loca ? log2f(eps) : -INFINITY; p.gscale = static_cast<float>(T * inv_norm);
+    if (ce_labels) {
+        p.ce_labels = ce_labels; p.ce_inv_count = ce_inv_count; p.ce_weight = ce_weight;
+        p.ceaux = reinterpret_cast<float2*>(ws + w.ceaux);
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (dtype) {
         case KD_DTYPE_BF16: return launch_regrad_v<__nv_bfloat16>(p, variant, skip_if_one, st);
         case KD_DTYPE_F16: return launch_regrad_v<__half>(p, variant, skip_if_one, st);
         default: return launch_regrad_v<float>(p, variant, skip_if_one, st);
     }
+}
+
+int kd_logit_kd_regrad(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, void* grad_student,
+                       int64_t ld_g, const void* workspace, size_t workspace_bytes, int64_t n_rows, int64_t V, int dtype,
+                       float T, float eps, int variant, double inv_norm, const float* upstream, const float* skip_if_one,
+                       void* stream) {
+    return logit_kd_regrad_impl(teacher, ld_t, student, ld_s, grad_student, ld_g, workspace, workspace_bytes, n_rows, V, dtype, T, eps,
+                                variant, inv_norm, upstream, skip_if_one, stream, nullptr, nullptr, 0.f);
+}
+
+int kd_logit_kd_ce_regrad(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* ce_labels,
+                          const float* ce_inv_count, float ce_weight, void* grad_student, int64_t ld_g, const void* workspace,
+                          size_t workspace_bytes, int64_t n_rows, int64_t V, int dtype, float T, float eps, double inv_norm,
+                          const float* upstream, const float* skip_if_one, void* stream) {
+    KD_CHECK_ARG(ce_labels && ce_inv_count, "kd_logit_kd_ce_regrad: null pointer");
+    return logit_kd_regrad_impl(teacher, ld_t, student, ld_s, grad_student, ld_g, workspace, workspace_bytes, n_rows, V, dtype, T, eps,
+                                KD_LOCA_REFERENCE, inv_norm, upstream, skip_if_one, stream, ce_labels, ce_inv_count, ce_weight);
 }
 
 int kd_scale_rows(void* grad, int64_t ld_g, int64_t n_rows, int64_t V, int dtype, const float* factor, void* stream) {

@@ -39,7 +39,14 @@ struct EmitParams {
     float thr2;                 // log2(eps)
     float gscale;               // T * inv_norm
     unsigned flags;
+    // Fused student cross-entropy (the HF loss the reference adds at P1:194 / P1:260: mean over the valid shifted labels of
+    // lse(xs) - xs[c], ignore_index -100, temperature 1) — computed from the student row the fused kernel already holds.
+    const int64_t* ce_labels;   // per row: the NEXT token's id (already shifted by the caller) or -100; null = no CE
+    const float* ce_inv_count;  // device scalar: 1 / number of valid ce_labels of the whole batch
+    float ce_weight;            // loss = KD + ce_weight * CE; the emitted gradient carries upstream * both
+    float2* ceaux;              // per row: {log2-sum-exp2 of xs*log2(e), CE term of the row (natural log; 0 when ignored)}
 };
+constexpr int64_t kCeIgnore = -100;
 
 template <int VARIANT>
 struct PointTerm {

@@ -849,6 +849,7 @@ int launch_emit_cluster(const EmitParams& p, int variant, int dtype, cudaStream_
         const int rc = launch_emit_fused(p, variant, dtype, stream, false, nullptr, clusters_launched, first_free_row, nullptr);
         if (rc != KD_ERR_UNSUPPORTED) return rc;
     }
+    if (p.ce_labels) return KD_ERR_UNSUPPORTED;      // the fused cross-entropy lives in the fused kernel only
     if (dtype == KD_DTYPE_BF16) return launch_dtype<__nv_bfloat16>(p, variant, stream, clusters_launched, first_free_row);
     return launch_dtype<__half>(p, variant, stream, clusters_launched, first_free_row);
 }

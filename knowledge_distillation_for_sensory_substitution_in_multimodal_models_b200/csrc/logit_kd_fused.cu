@@ -81,11 +81,13 @@ struct FusedParams {
 // KD_LOCA_PER_ROW uses 16 words: [0-5] as above, [6] teacher maximum of the warp's slice = its best cell's value, [7] that
 //   cell's column, [8] [9] runner-up value / column, [10] [11] student logits at those two cells, [12] [13] teacher / student
 //   logit at the row's label (meaningful in the slot of the warp that owns the column), [14] [15] second reduction
-template <int VARIANT, int CS, int NPIPE>
+// With the fused cross-entropy (CE, as-written LoCa only) a slot also carries [8] S1_w = sum 2^((xs - m_w) log2 e) and [9] the
+//   student logit at the row's CE label (meaningful in the slot of the warp that owns the column): 16 words.
+template <int VARIANT, int CS, int NPIPE, bool CE = false>
 struct FusedPlan {
     static constexpr int WPP = kWarps / NPIPE;
     static constexpr int NSLOT = CS * WPP;
-    static constexpr int SLOTB = (VARIANT == KD_LOCA_PER_ROW) ? 64 : 32;      // bytes per reduction slot
+    static constexpr int SLOTB = (VARIANT == KD_LOCA_PER_ROW || CE) ? 64 : 32;      // bytes per reduction slot
     static constexpr int BCASTB = 128;                                        // bytes of per-pipeline broadcast words
     int table, rows, bars, slots, bcast, tmem_word, total;
     __host__ __device__ FusedPlan(int vpc) {
@@ -125,23 +127,24 @@ __device__ __forceinline__ float own_xlogy2(float v1, float v2, bool same, int l
     return label < 0 ? __int_as_float(0x7fc00000) : x;
 }
 
-template <int VARIANT, typename T, int CS, int NPIPE, bool DYN>
+template <int VARIANT, typename T, int CS, int NPIPE, bool DYN, bool CE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 row_emit_fused_kernel(const FusedParams cp) {
+    static_assert(!CE || VARIANT == KD_LOCA_REFERENCE, "the fused cross-entropy rides the as-written LoCa kernel");
     constexpr bool TAB = (VARIANT == KD_LOCA_REFERENCE);            // shared override table (phase A + build_table)
     constexpr bool PER_ROW = (VARIANT == KD_LOCA_PER_ROW);          // the row's own label / runner-up cells only
     constexpr bool CLAMP = TAB || PER_ROW;                          // sp >= eps clamp: student minimum, masked pass B'
     constexpr int WPP = kWarps / NPIPE;
     constexpr int NSLOT = CS * WPP;
-    constexpr int SLOTB = FusedPlan<VARIANT, CS, NPIPE>::SLOTB;
+    constexpr int SLOTB = FusedPlan<VARIANT, CS, NPIPE, CE>::SLOTB;
     constexpr int SLOTV = SLOTB / 16;                               // float4s per slot
-    constexpr int BCASTB = FusedPlan<VARIANT, CS, NPIPE>::BCASTB;
-    constexpr uint32_t RED1_BYTES = NSLOT * (TAB ? 24 : PER_ROW ? 56 : 32);
+    constexpr int BCASTB = FusedPlan<VARIANT, CS, NPIPE, CE>::BCASTB;
+    constexpr uint32_t RED1_BYTES = NSLOT * (TAB ? (CE ? 32 : 24) : PER_ROW ? 56 : 32);
     constexpr uint32_t RED2_BYTES = NSLOT * 8;
-    constexpr uint32_t RED2_OFF = PER_ROW ? 56 : 24;                // byte offset of the second reduction's two words
+    constexpr uint32_t RED2_OFF = (PER_ROW || CE) ? 56 : 24;        // byte offset of the second reduction's two words (the slot's last two)
     extern __shared__ __align__(128) unsigned char smem[];
     const EmitParams& p = cp.e;
-    const FusedPlan<VARIANT, CS, NPIPE> plan(cp.vpc);
+    const FusedPlan<VARIANT, CS, NPIPE, CE> plan(cp.vpc);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pipe = warp / WPP, pw = warp % WPP;
@@ -267,6 +270,15 @@ row_emit_fused_kernel(const FusedParams cp) {
     if constexpr (PER_ROW) {
         if (r < p.n_rows) label64 = p.labels[r];
     }
+    // fused cross-entropy (temperature 1): exponent scale, upstream * ce_weight / n_valid, whether it shares the KD temperature
+    [[maybe_unused]] const float k1 = kLog2e;
+    [[maybe_unused]] const bool ce_same_t = (k2 == k1);
+    [[maybe_unused]] float g_ce = 0.f;
+    [[maybe_unused]] int64_t cel64 = kCeIgnore;
+    if constexpr (CE) {
+        g_ce = up * p.ce_weight * *p.ce_inv_count;
+        if (r < p.n_rows) cel64 = p.ce_labels[r];
+    }
     while (r < p.n_rows) {
         ++row_iter;
         KD_STAMP(0);
@@ -280,6 +292,16 @@ row_emit_fused_kernel(const FusedParams cp) {
             label = (label64 >= 0 && label64 < (int64_t)p.V) ? (int)label64 : -1;
             if (next_r < p.n_rows) label64 = p.labels[next_r];         // the next row's label: its latency hides behind this row
         }
+        // fused CE: the row's next-token id; -100 = ignored (prompt / padding: no CE work at all for the row), anything else outside
+        // [0, V) is an error like in F.cross_entropy (status bit + NaN)
+        [[maybe_unused]] bool ce_on = false, ce_bad = false;
+        [[maybe_unused]] int ce_c = -1;
+        if constexpr (CE) {
+            ce_on = (cel64 != kCeIgnore);
+            ce_bad = ce_on && !(cel64 >= 0 && cel64 < (int64_t)p.V);
+            ce_c = (ce_on && !ce_bad) ? (int)cel64 : -1;
+            if (next_r < p.n_rows) cel64 = p.ce_labels[next_r];
+        }
         warm_l2(next_r);
         const uint32_t epoch = (uint32_t)r;
         auto load_s = [&](int v) -> uint4 { return lds128_ep(s_s + v * 16, epoch); };
@@ -292,6 +314,7 @@ row_emit_fused_kernel(const FusedParams cp) {
         float m_w, min_w = INFINITY, mt_w = -INFINITY;
         uint32_t thrp = 0u;                 // per-row LoCa: a lower bound of the slice's runner-up teacher logit, in both halves
         float xt_lab = 0.f, xs_lab = 0.f;   // per-row LoCa: the row's label logits (held by the warp that owns the column)
+        [[maybe_unused]] float xs_ce = 0.f; // fused CE: the student logit at the row's next-token id (same ownership rule)
         {
             uint32_t smax2 = Pair<T>::kNegInf2, smin2 = Pair<T>::kPosInf2, tmax2 = Pair<T>::kNegInf2;
 #pragma unroll 4
@@ -337,6 +360,11 @@ row_emit_fused_kernel(const FusedParams cp) {
                     xs_lab = Elem<T>::to_float(*reinterpret_cast<const T*>(smem + (s_s - s_base) + vl * 16 + (label & 7) * 2));
                 }
             }
+            if constexpr (CE) {
+                const int vl = (ce_c >> 3) - g_v0;                    // warp-uniform
+                if (ce_c >= 0 && vl >= 0 && vl < w_n)
+                    xs_ce = Elem<T>::to_float(*reinterpret_cast<const T*>(smem + (s_s - s_base) + vl * 16 + (ce_c & 7) * 2));
+            }
         }
         KD_STAMP(2);
         if constexpr (NPIPE == 2) {
@@ -354,6 +382,9 @@ row_emit_fused_kernel(const FusedParams cp) {
 
         // ================= pass AB: statistics + accumulation in one sweep, q parked in tensor memory ==========
         float S_w, Q_w, R_w, P_w;
+        [[maybe_unused]] float S1_w = 0.f;       // fused CE: sum 2^((xs - m_w) log2 e) of the slice
+        // the CE needs its own exponentials only when the KD temperature is not 1 (and the row's label is not ignored)
+        [[maybe_unused]] const bool ce_extra = CE && ce_on && !ce_same_t;
         uint32_t top_k1 = 0u, top_k2 = 0u;       // per-row LoCa: keys of the slice's best / runner-up teacher cell (0 = none)
         {
             constexpr bool ECACHE = KD_ECACHE;        // every variant of this kernel parks its student exponentials
@@ -363,9 +394,14 @@ row_emit_fused_kernel(const FusedParams cp) {
             const float tref = TAB ? lse2_t : mtk;
             const u64 nlt = pk(-tref, -tref);
             u64 accS0 = pk(0.f, 0.f), accS1 = pk(0.f, 0.f), accQ = pk(0.f, 0.f), accR = pk(0.f, 0.f), accP = pk(0.f, 0.f);
+            [[maybe_unused]] u64 accCE = pk(0.f, 0.f);
+            [[maybe_unused]] const u64 k1p = pk(k1, k1);
+            [[maybe_unused]] const float mk1 = __fmul_rn((m_w == -INFINITY) ? 0.f : m_w, k1);
+            [[maybe_unused]] const u64 nm1 = pk(-mk1, -mk1);
             uint32_t cand = 0u;            // per-row LoCa: bit j = this lane's vector of iteration j may hold the best / runner-up cell
-            auto ab_body = [&](int j, bool act, auto tail_tag, auto poly_tag) {
+            auto ab_body = [&](int j, bool act, auto tail_tag, auto poly_tag, auto ce_tag) {
                 constexpr bool POLY = decltype(poly_tag)::value;
+                constexpr bool CE_X = decltype(ce_tag)::value;
                 uint32_t qb[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                 uint32_t eb[4] = {0u, 0u, 0u, 0u};
                 if (act) {
@@ -394,6 +430,7 @@ row_emit_fused_kernel(const FusedParams cp) {
                         }
                         if (i & 1) accS1 = add2(accS1, e2);
                         else accS0 = add2(accS0, e2);
+                        if constexpr (CE_X) accCE = add2(accCE, ex2_mufu2(fma2(Pair<T>::widen(ws[i]), k1p, nm1)));
                         const u64 b2 = fma2(Pair<T>::widen(wt[i]), k2p, nlt);        // log2 tp (table mode) / relative to mt_w otherwise
                         float e_lo, e_hi;
                         if constexpr (TAB) upk(fma2(ovp[i], pushp, b2), e_lo, e_hi);
@@ -416,22 +453,28 @@ row_emit_fused_kernel(const FusedParams cp) {
             // the FMA-pipe exponentials need xs*k2 - m_w*k2 >= -126 for every cell of the warp's slice
             const bool poly_ab = TAB && KD_POLY_AB > 0 && (fmaf(min_w, k2, esh - mk) >= kPolyFloor);
             bool token_given = false;
-            if (poly_ab) {
-#pragma unroll 2
-                for (int j = 0; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::true_type{});
-                if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::true_type{});
-            } else {
+            auto run_ab = [&](auto ce_tag) {
                 // the other pipeline may start its pass AB once this warp has `tok_after` iterations left (0 = strict alternation)
                 const int j_split = max(0, n_full - cp.tok_after);
 #pragma unroll 2
-                for (int j = 0; j < j_split; ++j) ab_body(j, true, std::false_type{}, std::false_type{});
+                for (int j = 0; j < j_split; ++j) ab_body(j, true, std::false_type{}, std::false_type{}, ce_tag);
                 if (NPIPE == 2 && cp.tok_after > 0) {
                     if (lane == 0) mbar_arrive_cta(tok_other);
                     token_given = true;
                 }
 #pragma unroll 2
-                for (int j = j_split; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::false_type{});
-                if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::false_type{});
+                for (int j = j_split; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::false_type{}, ce_tag);
+                if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::false_type{}, ce_tag);
+            };
+            if (poly_ab) {
+#pragma unroll 2
+                for (int j = 0; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::true_type{}, std::false_type{});
+                if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::true_type{}, std::false_type{});
+            } else if constexpr (CE) {
+                if (ce_extra) run_ab(std::true_type{});
+                else run_ab(std::false_type{});
+            } else {
+                run_ab(std::false_type{});
             }
             tmem_wait_st();
             if constexpr (!PER_ROW) {
@@ -442,6 +485,13 @@ row_emit_fused_kernel(const FusedParams cp) {
             float x0, x1;
             upk(add2(accS0, accS1), x0, x1);
             S_w = warp_sum(x0 + x1) * (ECACHE ? 1.f / 32768.f : 1.f);
+            if constexpr (CE) {
+                S1_w = S_w;                         // T == 1: the KD exponentials are the CE's
+                if (ce_extra) {
+                    upk(accCE, x0, x1);
+                    S1_w = warp_sum(x0 + x1);
+                }
+            }
             float q_l, r_l, p_l;                       // this lane's shares of Q_w, R_w, P_w
             upk(accQ, x0, x1);
             q_l = x0 + x1;
@@ -504,6 +554,7 @@ row_emit_fused_kernel(const FusedParams cp) {
             st_async_v4(dst, __float_as_uint(m_w), __float_as_uint(S_w), __float_as_uint(Q_w), __float_as_uint(R_w - P_w), rbar);
             if constexpr (TAB) {
                 st_async_v2(dst + 16, __float_as_uint(min_w), (uint32_t)claimed, rbar);
+                if constexpr (CE) st_async_v2(dst + 32, __float_as_uint(S1_w), __float_as_uint(xs_ce), rbar);
             } else if constexpr (PER_ROW) {
                 st_async_v4(dst + 16, __float_as_uint(min_w), (uint32_t)claimed, __float_as_uint(mt_w), (uint32_t)top_i1, rbar);
                 st_async_v4(dst + 32, __float_as_uint(top_a2), (uint32_t)top_i2, __float_as_uint(top_xs1), __float_as_uint(top_xs2), rbar);
@@ -755,6 +806,25 @@ row_emit_fused_kernel(const FusedParams cp) {
                 }
             }
             const float lse2_s = fmaf(m_s, k2, __log2f(s_sum));
+            [[maybe_unused]] float lse1 = 0.f, ce_row = 0.f;
+            if constexpr (CE) {
+                if (ce_on) {      // log-sum-exp at temperature 1 from the slices' S1_w, and the logit at the next-token id
+                    float s1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < SPL; ++i) {
+                        const int idx = lane + 32 * i;
+                        if ((NSLOT % 32 == 0 || idx < NSLOT) && sa[i].x != -INFINITY)
+                            s1 = fmaf(slot_v[SLOTV * idx + 2].x, ex2((sa[i].x - m_s) * k1), s1);
+                    }
+                    s1 = warp_sum(s1);
+                    lse1 = fmaf(m_s, k1, __log2f(s1));
+                    const int vl = max(ce_c, 0) >> 3, rank_o = vl / cp.vpc;
+                    const int cta_n_o = min(cp.vpc, cp.nvec - rank_o * cp.vpc);
+                    const int w_chunk_o = ((cta_n_o + WPP * 32 - 1) / (WPP * 32)) * 32;
+                    const float xs_c = slot_v[SLOTV * (rank_o * WPP + (vl - rank_o * cp.vpc) / w_chunk_o) + 2].y;
+                    ce_row = ce_bad ? NaN : (lse1 - xs_c * k1) * 0.69314718055994531f;
+                }
+            }
             float row;
             if constexpr (TAB) {
                 row = fmaf(lse2_s, Q, A);
@@ -789,6 +859,13 @@ row_emit_fused_kernel(const FusedParams cp) {
                 bcast[3] = all_kept ? 1.f : 0.f;
                 bcast[4] = __int_as_float(claim_all);
                 if (rank == 0 && all_kept) p.rowaux[r] = make_float4(lse2_t, lse2_s, Q, row);
+                if constexpr (CE) {
+                    bcast[5] = lse1;
+                    if (rank == 0) {
+                        p.ceaux[r] = make_float2(lse1, ce_row);
+                        if (ce_bad) atomicOr(p.status, KD_STATUS_BAD_LABEL);
+                    }
+                }
             }
         }
         named_bar_sync(bar1, WPP * 32);
@@ -797,6 +874,8 @@ row_emit_fused_kernel(const FusedParams cp) {
         if constexpr (!TAB) lse2_t = bcast[1];
         float Q = bcast[2];
         const bool all_kept = bcast[3] != 0.f;
+        [[maybe_unused]] float lse1_row = 0.f;
+        if constexpr (CE) lse1_row = bcast[5];
         int64_t after_next = 0;
         if (DYN) after_next = __float_as_int(bcast[4]);
         ph1 ^= 1;
@@ -868,7 +947,7 @@ row_emit_fused_kernel(const FusedParams cp) {
                 if constexpr (WRITE_BACK) {
                     tmem_wait_st();
                     q_masked = true;
-                    if (want_grad) {            // nothing reads the student slice any more: the cached gradient sweep will run
+                    if (want_grad && !ce_extra) {            // nothing reads the student slice any more: the cached gradient sweep will run
                         __syncwarp();
                         if (next_r < p.n_rows) issue_student(next_r);
                         student_refilled = true;
@@ -977,27 +1056,39 @@ row_emit_fused_kernel(const FusedParams cp) {
                 if (n_tail) c_body(n_full, lane < n_tail, std::true_type{});
             };
             // exponent cache (unclamped rows, and clamped rows whose q was masked by pass B'): no shared memory, no MUFU
-            auto sweepC_cached_impl = [&](float ce) {
+            // ce_tag: the fused cross-entropy at a KD temperature != 1 adds g_ce * 2^(xs log2 e - lse1) per cell, from the raw
+            // student slice (which then stays in shared memory until this sweep is over)
+            auto sweepC_cached_impl = [&](float ce, auto ce_tag, float gce_row) {
+                constexpr bool CE_X = decltype(ce_tag)::value;
                 const u64 cep = pk(ce, ce);
+                [[maybe_unused]] const u64 k1c = pk(k1, k1), nl1 = pk(-lse1_row, -lse1_row), gcp = pk(gce_row, gce_row);
                 auto c_step = [&](int j, auto nv_tag, bool act, auto tail_tag) {
                     constexpr int NV = decltype(nv_tag)::value;       // vectors per tensor-memory wait
                     uint32_t qb[NV][8], eb[NV][4];
+                    [[maybe_unused]] uint4 rsv[NV];
 #pragma unroll
                     for (int u = 0; u < NV; ++u) {
                         tmem_ld8(tq + 8 * (j + u), qb[u]);
                         tmem_ld4(tq + kTmE + 4 * (j + u), eb[u]);
+                        if constexpr (CE_X) {
+                            rsv[u] = make_uint4(0, 0, 0, 0);
+                            if (act) rsv[u] = load_s(lane + 32 * (j + u));
+                        }
                     }
                     tmem_wait_ld();
                     if (act) {
 #pragma unroll
                         for (int u = 0; u < NV; ++u) {
                             uint32_t out[4];
+                            [[maybe_unused]] const uint32_t wsv[4] = {CE_X ? rsv[u].x : 0u, CE_X ? rsv[u].y : 0u, CE_X ? rsv[u].z : 0u, CE_X ? rsv[u].w : 0u};
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const float2 ef = __half22float2(*reinterpret_cast<const __half2*>(&eb[u][i]));
                                 const u64 q2 = pk(__uint_as_float(qb[u][2 * i]), __uint_as_float(qb[u][2 * i + 1]));
                                 float n_lo, n_hi;
-                                upk(fma2(pk(ef.x, ef.y), cep, mul2(q2, negg)), n_lo, n_hi);
+                                u64 o2 = fma2(pk(ef.x, ef.y), cep, mul2(q2, negg));
+                                if constexpr (CE_X) o2 = fma2(ex2_mufu2(fma2(Pair<T>::widen(wsv[i]), k1c, nl1)), gcp, o2);
+                                upk(o2, n_lo, n_hi);
                                 out[i] = Pair<T>::narrow(n_lo, n_hi);
                             }
                             stg_stream(grow + (int64_t)(lane + 32 * (j + u)) * 8, make_uint4(out[0], out[1], out[2], out[3]));
@@ -1015,17 +1106,35 @@ row_emit_fused_kernel(const FusedParams cp) {
                 if (n_tail) c_step(n_full, V1{}, lane < n_tail, std::true_type{});
             };
             // g*Q*sp = gQ * e' * 2^(m_w*k2 - 15 - lse2_s): valid for any sign of g and g*Q
-            auto sweepC_cached = [&]() { sweepC_cached_impl(gQ * ex2((mk - kEScaleLog2) - lse2_s)); };
+            auto sweepC_cached = [&]() { sweepC_cached_impl(gQ * ex2((mk - kEScaleLog2) - lse2_s), std::false_type{}, 0.f); };
             using Yes = std::true_type;
             using No = std::false_type;
             // FMA-pipe exponentials in the common (folded, unmasked) sweep when log2(g*Q*sp) >= -126 for the whole slice
             const bool poly_c = TAB && KD_POLY_C > 0 && (fmaf(min_w, k2, lgQ - lse2_s) >= kPolyFloor);
             if ((all_kept || q_masked) && KD_ECACHE) {
-                if (!student_refilled) {
+                if (!student_refilled && !ce_extra) {
                     if (next_r < p.n_rows) issue_student(next_r);       // the cached sweep reads tensor memory only
                     student_refilled = true;
                 }
-                sweepC_cached();
+                if constexpr (CE) {
+                    static_assert(!CE || KD_ECACHE, "the fused cross-entropy relies on the cached gradient sweep");
+                    // d CE / d xs = g_ce * (softmax(xs) - onehot(c)); a bad label poisons the row like the reference's gather would
+                    const float gce_row = ce_bad ? NaN : g_ce;
+                    if (!ce_on) sweepC_cached();
+                    else if (ce_same_t)        // T == 1: softmax(xs) IS sp, the CE rides the same cached exponentials
+                        sweepC_cached_impl((gQ + gce_row) * ex2((mk - kEScaleLog2) - lse2_s), std::false_type{}, 0.f);
+                    else
+                        sweepC_cached_impl(gQ * ex2((mk - kEScaleLog2) - lse2_s), std::true_type{}, gce_row);
+                    if (ce_c >= 0) {           // the one-hot term: the lane that stored the vector rewrites that one element
+                        const int v = (ce_c >> 3) - g_v0;                   // warp-uniform
+                        if (v >= 0 && v < w_n && lane == (v & 31)) {
+                            T* cell = grow + v * 8 + (ce_c & 7);
+                            *cell = Elem<T>::from_float(Elem<T>::to_float(*cell) - g_ce);
+                        }
+                    }
+                } else {
+                    sweepC_cached();
+                }
             } else if (fold) {
                 if (all_kept) {
                     if (poly_c) sweepC(Yes{}, No{}, Yes{});
@@ -1070,13 +1179,13 @@ row_emit_fused_kernel(const FusedParams cp) {
 
 
 // --------------------------------------------------------------------------------------------------------
-template <int VARIANT, typename T, int CS, bool DYN>
+template <int VARIANT, typename T, int CS, bool DYN, bool CE = false>
 int launch_fused_d(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
     constexpr int NPIPE = 2;
-    auto kfn = row_emit_fused_kernel<VARIANT, T, CS, NPIPE, DYN>;
+    auto kfn = row_emit_fused_kernel<VARIANT, T, CS, NPIPE, DYN, CE>;
     const int nvec = e.V / 8;
     const int vpc = (nvec + CS - 1) / CS;
-    const FusedPlan<VARIANT, CS, NPIPE> plan(vpc);
+    const FusedPlan<VARIANT, CS, NPIPE, CE> plan(vpc);
     constexpr int WPP = kWarps / NPIPE;
     const int w_chunk = ((vpc + WPP * 32 - 1) / (WPP * 32)) * 32;
     // the thread's q cells (8 words per iteration, from word 0) and fp16 exponent pairs (4 per iteration, from word kTmE)
@@ -1160,30 +1269,35 @@ int launch_fused_d(const EmitParams& e, cudaStream_t st, bool query_only, int* c
     return KD_OK;
 }
 
-template <int VARIANT, typename T, int CS>
+template <int VARIANT, typename T, int CS, bool CE = false>
 int launch_fused_c(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
-    if (e.row_queue) return launch_fused_d<VARIANT, T, CS, true>(e, st, query_only, capacity, launched, first_free);
-    return launch_fused_d<VARIANT, T, CS, false>(e, st, query_only, capacity, launched, first_free);
+    if constexpr (CE) {      // the fused cross-entropy never shares rows with the streaming helper: static row striding only
+        return launch_fused_d<VARIANT, T, CS, false, true>(e, st, query_only, capacity, launched, first_free);
+    } else {
+        if (e.row_queue) return launch_fused_d<VARIANT, T, CS, true>(e, st, query_only, capacity, launched, first_free);
+        return launch_fused_d<VARIANT, T, CS, false>(e, st, query_only, capacity, launched, first_free);
+    }
 }
 
 // cluster size: whichever of 8 / 9 puts more SMs to work for this shape (KD_CLUSTER_SIZE=8|9 forces one)
 int g_last_cluster_size = 8;
-template <int VARIANT, typename T>
+template <int VARIANT, typename T, bool CE = false>
 int launch_fused_v(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
     static int forced = -1;
     if (forced < 0) { const char* ev = getenv("KD_CLUSTER_SIZE"); forced = ev ? atoi(ev) : 0; }
     int cap8 = 0, cap9 = 0;
-    const int rc8 = (forced == 9) ? KD_ERR_UNSUPPORTED : launch_fused_c<VARIANT, T, 8>(e, st, true, &cap8, nullptr, nullptr);
-    const int rc9 = (forced == 8) ? KD_ERR_UNSUPPORTED : launch_fused_c<VARIANT, T, 9>(e, st, true, &cap9, nullptr, nullptr);
+    const int rc8 = (forced == 9) ? KD_ERR_UNSUPPORTED : launch_fused_c<VARIANT, T, 8, CE>(e, st, true, &cap8, nullptr, nullptr);
+    const int rc9 = (forced == 8) ? KD_ERR_UNSUPPORTED : launch_fused_c<VARIANT, T, 9, CE>(e, st, true, &cap9, nullptr, nullptr);
     const bool use9 = (rc9 == KD_OK) && (rc8 != KD_OK || cap9 * 9 > cap8 * 8);
     if (!use9 && rc8 != KD_OK) return rc8;
     g_last_cluster_size = use9 ? 9 : 8;
-    if (use9) return launch_fused_c<VARIANT, T, 9>(e, st, query_only, capacity, launched, first_free);
-    return launch_fused_c<VARIANT, T, 8>(e, st, query_only, capacity, launched, first_free);
+    if (use9) return launch_fused_c<VARIANT, T, 9, CE>(e, st, query_only, capacity, launched, first_free);
+    return launch_fused_c<VARIANT, T, 8, CE>(e, st, query_only, capacity, launched, first_free);
 }
 
 template <typename T>
 int launch_fused_t(const EmitParams& e, int variant, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
+    if (variant == KD_LOCA_REFERENCE && e.ce_labels) return launch_fused_v<KD_LOCA_REFERENCE, T, true>(e, st, query_only, capacity, launched, first_free);
     if (variant == KD_LOCA_REFERENCE) return launch_fused_v<KD_LOCA_REFERENCE, T>(e, st, query_only, capacity, launched, first_free);
     if (variant == KD_LOCA_PER_ROW) return launch_fused_v<KD_LOCA_PER_ROW, T>(e, st, query_only, capacity, launched, first_free);
     return launch_fused_v<KD_KL_PLAIN, T>(e, st, query_only, capacity, launched, first_free);
@@ -1203,6 +1317,7 @@ int fused_mode() {
 
 bool fused_applies(const EmitParams& p, int variant, int dtype) {
     if (!fused_mode()) return false;
+    if (p.ce_labels && (variant != KD_LOCA_REFERENCE || !p.ce_inv_count || !p.ceaux || !p.status)) return false;
     if (variant == KD_LOCA_REFERENCE) {
         if (!(p.alpha >= 0.f && p.alpha <= 1.f)) return false;      // overrides outside [0, 1]: exact per-cell path
     } else if (variant == KD_LOCA_PER_ROW) {

@@ -157,6 +157,94 @@ class _LogitKD(torch.autograd.Function):
         return (None, grad.view(ctx.student_shape), None, None, None, None, None, None, None, None, None)
 
 
+CE_IGNORE = -100
+
+
+def shift_labels(labels: torch.Tensor, ignore_index: int = CE_IGNORE) -> torch.Tensor:
+    """Next-token targets aligned with the logit rows: ``out[b, s] = labels[b, s + 1]`` and ``ignore_index`` at the last
+    position — the shift HF's causal-LM loss applies to the ``labels`` the reference passes to the student (P1:238-240)."""
+    pad = torch.full_like(labels[..., :1], ignore_index)
+    return torch.cat([labels[..., 1:], pad], dim=-1)
+
+
+class _LocaKLWithCE(torch.autograd.Function):
+    """As-written LoCa KL + the student's shifted cross-entropy from one pass over the logits (``kd_logit_kd_ce_fwd_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, teacher, student, labels, ce_labels, T, alpha, eps, ce_weight, upstream, n_total, ce_valid_count):
+        dev = _require_cuda(teacher, student, labels, ce_labels)
+        if teacher.dtype != student.dtype:
+            raise TypeError(f"teacher ({teacher.dtype}) and student ({student.dtype}) must share a dtype")
+        if teacher.shape[:-1] != student.shape[:-1]:
+            raise ValueError(f"teacher {tuple(teacher.shape)} and student {tuple(student.shape)} disagree on token dims")
+        V = student.shape[-1]
+        if teacher.shape[-1] < V:
+            raise ValueError("teacher vocabulary is smaller than the student's (the reference slices the teacher, P1:155)")
+        t2, s2 = _rows(teacher.detach()), _rows(student.detach())
+        n_rows = s2.shape[0]
+        if labels.numel() != n_rows or ce_labels.numel() != n_rows:
+            raise ValueError(f"labels / ce_labels have {labels.numel()} / {ce_labels.numel()} entries for {n_rows} tokens")
+        lab = labels.detach().reshape(-1).to(torch.int64).contiguous()
+        cel = ce_labels.detach().reshape(-1).to(torch.int64).contiguous()
+        # 1 / (number of valid next-token targets) as a device scalar: nothing is read back (0 valid -> inf -> NaN like torch)
+        count = (cel != CE_IGNORE).sum() if ce_valid_count is None else torch.as_tensor(ce_valid_count, device=dev)
+        inv_count = (1.0 / count.to(torch.float32)).reshape(()).contiguous()
+        need_grad = student.requires_grad
+        flags = 0 if need_grad else _lib.FLAG_NO_GRAD
+        inv_norm = _inv_norm("mean", n_rows, V, 1, n_total)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            ws_bytes = _lib.size_query("kd_logit_kd_workspace_bytes", n_rows, V)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            ce = torch.empty((), dtype=torch.float32, device=dev)
+            grad = torch.empty((n_rows, V), dtype=student.dtype, device=dev) if need_grad else None
+            up_t, up_ptr = _upstream_ptr(upstream, dev)
+            _lib.check(lib.kd_logit_kd_ce_fwd_bwd(
+                t2.data_ptr(), t2.stride(0), s2.data_ptr(), s2.stride(0), lab.data_ptr(), cel.data_ptr(), inv_count.data_ptr(),
+                float(ce_weight), grad.data_ptr() if grad is not None else None, V, loss.data_ptr(), ce.data_ptr(),
+                ws.data_ptr(), ws_bytes, n_rows, V, _dtype_code(student), float(T), float(alpha), float(eps), inv_norm, up_ptr,
+                int(flags), _stream_ptr(dev)))
+        ctx.grad, ctx.need_grad, ctx.student_shape, ctx.dev, ctx.upstream, ctx.workspace = grad, need_grad, student.shape, dev, up_t, ws
+        if need_grad:
+            ctx.rows = (t2, s2, cel, inv_count)
+            ctx.call = (n_rows, V, _dtype_code(student), float(T), float(eps), float(ce_weight), inv_norm)
+        ctx.mark_non_differentiable(ce)
+        return loss, ce
+
+    @staticmethod
+    def backward(ctx, grad_output, _grad_ce):
+        if not ctx.need_grad:
+            return (None,) * 11
+        first = ctx.grad is not None           # see _LogitKD.backward: a repeated backward re-emits into a fresh buffer
+        go, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
+        t2, s2, cel, inv_count = ctx.rows
+        n_rows, V, dt, T, eps, ce_weight, inv_norm = ctx.call
+        ws = ctx.workspace
+        with torch.cuda.device(ctx.dev):
+            grad = ctx.grad if first else torch.empty((n_rows, V), dtype=s2.dtype, device=ctx.dev)
+            ctx.grad = None
+            _lib.check(_lib.load().kd_logit_kd_ce_regrad(t2.data_ptr(), t2.stride(0), s2.data_ptr(), s2.stride(0), cel.data_ptr(),
+                                                         inv_count.data_ptr(), ce_weight, grad.data_ptr(), grad.stride(0),
+                                                         ws.data_ptr(), ws.numel(), n_rows, V, dt, T, eps, inv_norm, go.data_ptr(),
+                                                         ratio.data_ptr() if first else None, _stream_ptr(ctx.dev)))
+        return (None, grad.view(ctx.student_shape)) + (None,) * 9
+
+
+def loca_kl_ce(teacher_logits, student_logits, labels, ce_labels, T: float, alpha: float = 0.8, eps: float = 1e-8,
+               ce_weight: float = 1.0, upstream=None, n_total=None, ce_valid_count=None):
+    """``(loca_kl + ce_weight * CE, CE)`` from ONE pass over the logits — SURVEY §8(f) rank 1.
+
+    ``CE`` is the loss the HF student returns at P1:238-240 and the reference adds at P1:194 / P1:260: mean over the valid
+    next-token targets of ``logsumexp(s) - s[target]`` (temperature 1).  ``ce_labels`` are those targets aligned with the
+    logit rows (:func:`shift_labels` of the ``labels`` given to the model; ``-100`` = ignored); ``labels`` are the UNSHIFTED
+    ids LoCa calibrates against (P1:166), all of which must lie in ``[0, V)``.  Call the student with ``labels=None`` so that
+    it does not compute its own loss.  The second result is the CE alone (detached, for logging).  As-written LoCa mode,
+    16-bit logits, ``V % 8 == 0``; ``ce_valid_count`` overrides the divisor when the rows are a shard of a larger batch."""
+    return _LocaKLWithCE.apply(teacher_logits, student_logits, labels, ce_labels, T, alpha, eps, ce_weight, upstream, n_total,
+                               ce_valid_count)
+
+
 def loca_kl(teacher_logits, student_logits, labels, T: float, alpha: float = 0.8, eps: float = 1e-8,
             mode: str = "reference", reduction: str = "mean", upstream=None, n_total=None, force_streaming=False):
     """LoCa-calibrated logit KL (P1:141-194) without the trailing ``+ student_loss``.
@@ -183,8 +271,10 @@ def temperature_kl(teacher_logits, student_logits, T: float, reduction: str = "m
 
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, student, teacher, temperature, upstream):
+    def forward(ctx, student, teacher, temperature, upstream, similarity="auto"):
         dev = _require_cuda(student, teacher)
+        if similarity not in ("auto", "cuda_core"):
+            raise ValueError("similarity: 'auto' (tensor cores for token-level M) or 'cuda_core' (the exact fp32 row kernel)")
         if student.shape != teacher.shape or student.dtype != teacher.dtype:
             raise ValueError("student and teacher features must have the same shape and dtype")
         if student.dim() == 2:
@@ -204,7 +294,9 @@ class _InfoNCE(torch.autograd.Function):
             up_t, up_ptr = _upstream_ptr(upstream, dev)
             _lib.check(lib.kd_info_nce_fwd_bwd(xs.data_ptr(), xt.data_ptr(), grad.data_ptr() if need_grad else None,
                                                loss.data_ptr(), ws.data_ptr(), ws_bytes, M, P, D, _dtype_code(xs),
-                                               float(temperature), up_ptr, 0 if need_grad else _lib.FLAG_NO_GRAD,
+                                               float(temperature), up_ptr,
+                                               (0 if need_grad else _lib.FLAG_NO_GRAD) |
+                                               (_lib.FLAG_FORCE_STREAMING if similarity == "cuda_core" else 0),
                                                _stream_ptr(dev)))
         ctx.grad, ctx.dev, ctx.upstream, ctx.need_grad = grad, dev, up_t, need_grad
         ctx.workspace, ctx.shape3, ctx.gdtype, ctx.gshape = ws, (M, P, D), xs.dtype, xs.shape
@@ -213,7 +305,7 @@ class _InfoNCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         if not ctx.need_grad:
-            return None, None, None, None
+            return None, None, None, None, None
         first = ctx.grad is not None           # see _LogitKD.backward: a repeated backward re-emits into a fresh buffer
         _, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
         M, P, D = ctx.shape3
@@ -224,22 +316,26 @@ class _InfoNCE(torch.autograd.Function):
             _lib.check(_lib.load().kd_info_nce_regrad(ws.data_ptr(), ws.numel(), grad.data_ptr(), M, P, D,
                                                       _dtype_code(grad), ratio.data_ptr(), ratio.data_ptr() if first else None,
                                                       _stream_ptr(ctx.dev)))
-        return grad, None, None, None
+        return grad, None, None, None, None
 
 
-def info_nce(student_feats, teacher_feats, temperature: float = 0.07, upstream=None, proj=None):
+def info_nce(student_feats, teacher_feats, temperature: float = 0.07, upstream=None, proj=None, similarity: str = "auto"):
     """Mean-pool over tokens (3-D input), L2-normalise, student x teacher^T / temperature, cross-entropy
     against the diagonal — P1:243-248 followed by ``contrastive_loss`` (P1:393-416).
 
     ``proj`` ([D_s, D_t], optional, not in the reference where both towers are SigLIP-1152): a learned projection of the
     student features, ``contrastive_loss(x_s @ proj, x_t)``.  Mean-pooling is linear, so the projection is applied to the pooled
-    student vectors (a plain library GEMM, differentiable w.r.t. ``proj``) instead of to every token."""
+    student vectors (a plain library GEMM, differentiable w.r.t. ``proj``) instead of to every token.
+
+    ``similarity``: with ``"auto"`` a token-level call (``M >= 1024`` rows, ``M`` and ``D`` multiples of 8 — e.g. the
+    46 656 x 1152 un-pooled SigLIP tokens) computes ``student @ teacher.T`` (P1:410) on the tcgen05 kernel with the row
+    log-softmax in its epilogue; the similarity matrix is never stored.  ``"cuda_core"`` forces the exact fp32 row kernel."""
     if proj is not None:
         # pooled in fp32 (like the kernel's own pooling), projected, then the 2-D form of the op (tokens == 1)
         pooled = student_feats.float().mean(dim=1) if student_feats.dim() == 3 else student_feats.float()
         student_feats = torch.matmul(pooled, proj.float())
         teacher_feats = teacher_feats.float().mean(dim=1) if teacher_feats.dim() == 3 else teacher_feats.float()
-    return _InfoNCE.apply(student_feats, teacher_feats, temperature, upstream)
+    return _InfoNCE.apply(student_feats, teacher_feats, temperature, upstream, similarity)
 
 
 class _FeatureMSE(torch.autograd.Function):

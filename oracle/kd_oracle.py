@@ -216,6 +216,25 @@ def temperature_kl(teacher, student, T: float, inv_norm: float | None = None, lo
 
 
 # --------------------------------------------------------------------------------------
+# (f)1 — the student's cross-entropy the reference adds at P1:194 / P1:260
+# --------------------------------------------------------------------------------------
+
+def student_cross_entropy(student, ce_labels, ignore_index: int = -100, dtype=torch.float64, want_grad: bool = True) -> KDResult:
+    """``student_outputs.loss`` of the HF causal LM called at P1:238-240 with ``labels=labels``: ``F.cross_entropy`` of the
+    logits against the NEXT token (the model shifts: logits[..., :-1, :] vs labels[..., 1:]), ``ignore_index=-100``
+    (the data module's padding value, DM:145-146), mean over the valid targets.  ``ce_labels`` are already aligned with the
+    logit rows (row (b, s) carries labels[b, s + 1]; the last position of a sequence carries ``ignore_index``), which is the
+    same sum over the same (row, target) pairs."""
+    s = student.detach().to(dtype).reshape(-1, student.shape[-1]).clone().requires_grad_(want_grad)
+    loss = torch.nn.functional.cross_entropy(s, ce_labels.reshape(-1).to(torch.int64), ignore_index=ignore_index)
+    grad = None
+    if want_grad:
+        (grad,) = torch.autograd.grad(loss, s)
+        grad = grad.reshape(student.shape)
+    return KDResult(loss.detach(), grad, {})
+
+
+# --------------------------------------------------------------------------------------
 # A4 — InfoNCE on (optionally mean-pooled) features (P1:243-248 + P1:393-416)
 # --------------------------------------------------------------------------------------
 

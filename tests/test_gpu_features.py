@@ -49,6 +49,33 @@ def test_info_nce_2d_features_as_the_reference_passes_them():
     assert rel_err(fd.grad.cpu(), ref.grad) <= 1e-4
 
 
+@pytest.mark.parametrize("M,P,D,related", [(2048, 1, 1152, True), (1032, 1, 256, False), (4096, 1, 1152, False), (1024, 3, 512, True)])
+def test_info_nce_token_level_on_the_tensor_cores(M, P, D, related):
+    """contrastive_loss accepts any [M, D] (P1:393-416); at token-level M the similarity GEMM (P1:410) runs on the tcgen05
+    kernel with the row log-softmax in its epilogue.  Oracle: the fp64 restatement on the GPU (same bf16-rounded inputs).
+    Gates: loss 1e-5 relative, bf16 gradient 2e-3 (tests/_util.grad_close), and agreement with the exact fp32 row kernel."""
+    xs, xt = synthetic.vision_feature_batch(M, P, D, seed=M + P)
+    if not related:
+        xt = synthetic.vision_feature_batch(M, P, D, seed=4242)[0]
+    if P == 1:
+        xs, xt = xs[:, 0], xt[:, 0]
+    ref = O.info_nce(xs.cuda(), xt.cuda())
+    xd = xs.cuda().requires_grad_(True)
+    loss = kd.info_nce(xd, xt.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref.loss.item()) <= max(1e-5 * abs(ref.loss.item()), 2e-7)
+    assert grad_close(xd.grad.float().cpu(), ref.grad.cpu())
+    xc = xs.cuda().requires_grad_(True)
+    loss_c = kd.info_nce(xc, xt.cuda(), similarity="cuda_core")
+    loss_c.backward()
+    assert abs(loss.item() - loss_c.item()) <= max(1e-5 * abs(loss_c.item()), 2e-7)
+    assert rel_err(xd.grad.float(), xc.grad.float()) <= 2e-3
+    # a different incoming gradient re-emits from the pooled gradient kept in the workspace
+    xe = xs.cuda().requires_grad_(True)
+    (kd.info_nce(xe, xt.cuda()) * 0.5).backward()
+    assert grad_close(xe.grad.float().cpu(), ref.grad.cpu() * 0.5)
+
+
 def test_mse_golden_and_oracle():
     g = load_golden("mse_small")
     a = torch.from_numpy(g["input"]).to("cuda", torch.bfloat16).requires_grad_(True)

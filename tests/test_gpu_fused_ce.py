@@ -1,0 +1,80 @@
+"""GPU parity of the fused LoCa KL + student cross-entropy: ``kd.loca_kl_ce`` through the C ABI against
+the oracle's ``loca_kl`` + ``student_cross_entropy`` (fp64 on the GPU) — the sum the reference forms at P1:194 from the HF
+student's loss (P1:238-240).  Gates: losses 1e-5 relative, bf16 gradient 2e-3 relative (tests/_util.grad_close)."""
+import pytest
+import torch
+
+from _util import grad_close
+from oracle import kd_oracle as O
+import knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 as kd
+from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import _lib, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(n, V, seed, peaked, ignore_frac):
+    t, s, lab = synthetic.logit_batch(n, V, seed=seed, peaked=peaked)
+    g = torch.Generator().manual_seed(seed + 17)
+    cel = torch.randint(0, V, (n,), generator=g)
+    cel[torch.rand(n, generator=g) < ignore_frac] = -100
+    if ignore_frac > 0:
+        cel[0] = -100          # at least one ignored and one valid row
+        cel[1] = 5
+    return t.cuda(), s.cuda(), lab.cuda(), cel.cuda()
+
+
+def _oracle(t, s, lab, cel, T, w):
+    kl = O.loca_kl(t, s, lab, T)
+    ce = O.student_cross_entropy(s, cel)
+    return kl.loss + w * ce.loss, ce.loss, kl.grad + w * ce.grad.reshape(kl.grad.shape)
+
+
+@pytest.mark.parametrize("n,V,T,peaked,ignore,w", [
+    (64, synthetic.VOCAB, 2.0, False, 0.5, 1.0),     # BASELINE configs[1] temperature; half the rows are prompt / padding
+    (48, synthetic.VOCAB, 0.8, True, 0.3, 1.0),      # the reference's T (P1:71): every row takes the clamped path
+    (40, synthetic.VOCAB, 1.0, False, 0.0, 1.25),    # LG:75 T = 1: the CE shares the KD's exponentials; weight 1/gamma of phase 3
+    (33, 40000, 2.0, False, 0.6, 0.5),               # another vocabulary, odd row count
+])
+def test_fused_ce_matches_kl_plus_cross_entropy(n, V, T, peaked, ignore, w):
+    t, s, lab, cel = _batch(n, V, seed=n, peaked=peaked, ignore_frac=ignore)
+    ref_loss, ref_ce, ref_grad = _oracle(t, s, lab, cel, T, w)
+    sd = s.clone().requires_grad_(True)
+    loss, ce = kd.loca_kl_ce(t, sd, lab, cel, T, ce_weight=w)
+    loss.backward()
+    assert abs(ce.item() - ref_ce.item()) <= 1e-5 * abs(ref_ce.item())
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert grad_close(sd.grad.float().cpu(), ref_grad.cpu())
+    # the KD part alone is what loca_kl returns
+    kl_only = kd.loca_kl(t, s, lab, T)
+    assert abs((loss.item() - w * ce.item()) - kl_only.item()) <= 1e-5 * abs(kl_only.item()) + 1e-6 * abs(w * ce.item())
+
+
+def test_fused_ce_backward_with_another_grad_output_and_repeated_backward():
+    t, s, lab, cel = _batch(24, synthetic.VOCAB, seed=5, peaked=False, ignore_frac=0.4)
+    _, _, ref_grad = _oracle(t, s, lab, cel, 2.0, 1.0)
+    sd = s.clone().requires_grad_(True)
+    loss, _ = kd.loca_kl_ce(t, sd, lab, cel, 2.0)
+    (0.25 * loss).backward(retain_graph=True)                 # re-emission kernel, CE terms included
+    assert grad_close(sd.grad.float().cpu(), 0.25 * ref_grad.cpu())
+    sd.grad = None
+    loss.backward()                                           # second backward through the same node: fresh buffer
+    assert grad_close(sd.grad.float().cpu(), ref_grad.cpu())
+    # phase 3 (P1:257-260): gamma * (loca + CE) + (1 - gamma) * CE = gamma * (loca + CE / gamma), gamma folded in as `upstream`
+    gamma = 0.8
+    _, _, ref3 = _oracle(t, s, lab, cel, 2.0, 1.0 / gamma)
+    s3 = s.clone().requires_grad_(True)
+    l3, _ = kd.loca_kl_ce(t, s3, lab, cel, 2.0, ce_weight=1.0 / gamma, upstream=gamma)
+    (gamma * l3).backward()
+    assert grad_close(s3.grad.float().cpu(), gamma * ref3.cpu())
+
+
+def test_fused_ce_label_errors_and_shapes():
+    t, s, lab, cel = _batch(16, synthetic.VOCAB, seed=9, peaked=False, ignore_frac=0.3)
+    bad = cel.clone()
+    bad[3] = synthetic.VOCAB + 7                              # F.cross_entropy raises on it; here: status bit + NaN, no host sync
+    loss, ce = kd.loca_kl_ce(t, s.clone().requires_grad_(True), lab, bad, 2.0)
+    assert torch.isnan(loss).item() and torch.isnan(ce).item()
+    with pytest.raises(_lib.KDError):                         # no fused kernel for fp32 logits: the caller adds its own CE
+        kd.loca_kl_ce(t.float(), s.float(), lab, cel, 2.0)
+    shifted = kd.shift_labels(torch.tensor([[1, 2, 3], [4, -100, 6]]))
+    assert shifted.tolist() == [[2, 3, -100], [-100, 6, -100]]

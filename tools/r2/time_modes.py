@@ -9,7 +9,14 @@ t, s, lab = synthetic.logit_batch(N, V, seed=1234, device="cuda")
 tp, sp_, labp = synthetic.logit_batch(N, V, seed=1234, device="cuda", peaked=True)
 sp_ = (sp_.float() * 4).to(torch.bfloat16)
 s.requires_grad_(True); sp_.requires_grad_(True)
+g = torch.Generator().manual_seed(3)
+cel = torch.randint(0, V, (N,), generator=g)
+cel[torch.rand(N, generator=g) < 0.5] = -100          # half the rows are prompt / padding
+cel = cel.cuda()
 def run(name):
+    if name == "reference_ce": return kd.loca_kl_ce(t, s, lab, cel, 2.0)[0]
+    if name == "reference_T0.8p_ce": return kd.loca_kl_ce(tp, sp_, labp, cel, 0.8)[0]
+    if name == "reference_T1_ce": return kd.loca_kl_ce(t, s, lab, cel, 1.0)[0]
     if name == "per_row": return kd.loca_kl(t, s, lab, 2.0, mode="per_row")
     if name == "reference": return kd.loca_kl(t, s, lab, 2.0)
     if name == "per_row_T0.8p": return kd.loca_kl(tp, sp_, labp, 0.8, mode="per_row")
