@@ -537,6 +537,40 @@ def main() -> None:
             ms = timeit(f, k=5, w=2)
             side[name] = {"ms": ms, "tokens_per_s": N / (ms / 1e3), "achieved_gbs": byt / (ms / 1e3) / 1e9,
                           "frac": byt / (ms / 1e3) / 1e9 / peak_gbs, "algorithmic_bytes_per_token": byt // N}
+        # the student's shifted cross-entropy (student_outputs.loss, P1:238-240 -> P1:194) out of the SAME pass
+        # as the logit KD.  Half of the rows carry a next-token target (the rest are prompt / padding, -100).  Beside it: what the
+        # unfused step costs — the KD op plus the library F.cross_entropy on the same bf16 logits (chunked over rows so that its
+        # fp32 temporaries fit; a HF model's own loss upcasts the whole [N, V] tensor at once).
+        try:
+            gce = torch.Generator(device="cpu").manual_seed(77)
+            cel = torch.randint(0, V, (N,), generator=gce)
+            cel[torch.rand(N, generator=gce) < 0.5] = -100
+            cel = cel.to(dev)
+
+            def lib_ce_step():
+                student.grad = None
+                kl = kd.loca_kl(teacher, student, labels, T_KD, alpha=ALPHA)
+                n_valid = (cel != -100).sum()
+                ce = 0.0
+                for r0 in range(0, N, 2048):
+                    ce = ce + torch.nn.functional.cross_entropy(student[r0:r0 + 2048].float(), cel[r0:r0 + 2048], ignore_index=-100,
+                                                                reduction="sum")
+                (kl + ce / n_valid).backward()
+            ce_lines = {}
+            for name, f in (("T2.0", fb(lambda: kd.loca_kl_ce(teacher, student, labels, cel, T_KD, alpha=ALPHA)[0])),
+                            ("T1.0", fb(lambda: kd.loca_kl_ce(teacher, student, labels, cel, 1.0, alpha=ALPHA)[0]))):
+                ms = timeit(f, k=5, w=2)
+                ce_lines[name] = {"ms": ms, "tokens_per_s": N / (ms / 1e3), "achieved_gbs": 8 * V * N / (ms / 1e3) / 1e9,
+                                  "frac": 8 * V * N / (ms / 1e3) / 1e9 / peak_gbs}
+            ms_lib = timeit(lib_ce_step, k=3, w=1)
+            student.grad = None
+            torch.cuda.empty_cache()
+            side["loca_reference_plus_fused_ce"] = {**ce_lines, "valid_target_fraction": 0.5, "algorithmic_bytes_per_token": 8 * V,
+                                                    "unfused_kd_plus_library_cross_entropy_ms": ms_lib,
+                                                    "note": "loss = LoCa KL + CE, gradient of both, one pass over the student logits; "
+                                                            "T = 1 shares the KD exponentials, T = 2 pays one more ex2 per cell and sweep on valid rows"}
+        except Exception as exc:  # noqa: BLE001
+            side["loca_reference_plus_fused_ce"] = {"error": f"{type(exc).__name__}: {exc}"}
         del tpk, spk, lpk
         torch.cuda.empty_cache()
         xs, xt = synthetic.vision_feature_batch(64, 729, 1152, device=dev)
@@ -547,7 +581,49 @@ def main() -> None:
             kd.info_nce(xs, xt).backward()
         ms = timeit(nce)
         side["info_nce_64x729x1152"] = {"us": ms * 1e3, "achieved_gbs": 3 * xs.numel() * 2 / (ms / 1e3) / 1e9}
+        # BASELINE configs[2] with its learned projection (1152 -> 896 on the pooled student vectors; the repo's tcgen05 GEMM on
+        # hi + lo bf16 parts of the fp32 pooled features), teacher features 896 wide
+        try:
+            wp = (torch.randn(1152, 896, device=dev) * 0.03).to(torch.bfloat16).requires_grad_(True)
+            xt896 = torch.randn(64, 729, 896, device=dev).to(torch.bfloat16)
+
+            def nce_proj():
+                xs.grad = None
+                wp.grad = None
+                kd.info_nce(xs, xt896, proj=wp).backward()
+            ms = timeit(nce_proj)
+            side["info_nce_64x729x1152_proj896"] = {"us": ms * 1e3, "note": "torch pools the 3-D features in fp32 (mean over tokens) before "
+                                                    "the projection; projection + its two backward products on kd_gemm"}
+            del wp, xt896
+        except Exception as exc:  # noqa: BLE001
+            side["info_nce_64x729x1152_proj896"] = {"error": f"{type(exc).__name__}: {exc}"}
         del xs, xt
+        # token-level contrastive loss: all 64 x 729 = 46 656 un-pooled SigLIP tokens as rows (contrastive_loss takes any [M, D],
+        # P1:393-416): the similarity GEMM (P1:410) on the tensor cores with the row log-softmax in its epilogue, 3 x 5.0 TFLOP
+        try:
+            tf_pk = 1401.6
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    tf_pk = float(json.load(f)["bf16_tflops_sustained"])
+            except Exception:  # noqa: BLE001
+                pass
+            Mt, Dt = 46_656, 1152
+            ts_, tt_ = synthetic.vision_feature_batch(Mt, 1, Dt, seed=7, device=dev)
+            ts_, tt_ = ts_[:, 0].contiguous().requires_grad_(True), tt_[:, 0].contiguous()
+
+            def nce_tok():
+                ts_.grad = None
+                kd.info_nce(ts_, tt_).backward()
+            ms = timeit(nce_tok, k=5, w=2)
+            fl = 3 * 2.0 * Mt * Mt * Dt / 1e12
+            side["info_nce_token_level_46656x1152"] = {"ms": ms, "tflops": fl / (ms / 1e3), "bound": "tensor", "peak_tflops": tf_pk,
+                                                       "frac": fl / (ms / 1e3) / tf_pk, "rows_per_s": Mt / (ms / 1e3),
+                                                       "note": "forward + backward; three M x M x D products on the tcgen05 kernel (statistics, "
+                                                               "softmax - I from a recomputation, G . u_t); the similarity matrix is never stored"}
+            del ts_, tt_
+        except Exception as exc:  # noqa: BLE001
+            side["info_nce_token_level_46656x1152"] = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
         ha = torch.randn(65_536, 3584, device=dev, dtype=torch.bfloat16).requires_grad_(True)
         hb = torch.randn(65_536, 3584, device=dev, dtype=torch.bfloat16)
 

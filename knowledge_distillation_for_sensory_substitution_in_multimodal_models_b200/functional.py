@@ -269,6 +269,63 @@ def temperature_kl(teacher_logits, student_logits, T: float, reduction: str = "m
     return _LogitKD.apply(teacher_logits, student_logits, None, T, 0.0, 1e-8, variant, reduction, upstream, n_total, flags)
 
 
+def _parts16(x: torch.Tensor, dtype):
+    """A 16-bit tensor as itself; an fp32 one as (hi, lo) 16-bit parts with hi + lo = x to ~2^-17, so that tensor-core
+    products carry an fp32 operand (the lo x lo term is dropped)."""
+    if x.dtype != torch.float32:
+        return [x.to(dtype)]
+    hi = x.to(dtype)
+    return [hi, (x - hi.float()).to(dtype)]
+
+
+def _gemm_parts(a_parts, b_parts, **kw):
+    out = None
+    for i, a in enumerate(a_parts):
+        for j, b in enumerate(b_parts):
+            if i and j:
+                continue
+            y = gemm(a, b, out_dtype=torch.float32, **kw)
+            out = y if out is None else out + y
+    return out
+
+
+class _Project(torch.autograd.Function):
+    """``y = x @ W`` (x: [M, K], W: [K, N]) on ``kd_gemm`` — the learned projection of BASELINE configs[2] (1152 -> 896 / 3584).
+    fp32 operands (pooled features, an fp32 master weight) are split into 16-bit hi + lo parts so that the tensor-core product
+    keeps its digits; the result is fp32 unless both operands are 16-bit (then it has their type, like the library GEMM of an
+    autocast forward).  No operand is transposed in HBM: W and the gradients are read through MN-major descriptors."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        _require_cuda(x, w)
+        if x.dim() != 2 or w.dim() != 2 or x.shape[1] != w.shape[0]:
+            raise ValueError("project: x [M, K] and W [K, N] expected")
+        d16 = torch.float16 if torch.float16 in (x.dtype, w.dtype) and torch.bfloat16 not in (x.dtype, w.dtype) else torch.bfloat16
+        xd, wd = x.detach().contiguous(), w.detach().contiguous()
+        ctx.save_for_backward(xd, wd)
+        ctx.needs, ctx.d16 = (x.requires_grad, w.requires_grad), d16
+        y = _gemm_parts(_parts16(xd, d16), _parts16(wd, d16), b_mn_major=True)
+        return y if torch.float32 in (x.dtype, w.dtype) else y.to(d16)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        g = _parts16(gy.contiguous(), ctx.d16)
+        if ctx.needs[0]:                                   # dx[M, K] = gy[M, N] . W[K, N]^T  (both K-major as stored)
+            dx = _gemm_parts(g, _parts16(w, ctx.d16)).to(x.dtype)
+        if ctx.needs[1]:                                   # dW[K, N] = x[M, K]^T . gy[M, N]  (both MN-major as stored)
+            dw = _gemm_parts(_parts16(x, ctx.d16), g, a_mn_major=True, b_mn_major=True).to(w.dtype)
+        return dx, dw
+
+
+def project(x: torch.Tensor, proj: torch.Tensor) -> torch.Tensor:
+    """``x @ proj`` on the tcgen05 GEMM, differentiable w.r.t. both (see :class:`_Project`); leading dims are flattened."""
+    lead = x.shape[:-1]
+    y = _Project.apply(x.reshape(-1, x.shape[-1]), proj)
+    return y.reshape(*lead, proj.shape[1])
+
+
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, student, teacher, temperature, upstream, similarity="auto"):
@@ -325,16 +382,19 @@ def info_nce(student_feats, teacher_feats, temperature: float = 0.07, upstream=N
 
     ``proj`` ([D_s, D_t], optional, not in the reference where both towers are SigLIP-1152): a learned projection of the
     student features, ``contrastive_loss(x_s @ proj, x_t)``.  Mean-pooling is linear, so the projection is applied to the pooled
-    student vectors (a plain library GEMM, differentiable w.r.t. ``proj``) instead of to every token.
+    student vectors (``project``: the repo's tcgen05 GEMM, differentiable w.r.t. ``proj``) instead of to every token.
 
     ``similarity``: with ``"auto"`` a token-level call (``M >= 1024`` rows, ``M`` and ``D`` multiples of 8 — e.g. the
     46 656 x 1152 un-pooled SigLIP tokens) computes ``student @ teacher.T`` (P1:410) on the tcgen05 kernel with the row
     log-softmax in its epilogue; the similarity matrix is never stored.  ``"cuda_core"`` forces the exact fp32 row kernel."""
     if proj is not None:
-        # pooled in fp32 (like the kernel's own pooling), projected, then the 2-D form of the op (tokens == 1)
-        pooled = student_feats.float().mean(dim=1) if student_feats.dim() == 3 else student_feats.float()
-        student_feats = torch.matmul(pooled, proj.float())
-        teacher_feats = teacher_feats.float().mean(dim=1) if teacher_feats.dim() == 3 else teacher_feats.float()
+        # mean-pooling is linear: pool first (fp32, like the kernel's own pooling), project the [M, D_s] vectors on the tcgen05
+        # kernel, then the 2-D form of the op (tokens == 1).  Token-level 2-D features are projected as they are.
+        pooled = student_feats.float().mean(dim=1) if student_feats.dim() == 3 else student_feats
+        student_feats = project(pooled, proj)
+        teacher_feats = teacher_feats.float().mean(dim=1) if teacher_feats.dim() == 3 else teacher_feats
+        if teacher_feats.dtype != student_feats.dtype:
+            teacher_feats = teacher_feats.to(student_feats.dtype)
     return _InfoNCE.apply(student_feats, teacher_feats, temperature, upstream, similarity)
 
 

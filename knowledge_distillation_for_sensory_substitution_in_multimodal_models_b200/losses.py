@@ -23,9 +23,24 @@ class KDLossMethods:
     kd_exchange = "nccl"     # record exchange of the as-written mode: "nccl" (all-gather) or "peer" (stores from phase A over NVLink)
 
     # P1:141-194 / LG:208-261 — returns loca + student_loss like the reference (P1:194)
-    def compute_loca_loss(self, teacher_logits, student_logits, student_loss, labels, alpha=0.8):
+    def compute_loca_loss(self, teacher_logits, student_logits, student_loss, labels, alpha=0.8, ce_labels=None, ce_weight=1.0,
+                          upstream=None):
+        """``student_loss=None`` asks for the FUSED form: the student's cross-entropy (what
+        ``student_outputs.loss`` would have been, P1:238-240) is computed from the same pass over ``student_logits`` — call the
+        student with ``labels=None`` so it does not compute it a second time.  ``ce_labels`` defaults to the next-token shift
+        of ``labels``; the CE alone is left in ``self.last_student_loss`` (detached) for logging / the phase-3 mix."""
         mode = getattr(self, "loca_mode", "reference")
         group = getattr(self, "kd_group", None)
+        if student_loss is None:
+            if group is not None or mode != "reference":
+                raise NotImplementedError("the fused cross-entropy rides the single-process as-written LoCa kernel; "
+                                          "pass student_loss for per_row / token-sharded calls")
+            if ce_labels is None:
+                ce_labels = F_kd.shift_labels(labels)
+            total, ce = F_kd.loca_kl_ce(teacher_logits, student_logits, labels, ce_labels, self.T, alpha=alpha, ce_weight=ce_weight,
+                                        upstream=upstream)
+            self.last_student_loss = ce
+            return total
         if group is not None:
             # tokens sharded over the ranks of `group`: the loss is the one of the CONCATENATED batch (one 16 B/token exchange in
             # the as-written mode, none otherwise), the gradient is this rank's rows'

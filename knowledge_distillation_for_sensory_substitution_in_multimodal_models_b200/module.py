@@ -28,6 +28,7 @@ import types
 
 import torch
 
+from . import functional as F_kd
 from .losses import KDLossMethods
 
 try:  # Lightning is optional (absent in this image)
@@ -51,7 +52,7 @@ class OnlineKnowledgeDistillationModule(_Base, KDLossMethods):
     def __init__(self, student_model: torch.nn.Module, teacher_model: torch.nn.Module, processor=None, phase: int = 2,
                  learning_rate: float = 1e-5, T: float = 0.8, soft_target_loss_weight: float = 0.1, ce_loss_weight: float = 0.5,
                  gamma: float = 0.8, loca_mode: str = "reference", sanitize_labels: bool = True, vision_hook: str | None = VISION_HOOK,
-                 group=None, exchange: str = "nccl"):
+                 group=None, exchange: str = "nccl", fuse_ce: bool = False):
         super().__init__()
         self.phase, self.learning_rate, self.processor = phase, learning_rate, processor
         self.student_model, self.teacher_model = student_model, teacher_model
@@ -61,6 +62,9 @@ class OnlineKnowledgeDistillationModule(_Base, KDLossMethods):
         self.soft_target_loss_weight, self.ce_loss_weight, self.gamma, self.T = soft_target_loss_weight, ce_loss_weight, gamma, T
         self.loca_mode, self.sanitize_labels = loca_mode, sanitize_labels
         self.kd_group, self.kd_exchange = group, exchange
+        # fuse_ce: the student is called WITHOUT labels and its cross-entropy comes out of the logit-KD kernel's pass over the
+        # student logits — single process, as-written LoCa mode, phases 2 / 3
+        self.fuse_ce = bool(fuse_ce) and group is None and loca_mode == "reference"
         self.student_representation_output = None
         self.teacher_representation_output = None
         if vision_hook:
@@ -92,9 +96,12 @@ class OnlineKnowledgeDistillationModule(_Base, KDLossMethods):
         with torch.no_grad():
             teacher_outputs = self.teacher_model(input_ids=batch["rgb_input_ids"], pixel_values=batch["rgb_pixel_values"],
                                                  labels=labels, **extra)
+        fused = self.fuse_ce and self.phase in (2, 3)
         student_outputs = self.student_model(input_ids=batch["depth_input_ids"], pixel_values=batch["depth_pixel_values"],
-                                             labels=labels, **extra)
+                                             labels=None if fused else labels, **extra)
         teacher_logits = teacher_outputs.logits
+        if fused:
+            return self._fused_logit_phase(teacher_logits, student_outputs.logits, labels)
         if self.phase == 1:
             # un-pooled [B', tokens, D] features: pooling + normalisation + loss + gradient broadcast are one fused op
             return self.compute_vision_loss(self.student_representation_output, self.teacher_representation_output.detach(),
@@ -104,6 +111,33 @@ class OnlineKnowledgeDistillationModule(_Base, KDLossMethods):
         if self.phase == 2:
             return loca_loss
         return self.gamma * loca_loss + (1 - self.gamma) * student_outputs.loss        # P1:257-260
+
+    def _fused_logit_phase(self, teacher_logits, student_logits, labels):
+        """Phases 2 / 3 with the cross-entropy fused: loca + CE (P1:254), or gamma * (loca + CE) + (1 - gamma) * CE
+        = gamma * (loca + CE / gamma) (P1:257-260), from one pass over the logits.  The CE is the mean over ALL valid next-token
+        targets; rows LoCa cannot use (label outside [0, V), e.g. the -100 of a prompt token) but whose NEXT token is a target
+        are few (one per answer start) and go through a plain cross-entropy on just those rows."""
+        V = student_logits.shape[-1]
+        ce_labels = F_kd.shift_labels(labels).reshape(-1)
+        flat = labels.reshape(-1)
+        n_valid = (ce_labels != F_kd.CE_IGNORE).sum()
+        gamma = self.gamma if self.phase == 3 else 1.0
+        s2, t2 = student_logits.reshape(-1, V), teacher_logits.reshape(-1, teacher_logits.shape[-1])
+        extra = None
+        if self.sanitize_labels:
+            ok = (flat >= 0) & (flat < V)
+            if not bool(ok.all()):
+                idx = ok.nonzero(as_tuple=True)[0]
+                rest = ((~ok) & (ce_labels != F_kd.CE_IGNORE)).nonzero(as_tuple=True)[0]
+                if rest.numel():
+                    extra = torch.nn.functional.cross_entropy(s2.index_select(0, rest).float(), ce_labels.index_select(0, rest),
+                                                              reduction="sum") / n_valid
+                s2, t2, flat, ce_labels = s2.index_select(0, idx), t2.index_select(0, idx), flat.index_select(0, idx), ce_labels.index_select(0, idx)
+        total, ce = F_kd.loca_kl_ce(t2, s2, flat, ce_labels, self.T, ce_weight=1.0 / gamma, upstream=gamma if gamma != 1.0 else None,
+                                    ce_valid_count=n_valid)
+        self.last_student_loss = ce if extra is None else ce + extra.detach()
+        loss = gamma * total
+        return loss if extra is None else loss + extra
 
     def _valid_rows(self, student_logits, teacher_logits, labels):
         """Drop the token rows whose label cannot be indexed (pads are -100, DM:145-146).  No copy when every label is valid —

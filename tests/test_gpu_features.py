@@ -127,7 +127,29 @@ def test_learned_projections_match_the_reference_applied_to_projected_features()
     loss = kd.info_nce(xd, xt_wide.cuda(), proj=Wd)
     loss.backward()
     assert abs(loss.item() - ref.loss.item()) <= 2e-5 * abs(ref.loss.item())
-    assert Wd.grad is not None and torch.isfinite(Wd.grad).all() and torch.isfinite(xd.grad.float()).all()
+    # gradients w.r.t. the features AND the projection (tcgen05 products of hi + lo parts) against fp64 autograd of the same formula
+    x64, W64 = xs.double().requires_grad_(True), W.double().requires_grad_(True)
+    us = torch.nn.functional.normalize((x64 @ W64).mean(1), dim=-1)
+    ut = torch.nn.functional.normalize(xt_wide.double().mean(1), dim=-1)
+    lg = us @ ut.T / 0.07
+    l64 = (torch.logsumexp(lg, -1) - lg.diagonal()).mean()
+    gx, gW = torch.autograd.grad(l64, (x64, W64))
+    assert abs(l64.item() - ref.loss.item()) <= 1e-12
+    assert rel_err(Wd.grad.cpu(), gW) <= 1e-4
+    assert grad_close(xd.grad.float().cpu(), gx)
+    # token-level 2-D bf16 features through a bf16 projection (the 1152 -> 896 case of BASELINE configs[2], at a size the oracle fits)
+    xs2, xt2 = synthetic.vision_feature_batch(1536, 1, 256, seed=8)
+    xs2, xt2 = xs2[:, 0].contiguous(), synthetic.vision_feature_batch(1536, 1, 128, seed=9)[1][:, 0].contiguous()
+    Wb = (torch.randn(256, 128, generator=g) * 0.08).to(torch.bfloat16)
+    y_ref = (xs2.double() @ Wb.double()).to(torch.bfloat16)          # what a bf16 GEMM hands to the loss
+    ref2 = O.info_nce(y_ref.cuda(), xt2.cuda())
+    x2d, Wbd = xs2.cuda().requires_grad_(True), Wb.cuda().requires_grad_(True)
+    l2 = kd.info_nce(x2d, xt2.cuda(), proj=Wbd)
+    l2.backward()
+    assert abs(l2.item() - ref2.loss.item()) <= 1e-4 * abs(ref2.loss.item())      # bf16 rounding boundaries of the projected tensor
+    gx2 = ref2.grad.double() @ Wb.double().cuda().T
+    assert rel_err(x2d.grad.double(), gx2) <= 6e-3                                # two bf16 roundings (d projected, d features)
+    assert torch.isfinite(Wbd.grad.float()).all()
     a = torch.randn(300, 48, generator=g).to(torch.bfloat16)
     b = torch.randn(300, 80, generator=g).to(torch.bfloat16)
     P = (torch.randn(48, 80, generator=g) * 0.2).to(torch.bfloat16)

@@ -47,3 +47,24 @@ def test_training_loop_reduces_the_loss():
     hist = train_online_kd.main(["--synthetic", "--phase", "2", "--batch_size", "2", "--max_epochs", "6", "--accumulate_grad_batches", "2",
                                  "--learning_rate", "3e-3", "--steps_per_epoch", "4"])
     assert hist[-1] < hist[0]
+
+
+@pytest.mark.parametrize("phase", [2, 3])
+@pytest.mark.parametrize("pad", [False, True])
+def test_fused_cross_entropy_equals_the_students_own_loss(phase, pad):
+    """fuse_ce=True: the student runs without labels and its CE (P1:238-240) comes out of the logit-KD kernel — same total as
+    the unfused module (loca + student_outputs.loss, P1:254 / P1:257-260), same parameter gradients."""
+    b = _batch(2, pad=pad)
+    out = []
+    for fused in (False, True):
+        student, teacher = TinyCausalLM(2048, 64, seed=1).cuda(), TinyCausalLM(2048, 128, seed=2).cuda()
+        m = OnlineKnowledgeDistillationModule(student, teacher, phase=phase, fuse_ce=fused)
+        loss = m.training_step(b, 0)
+        loss.backward()
+        out.append((loss.item(), torch.cat([p.grad.reshape(-1).float() for p in student.parameters() if p.grad is not None]), m))
+    (l0, g0, _), (l1, g1, m1) = out
+    assert abs(l1 - l0) <= 2e-5 * abs(l0)
+    assert ((g1 - g0).norm() / g0.norm()).item() <= 5e-3          # two bf16 gradient roundings (KD, CE) against one
+    with torch.no_grad():
+        so = TinyCausalLM(2048, 64, seed=1).cuda()(b["depth_input_ids"], b["depth_pixel_values"], labels=b["labels"])
+    assert abs(m1.last_student_loss.item() - so.loss.item()) <= 1e-5 * abs(so.loss.item())
