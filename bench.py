@@ -592,8 +592,8 @@ def main() -> None:
                 wp.grad = None
                 kd.info_nce(xs, xt896, proj=wp).backward()
             ms = timeit(nce_proj)
-            side["info_nce_64x729x1152_proj896"] = {"us": ms * 1e3, "note": "torch pools the 3-D features in fp32 (mean over tokens) before "
-                                                    "the projection; projection + its two backward products on kd_gemm"}
+            side["info_nce_64x729x1152_proj896"] = {"us": ms * 1e3, "note": "pooling kernels -> projection on kd_gemm (hi + lo bf16 parts of the fp32 "
+                                                    "pooled vectors; its two backward products too) -> the 2-D loss op -> store-only broadcast"}
             del wp, xt896
         except Exception as exc:  # noqa: BLE001
             side["info_nce_64x729x1152_proj896"] = {"error": f"{type(exc).__name__}: {exc}"}

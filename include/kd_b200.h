@@ -257,6 +257,15 @@ int kd_info_nce_fwd_bwd(const void* student, const void* teacher, void* grad_stu
 int kd_info_nce_regrad(const void* workspace, size_t workspace_bytes, void* grad_student, int64_t M, int64_t tokens,
                        int64_t D, int dtype, const float* ratio, const float* skip_if_one, void* stream);
 
+/* The pooling pass on its own — `.mean(dim=1)` over the tokens of the hooked [M, tokens, D] features (P1:243-246) in fp32 — for
+ * callers that put a learned projection between pooling and the loss (BASELINE configs[2]: 1152 -> 896 / 3584), and its
+ * backward: dx[m, p, :] = (*scale) * d_mean[m, :] for every token p (d_mean = d_pooled / tokens is the caller's; scale NULL = 1). */
+int kd_feature_pool_workspace_bytes(int64_t M, int64_t tokens, int64_t D, size_t* bytes);
+int kd_feature_pool_fwd(const void* x, float* pooled, void* workspace, size_t workspace_bytes, int64_t M, int64_t tokens,
+                        int64_t D, int dtype, void* stream);
+int kd_feature_pool_bwd(const float* d_mean, void* dx, int64_t M, int64_t tokens, int64_t D, int dtype, const float* scale,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Feature MSE — replaces mse_loss (EV:160-165): mean((input.float() - target.float())^2) and
  * grad_input = upstream * 2 (a - b) / numel, written in input's dtype.

@@ -56,6 +56,9 @@ SIGNATURES = {
     "kd_info_nce_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "kd_info_nce_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i64, _i64, _i64, _i, _f, _p, _u, _p]),
     "kd_info_nce_regrad": (_i, [_p, _sz, _p, _i64, _i64, _i64, _i, _p, _p, _p]),
+    "kd_feature_pool_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),
+    "kd_feature_pool_fwd": (_i, [_p, _p, _p, _sz, _i64, _i64, _i64, _i, _p]),
+    "kd_feature_pool_bwd": (_i, [_p, _p, _i64, _i64, _i64, _i, _p, _p]),
     "kd_feature_mse_workspace_bytes": (_i, [_i64, C.POINTER(_sz)]),
     "kd_feature_mse_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i64, _i, _p, _u, _p]),
     "kd_feature_mse_regrad": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p]),

@@ -73,7 +73,8 @@ pool_partial_kernel(const T* __restrict__ xs, const T* __restrict__ xt, float* _
 // ---- finish: add the partials, take the mean, L2-normalise (F.normalize eps) -------------------------------------
 __global__ void __launch_bounds__(256)
 pool_finish_kernel(const float* __restrict__ partials, float* __restrict__ us, float* __restrict__ ut, float* __restrict__ norm_s,
-                   int M, int P, int D, int nsplit, __half* __restrict__ us16 = nullptr, __half* __restrict__ ut16 = nullptr) {
+                   int M, int P, int D, int nsplit, __half* __restrict__ us16 = nullptr, __half* __restrict__ ut16 = nullptr,
+                   bool normalize = true) {
     extern __shared__ float sm[];        // [D] pooled vector
     __shared__ float red[8];
     const int mt = blockIdx.x, m = mt % M;
@@ -94,13 +95,13 @@ pool_finish_kernel(const float* __restrict__ partials, float* __restrict__ us, f
     float tot = 0.f;
     for (int i = 0; i < 8; ++i) tot += red[i];
     const float nrm = sqrtf(tot);
-    const float inv = 1.f / fmaxf(nrm, kNormEps);
+    const float inv = normalize ? 1.f / fmaxf(nrm, kNormEps) : 1.f;      // kd_feature_pool: the plain mean
     for (int d = threadIdx.x; d < D; d += 256) u[d] = sm[d] * inv;
     if (us16) {          // tensor-core similarity: the unit vectors as fp16 operands (|x| <= 1: 11 mantissa bits)
         __half* h = (is_teacher ? ut16 : us16) + (int64_t)m * D;
         for (int d = threadIdx.x; d < D; d += 256) h[d] = __float2half_rn(sm[d] * inv);
     }
-    if (!is_teacher && threadIdx.x == 0) norm_s[m] = nrm;
+    if (!is_teacher && threadIdx.x == 0 && norm_s) norm_s[m] = nrm;
 }
 
 // ---- one similarity row per CTA: logits, log-softmax, gradient w.r.t. the pooled student vector -----
@@ -535,6 +536,79 @@ int kd_info_nce_regrad(const void* workspace, size_t workspace_bytes, void* grad
         case KD_DTYPE_BF16: return kd::run_regrad<__nv_bfloat16>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, skip_if_one, st);
         case KD_DTYPE_F16: return kd::run_regrad<__half>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, skip_if_one, st);
         default: return kd::run_regrad<float>(dmean, grad_student, (int)M, (int)tokens, (int)D, ratio, skip_if_one, st);
+    }
+}
+
+/* mean over the token dimension in fp32 (the `.mean(dim=1)` of P1:243-246) — the pooling pass of kd_info_nce_fwd_bwd on its own,
+ * for callers that put a learned projection between pooling and the loss (BASELINE configs[2]) */
+int kd_feature_pool_workspace_bytes(int64_t M, int64_t tokens, int64_t D, size_t* bytes) {
+    KD_CHECK_ARG(bytes != nullptr && M >= 1 && tokens >= 1 && D >= 1, "kd_feature_pool_workspace_bytes: bad arguments");
+    *bytes = sizeof(float) * (size_t)kd::kMaxPoolSplit * 2 * M * D + 256;
+    return KD_OK;
+}
+
+int kd_feature_pool_fwd(const void* x, float* pooled, void* workspace, size_t workspace_bytes, int64_t M, int64_t tokens, int64_t D,
+                        int dtype, void* stream) {
+    using namespace kd;
+    KD_CHECK_ARG(x && pooled && workspace, "kd_feature_pool_fwd: null pointer");
+    KD_CHECK_ARG(M >= 1 && tokens >= 1 && D >= 1 && M < (1 << 20) && D < (1 << 20) && tokens < (1 << 24), "kd_feature_pool_fwd: bad shape");
+    KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
+    size_t need = 0;
+    kd_feature_pool_workspace_bytes(M, tokens, D, &need);
+    if (workspace_bytes < need) {
+        set_error("kd_feature_pool_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
+        return KD_ERR_WORKSPACE_TOO_SMALL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* partials = static_cast<float*>(workspace);
+    const int Mi = (int)M, P = (int)tokens, Di = (int)D;
+    // the pooling kernels handle a (student, teacher) pair of M rows each: a single tensor of M rows is M/2 + M/2 when M is even,
+    // otherwise both halves point at the same tensor and the "teacher" half is simply computed twice into the same place
+    auto go = [&](auto tag) -> int {
+        using T = decltype(tag);
+        constexpr int E = Elem<T>::kPack;
+        const bool vec = (Di % E == 0) && (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+        const int ncol = vec ? Di / E : Di;
+        const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
+        const size_t smem = sizeof(float) * (size_t)(kPoolThreads / lanes) * Di;
+        KD_CHECK_ARG(smem <= 200 * 1024 && sizeof(float) * (size_t)Di <= 200 * 1024, "kd_feature_pool_fwd: feature dimension %d too large", Di);
+        int nsplit = (148 * 4) / Mi;
+        if (nsplit > kMaxPoolSplit) nsplit = kMaxPoolSplit;
+        if (nsplit > (P + 63) / 64) nsplit = (P + 63) / 64;
+        if (nsplit < 1) nsplit = 1;
+        const T* xp = static_cast<const T*>(x);
+        const int half = (Mi + 1) / 2;                     // rows [0, half) as the "student", [Mi - half, Mi) as the "teacher"
+        const T* xt_ = xp + (int64_t)(Mi - half) * P * Di;
+        auto kfn = pool_partial_kernel<T>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kfn<<<(unsigned)(nsplit * 2 * (int64_t)half), kPoolThreads, smem, st>>>(xp, xt_, partials, half, P, Di, nsplit, vec);
+        KD_CHECK_LAUNCH("pool_partial_kernel");
+        if (sizeof(float) * (size_t)Di > 48 * 1024)
+            cudaFuncSetAttribute(pool_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * Di));
+        pool_finish_kernel<<<2 * half, 256, sizeof(float) * (size_t)Di, st>>>(partials, pooled, pooled + (int64_t)(Mi - half) * Di, nullptr,
+                                                                             half, P, Di, nsplit, nullptr, nullptr, false);
+        KD_CHECK_LAUNCH("pool_finish_kernel");
+        return KD_OK;
+    };
+    switch (dtype) {
+        case KD_DTYPE_BF16: return go(__nv_bfloat16{});
+        case KD_DTYPE_F16: return go(__half{});
+        default: return go(float{});
+    }
+}
+
+/* backward of the pooling: dx[m, p, :] = (*scale) * d_mean[m, :] for every token p, in x's dtype; d_mean = d_pooled / tokens is
+ * the caller's (an [M, D] fp32 tensor); scale: device scalar or NULL = 1 */
+int kd_feature_pool_bwd(const float* d_pooled, void* dx, int64_t M, int64_t tokens, int64_t D, int dtype, const float* scale, void* stream) {
+    using namespace kd;
+    KD_CHECK_ARG(d_pooled && dx, "kd_feature_pool_bwd: null pointer");
+    KD_CHECK_ARG(M >= 1 && tokens >= 1 && D >= 1 && M < (1 << 20) && D < (1 << 20) && tokens < (1 << 24), "kd_feature_pool_bwd: bad shape");
+    KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32, "unknown dtype %d", dtype);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case KD_DTYPE_BF16: return run_regrad<__nv_bfloat16>(d_pooled, dx, (int)M, (int)tokens, (int)D, scale, nullptr, st);
+        case KD_DTYPE_F16: return run_regrad<__half>(d_pooled, dx, (int)M, (int)tokens, (int)D, scale, nullptr, st);
+        default: return run_regrad<float>(d_pooled, dx, (int)M, (int)tokens, (int)D, scale, nullptr, st);
     }
 }
 

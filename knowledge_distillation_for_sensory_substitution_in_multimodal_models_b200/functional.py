@@ -326,6 +326,41 @@ def project(x: torch.Tensor, proj: torch.Tensor) -> torch.Tensor:
     return y.reshape(*lead, proj.shape[1])
 
 
+class _PoolTokens(torch.autograd.Function):
+    """``x.float().mean(dim=1)`` of ``[M, tokens, D]`` features (P1:243-246) on the library's pooling kernels; the backward is the
+    store-only broadcast ``dx[m, p, :] = d_pooled[m, :] / tokens`` in ``x``'s dtype."""
+
+    @staticmethod
+    def forward(ctx, x):
+        dev = _require_cuda(x)
+        if x.dim() != 3:
+            raise ValueError("pool_tokens: [M, tokens, D] features expected")
+        xd = x.detach().contiguous()
+        M, P, D = xd.shape
+        with torch.cuda.device(dev):
+            ws_bytes = _lib.size_query("kd_feature_pool_workspace_bytes", M, P, D)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            out = torch.empty((M, D), dtype=torch.float32, device=dev)
+            _lib.check(_lib.load().kd_feature_pool_fwd(xd.data_ptr(), out.data_ptr(), ws.data_ptr(), ws_bytes, M, P, D, _dtype_code(xd),
+                                                       _stream_ptr(dev)))
+        ctx.shape3, ctx.dtype, ctx.dev = (M, P, D), xd.dtype, dev
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        M, P, D = ctx.shape3
+        gm = (g.to(torch.float32) * (1.0 / P)).contiguous()
+        with torch.cuda.device(ctx.dev):
+            dx = torch.empty((M, P, D), dtype=ctx.dtype, device=ctx.dev)
+            _lib.check(_lib.load().kd_feature_pool_bwd(gm.data_ptr(), dx.data_ptr(), M, P, D, _DTYPES[ctx.dtype], None, _stream_ptr(ctx.dev)))
+        return dx
+
+
+def pool_tokens(x: torch.Tensor) -> torch.Tensor:
+    """fp32 mean over the token dimension of ``[M, tokens, D]`` features, differentiable (see :class:`_PoolTokens`)."""
+    return _PoolTokens.apply(x)
+
+
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, student, teacher, temperature, upstream, similarity="auto"):
@@ -390,9 +425,9 @@ def info_nce(student_feats, teacher_feats, temperature: float = 0.07, upstream=N
     if proj is not None:
         # mean-pooling is linear: pool first (fp32, like the kernel's own pooling), project the [M, D_s] vectors on the tcgen05
         # kernel, then the 2-D form of the op (tokens == 1).  Token-level 2-D features are projected as they are.
-        pooled = student_feats.float().mean(dim=1) if student_feats.dim() == 3 else student_feats
+        pooled = pool_tokens(student_feats) if student_feats.dim() == 3 else student_feats
         student_feats = project(pooled, proj)
-        teacher_feats = teacher_feats.float().mean(dim=1) if teacher_feats.dim() == 3 else teacher_feats
+        teacher_feats = pool_tokens(teacher_feats.detach()) if teacher_feats.dim() == 3 else teacher_feats
         if teacher_feats.dtype != student_feats.dtype:
             teacher_feats = teacher_feats.to(student_feats.dtype)
     return _InfoNCE.apply(student_feats, teacher_feats, temperature, upstream, similarity)

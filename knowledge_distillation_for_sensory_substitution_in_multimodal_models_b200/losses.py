@@ -23,24 +23,12 @@ class KDLossMethods:
     kd_exchange = "nccl"     # record exchange of the as-written mode: "nccl" (all-gather) or "peer" (stores from phase A over NVLink)
 
     # P1:141-194 / LG:208-261 — returns loca + student_loss like the reference (P1:194)
-    def compute_loca_loss(self, teacher_logits, student_logits, student_loss, labels, alpha=0.8, ce_labels=None, ce_weight=1.0,
-                          upstream=None):
-        """``student_loss=None`` asks for the FUSED form: the student's cross-entropy (what
-        ``student_outputs.loss`` would have been, P1:238-240) is computed from the same pass over ``student_logits`` — call the
-        student with ``labels=None`` so it does not compute it a second time.  ``ce_labels`` defaults to the next-token shift
-        of ``labels``; the CE alone is left in ``self.last_student_loss`` (detached) for logging / the phase-3 mix."""
+    def compute_loca_loss(self, teacher_logits, student_logits, student_loss, labels, alpha=0.8):
+        """Same signature as the reference.  ``student_loss=None`` asks for the FUSED form (:meth:`compute_loca_loss_fused`)."""
         mode = getattr(self, "loca_mode", "reference")
         group = getattr(self, "kd_group", None)
         if student_loss is None:
-            if group is not None or mode != "reference":
-                raise NotImplementedError("the fused cross-entropy rides the single-process as-written LoCa kernel; "
-                                          "pass student_loss for per_row / token-sharded calls")
-            if ce_labels is None:
-                ce_labels = F_kd.shift_labels(labels)
-            total, ce = F_kd.loca_kl_ce(teacher_logits, student_logits, labels, ce_labels, self.T, alpha=alpha, ce_weight=ce_weight,
-                                        upstream=upstream)
-            self.last_student_loss = ce
-            return total
+            return self.compute_loca_loss_fused(teacher_logits, student_logits, labels, alpha=alpha)
         if group is not None:
             # tokens sharded over the ranks of `group`: the loss is the one of the CONCATENATED batch (one 16 B/token exchange in
             # the as-written mode, none otherwise), the gradient is this rank's rows'
@@ -55,6 +43,21 @@ class KDLossMethods:
         else:
             loca = F_kd.loca_kl(teacher_logits, student_logits, labels, self.T, alpha=alpha, mode=mode)
         return loca + student_loss
+
+    # SURVEY §8(f) rank 1 — P1:194 with the student's own loss (P1:238-240) computed in the same pass over its logits
+    def compute_loca_loss_fused(self, teacher_logits, student_logits, labels, alpha=0.8, ce_labels=None, ce_weight=1.0, upstream=None):
+        """``loca + ce_weight * CE`` where CE is what ``student_outputs.loss`` would have been — call the student with
+        ``labels=None`` so it is not computed twice.  ``ce_labels`` defaults to the next-token shift of ``labels``; the CE alone
+        is left in ``self.last_student_loss`` (detached) for logging / the phase-3 mix."""
+        if getattr(self, "kd_group", None) is not None or getattr(self, "loca_mode", "reference") != "reference":
+            raise NotImplementedError("the fused cross-entropy rides the single-process as-written LoCa kernel; "
+                                      "pass student_loss for per_row / token-sharded calls")
+        if ce_labels is None:
+            ce_labels = F_kd.shift_labels(labels)
+        total, ce = F_kd.loca_kl_ce(teacher_logits, student_logits, labels, ce_labels, self.T, alpha=alpha, ce_weight=ce_weight,
+                                    upstream=upstream)
+        self.last_student_loss = ce
+        return total
 
     # P1:316-354 / EV:246-283 — features arrive pooled + normalised (P1:243-248)
     def compute_vision_loss(self, student_features, teacher_features, teacher_logits, student_outputs):
@@ -132,6 +135,9 @@ def patch_reference(target, loca_mode: str = "reference", only_existing: bool = 
         else:
             setattr(target, name, types.MethodType(fn, target))
         patched.append(name)
+    # helper the patched compute_loca_loss(student_loss=None) forwards to (not a reference method: always attached)
+    fused = KDLossMethods.compute_loca_loss_fused
+    setattr(target, "compute_loca_loss_fused", fused if is_class else types.MethodType(fused, target))
     setattr(target, "loca_mode", loca_mode)
     setattr(target, "kd_group", group)
     setattr(target, "kd_exchange", exchange)

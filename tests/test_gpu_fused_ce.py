@@ -78,3 +78,28 @@ def test_fused_ce_label_errors_and_shapes():
         kd.loca_kl_ce(t.float(), s.float(), lab, cel, 2.0)
     shifted = kd.shift_labels(torch.tensor([[1, 2, 3], [4, -100, 6]]))
     assert shifted.tolist() == [[2, 3, -100], [-100, 6, -100]]
+
+
+def test_patched_reference_method_fuses_the_ce_when_student_loss_is_none():
+    """compute_loca_loss(teacher, student, None, labels) on a patched reference-shaped object == loca + the HF student's loss
+    (P1:194 with P1:238-240's shifted, ignore_index=-100 cross-entropy), labels [B, S] as the reference passes them."""
+    class Ref:
+        T = 2.0
+
+        def compute_loca_loss(self, teacher_logits, student_logits, student_loss, labels, alpha=0.8):
+            raise AssertionError("not patched")
+    obj = Ref()
+    kd.patch_reference(obj)
+    B, S, V = 2, 12, 40000
+    t, s, lab = synthetic.logit_batch(B * S, V, seed=21)
+    t, s, lab = t.cuda().view(B, S, V), s.cuda().view(B, S, V), lab.cuda().view(B, S)
+    sd = s.clone().requires_grad_(True)
+    total = obj.compute_loca_loss(t, sd, None, lab)
+    total.backward()
+    kl = O.loca_kl(t, s, lab, 2.0)
+    hf = torch.nn.functional.cross_entropy(s[:, :-1].double().reshape(-1, V), lab[:, 1:].reshape(-1), ignore_index=-100)   # HF's shift
+    ce = O.student_cross_entropy(s, kd.shift_labels(lab))
+    assert abs(ce.loss.item() - hf.item()) <= 1e-12 * abs(hf.item())
+    assert abs(total.item() - (kl.loss + ce.loss).item()) <= 1e-5 * abs((kl.loss + ce.loss).item())
+    assert abs(obj.last_student_loss.item() - hf.item()) <= 1e-5 * abs(hf.item())
+    assert grad_close(sd.grad.float().cpu(), (kl.grad.reshape(B, S, V) + ce.grad).cpu())
