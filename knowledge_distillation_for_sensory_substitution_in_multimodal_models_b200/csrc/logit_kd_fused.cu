@@ -19,7 +19,12 @@
 //
 // Variants: KD_LOCA_REFERENCE (teacher lse2_t and the override table come from phase A), KD_KL_PLAIN (teacher
 // statistics are folded into the same single reduction through a per-warp teacher reference maximum) and
-// KD_LOCA_PER_ROW, which is the plain sweep plus, in the SAME reduction, each warp's best / runner-up teacher cell (value,
+// KD_KL_LOG_TARGET (FB:206-219: w = e^{tp} in place of q) — e^{tp} is NOT linear in the unknown teacher log-sum-exp, but its
+// power series is: with tp = sigma_w * t' (t' = teacher exponential against the warp's reference maximum, sigma_w known after the
+// fold) sum_v e^{tp} = n + sum_k sigma^k T_k / k!, T_k = sum t'^k, and likewise for sum e^{tp} tp and sum e^{tp} a with the cross
+// sums U_k = sum t'^k a'.  tp <= 1 and the totals are dominated by the order-0 terms (~V, ~V log V), so T_1..T_3 and U_0..U_3
+// bound the truncation at 3e-7 of Q_r and 1e-6 of the row sum; the gradient's e^{tp} is exact (one ex2 per cell in pass C) —
+// and KD_LOCA_PER_ROW, which is the plain sweep plus, in the SAME reduction, each warp's best / runner-up teacher cell (value,
 // column, student logit there), the row's label logits and the student minimum: the fold derives v1, v2 (P1:166-185),
 // corrects Q_r and the row sum for the row's own two override cells analytically and the two gradient cells are
 // re-written after the gradient sweep — the teacher row is read ONCE (6V bytes per token, no phase A).
@@ -78,6 +83,8 @@ struct FusedParams {
 // Shared-memory plan (dynamic, byte offsets).  A reduction slot is 8 words:
 //   [0] m_w  [1] S_w  [2] Q_w  [3] R_w - P_w  [4] min_w  [5] next-row claim (leader slot)  [6] [7] second reduction
 //   (KD_KL_PLAIN: [6] teacher reference maximum, no second reduction)
+// KD_KL_LOG_TARGET uses 12 of 16 words: [0] m_w [1] S_w [2] T_1 [3] U_1 [4] T_2 [5] claim [6] mt_w [7] T_3 [8] U_0 [9] U_2 [10] U_3
+//   [11] number of cells in the warp's slice
 // KD_LOCA_PER_ROW uses 16 words: [0-5] as above, [6] teacher maximum of the warp's slice = its best cell's value, [7] that
 //   cell's column, [8] [9] runner-up value / column, [10] [11] student logits at those two cells, [12] [13] teacher / student
 //   logit at the row's label (meaningful in the slot of the warp that owns the column), [14] [15] second reduction
@@ -87,7 +94,7 @@ template <int VARIANT, int CS, int NPIPE, bool CE = false>
 struct FusedPlan {
     static constexpr int WPP = kWarps / NPIPE;
     static constexpr int NSLOT = CS * WPP;
-    static constexpr int SLOTB = (VARIANT == KD_LOCA_PER_ROW || CE) ? 64 : 32;      // bytes per reduction slot
+    static constexpr int SLOTB = (VARIANT == KD_LOCA_PER_ROW || VARIANT == KD_KL_LOG_TARGET || CE) ? 64 : 32;      // bytes per reduction slot
     static constexpr int BCASTB = 128;                                        // bytes of per-pipeline broadcast words
     int table, rows, bars, slots, bcast, tmem_word, total;
     __host__ __device__ FusedPlan(int vpc) {
@@ -131,15 +138,17 @@ template <int VARIANT, typename T, int CS, int NPIPE, bool DYN, bool CE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 row_emit_fused_kernel(const FusedParams cp) {
     static_assert(!CE || VARIANT == KD_LOCA_REFERENCE, "the fused cross-entropy rides the as-written LoCa kernel");
+    static_assert(VARIANT != KD_KL_LOG_TARGET || KD_ECACHE, "the log_target variant relies on the cached gradient sweep");
     constexpr bool TAB = (VARIANT == KD_LOCA_REFERENCE);            // shared override table (phase A + build_table)
     constexpr bool PER_ROW = (VARIANT == KD_LOCA_PER_ROW);          // the row's own label / runner-up cells only
+    constexpr bool KLLT = (VARIANT == KD_KL_LOG_TARGET);            // w = e^{tp}: power sums of the teacher exponentials
     constexpr bool CLAMP = TAB || PER_ROW;                          // sp >= eps clamp: student minimum, masked pass B'
     constexpr int WPP = kWarps / NPIPE;
     constexpr int NSLOT = CS * WPP;
     constexpr int SLOTB = FusedPlan<VARIANT, CS, NPIPE, CE>::SLOTB;
     constexpr int SLOTV = SLOTB / 16;                               // float4s per slot
     constexpr int BCASTB = FusedPlan<VARIANT, CS, NPIPE, CE>::BCASTB;
-    constexpr uint32_t RED1_BYTES = NSLOT * (TAB ? (CE ? 32 : 24) : PER_ROW ? 56 : 32);
+    constexpr uint32_t RED1_BYTES = NSLOT * (TAB ? (CE ? 32 : 24) : PER_ROW ? 56 : KLLT ? 48 : 32);
     constexpr uint32_t RED2_BYTES = NSLOT * 8;
     constexpr uint32_t RED2_OFF = (PER_ROW || CE) ? 56 : 24;        // byte offset of the second reduction's two words (the slot's last two)
     extern __shared__ __align__(128) unsigned char smem[];
@@ -382,6 +391,7 @@ row_emit_fused_kernel(const FusedParams cp) {
 
         // ================= pass AB: statistics + accumulation in one sweep, q parked in tensor memory ==========
         float S_w, Q_w, R_w, P_w;
+        [[maybe_unused]] float kl_T2 = 0.f, kl_T3 = 0.f, kl_U0 = 0.f, kl_U2 = 0.f, kl_U3 = 0.f, kl_n = 0.f;      // log_target power sums
         [[maybe_unused]] float S1_w = 0.f;       // fused CE: sum 2^((xs - m_w) log2 e) of the slice
         // the CE needs its own exponentials only when the KD temperature is not 1 (and the row's label is not ignored)
         [[maybe_unused]] const bool ce_extra = CE && ce_on && !ce_same_t;
@@ -395,6 +405,7 @@ row_emit_fused_kernel(const FusedParams cp) {
             const u64 nlt = pk(-tref, -tref);
             u64 accS0 = pk(0.f, 0.f), accS1 = pk(0.f, 0.f), accQ = pk(0.f, 0.f), accR = pk(0.f, 0.f), accP = pk(0.f, 0.f);
             [[maybe_unused]] u64 accCE = pk(0.f, 0.f);
+            [[maybe_unused]] u64 accT2 = pk(0.f, 0.f), accT3 = pk(0.f, 0.f), accU0 = pk(0.f, 0.f), accU2 = pk(0.f, 0.f), accU3 = pk(0.f, 0.f);
             [[maybe_unused]] const u64 k1p = pk(k1, k1);
             [[maybe_unused]] const float mk1 = __fmul_rn((m_w == -INFINITY) ? 0.f : m_w, k1);
             [[maybe_unused]] const u64 nm1 = pk(-mk1, -mk1);
@@ -438,7 +449,16 @@ row_emit_fused_kernel(const FusedParams cp) {
                         const u64 t2 = pk(ex2(e_lo), ex2(e_hi));
                         const u64 q2 = TAB ? add2(t2, ovp[i]) : t2;
                         accQ = add2(accQ, q2);
-                        accR = fma2(t2, b2, accR);
+                        if constexpr (KLLT) {      // power sums T_2, T_3 and cross sums U_0, U_2, U_3 (U_1 is accP, T_1 is accQ)
+                            const u64 tt = mul2(t2, t2), ttt = mul2(tt, t2);
+                            accT2 = add2(accT2, tt);
+                            accT3 = add2(accT3, ttt);
+                            accU0 = add2(accU0, a2);
+                            accU2 = fma2(tt, a2, accU2);
+                            accU3 = fma2(ttt, a2, accU3);
+                        } else {
+                            accR = fma2(t2, b2, accR);
+                        }
                         accP = fma2(q2, a2, accP);
                         float q_lo, q_hi;
                         upk(q2, q_lo, q_hi);
@@ -525,6 +545,19 @@ row_emit_fused_kernel(const FusedParams cp) {
             Q_w = warp_sum(q_l);
             R_w = warp_sum(r_l) + poison;
             P_w = warp_sum(p_l) - esh * Q_w;          // sum q*(a + 15) -> sum q*a
+            if constexpr (KLLT) {                     // the cross sums carry a' + 15 too: U_k = U_k' - 15 T_k  (T_0 = cells of the slice)
+                upk(accT2, x0, x1);
+                kl_T2 = warp_sum(x0 + x1);
+                upk(accT3, x0, x1);
+                kl_T3 = warp_sum(x0 + x1);
+                kl_n = (float)(w_n * 8);
+                upk(accU0, x0, x1);
+                kl_U0 = warp_sum(x0 + x1) - esh * kl_n;
+                upk(accU2, x0, x1);
+                kl_U2 = warp_sum(x0 + x1) - esh * kl_T2;
+                upk(accU3, x0, x1);
+                kl_U3 = warp_sum(x0 + x1) - esh * kl_T3;
+            }
         }
         // per-row LoCa: decode the slice's best / runner-up cell -> (value, global column, student logit in that column)
         float top_a2 = -INFINITY, top_xs1 = 0.f, top_xs2 = 0.f;
@@ -559,6 +592,10 @@ row_emit_fused_kernel(const FusedParams cp) {
                 st_async_v4(dst + 16, __float_as_uint(min_w), (uint32_t)claimed, __float_as_uint(mt_w), (uint32_t)top_i1, rbar);
                 st_async_v4(dst + 32, __float_as_uint(top_a2), (uint32_t)top_i2, __float_as_uint(top_xs1), __float_as_uint(top_xs2), rbar);
                 st_async_v2(dst + 48, __float_as_uint(xt_lab), __float_as_uint(xs_lab), rbar);
+            } else if constexpr (KLLT) {
+                // (word [3] was pushed as R_w - P_w with R_w = 0: the fold reads U_1 = -word[3])
+                st_async_v4(dst + 16, __float_as_uint(kl_T2), (uint32_t)claimed, __float_as_uint(mt_w), __float_as_uint(kl_T3), rbar);
+                st_async_v4(dst + 32, __float_as_uint(kl_U0), __float_as_uint(kl_U2), __float_as_uint(kl_U3), __float_as_uint(kl_n), rbar);
             } else {
                 st_async_v4(dst + 16, 0u, (uint32_t)claimed, __float_as_uint(mt_w), 0u, rbar);
             }
@@ -836,8 +873,23 @@ row_emit_fused_kernel(const FusedParams cp) {
                     const float mki = __fmul_rn((sa[i].x == -INFINITY) ? 0.f : sa[i].x, k2);
                     const float mti = __fmul_rn((sb[i].z == -INFINITY) ? 0.f : sb[i].z, k2);
                     const float sc_i = ex2(mti - lse2_t);             // this warp's teacher partials are relative to its mt_w
-                    Q = fmaf(sc_i, sa[i].z, Q);
-                    row = fmaf(sc_i, sa[i].w + ((mti - lse2_t) - (mki - lse2_s)) * sa[i].z, row);
+                    if constexpr (KLLT) {
+                        // tp = sc_i * t', a = a' + c:  sum e^{tp} = n + s T1 + s^2 T2 / 2 + s^3 T3 / 6,  sum e^{tp} tp = s T1 + s^2 T2 + s^3 T3 / 2,
+                        // sum e^{tp} a = (U0 + c n) + s (U1 + c T1) + s^2 (U2 + c T2) / 2 + s^3 (U3 + c T3) / 6      (natural-log row term below)
+                        const int idx = lane + 32 * i;
+                        const bool live = (NSLOT % 32 == 0 || idx < NSLOT);       // (a missing slot's neutral word [4] is +inf: the LoCa minimum)
+                        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) sc = slot_v[SLOTV * idx + 2];
+                        const float c = mki - lse2_s, T1 = sa[i].z, U1 = -sa[i].w, T2 = live ? sb[i].x : 0.f, T3 = live ? sb[i].w : 0.f;
+                        const float s2h = 0.5f * sc_i * sc_i, s3s = s2h * sc_i * (1.f / 3.f);
+                        Q += sc.w + fmaf(sc_i, T1, fmaf(s2h, T2, s3s * T3));
+                        const float a_tp = fmaf(sc_i, T1, fmaf(2.f * s2h, T2, 3.f * s3s * T3));
+                        const float a_a = fmaf(c, sc.w, sc.x) + fmaf(sc_i, fmaf(c, T1, U1), fmaf(s2h, fmaf(c, T2, sc.y), s3s * fmaf(c, T3, sc.z)));
+                        row += fmaf(-0.69314718055994531f, a_a, a_tp);
+                    } else {
+                        Q = fmaf(sc_i, sa[i].z, Q);
+                        row = fmaf(sc_i, sa[i].w + ((mti - lse2_t) - (mki - lse2_s)) * sa[i].z, row);
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -1015,7 +1067,9 @@ row_emit_fused_kernel(const FusedParams cp) {
             const float lgQ = fold ? __log2f(gQ) : 0.f;
             const u64 nls = pk(lgQ - lse2_s, lgQ - lse2_s);
             const float thrC = thr2 + lgQ;
-            const float gq = TAB ? g : g * ex2(mtk - lse2_t);         // no phase A: the parked values are relative to mt_w
+            const float gq = (TAB || KLLT) ? g : g * ex2(mtk - lse2_t);         // no phase A: the parked values are relative to mt_w
+            // log_target: the parked t' becomes w = e^{tp} = 2^(t' * sigma_w * log2 e), exactly, cell by cell
+            [[maybe_unused]] const float sl2e = ex2(mtk - lse2_t) * 1.4426950408889634f;
             const u64 negg = pk(-gq, -gq), gQp = pk(gQ, gQ);
             T* grow = static_cast<T*>(p.grad) + r * p.ld_g + (int64_t)g_v0 * 8;
             auto sweepC = [&](auto fold_tag, auto mask_tag, auto poly_tag) {
@@ -1084,7 +1138,8 @@ row_emit_fused_kernel(const FusedParams cp) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const float2 ef = __half22float2(*reinterpret_cast<const __half2*>(&eb[u][i]));
-                                const u64 q2 = pk(__uint_as_float(qb[u][2 * i]), __uint_as_float(qb[u][2 * i + 1]));
+                                u64 q2 = pk(__uint_as_float(qb[u][2 * i]), __uint_as_float(qb[u][2 * i + 1]));
+                                if constexpr (KLLT) q2 = ex2_mufu2(mul2(q2, pk(sl2e, sl2e)));
                                 float n_lo, n_hi;
                                 u64 o2 = fma2(pk(ef.x, ef.y), cep, mul2(q2, negg));
                                 if constexpr (CE_X) o2 = fma2(ex2_mufu2(fma2(Pair<T>::widen(wsv[i]), k1c, nl1)), gcp, o2);
@@ -1300,6 +1355,7 @@ int launch_fused_t(const EmitParams& e, int variant, cudaStream_t st, bool query
     if (variant == KD_LOCA_REFERENCE && e.ce_labels) return launch_fused_v<KD_LOCA_REFERENCE, T, true>(e, st, query_only, capacity, launched, first_free);
     if (variant == KD_LOCA_REFERENCE) return launch_fused_v<KD_LOCA_REFERENCE, T>(e, st, query_only, capacity, launched, first_free);
     if (variant == KD_LOCA_PER_ROW) return launch_fused_v<KD_LOCA_PER_ROW, T>(e, st, query_only, capacity, launched, first_free);
+    if (variant == KD_KL_LOG_TARGET) return launch_fused_v<KD_KL_LOG_TARGET, T>(e, st, query_only, capacity, launched, first_free);
     return launch_fused_v<KD_KL_PLAIN, T>(e, st, query_only, capacity, launched, first_free);
 }
 
@@ -1322,7 +1378,7 @@ bool fused_applies(const EmitParams& p, int variant, int dtype) {
         if (!(p.alpha >= 0.f && p.alpha <= 1.f)) return false;      // overrides outside [0, 1]: exact per-cell path
     } else if (variant == KD_LOCA_PER_ROW) {
         if (!p.labels || !p.records || !p.status) return false;     // labels in, token records out (backward re-emission)
-    } else if (variant != KD_KL_PLAIN) {
+    } else if (variant != KD_KL_PLAIN && variant != KD_KL_LOG_TARGET) {
         return false;
     }
     return dtype == KD_DTYPE_BF16 || dtype == KD_DTYPE_F16;
