@@ -1,7 +1,7 @@
 """Driver for ncu: runs ONE op of the path a few times at its benchmark shape (the ncu command line picks the kernel).
 
-usage: python tools/profile_ops.py <op> [rows]      op in: loca_reference loca_per_row loca_reference_T08 kl kl_log_target regrad mse proj_mse
-                                                          info_nce gemm_dh gemm_dw lm_head vshard
+usage: python tools/profile_ops.py <op> [rows]      op in: loca_reference loca_reference_ce loca_per_row loca_reference_T08 kl kl_log_target regrad
+                                                          mse proj_mse info_nce nce_tc gemm_dh gemm_dw lm_head vshard
 """
 import os
 import sys
@@ -26,13 +26,18 @@ def logits(peaked=False, boost=1.0):
     return t, s.requires_grad_(True), lab
 
 
-if op in ("loca_reference", "loca_per_row", "loca_reference_T08", "kl", "kl_log_target", "regrad"):
+if op in ("loca_reference", "loca_reference_ce", "loca_per_row", "loca_reference_T08", "kl", "kl_log_target", "regrad"):
     peaked = op == "loca_reference_T08"
     t, s, lab = logits(peaked, 4.0 if peaked else 1.0)
     for _ in range(REPS):
         s.grad = None
         if op == "loca_reference":
             loss = kd.loca_kl(t, s, lab, 2.0)
+        elif op == "loca_reference_ce":           # fused student cross-entropy, half of the rows carry a target
+            g = torch.Generator().manual_seed(77)
+            cel = torch.randint(0, V, (rows,), generator=g)
+            cel[torch.rand(rows, generator=g) < 0.5] = -100
+            loss = kd.loca_kl_ce(t, s, lab, cel.cuda(), 2.0)[0]
         elif op == "loca_per_row":
             loss = kd.loca_kl(t, s, lab, 2.0, mode="per_row")
         elif op == "loca_reference_T08":
@@ -63,6 +68,14 @@ elif op == "proj_mse":
 elif op == "info_nce":
     xs, xt = synthetic.vision_feature_batch(64, 729, 1152, device=dev)
     xs.requires_grad_(True)
+    for _ in range(REPS):
+        xs.grad = None
+        loss = kd.info_nce(xs, xt)
+        loss.backward()
+elif op == "nce_tc":                              # token-level contrastive loss: 64 x 729 un-pooled SigLIP tokens as rows
+    M = rows if len(sys.argv) > 2 else 46656
+    xs, xt = synthetic.vision_feature_batch(M, 1, 1152, seed=7, device=dev)
+    xs, xt = xs[:, 0].contiguous().requires_grad_(True), xt[:, 0].contiguous()
     for _ in range(REPS):
         xs.grad = None
         loss = kd.info_nce(xs, xt)
