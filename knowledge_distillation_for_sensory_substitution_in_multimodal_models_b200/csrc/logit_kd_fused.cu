@@ -282,6 +282,8 @@ row_emit_fused_kernel(const FusedParams cp) {
     // fused cross-entropy (temperature 1): exponent scale, upstream * ce_weight / n_valid, whether it shares the KD temperature
     [[maybe_unused]] const float k1 = kLog2e;
     [[maybe_unused]] const bool ce_same_t = (k2 == k1);
+    // T == 2: 2^((xs - m) log2 e) is the SQUARE of the KD exponential 2^((xs - m) log2 e / 2) — no second ex2 in either sweep
+    [[maybe_unused]] const bool ce_square = (k2 + k2 == k1);
     [[maybe_unused]] float g_ce = 0.f;
     [[maybe_unused]] int64_t cel64 = kCeIgnore;
     if constexpr (CE) {
@@ -394,7 +396,8 @@ row_emit_fused_kernel(const FusedParams cp) {
         [[maybe_unused]] float kl_T2 = 0.f, kl_T3 = 0.f, kl_U0 = 0.f, kl_U2 = 0.f, kl_U3 = 0.f, kl_n = 0.f;      // log_target power sums
         [[maybe_unused]] float S1_w = 0.f;       // fused CE: sum 2^((xs - m_w) log2 e) of the slice
         // the CE needs its own exponentials only when the KD temperature is not 1 (and the row's label is not ignored)
-        [[maybe_unused]] const bool ce_extra = CE && ce_on && !ce_same_t;
+        [[maybe_unused]] const bool ce_extra = CE && ce_on && !ce_same_t && !ce_square;      // own exponentials from the raw student slice
+        [[maybe_unused]] const bool ce_sq = CE && ce_on && ce_square;
         uint32_t top_k1 = 0u, top_k2 = 0u;       // per-row LoCa: keys of the slice's best / runner-up teacher cell (0 = none)
         {
             constexpr bool ECACHE = KD_ECACHE;        // every variant of this kernel parks its student exponentials
@@ -412,7 +415,7 @@ row_emit_fused_kernel(const FusedParams cp) {
             uint32_t cand = 0u;            // per-row LoCa: bit j = this lane's vector of iteration j may hold the best / runner-up cell
             auto ab_body = [&](int j, bool act, auto tail_tag, auto poly_tag, auto ce_tag) {
                 constexpr bool POLY = decltype(poly_tag)::value;
-                constexpr bool CE_X = decltype(ce_tag)::value;
+                constexpr int CE_X = decltype(ce_tag)::value;        // 0: nothing extra, 1: own ex2 per cell, 2: square of the KD exponential
                 uint32_t qb[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                 uint32_t eb[4] = {0u, 0u, 0u, 0u};
                 if (act) {
@@ -441,7 +444,8 @@ row_emit_fused_kernel(const FusedParams cp) {
                         }
                         if (i & 1) accS1 = add2(accS1, e2);
                         else accS0 = add2(accS0, e2);
-                        if constexpr (CE_X) accCE = add2(accCE, ex2_mufu2(fma2(Pair<T>::widen(ws[i]), k1p, nm1)));
+                        if constexpr (CE_X == 1) accCE = add2(accCE, ex2_mufu2(fma2(Pair<T>::widen(ws[i]), k1p, nm1)));
+                        if constexpr (CE_X == 2) accCE = fma2(e2, e2, accCE);          // (e * 2^15)^2: scaled back below
                         const u64 b2 = fma2(Pair<T>::widen(wt[i]), k2p, nlt);        // log2 tp (table mode) / relative to mt_w otherwise
                         float e_lo, e_hi;
                         if constexpr (TAB) upk(fma2(ovp[i], pushp, b2), e_lo, e_hi);
@@ -488,13 +492,14 @@ row_emit_fused_kernel(const FusedParams cp) {
             };
             if (poly_ab) {
 #pragma unroll 2
-                for (int j = 0; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::true_type{}, std::false_type{});
-                if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::true_type{}, std::false_type{});
+                for (int j = 0; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::true_type{}, std::integral_constant<int, 0>{});
+                if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::true_type{}, std::integral_constant<int, 0>{});
             } else if constexpr (CE) {
-                if (ce_extra) run_ab(std::true_type{});
-                else run_ab(std::false_type{});
+                if (ce_extra) run_ab(std::integral_constant<int, 1>{});
+                else if (ce_sq) run_ab(std::integral_constant<int, 2>{});
+                else run_ab(std::integral_constant<int, 0>{});
             } else {
-                run_ab(std::false_type{});
+                run_ab(std::integral_constant<int, 0>{});
             }
             tmem_wait_st();
             if constexpr (!PER_ROW) {
@@ -507,9 +512,9 @@ row_emit_fused_kernel(const FusedParams cp) {
             S_w = warp_sum(x0 + x1) * (ECACHE ? 1.f / 32768.f : 1.f);
             if constexpr (CE) {
                 S1_w = S_w;                         // T == 1: the KD exponentials are the CE's
-                if (ce_extra) {
+                if (ce_extra || ce_sq) {
                     upk(accCE, x0, x1);
-                    S1_w = warp_sum(x0 + x1);
+                    S1_w = warp_sum(x0 + x1) * (ce_sq ? (ECACHE ? 1.f / 1073741824.f : 1.f) : 1.f);
                 }
             }
             float q_l, r_l, p_l;                       // this lane's shares of Q_w, R_w, P_w
@@ -1113,7 +1118,7 @@ row_emit_fused_kernel(const FusedParams cp) {
             // ce_tag: the fused cross-entropy at a KD temperature != 1 adds g_ce * 2^(xs log2 e - lse1) per cell, from the raw
             // student slice (which then stays in shared memory until this sweep is over)
             auto sweepC_cached_impl = [&](float ce, auto ce_tag, float gce_row) {
-                constexpr bool CE_X = decltype(ce_tag)::value;
+                constexpr int CE_X = decltype(ce_tag)::value;          // 0: no CE term here, 1: from the raw student slice, 2: e^2 from the cache
                 const u64 cep = pk(ce, ce);
                 [[maybe_unused]] const u64 k1c = pk(k1, k1), nl1 = pk(-lse1_row, -lse1_row), gcp = pk(gce_row, gce_row);
                 auto c_step = [&](int j, auto nv_tag, bool act, auto tail_tag) {
@@ -1124,7 +1129,7 @@ row_emit_fused_kernel(const FusedParams cp) {
                     for (int u = 0; u < NV; ++u) {
                         tmem_ld8(tq + 8 * (j + u), qb[u]);
                         tmem_ld4(tq + kTmE + 4 * (j + u), eb[u]);
-                        if constexpr (CE_X) {
+                        if constexpr (CE_X == 1) {
                             rsv[u] = make_uint4(0, 0, 0, 0);
                             if (act) rsv[u] = load_s(lane + 32 * (j + u));
                         }
@@ -1134,7 +1139,7 @@ row_emit_fused_kernel(const FusedParams cp) {
 #pragma unroll
                         for (int u = 0; u < NV; ++u) {
                             uint32_t out[4];
-                            [[maybe_unused]] const uint32_t wsv[4] = {CE_X ? rsv[u].x : 0u, CE_X ? rsv[u].y : 0u, CE_X ? rsv[u].z : 0u, CE_X ? rsv[u].w : 0u};
+                            [[maybe_unused]] const uint32_t wsv[4] = {CE_X == 1 ? rsv[u].x : 0u, CE_X == 1 ? rsv[u].y : 0u, CE_X == 1 ? rsv[u].z : 0u, CE_X == 1 ? rsv[u].w : 0u};
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const float2 ef = __half22float2(*reinterpret_cast<const __half2*>(&eb[u][i]));
@@ -1142,7 +1147,8 @@ row_emit_fused_kernel(const FusedParams cp) {
                                 if constexpr (KLLT) q2 = ex2_mufu2(mul2(q2, pk(sl2e, sl2e)));
                                 float n_lo, n_hi;
                                 u64 o2 = fma2(pk(ef.x, ef.y), cep, mul2(q2, negg));
-                                if constexpr (CE_X) o2 = fma2(ex2_mufu2(fma2(Pair<T>::widen(wsv[i]), k1c, nl1)), gcp, o2);
+                                if constexpr (CE_X == 1) o2 = fma2(ex2_mufu2(fma2(Pair<T>::widen(wsv[i]), k1c, nl1)), gcp, o2);
+                                if constexpr (CE_X == 2) o2 = fma2(mul2(pk(ef.x, ef.y), pk(ef.x, ef.y)), gcp, o2);      // gcp carries 2^(2 m_w k2 - 30 - lse1)
                                 upk(o2, n_lo, n_hi);
                                 out[i] = Pair<T>::narrow(n_lo, n_hi);
                             }
@@ -1161,7 +1167,7 @@ row_emit_fused_kernel(const FusedParams cp) {
                 if (n_tail) c_step(n_full, V1{}, lane < n_tail, std::true_type{});
             };
             // g*Q*sp = gQ * e' * 2^(m_w*k2 - 15 - lse2_s): valid for any sign of g and g*Q
-            auto sweepC_cached = [&]() { sweepC_cached_impl(gQ * ex2((mk - kEScaleLog2) - lse2_s), std::false_type{}, 0.f); };
+            auto sweepC_cached = [&]() { sweepC_cached_impl(gQ * ex2((mk - kEScaleLog2) - lse2_s), std::integral_constant<int, 0>{}, 0.f); };
             using Yes = std::true_type;
             using No = std::false_type;
             // FMA-pipe exponentials in the common (folded, unmasked) sweep when log2(g*Q*sp) >= -126 for the whole slice
@@ -1177,9 +1183,12 @@ row_emit_fused_kernel(const FusedParams cp) {
                     const float gce_row = ce_bad ? NaN : g_ce;
                     if (!ce_on) sweepC_cached();
                     else if (ce_same_t)        // T == 1: softmax(xs) IS sp, the CE rides the same cached exponentials
-                        sweepC_cached_impl((gQ + gce_row) * ex2((mk - kEScaleLog2) - lse2_s), std::false_type{}, 0.f);
+                        sweepC_cached_impl((gQ + gce_row) * ex2((mk - kEScaleLog2) - lse2_s), std::integral_constant<int, 0>{}, 0.f);
+                    else if (ce_sq)            // T == 2: softmax(xs) = (cached e)^2 * 2^(2 (m_w k2 - 15) - lse1)
+                        sweepC_cached_impl(gQ * ex2((mk - kEScaleLog2) - lse2_s), std::integral_constant<int, 2>{},
+                                           gce_row * ex2(2.f * (mk - kEScaleLog2) - lse1_row));
                     else
-                        sweepC_cached_impl(gQ * ex2((mk - kEScaleLog2) - lse2_s), std::true_type{}, gce_row);
+                        sweepC_cached_impl(gQ * ex2((mk - kEScaleLog2) - lse2_s), std::integral_constant<int, 1>{}, gce_row);
                     if (ce_c >= 0) {           // the one-hot term: the lane that stored the vector rewrites that one element
                         const int v = (ce_c >> 3) - g_v0;                   // warp-uniform
                         if (v >= 0 && v < w_n && lane == (v & 31)) {
