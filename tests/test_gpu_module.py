@@ -43,9 +43,10 @@ def test_padded_labels_equal_the_unpadded_rows_alone():
     assert torch.isnan(m2(b)).item()                    # what the reference does here is raise (P1:166): we poison, never accept
 
 
-def test_training_loop_reduces_the_loss():
+@pytest.mark.parametrize("extra", [[], ["--fuse_ce"]], ids=["unfused", "fuse_ce"])
+def test_training_loop_reduces_the_loss(extra):
     hist = train_online_kd.main(["--synthetic", "--phase", "2", "--batch_size", "2", "--max_epochs", "6", "--accumulate_grad_batches", "2",
-                                 "--learning_rate", "3e-3", "--steps_per_epoch", "4"])
+                                 "--learning_rate", "3e-3", "--steps_per_epoch", "4"] + extra)
     assert hist[-1] < hist[0]
 
 

@@ -48,6 +48,8 @@ def main(argv=None):
     ap.add_argument("--phase", type=int, default=2, choices=[1, 2, 3])
     ap.add_argument("--loca_mode", default="reference", choices=["reference", "per_row"])
     ap.add_argument("--learning_rate", type=float, default=1e-5)
+    ap.add_argument("--fuse_ce", action="store_true",
+                    help="phases 2 / 3: call the student without labels and take its cross-entropy from the logit-KD kernel's own pass")
     ap.add_argument("--student", default=None)
     ap.add_argument("--teacher", default=None)
     ap.add_argument("--datamodule", default=None, help="pkg.module:factory returning an object with train_dataloader()")
@@ -75,7 +77,7 @@ def main(argv=None):
         loaders = dm.train_dataloader
 
     model = OnlineKnowledgeDistillationModule(student, teacher, processor, phase=args.phase, learning_rate=args.learning_rate,
-                                              loca_mode=args.loca_mode)
+                                              loca_mode=args.loca_mode, fuse_ce=args.fuse_ce)
     model.freeze_student_vision_layers()                                        # TR2:105
 
     if HAVE_LIGHTNING and not args.synthetic:
