@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KD_B200_ABI_VERSION 3
+#define KD_B200_ABI_VERSION 4
 
 /* element types of logits / features (gradients are written in the same type as the student tensor) */
 enum { KD_DTYPE_BF16 = 0, KD_DTYPE_F16 = 1, KD_DTYPE_F32 = 2 };
@@ -256,6 +256,26 @@ int kd_info_nce_fwd_bwd(const void* student, const void* teacher, void* grad_stu
  * NULL = never skip: a repeated backward that writes a fresh buffer). */
 int kd_info_nce_regrad(const void* workspace, size_t workspace_bytes, void* grad_student, int64_t M, int64_t tokens,
                        int64_t D, int dtype, const float* ratio, const float* skip_if_one, void* stream);
+
+/* Pooled contrastive loss through a LEARNED PROJECTION of the student features (BASELINE configs[2]: SigLIP 1152 -> 896 / 3584).
+ * Not in the reference, whose two towers are both 1152 wide: the oracle is contrastive_loss(x_s @ proj, x_t) (P1:393-416) after the
+ * pooling of P1:243-248.  Mean-pooling is linear, so the projection is applied to the pooled vectors:
+ *   ps = mean_p student[m, p, :]  (fp32)      y = ps . proj  [M, D_t]      loss = contrastive_loss(y, mean_p teacher)
+ *   grad_proj[D_s, D_t] = upstream * ps^T . dy   (in proj's dtype)     grad_student[m, p, :] = upstream * (dy . proj^T)[m, :] / tokens_s
+ * One call = balanced pooling of both tensors (one launch), three fp32 CUDA-core products (M <= 4096 rows: too few for a
+ * tensor-core tile; larger M returns KD_ERR_UNSUPPORTED — project with kd_gemm and call kd_info_nce_fwd_bwd), the row kernel
+ * and the store-only broadcast.  student [M, tokens_s, D_s] and teacher [M, tokens_t, D_t] share `dtype` (tokens == 1: already
+ * pooled); proj [D_s, D_t] row-major in `dtype_proj`.  grad_student / grad_proj may be NULL (not wanted). */
+int kd_info_nce_proj_workspace_bytes(int64_t M, int64_t D_s, int64_t D_t, size_t* bytes);
+int kd_info_nce_proj_fwd_bwd(const void* student, int64_t tokens_s, const void* teacher, int64_t tokens_t, const void* proj,
+                             void* grad_student, void* grad_proj, float* loss_out, void* workspace, size_t workspace_bytes,
+                             int64_t M, int64_t D_s, int64_t D_t, int dtype, int dtype_proj, float temperature, const float* upstream,
+                             unsigned flags, void* stream);
+/* backward re-emission from the fp32 operands kept in `workspace`: both gradients times (*ratio), rounded once; skipped when
+ * *skip_if_one == 1 (NULL = never skip: a repeated backward that writes fresh buffers). */
+int kd_info_nce_proj_regrad(const void* workspace, size_t workspace_bytes, void* grad_student, void* grad_proj,
+                            int64_t M, int64_t tokens_s, int64_t D_s, int64_t D_t, int dtype, int dtype_proj, const float* ratio,
+                            const float* skip_if_one, void* stream);
 
 /* The pooling pass on its own — `.mean(dim=1)` over the tokens of the hooked [M, tokens, D] features (P1:243-246) in fp32 — for
  * callers that put a learned projection between pooling and the loss (BASELINE configs[2]: 1152 -> 896 / 3584), and its

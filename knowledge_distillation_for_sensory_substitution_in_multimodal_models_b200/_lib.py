@@ -15,7 +15,7 @@ _lock = threading.Lock()
 _lib: C.CDLL | None = None
 
 # mirrors of the header enums
-ABI_VERSION = 3
+ABI_VERSION = 4
 DTYPE_BF16, DTYPE_F16, DTYPE_F32 = 0, 1, 2
 LOCA_REFERENCE, LOCA_PER_ROW, KL_PLAIN, KL_LOG_TARGET = 0, 1, 2, 3
 FLAG_NO_GRAD, FLAG_FORCE_STREAMING = 1, 2
@@ -56,6 +56,9 @@ SIGNATURES = {
     "kd_info_nce_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "kd_info_nce_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i64, _i64, _i64, _i, _f, _p, _u, _p]),
     "kd_info_nce_regrad": (_i, [_p, _sz, _p, _i64, _i64, _i64, _i, _p, _p, _p]),
+    "kd_info_nce_proj_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),
+    "kd_info_nce_proj_fwd_bwd": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _sz, _i64, _i64, _i64, _i, _i, _f, _p, _u, _p]),
+    "kd_info_nce_proj_regrad": (_i, [_p, _sz, _p, _p, _i64, _i64, _i64, _i64, _i, _i, _p, _p, _p]),
     "kd_feature_pool_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "kd_feature_pool_fwd": (_i, [_p, _p, _p, _sz, _i64, _i64, _i64, _i, _p]),
     "kd_feature_pool_bwd": (_i, [_p, _p, _i64, _i64, _i64, _i, _p, _p]),

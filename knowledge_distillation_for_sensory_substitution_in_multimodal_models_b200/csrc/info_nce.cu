@@ -108,7 +108,9 @@ pool_finish_kernel(const float* __restrict__ partials, float* __restrict__ us, f
 __global__ void __launch_bounds__(kRowThreads)
 similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut, const float* __restrict__ norm_s,
                       float* __restrict__ dmean, float* __restrict__ rowloss, int M, int D, float inv_temp,
-                      float inv_tokens /* 1/P */, const float* upstream, bool want_grad) {
+                      float inv_tokens /* 1/P */, const float* upstream, bool want_grad,
+                      int raw_parts = 0 /* > 0: `us` holds that many [M, D] partials of the UN-normalised student rows */,
+                      float* __restrict__ dmeanT = nullptr /* optional [D, M] copy of the gradient rows */) {
     extern __shared__ float sm[];   // [D] u_s row | [M] logits / G row
     float* su = sm;
     float* sl = sm + D;
@@ -116,7 +118,27 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
     __shared__ float bc[2];
     const int i = blockIdx.x;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    for (int d = threadIdx.x; d < D; d += kRowThreads) su[d] = us[(int64_t)i * D + d];
+    float nrm_raw = 0.f;
+    if (raw_parts > 0) {
+        // projected student row: add the split-reduction partials in order, then F.normalize it here
+        float ss = 0.f;
+        for (int d = threadIdx.x; d < D; d += kRowThreads) {
+            float a = 0.f;
+            for (int z = 0; z < raw_parts; ++z) a += us[((int64_t)z * M + i) * D + d];
+            su[d] = a;
+            ss = fmaf(a, a, ss);
+        }
+        ss = warp_sum(ss);
+        if (l == 0) red[w] = ss;
+        __syncthreads();
+        float tot = 0.f;
+        for (int k = 0; k < kRowThreads / 32; ++k) tot += red[k];
+        nrm_raw = sqrtf(tot);
+        const float inv = 1.f / fmaxf(nrm_raw, kNormEps);
+        for (int d = threadIdx.x; d < D; d += kRowThreads) su[d] *= inv;
+    } else {
+        for (int d = threadIdx.x; d < D; d += kRowThreads) su[d] = us[(int64_t)i * D + d];
+    }
     __syncthreads();
     const bool vec4 = (D % 4 == 0);
     for (int j = w; j < M; j += kRowThreads / 32) {
@@ -169,7 +191,7 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
         sl[j] = (j == i) ? -r * gsc : __expf(sl[j] - mx) * gsc;
     __syncthreads();
     // du[d] = sum_j G[j] * ut[j,d]  (coalesced over d; ut is L2 resident)
-    const float nrm = norm_s[i];
+    const float nrm = raw_parts > 0 ? nrm_raw : norm_s[i];
     float dots = 0.f;
     for (int d = threadIdx.x; d < D; d += kRowThreads) {
         float acc = 0.f;
@@ -191,7 +213,9 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
     const float sc = inv_tokens * (upstream ? *upstream : 1.f) / fmaxf(nrm, kNormEps);
     for (int d = threadIdx.x; d < D; d += kRowThreads) {
         const float du = dmean[(int64_t)i * D + d];
-        dmean[(int64_t)i * D + d] = (du - dot * su[d]) * sc;
+        const float v = (du - dot * su[d]) * sc;
+        dmean[(int64_t)i * D + d] = v;
+        if (dmeanT) dmeanT[(int64_t)d * M + i] = v;
     }
 }
 
@@ -216,10 +240,11 @@ __global__ void __launch_bounds__(1024) nce_finalize_kernel(const float* __restr
 template <typename T>
 __global__ void __launch_bounds__(256)
 broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P, int D, bool vec, const float* ratio,
-                      const float* skip_if_one) {
+                      const float* skip_if_one, int nsrc = 1 /* the source is the sum of this many partials ... */,
+                      int64_t src_stride = 0 /* ... this many floats apart */, float host_scale = 1.f) {
     constexpr int E = Elem<T>::kPack;
     if (skip_if_one && *skip_if_one == 1.f) return;      // backward re-emission: grad_output is what forward assumed
-    const float f = ratio ? *ratio : 1.f;
+    const float f = (ratio ? *ratio : 1.f) * host_scale;
     const int m = blockIdx.x;                              // rows on x (no 65 535 limit), token chunks on y
     const float* src = dmean + (int64_t)m * D;
     T* dst = dx + (int64_t)m * P * D;
@@ -232,7 +257,11 @@ broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P
         for (int c = c0; c < ncol; c += lanes) {
             float v[E];
 #pragma unroll
-            for (int i = 0; i < E; ++i) v[i] = src[c * E + i] * f;
+            for (int i = 0; i < E; ++i) {
+                float a = src[c * E + i];
+                for (int z = 1; z < nsrc; ++z) a += src[z * src_stride + c * E + i];
+                v[i] = a * f;
+            }
             const uint4 packed = Elem<T>::pack(v);
             uint4* col = reinterpret_cast<uint4*>(dst) + c;
 #pragma unroll 4
@@ -240,8 +269,11 @@ broadcast_rows_kernel(const float* __restrict__ dmean, T* __restrict__ dx, int P
         }
     } else {
         const int64_t total = (int64_t)P * D;
-        for (int64_t idx = blockIdx.y * 256ll + threadIdx.x; idx < total; idx += (int64_t)gridDim.y * 256)
-            dst[idx] = Elem<T>::from_float(src[idx % D] * f);
+        for (int64_t idx = blockIdx.y * 256ll + threadIdx.x; idx < total; idx += (int64_t)gridDim.y * 256) {
+            float a = src[idx % D];
+            for (int z = 1; z < nsrc; ++z) a += src[z * src_stride + idx % D];
+            dst[idx] = Elem<T>::from_float(a * f);
+        }
     }
 }
 
@@ -342,6 +374,303 @@ nce_tc_finish_kernel(const float* __restrict__ dU, const float* __restrict__ us,
     for (int d = threadIdx.x; d < D; d += 256) dmean[(int64_t)i * D + d] = (du[d] * du_scale - dot * u[d]) * sc;
 }
 
+// ---- balanced pooling (the CUDA-core forms: pooled M = 64 and friends) ----------------------------------------------
+// A tensor's token rows ([M, P, D] contiguous = M * P rows of D elements) are cut into G contiguous, equally long ranges,
+// one per CTA: every SM streams the same number of bytes whatever M is (the (image, split) grid above leaves 80 of its 592
+// CTA slots empty at M = 64), and two tensors of different width share one launch with CTA counts in proportion to their
+// bytes.  G >= M, so a range touches at most two images: the CTA writes one fp32 partial per image piece and
+// pool_ranges_finish_kernel adds an image's pieces in CTA order (deterministic).  The loads go out in explicit batches of
+// kPoolBatch 16-byte vectors per thread before any is consumed: an unrolled loop with an exit test per iteration compiles to
+// one load in flight per thread (SASS of pool_partial_kernel), 27 KB per SM — half of what the HBM latency asks for.
+constexpr int kPoolBatch = 8;
+struct PoolTensor { const void* x; int M, P, D, G, cta0; };
+struct PoolPlan { PoolTensor t[2]; int n, dmax; };
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kPoolThreads, 2)
+pool_ranges_kernel(const PoolPlan plan, float* __restrict__ partials) {
+    extern __shared__ float sm[];        // [groups][D] partial sums
+    constexpr int E = VEC ? Elem<T>::kPack : 1;
+    const PoolTensor t = (plan.n > 1 && (int)blockIdx.x >= plan.t[1].cta0) ? plan.t[1] : plan.t[0];      // (a select, not an indexed copy)
+    const int b = (int)blockIdx.x - t.cta0;
+    const int D = t.D, P = t.P;
+    const int64_t R = (int64_t)t.M * P;
+    const int64_t r0 = R * b / t.G, r1 = R * (b + 1) / t.G;
+    const int64_t m0 = r0 / P;
+    const int ncol = D / E;
+    const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
+    const int groups = kPoolThreads / lanes;                // row groups working on disjoint token subsets
+    const int c0 = threadIdx.x % lanes, grp = threadIdx.x / lanes;
+    const T* x = static_cast<const T*>(t.x);
+    for (int s = 0; s < 2; ++s) {
+        const int64_t lo = (m0 + s) * P, hi = lo + P;
+        const int64_t a = r0 > lo ? r0 : lo, e = r1 < hi ? r1 : hi;
+        if (a >= e) break;                                  // (uniform) the range ends inside its first image
+        if (grp < groups) {
+            for (int c = c0; c < ncol; c += lanes) {
+                float acc[E];
+#pragma unroll
+                for (int i = 0; i < E; ++i) acc[i] = 0.f;
+                for (int64_t r = a + grp; r < e; r += (int64_t)groups * kPoolBatch) {
+                    if constexpr (VEC) {
+                        uint4 v[kPoolBatch];
+#pragma unroll
+                        for (int u = 0; u < kPoolBatch; ++u) {
+                            const int64_t rr = r + (int64_t)u * groups;
+                            v[u] = make_uint4(0u, 0u, 0u, 0u);              // all-zero bits are 0.0 in the three element types
+                            if (rr < e) v[u] = ldg_stream(reinterpret_cast<const uint4*>(x + rr * D) + c);
+                        }
+#pragma unroll
+                        for (int u = 0; u < kPoolBatch; ++u) {
+                            float f[Elem<T>::kPack];
+                            Elem<T>::unpack(v[u], f);
+#pragma unroll
+                            for (int i = 0; i < E; ++i) acc[i] += f[i];
+                        }
+                    } else {
+                        float v[kPoolBatch];
+#pragma unroll
+                        for (int u = 0; u < kPoolBatch; ++u) {
+                            const int64_t rr = r + (int64_t)u * groups;
+                            v[u] = (rr < e) ? Elem<T>::to_float(x[rr * D + c]) : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < kPoolBatch; ++u) acc[0] += v[u];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < E; ++i) sm[grp * D + c * E + i] = acc[i];
+            }
+        }
+        __syncthreads();
+        float* out = partials + ((int64_t)blockIdx.x * 2 + s) * plan.dmax;
+        for (int d = threadIdx.x; d < D; d += kPoolThreads) {
+            float v = 0.f;
+            for (int gI = 0; gI < groups; ++gI) v += sm[gI * D + d];
+            out[d] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// One CTA per (tensor, image): add the image's pieces in CTA order, take the mean and (bit k of normalize_mask) L2-normalise
+// tensor k's rows (F.normalize eps); the student's norm goes to norm0 when that is given.
+__global__ void __launch_bounds__(256)
+pool_ranges_finish_kernel(const PoolPlan plan, const float* __restrict__ partials, float* __restrict__ out0, float* __restrict__ out1,
+                          float* __restrict__ norm0, unsigned normalize_mask) {
+    extern __shared__ float sm[];        // [D] pooled vector
+    __shared__ float red[8];
+    const int k = (plan.n > 1 && (int)blockIdx.x >= plan.t[0].M) ? 1 : 0;
+    const PoolTensor t = k ? plan.t[1] : plan.t[0];
+    const int m = (int)blockIdx.x - (k ? plan.t[0].M : 0);
+    const int D = t.D, P = t.P, G = t.G;
+    const int64_t R = (int64_t)t.M * P;
+    const int64_t lo = (int64_t)m * P, hi = lo + P;
+    int b = (int)(lo * G / R);
+    b = b > 0 ? b - 1 : 0;
+    while (R * (b + 1) / G <= lo) ++b;                       // first CTA whose range reaches into the image
+    for (int d = threadIdx.x; d < D; d += 256) sm[d] = 0.f;
+    for (; b < G && R * b / G < hi; ++b) {
+        const int seg = ((R * b / G) / P == m) ? 0 : 1;      // the image is the first / second one of that CTA's range
+        const float* src = partials + ((int64_t)(t.cta0 + b) * 2 + seg) * plan.dmax;
+        for (int d = threadIdx.x; d < D; d += 256) sm[d] += src[d];      // a thread owns its d's: no barrier needed
+    }
+    const float invP = 1.f / (float)P;
+    float ss = 0.f;
+    for (int d = threadIdx.x; d < D; d += 256) {
+        const float a = sm[d] * invP;
+        ss = fmaf(a, a, ss);
+        sm[d] = a;
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float nrm = sqrtf(tot);
+    const float inv = ((normalize_mask >> k) & 1u) ? 1.f / fmaxf(nrm, kNormEps) : 1.f;
+    float* u = (k ? out1 : out0) + (int64_t)m * D;
+    for (int d = threadIdx.x; d < D; d += 256) u[d] = sm[d] * inv;
+    if (k == 0 && threadIdx.x == 0 && norm0) norm0[m] = nrm;
+}
+
+// CTA counts of the balanced pooling: two CTAs per SM shared out by bytes, at least M (a range then spans at most two images) and at
+// most 4 M / one row per CTA (the partials fit the block the (image, split) form already reserves: 8 * 2 M rows of D floats)
+int sm_count_cached() {
+    static int dev_cached = -1, sms = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != dev_cached) {
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        dev_cached = dev;
+    }
+    return sms > 0 ? sms : 148;
+}
+void pool_plan_fill(PoolPlan& pl, int elem_bytes) {
+    const int budget = 2 * sm_count_cached();
+    double total = 0.0;
+    for (int k = 0; k < pl.n; ++k) total += (double)pl.t[k].M * pl.t[k].P * pl.t[k].D * elem_bytes;
+    int cta0 = 0;
+    pl.dmax = 0;
+    for (int k = 0; k < pl.n; ++k) {
+        PoolTensor& t = pl.t[k];
+        const int64_t R = (int64_t)t.M * t.P;
+        int64_t G = (int64_t)(budget * ((double)t.M * t.P * t.D * elem_bytes / total) + 0.5);
+        if (G < t.M) G = t.M;
+        const int64_t cap = R < 4ll * t.M ? R : 4ll * t.M;
+        if (G > cap) G = cap;
+        t.G = (int)G;
+        t.cta0 = cta0;
+        cta0 += t.G;
+        if (t.D > pl.dmax) pl.dmax = t.D;
+    }
+}
+// upper bound for workspace queries (before the pointers are known)
+size_t pool_ranges_partial_bound(int64_t M0, int64_t D0, int64_t M1, int64_t D1) {
+    return (size_t)(4 * (M0 + M1)) * 2 * (size_t)(D0 > D1 ? D0 : D1);
+}
+
+template <typename T>
+int launch_pool_ranges(PoolPlan& pl, float* partials, float* out0, float* out1, float* norm0, unsigned normalize_mask, cudaStream_t st) {
+    constexpr int E = Elem<T>::kPack;
+    bool vec = true;
+    for (int k = 0; k < pl.n; ++k) vec = vec && (pl.t[k].D % E == 0) && (reinterpret_cast<uintptr_t>(pl.t[k].x) & 15u) == 0;
+    pool_plan_fill(pl, (int)sizeof(T));
+    size_t smem = 0;
+    int ctas = 0, images = 0;
+    for (int k = 0; k < pl.n; ++k) {
+        const int ncol = vec ? pl.t[k].D / E : pl.t[k].D;
+        const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
+        const size_t s = sizeof(float) * (size_t)(kPoolThreads / lanes) * pl.t[k].D;
+        smem = s > smem ? s : smem;
+        ctas += pl.t[k].G;
+        images += pl.t[k].M;
+    }
+    KD_CHECK_ARG(smem <= 200 * 1024 && sizeof(float) * (size_t)pl.dmax <= 200 * 1024, "pooling: feature dimension %d too large", pl.dmax);
+    if (vec) {
+        auto kfn = pool_ranges_kernel<T, true>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kfn<<<ctas, kPoolThreads, smem, st>>>(pl, partials);
+    } else {
+        auto kfn = pool_ranges_kernel<T, false>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kfn<<<ctas, kPoolThreads, smem, st>>>(pl, partials);
+    }
+    KD_CHECK_LAUNCH("pool_ranges_kernel");
+    const size_t fsmem = sizeof(float) * (size_t)pl.dmax;
+    if (fsmem > 48 * 1024) cudaFuncSetAttribute(pool_ranges_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    pool_ranges_finish_kernel<<<images, 256, fsmem, st>>>(pl, partials, out0, out1, norm0, normalize_mask);
+    KD_CHECK_LAUNCH("pool_ranges_finish_kernel");
+    return KD_OK;
+}
+
+// ---- few-row fp32 products around the pooled contrastive loss (learned projection, BASELINE configs[2]) ---------------
+// C[i, j] = sum_r A(i, r) * B(j, r) on the CUDA cores, fp32 accumulation: with M = 64 rows these products (66 MFMA each) are
+// too small for a 256-row tensor-core tile, and fp32 FMAs keep the pooled features' digits without hi + lo operand splitting.
+// *_RM ("reduction-major") says the operand is stored [r][i]: its 64-wide tile row is read with 128-bit shared-memory loads
+// by the fast thread index; an operand stored [i][r] is read as warp-wide broadcasts by the slow index — so no operand is ever
+// transposed in memory as long as one of the two is reduction-major.  64 x 64 tile, 4 x 4 outputs per thread, blockIdx.z
+// splits the reduction (partials [z][I][J] for the consumer to add in order: deterministic).
+constexpr int kSgTile = 64, kSgRc = 32;
+template <typename TA, typename TB, bool A_RM, bool B_RM, typename TC>
+__global__ void __launch_bounds__(256)
+small_gemm_kernel(const TA* __restrict__ A, int64_t lda, const TB* __restrict__ B, int64_t ldb, TC* __restrict__ C, int64_t ldc,
+                  int64_t split_stride, int I, int J, int Rr, int rsplit, const float* out_scale = nullptr,
+                  const float* skip_if_one = nullptr) {
+    static_assert(A_RM || B_RM, "one operand must be reduction-major");
+    if (skip_if_one && *skip_if_one == 1.f) return;      // backward re-emission: grad_output is what forward assumed
+    const float oscale = out_scale ? *out_scale : 1.f;
+    __shared__ __align__(16) float As[A_RM ? kSgRc * kSgTile : kSgTile * (kSgRc + 1)];
+    __shared__ __align__(16) float Bs[B_RM ? kSgRc * kSgTile : kSgTile * (kSgRc + 1)];
+    const int tid = threadIdx.x;
+    const int ti = A_RM ? tid % 16 : tid / 16;       // the broadcast operand takes the slow index
+    const int tj = A_RM ? tid / 16 : tid % 16;
+    const int i0 = blockIdx.x * kSgTile, j0 = blockIdx.y * kSgTile;
+    const int rbeg = blockIdx.z * rsplit, rend = min(Rr, rbeg + rsplit);
+    float acc[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[q][p] = 0.f;
+    for (int rc = rbeg; rc < rend; rc += kSgRc) {
+#pragma unroll
+        for (int q = 0; q < (kSgRc * kSgTile) / 256; ++q) {
+            const int idx = tid + 256 * q;
+            if constexpr (A_RM) {
+                const int r = idx / kSgTile, i = idx % kSgTile;
+                As[r * kSgTile + i] = (rc + r < rend && i0 + i < I) ? Elem<TA>::to_float(A[(int64_t)(rc + r) * lda + i0 + i]) : 0.f;
+            } else {
+                const int i = idx / kSgRc, r = idx % kSgRc;
+                As[i * (kSgRc + 1) + r] = (rc + r < rend && i0 + i < I) ? Elem<TA>::to_float(A[(int64_t)(i0 + i) * lda + rc + r]) : 0.f;
+            }
+            if constexpr (B_RM) {
+                const int r = idx / kSgTile, j = idx % kSgTile;
+                Bs[r * kSgTile + j] = (rc + r < rend && j0 + j < J) ? Elem<TB>::to_float(B[(int64_t)(rc + r) * ldb + j0 + j]) : 0.f;
+            } else {
+                const int j = idx / kSgRc, r = idx % kSgRc;
+                Bs[j * (kSgRc + 1) + r] = (rc + r < rend && j0 + j < J) ? Elem<TB>::to_float(B[(int64_t)(j0 + j) * ldb + rc + r]) : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < kSgRc; ++r) {
+            float a[4], bb[4];
+            if constexpr (A_RM) {
+                const float4 v = *reinterpret_cast<const float4*>(&As[r * kSgTile + ti * 4]);
+                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] = As[(ti * 4 + q) * (kSgRc + 1) + r];
+            }
+            if constexpr (B_RM) {
+                const float4 v = *reinterpret_cast<const float4*>(&Bs[r * kSgTile + tj * 4]);
+                bb[0] = v.x; bb[1] = v.y; bb[2] = v.z; bb[3] = v.w;
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) bb[p] = Bs[(tj * 4 + p) * (kSgRc + 1) + r];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int p = 0; p < 4; ++p) acc[q][p] = fmaf(a[q], bb[p], acc[q][p]);
+        }
+        __syncthreads();
+    }
+    TC* out = C + (int64_t)blockIdx.z * split_stride;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = i0 + ti * 4 + q;
+        if (i >= I) continue;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int j = j0 + tj * 4 + p;
+            if (j < J) out[(int64_t)i * ldc + j] = Elem<TC>::from_float(acc[q][p] * oscale);
+        }
+    }
+}
+
+template <typename TA, typename TB, bool A_RM, bool B_RM, typename TC>
+int launch_small_gemm(const TA* A, int64_t lda, const TB* B, int64_t ldb, TC* C, int64_t ldc, int I, int J, int Rr, int nsplit,
+                      cudaStream_t st, const float* out_scale = nullptr, const float* skip_if_one = nullptr) {
+    const int rsplit = ((Rr + nsplit - 1) / nsplit + kSgRc - 1) / kSgRc * kSgRc;
+    const dim3 grid((I + kSgTile - 1) / kSgTile, (J + kSgTile - 1) / kSgTile, (Rr + rsplit - 1) / rsplit);
+    small_gemm_kernel<TA, TB, A_RM, B_RM, TC><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, (int64_t)I * ldc, I, J, Rr, rsplit, out_scale,
+                                                                    skip_if_one);
+    KD_CHECK_LAUNCH("small_gemm_kernel");
+    return KD_OK;
+}
+// how many ways a reduction of length Rr is split so that the grid reaches ~one CTA per SM; the consumers add the partials in order
+int small_gemm_splits(int I, int J, int Rr) {
+    const int tiles = ((I + kSgTile - 1) / kSgTile) * ((J + kSgTile - 1) / kSgTile);
+    int want = (sm_count_cached() + tiles - 1) / tiles;
+    const int most = (Rr + 127) / 128;                     // at least 128 reduction steps per CTA
+    if (want > most) want = most;
+    if (want > 16) want = 16;
+    if (want < 1) want = 1;
+    const int rsplit = ((Rr + want - 1) / want + kSgRc - 1) / kSgRc * kSgRc;
+    return (Rr + rsplit - 1) / rsplit;
+}
+
 constexpr int kMaxPoolSplit = 8;
 struct NceWorkspace { size_t us, ut, norm_s, dmean, rowloss, partials, total; };
 NceWorkspace nce_layout(int64_t M, int64_t D) {
@@ -396,18 +725,20 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
                                                                  reinterpret_cast<__half*>(ws + tc->us16), reinterpret_cast<__half*>(ws + tc->ut16),
                                                                  norm_s, reinterpret_cast<float*>(ws + tc->diag_exact), M, D);
         KD_CHECK_LAUNCH("nce_normalize_pair_kernel");
+    } else if (!tc) {
+        // pooled M (the 64-image case): balanced contiguous ranges, both tensors in one launch
+        PoolPlan pl{};
+        pl.n = 2;
+        pl.t[0] = PoolTensor{xs, M, P, D, 0, 0};
+        pl.t[1] = PoolTensor{xt, M, P, D, 0, 0};
+        if (int rc = launch_pool_ranges<T>(pl, reinterpret_cast<float*>(ws + w.partials), us, ut, norm_s, 3u, st)) return rc;
     } else {
         float* partials = reinterpret_cast<float*>(ws + w.partials);
         const int ncol = vec_in ? D / E : D;
         const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
         const size_t smem = sizeof(float) * (size_t)(kPoolThreads / lanes) * D;
         KD_CHECK_ARG(smem <= 200 * 1024, "info_nce: feature dimension %d too large for the pooling kernel", D);
-        // one wave: at most 4 resident CTAs (512 threads) per SM on 148 SMs — a partial second wave doubled the time —
-        // and never fewer than ~64 tokens per chunk
-        int nsplit = (148 * 4) / (2 * M);
-        if (nsplit > kMaxPoolSplit) nsplit = kMaxPoolSplit;
-        if (nsplit > (P + 63) / 64) nsplit = (P + 63) / 64;
-        if (nsplit < 1 || tc) nsplit = 1;
+        const int nsplit = 1;        // token-level M: one CTA per (tensor, row) already fills the machine
         auto kfn = pool_partial_kernel<T>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kfn<<<(unsigned)(nsplit * 2 * (int64_t)M), kPoolThreads, smem, st>>>(static_cast<const T*>(xs), static_cast<const T*>(xt), partials, M, P, D, nsplit, vec_in);
@@ -416,8 +747,8 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
         if (sizeof(float) * (size_t)D > 48 * 1024)
             cudaFuncSetAttribute(pool_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * D));
         pool_finish_kernel<<<2 * M, 256, sizeof(float) * (size_t)D, st>>>(partials, us, ut, norm_s, M, P, D, nsplit,
-                                                                          tc ? reinterpret_cast<__half*>(ws + tc->us16) : nullptr,
-                                                                          tc ? reinterpret_cast<__half*>(ws + tc->ut16) : nullptr);
+                                                                          reinterpret_cast<__half*>(ws + tc->us16),
+                                                                          reinterpret_cast<__half*>(ws + tc->ut16));
         KD_CHECK_LAUNCH("pool_finish_kernel");
     }
     if (tc) {
@@ -476,6 +807,115 @@ int run_regrad(const float* dmean, void* dx, int M, int P, int D, const float* r
     broadcast_rows_kernel<T><<<dim3(M, bx), 256, 0, st>>>(dmean, static_cast<T*>(dx), P, D, vec_out, ratio, skip);
     KD_CHECK_LAUNCH("broadcast_rows_kernel");
     return KD_OK;
+}
+
+
+// ---- pooled contrastive loss through a learned projection (BASELINE configs[2]: 1152 -> 896 / 3584) ------------------
+//   ps = mean_p x_s [M, Ds] (fp32)    y = ps . W [M, Dt]    u_s = normalize(y)    u_t = normalize(mean_p x_t)
+//   loss = contrastive_loss(y, mean_p x_t)  (P1:393-416 on the projected student vectors — pooling is linear, so projecting the
+//   pooled vectors equals pooling the projected tokens);  dy from the row kernel,  dW = ps^T . dy,  d ps = dy . W^T,
+//   dx_s[m, p, :] = d ps[m, :] / P.  Eight launches, every product in fp32 on the CUDA cores.
+struct NceProjWorkspace { size_t ps, ut, ypart, dy, dyT, rowloss, dpspart, pool, total; };
+constexpr int kProjMaxSplit = 16;
+NceProjWorkspace nce_proj_layout(int64_t M, int64_t Ds, int64_t Dt) {
+    NceProjWorkspace w{};
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
+    w.ps = take(sizeof(float) * M * Ds);
+    w.ut = take(sizeof(float) * M * Dt);
+    w.dy = take(sizeof(float) * M * Dt);
+    w.dyT = take(sizeof(float) * M * Dt);
+    w.rowloss = take(sizeof(float) * M);
+    w.dpspart = take(sizeof(float) * kProjMaxSplit * M * Ds);
+    w.ypart = take(sizeof(float) * kProjMaxSplit * M * Dt);
+    w.pool = take(sizeof(float) * pool_ranges_partial_bound(M, Ds, M, Dt));
+    w.total = off;
+    return w;
+}
+constexpr int64_t kProjMaxRows = 4096;      // beyond this the similarity rows belong on the tensor cores (kd_info_nce_fwd_bwd)
+
+template <typename T, typename TW>
+int run_proj(const void* xs, int Ps, const void* xt, int Pt, const TW* W, void* dx, TW* dW, float* loss, char* ws,
+             const NceProjWorkspace& w, int M, int Ds, int Dt, float temperature, const float* upstream, bool want_dx, bool want_dw,
+             cudaStream_t st) {
+    constexpr int E = Elem<T>::kPack;
+    float* ps = reinterpret_cast<float*>(ws + w.ps);
+    float* ut = reinterpret_cast<float*>(ws + w.ut);
+    float* ypart = reinterpret_cast<float*>(ws + w.ypart);
+    float* dy = reinterpret_cast<float*>(ws + w.dy);
+    float* dyT = reinterpret_cast<float*>(ws + w.dyT);
+    float* rowloss = reinterpret_cast<float*>(ws + w.rowloss);
+    float* dpspart = reinterpret_cast<float*>(ws + w.dpspart);
+    PoolPlan pl{};
+    pl.n = 2;
+    pl.t[0] = PoolTensor{xs, M, Ps, Ds, 0, 0};
+    pl.t[1] = PoolTensor{xt, M, Pt, Dt, 0, 0};
+    // student: the plain mean (the projection comes first); teacher: mean + F.normalize
+    if (int rc = launch_pool_ranges<T>(pl, reinterpret_cast<float*>(ws + w.pool), ps, ut, nullptr, 2u, st)) return rc;
+    const int sy = small_gemm_splits(M, Dt, Ds);
+    if (int rc = launch_small_gemm<float, TW, false, true, float>(ps, Ds, W, Dt, ypart, Dt, M, Dt, Ds, sy, st)) return rc;
+    const bool want_grad = want_dx || want_dw;
+    const size_t smem = sizeof(float) * ((size_t)Dt + M);
+    KD_CHECK_ARG(smem <= 220 * 1024, "info_nce (projected): M + D_t = %d floats exceed the row kernel's shared memory", M + Dt);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(similarity_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    similarity_row_kernel<<<M, kRowThreads, smem, st>>>(ypart, ut, nullptr, dy, rowloss, M, Dt, 1.f / temperature, 1.f, upstream, want_grad,
+                                                        sy, dyT);
+    KD_CHECK_LAUNCH("similarity_row_kernel");
+    nce_finalize_kernel<<<1, M >= 1024 ? 1024 : 32, 0, st>>>(rowloss, M, loss);
+    KD_CHECK_LAUNCH("nce_finalize_kernel");
+    if (want_dw) {       // dW[k, n] = sum_m ps[m, k] dy[m, n]: both operands reduction-major as stored
+        if (int rc = launch_small_gemm<float, float, true, true, TW>(ps, Ds, dy, Dt, dW, Dt, Ds, Dt, M, 1, st)) return rc;
+    }
+    if (want_dx) {       // d ps[m, k] = sum_n dy[m, n] W[k, n]: the transposed copy of dy is the reduction-major operand
+        const int sd = small_gemm_splits(M, Ds, Dt);
+        if (int rc = launch_small_gemm<float, TW, true, false, float>(dyT, M, W, Dt, dpspart, Ds, M, Ds, Dt, sd, st)) return rc;
+        const bool vec_out = (Ds % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
+        int bx = vec_out ? (Ps + 15) / 16 : (int)(((int64_t)Ps * Ds + 255) / 256);
+        bx = bx > 32 ? 32 : (bx < 1 ? 1 : bx);
+        broadcast_rows_kernel<T><<<dim3(M, bx), 256, 0, st>>>(dpspart, static_cast<T*>(dx), Ps, Ds, vec_out, nullptr, nullptr, sd,
+                                                              (int64_t)M * Ds, 1.f / (float)Ps);
+        KD_CHECK_LAUNCH("broadcast_rows_kernel");
+    }
+    return KD_OK;
+}
+
+template <typename T, typename TW>
+int run_proj_regrad(const char* ws, const NceProjWorkspace& w, void* dx, TW* dW, int M, int Ps, int Ds, int Dt,
+                    const float* ratio, const float* skip, cudaStream_t st) {
+    constexpr int E = Elem<T>::kPack;
+    if (dx) {
+        const float* dpspart = reinterpret_cast<const float*>(ws + w.dpspart);
+        const int sd = small_gemm_splits(M, Ds, Dt);
+        const bool vec_out = (Ds % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
+        int bx = vec_out ? (Ps + 15) / 16 : (int)(((int64_t)Ps * Ds + 255) / 256);
+        bx = bx > 32 ? 32 : (bx < 1 ? 1 : bx);
+        broadcast_rows_kernel<T><<<dim3(M, bx), 256, 0, st>>>(dpspart, static_cast<T*>(dx), Ps, Ds, vec_out, ratio, skip, sd,
+                                                              (int64_t)M * Ds, 1.f / (float)Ps);
+        KD_CHECK_LAUNCH("broadcast_rows_kernel");
+    }
+    if (dW) {      // rebuilt from the fp32 operands with the ratio applied before the one rounding to proj's dtype
+        const float* ps = reinterpret_cast<const float*>(ws + w.ps);
+        const float* dy = reinterpret_cast<const float*>(ws + w.dy);
+        if (int rc = launch_small_gemm<float, float, true, true, TW>(ps, Ds, dy, Dt, dW, Dt, Ds, Dt, M, 1, st, ratio, skip)) return rc;
+    }
+    return KD_OK;
+}
+
+// (feature dtype, projection dtype) -> instantiation
+template <typename F>
+int dispatch2(int dtype, int dtype_w, F&& f) {
+    auto inner = [&](auto t) -> int {
+        switch (dtype_w) {
+            case KD_DTYPE_BF16: return f(t, __nv_bfloat16{});
+            case KD_DTYPE_F16: return f(t, __half{});
+            default: return f(t, float{});
+        }
+    };
+    switch (dtype) {
+        case KD_DTYPE_BF16: return inner(__nv_bfloat16{});
+        case KD_DTYPE_F16: return inner(__half{});
+        default: return inner(float{});
+    }
 }
 
 }  // namespace
@@ -562,33 +1002,12 @@ int kd_feature_pool_fwd(const void* x, float* pooled, void* workspace, size_t wo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* partials = static_cast<float*>(workspace);
     const int Mi = (int)M, P = (int)tokens, Di = (int)D;
-    // the pooling kernels handle a (student, teacher) pair of M rows each: a single tensor of M rows is M/2 + M/2 when M is even,
-    // otherwise both halves point at the same tensor and the "teacher" half is simply computed twice into the same place
     auto go = [&](auto tag) -> int {
         using T = decltype(tag);
-        constexpr int E = Elem<T>::kPack;
-        const bool vec = (Di % E == 0) && (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
-        const int ncol = vec ? Di / E : Di;
-        const int lanes = ncol < kPoolThreads ? ncol : kPoolThreads;
-        const size_t smem = sizeof(float) * (size_t)(kPoolThreads / lanes) * Di;
-        KD_CHECK_ARG(smem <= 200 * 1024 && sizeof(float) * (size_t)Di <= 200 * 1024, "kd_feature_pool_fwd: feature dimension %d too large", Di);
-        int nsplit = (148 * 4) / Mi;
-        if (nsplit > kMaxPoolSplit) nsplit = kMaxPoolSplit;
-        if (nsplit > (P + 63) / 64) nsplit = (P + 63) / 64;
-        if (nsplit < 1) nsplit = 1;
-        const T* xp = static_cast<const T*>(x);
-        const int half = (Mi + 1) / 2;                     // rows [0, half) as the "student", [Mi - half, Mi) as the "teacher"
-        const T* xt_ = xp + (int64_t)(Mi - half) * P * Di;
-        auto kfn = pool_partial_kernel<T>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kfn<<<(unsigned)(nsplit * 2 * (int64_t)half), kPoolThreads, smem, st>>>(xp, xt_, partials, half, P, Di, nsplit, vec);
-        KD_CHECK_LAUNCH("pool_partial_kernel");
-        if (sizeof(float) * (size_t)Di > 48 * 1024)
-            cudaFuncSetAttribute(pool_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * Di));
-        pool_finish_kernel<<<2 * half, 256, sizeof(float) * (size_t)Di, st>>>(partials, pooled, pooled + (int64_t)(Mi - half) * Di, nullptr,
-                                                                             half, P, Di, nsplit, nullptr, nullptr, false);
-        KD_CHECK_LAUNCH("pool_finish_kernel");
-        return KD_OK;
+        PoolPlan pl{};
+        pl.n = 1;
+        pl.t[0] = PoolTensor{x, Mi, P, Di, 0, 0};
+        return launch_pool_ranges<T>(pl, partials, pooled, nullptr, nullptr, 0u, st);      // the plain mean
     };
     switch (dtype) {
         case KD_DTYPE_BF16: return go(__nv_bfloat16{});
@@ -611,5 +1030,67 @@ int kd_feature_pool_bwd(const float* d_pooled, void* dx, int64_t M, int64_t toke
         default: return run_regrad<float>(d_pooled, dx, (int)M, (int)tokens, (int)D, scale, nullptr, st);
     }
 }
+
+/* Pooled contrastive loss through a learned projection of the student features — see include/kd_b200.h */
+int kd_info_nce_proj_workspace_bytes(int64_t M, int64_t D_s, int64_t D_t, size_t* bytes) {
+    KD_CHECK_ARG(bytes != nullptr && M >= 1 && D_s >= 1 && D_t >= 1, "kd_info_nce_proj_workspace_bytes: bad arguments");
+    *bytes = kd::nce_proj_layout(M, D_s, D_t).total;
+    return KD_OK;
+}
+
+int kd_info_nce_proj_fwd_bwd(const void* student, int64_t tokens_s, const void* teacher, int64_t tokens_t, const void* proj,
+                             void* grad_student, void* grad_proj, float* loss_out, void* workspace, size_t workspace_bytes,
+                             int64_t M, int64_t D_s, int64_t D_t, int dtype, int dtype_proj, float temperature, const float* upstream,
+                             unsigned flags, void* stream) {
+    using namespace kd;
+    KD_CHECK_ARG(student && teacher && proj && loss_out && workspace, "kd_info_nce_proj_fwd_bwd: null pointer");
+    KD_CHECK_ARG(M >= 1 && tokens_s >= 1 && tokens_t >= 1 && D_s >= 1 && D_t >= 1 && D_s < (1 << 20) && D_t < (1 << 20) &&
+                 tokens_s < (1 << 24) && tokens_t < (1 << 24), "kd_info_nce_proj_fwd_bwd: bad shape");
+    if (M > kProjMaxRows) {
+        set_error("kd_info_nce_proj_fwd_bwd: M = %lld rows: project with kd_gemm and call kd_info_nce_fwd_bwd (tensor-core similarity)", (long long)M);
+        return KD_ERR_UNSUPPORTED;
+    }
+    KD_CHECK_ARG(temperature > 0.f, "temperature must be positive");
+    KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32 && dtype_proj >= KD_DTYPE_BF16 && dtype_proj <= KD_DTYPE_F32, "unknown dtype");
+    const NceProjWorkspace w = nce_proj_layout(M, D_s, D_t);
+    if (workspace_bytes < w.total) {
+        set_error("kd_info_nce_proj_fwd_bwd: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return KD_ERR_WORKSPACE_TOO_SMALL;
+    }
+    const bool no_grad = (flags & KD_FLAG_NO_GRAD) != 0;
+    const bool want_dx = !no_grad && grad_student, want_dw = !no_grad && grad_proj;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    return dispatch2(dtype, dtype_proj, [&](auto t, auto tw) -> int {
+        using T = decltype(t);
+        using TW = decltype(tw);
+        return run_proj<T, TW>(student, (int)tokens_s, teacher, (int)tokens_t, static_cast<const TW*>(proj), grad_student,
+                               static_cast<TW*>(grad_proj), loss_out, ws, w, (int)M, (int)D_s, (int)D_t, temperature, upstream,
+                               want_dx, want_dw, st);
+    });
+}
+
+int kd_info_nce_proj_regrad(const void* workspace, size_t workspace_bytes, void* grad_student, void* grad_proj,
+                            int64_t M, int64_t tokens_s, int64_t D_s, int64_t D_t, int dtype, int dtype_proj, const float* ratio,
+                            const float* skip_if_one, void* stream) {
+    using namespace kd;
+    KD_CHECK_ARG(workspace && ratio && (grad_student || grad_proj), "kd_info_nce_proj_regrad: null pointer");
+    KD_CHECK_ARG(M >= 1 && M <= kProjMaxRows && tokens_s >= 1 && D_s >= 1 && D_t >= 1, "kd_info_nce_proj_regrad: bad shape");
+    KD_CHECK_ARG(dtype >= KD_DTYPE_BF16 && dtype <= KD_DTYPE_F32 && dtype_proj >= KD_DTYPE_BF16 && dtype_proj <= KD_DTYPE_F32, "unknown dtype");
+    const NceProjWorkspace w = nce_proj_layout(M, D_s, D_t);
+    if (workspace_bytes < w.total) {
+        set_error("kd_info_nce_proj_regrad: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return KD_ERR_WORKSPACE_TOO_SMALL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const char* ws = static_cast<const char*>(workspace);
+    return dispatch2(dtype, dtype_proj, [&](auto t, auto tw) -> int {
+        using T = decltype(t);
+        using TW = decltype(tw);
+        return run_proj_regrad<T, TW>(ws, w, grad_student, static_cast<TW*>(grad_proj), (int)M, (int)tokens_s,
+                                      (int)D_s, (int)D_t, ratio, skip_if_one, st);
+    });
+}
+
 
 }  // extern "C"

@@ -411,20 +411,90 @@ class _InfoNCE(torch.autograd.Function):
         return grad, None, None, None, None
 
 
+class _InfoNCEProjected(torch.autograd.Function):
+    """Pooled contrastive loss through a learned projection in ONE library call (``kd_info_nce_proj_fwd_bwd``): balanced pooling
+    of both tensors, ``y = mean(x_s) @ proj`` and the two backward products in fp32 on the CUDA cores (a few dozen rows are no
+    tensor-core tile), the row kernel, the store-only broadcast.  Gradients w.r.t. the student features and ``proj`` are written in
+    the forward launch; ``backward`` re-emits them only when ``grad_output`` differs from what forward assumed."""
+
+    @staticmethod
+    def forward(ctx, student, teacher, proj, temperature, upstream):
+        dev = _require_cuda(student, teacher, proj)
+        if student.dim() not in (2, 3) or teacher.dim() not in (2, 3) or student.shape[0] != teacher.shape[0]:
+            raise ValueError("features must be [M, D] or [M, tokens, D] with the same M")
+        if teacher.dtype != student.dtype:
+            teacher = teacher.to(student.dtype)
+        xs, xt, w = student.detach().contiguous(), teacher.detach().contiguous(), proj.detach().contiguous()
+        M, Ds, Dt = xs.shape[0], xs.shape[-1], xt.shape[-1]
+        Ps = xs.shape[1] if xs.dim() == 3 else 1
+        Pt = xt.shape[1] if xt.dim() == 3 else 1
+        if w.dim() != 2 or tuple(w.shape) != (Ds, Dt):
+            raise ValueError(f"proj must be [{Ds}, {Dt}] (student width x teacher width), got {tuple(w.shape)}")
+        need_x, need_w = student.requires_grad, proj.requires_grad
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            ws_bytes = _lib.size_query("kd_info_nce_proj_workspace_bytes", M, Ds, Dt)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            gx = torch.empty_like(xs) if need_x else None
+            gw = torch.empty_like(w) if need_w else None
+            up_t, up_ptr = _upstream_ptr(upstream, dev)
+            _lib.check(lib.kd_info_nce_proj_fwd_bwd(
+                xs.data_ptr(), Ps, xt.data_ptr(), Pt, w.data_ptr(), gx.data_ptr() if need_x else None,
+                gw.data_ptr() if need_w else None, loss.data_ptr(), ws.data_ptr(), ws_bytes, M, Ds, Dt, _dtype_code(xs),
+                _dtype_code(w), float(temperature), up_ptr, 0 if (need_x or need_w) else _lib.FLAG_NO_GRAD, _stream_ptr(dev)))
+        ctx.grads, ctx.dev, ctx.upstream, ctx.needs = (gx, gw), dev, up_t, (need_x, need_w)
+        ctx.workspace, ctx.dims = ws, (M, Ps, Ds, Dt)
+        ctx.meta = (xs.shape, xs.dtype, w.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        need_x, need_w = ctx.needs
+        if not (need_x or need_w):
+            return None, None, None, None, None
+        first = ctx.grads is not None           # a repeated backward re-emits into fresh buffers
+        _, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
+        M, Ps, Ds, Dt = ctx.dims
+        xshape, xdtype, wdtype = ctx.meta
+        ws = ctx.workspace
+        with torch.cuda.device(ctx.dev):
+            if first:
+                gx, gw = ctx.grads
+            else:
+                gx = torch.empty(xshape, dtype=xdtype, device=ctx.dev) if need_x else None
+                gw = torch.empty((Ds, Dt), dtype=wdtype, device=ctx.dev) if need_w else None
+            ctx.grads = None
+            _lib.check(_lib.load().kd_info_nce_proj_regrad(
+                ws.data_ptr(), ws.numel(), gx.data_ptr() if need_x else None, gw.data_ptr() if need_w else None,
+                M, Ps, Ds, Dt, _DTYPES[xdtype], _DTYPES[wdtype], ratio.data_ptr(), ratio.data_ptr() if first else None,
+                _stream_ptr(ctx.dev)))
+        return gx, None, gw, None, None
+
+
+_PROJ_FUSED_MAX_ROWS = 4096        # kd_info_nce_proj_fwd_bwd's limit; more rows = token-level features -> tensor-core similarity
+
+
 def info_nce(student_feats, teacher_feats, temperature: float = 0.07, upstream=None, proj=None, similarity: str = "auto"):
     """Mean-pool over tokens (3-D input), L2-normalise, student x teacher^T / temperature, cross-entropy
     against the diagonal — P1:243-248 followed by ``contrastive_loss`` (P1:393-416).
 
     ``proj`` ([D_s, D_t], optional, not in the reference where both towers are SigLIP-1152): a learned projection of the
     student features, ``contrastive_loss(x_s @ proj, x_t)``.  Mean-pooling is linear, so the projection is applied to the pooled
-    student vectors (``project``: the repo's tcgen05 GEMM, differentiable w.r.t. ``proj``) instead of to every token.
+    student vectors.  Up to 4096 rows (the pooled 64-image batch of BASELINE configs[2]) the whole chain is one library call
+    (:class:`_InfoNCEProjected`, fp32 products on the CUDA cores, differentiable w.r.t. ``proj``); token-level features are
+    projected on the tcgen05 GEMM (``project``) and take the tensor-core similarity path.
 
     ``similarity``: with ``"auto"`` a token-level call (``M >= 1024`` rows, ``M`` and ``D`` multiples of 8 — e.g. the
     46 656 x 1152 un-pooled SigLIP tokens) computes ``student @ teacher.T`` (P1:410) on the tcgen05 kernel with the row
     log-softmax in its epilogue; the similarity matrix is never stored.  ``"cuda_core"`` forces the exact fp32 row kernel."""
     if proj is not None:
-        # mean-pooling is linear: pool first (fp32, like the kernel's own pooling), project the [M, D_s] vectors on the tcgen05
-        # kernel, then the 2-D form of the op (tokens == 1).  Token-level 2-D features are projected as they are.
+        M = student_feats.shape[0]
+        token_level = (similarity == "auto" and student_feats.dim() == 2 and M >= 1024 and M % 8 == 0
+                       and proj.shape[1] % 8 == 0)
+        if M <= _PROJ_FUSED_MAX_ROWS and not token_level:
+            return _InfoNCEProjected.apply(student_feats, teacher_feats, proj, temperature, upstream)
+        # token-level features: pool (if 3-D), project the [M, D_s] rows on the tcgen05 kernel, then the 2-D form of the op
         pooled = pool_tokens(student_feats) if student_feats.dim() == 3 else student_feats
         student_feats = project(pooled, proj)
         teacher_feats = pool_tokens(teacher_feats.detach()) if teacher_feats.dim() == 3 else teacher_feats

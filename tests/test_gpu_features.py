@@ -103,6 +103,86 @@ def test_info_nce_grad_output_scaling():
     assert grad_close(xd.grad.float().cpu(), ref.grad * 0.5)
 
 
+def _proj_reference(xs, xt, W, temperature=0.07):
+    """contrastive_loss(x_s @ W, x_t) after the pooling of P1:243-248, in fp64 with autograd gradients."""
+    x64, W64 = xs.double().requires_grad_(True), W.double().requires_grad_(True)
+    y = x64 @ W64
+    us = torch.nn.functional.normalize(y.mean(1) if y.dim() == 3 else y, dim=-1)
+    t64 = xt.double()
+    ut = torch.nn.functional.normalize(t64.mean(1) if t64.dim() == 3 else t64, dim=-1)
+    lg = us @ ut.T / temperature
+    loss = (torch.logsumexp(lg, -1) - lg.diagonal()).mean()
+    gx, gW = torch.autograd.grad(loss, (x64, W64))
+    return loss.item(), gx, gW
+
+
+@pytest.mark.parametrize("M,P,Ds,Dt,xdtype,wdtype,teacher_2d", [
+    (64, 27, 1152, 896, torch.bfloat16, torch.bfloat16, False),      # BASELINE configs[2] widths, fewer tokens
+    (12, 9, 256, 640, torch.bfloat16, torch.float32, False),
+    (7, 5, 100, 36, torch.float32, torch.float32, False),            # nothing 16-byte vectorisable
+    (33, 4, 128, 72, torch.float16, torch.float16, True),            # teacher already pooled
+    (130, 1, 64, 200, torch.bfloat16, torch.bfloat16, True),         # 2-D student rows, more than one row tile
+])
+def test_pooled_info_nce_through_a_projection_in_one_call(M, P, Ds, Dt, xdtype, wdtype, teacher_2d):
+    """BASELINE configs[2]: the fused projected form (`kd_info_nce_proj_fwd_bwd`).  The oracle is the reference's
+    contrastive_loss applied to x_s @ W (the projection is not in the reference); gradients w.r.t. the features AND the
+    projection against fp64 autograd of the same formula."""
+    g = torch.Generator().manual_seed(M * 1000 + Ds)
+    xs = torch.randn(M, P, Ds, generator=g).to(xdtype)
+    W = (torch.randn(Ds, Dt, generator=g) * 0.1).to(wdtype)
+    # a related teacher: its features are a noisy linear image of the student's, so the diagonal means something
+    xt = ((xs.float() @ W.float()) + 0.5 * torch.randn(M, P, Dt, generator=g)).to(xdtype)
+    if teacher_2d:
+        xt = xt.float().mean(1).to(xdtype)
+    if P == 1:
+        xs = xs[:, 0].contiguous()
+        if not teacher_2d:
+            xt = xt[:, 0].contiguous()
+    want, gx, gW = _proj_reference(xs, xt, W)
+    y64 = xs.double() @ W.double()
+    if y64.dim() == 3 and xt.dim() == 2:            # the oracle pools both or neither
+        y64 = y64.mean(1)
+    assert abs(O.info_nce(y64, xt).loss.item() - want) <= 1e-9 * max(abs(want), 1e-3)
+    xd, Wd = xs.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+    # fp16 gradients of a mean loss sit in fp16's subnormal range: scale the loss as the reference's fp16 AMP does (TR2:145)
+    scale = 4096.0 if torch.float16 in (xdtype, wdtype) else 1.0
+    loss = kd.info_nce(xd, xt.cuda(), proj=Wd, upstream=scale if scale != 1.0 else None)
+    (loss * scale).backward()
+    gx, gW = gx * scale, gW * scale
+    assert abs(loss.item() - want) <= max(2e-5 * abs(want), 2e-7)
+    if wdtype == torch.float32:
+        assert rel_err(Wd.grad.cpu(), gW) <= 1e-4
+    else:
+        assert grad_close(Wd.grad.float().cpu(), gW, dtype=wdtype)
+    if xdtype == torch.float32:
+        assert rel_err(xd.grad.cpu(), gx) <= 1e-4
+    else:
+        assert grad_close(xd.grad.float().cpu(), gx, dtype=xdtype)
+
+
+def test_projected_info_nce_weights_and_repeated_backward():
+    """phase-1 weight 0.5 (P1:68, P1:351) through `upstream` and through a plain multiplication; a second backward through the
+    same node re-emits both gradients into fresh buffers."""
+    g = torch.Generator().manual_seed(77)
+    xs = torch.randn(10, 6, 64, generator=g).to(torch.bfloat16)
+    W = (torch.randn(64, 48, generator=g) * 0.1).to(torch.bfloat16)
+    xt = torch.randn(10, 6, 48, generator=g).to(torch.bfloat16)
+    _, gx, gW = _proj_reference(xs, xt, W)
+    for use_upstream in (True, False):
+        xd, Wd = xs.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+        loss = kd.info_nce(xd, xt.cuda(), proj=Wd, upstream=0.5 if use_upstream else None)
+        (loss * 0.5).backward(retain_graph=True)
+        assert grad_close(xd.grad.float().cpu(), gx * 0.5) and grad_close(Wd.grad.float().cpu(), gW * 0.5)
+        xd.grad = None
+        Wd.grad = None
+        (loss * 2.0).backward()                 # repeated backward, another weight
+        assert grad_close(xd.grad.float().cpu(), gx * 2.0) and grad_close(Wd.grad.float().cpu(), gW * 2.0)
+    # only the projection is trained (frozen features): no feature gradient is written
+    Wd = W.cuda().requires_grad_(True)
+    kd.info_nce(xs.cuda(), xt.cuda(), proj=Wd).backward()
+    assert grad_close(Wd.grad.float().cpu(), gW)
+
+
 def test_mse_odd_sizes_and_unaligned():
     for n in (1, 7, 1025, 8191):
         a = torch.randn(n + 1, device="cuda", dtype=torch.bfloat16)[1:]     # 2-byte offset: not 16-B aligned
