@@ -505,6 +505,29 @@ def main() -> None:
             torch.cuda.synchronize()
             return a.elapsed_time(b) / k
 
+        def timeit_graph(fn, k=50):
+            """The same step replayed from a CUDA graph: the device time of its launch chain without the host between launches."""
+            side_stream = torch.cuda.Stream()
+            side_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side_stream):
+                for _ in range(2):
+                    fn()
+            torch.cuda.current_stream().wait_stream(side_stream)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(k):
+                g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / k
+
         def fb(f):
             def run():
                 student.grad = None
@@ -579,8 +602,18 @@ def main() -> None:
         def nce():
             xs.grad = None
             kd.info_nce(xs, xt).backward()
-        ms = timeit(nce)
-        side["info_nce_64x729x1152"] = {"us": ms * 1e3, "achieved_gbs": 3 * xs.numel() * 2 / (ms / 1e3) / 1e9}
+        ms = timeit(nce, k=50)
+        nce_bytes = 3 * xs.numel() * 2           # read both feature tensors, write the gradient
+        side["info_nce_64x729x1152"] = {"us": ms * 1e3, "achieved_gbs": nce_bytes / (ms / 1e3) / 1e9,
+                                        "frac": nce_bytes / (ms / 1e3) / 1e9 / peak_gbs,
+                                        "note": "eager autograd step: host-bound (five launches + the autograd engine per step)"}
+        try:
+            msg = timeit_graph(nce)
+            side["info_nce_64x729x1152"].update({"graph_replay_us": msg * 1e3, "graph_replay_gbs": nce_bytes / (msg / 1e3) / 1e9,
+                                                 "graph_replay_frac": nce_bytes / (msg / 1e3) / 1e9 / peak_gbs})
+        except Exception as exc:  # noqa: BLE001
+            side["info_nce_64x729x1152"]["graph_replay_error"] = f"{type(exc).__name__}: {exc}"
+        xs.grad = None
         # BASELINE configs[2] with its learned projection (1152 -> 896 on the pooled student vectors; the repo's tcgen05 GEMM on
         # hi + lo bf16 parts of the fp32 pooled features), teacher features 896 wide
         try:
@@ -591,9 +624,20 @@ def main() -> None:
                 xs.grad = None
                 wp.grad = None
                 kd.info_nce(xs, xt896, proj=wp).backward()
-            ms = timeit(nce_proj)
-            side["info_nce_64x729x1152_proj896"] = {"us": ms * 1e3, "note": "pooling kernels -> projection on kd_gemm (hi + lo bf16 parts of the fp32 "
-                                                    "pooled vectors; its two backward products too) -> the 2-D loss op -> store-only broadcast"}
+            ms = timeit(nce_proj, k=50)
+            proj_bytes = (2 * xs.numel() + xt896.numel()) * 2      # read student + teacher features, write the student gradient
+            side["info_nce_64x729x1152_proj896"] = {"us": ms * 1e3, "achieved_gbs": proj_bytes / (ms / 1e3) / 1e9,
+                                                    "frac": proj_bytes / (ms / 1e3) / 1e9 / peak_gbs,
+                                                    "note": "one library call (kd_info_nce_proj_fwd_bwd): balanced pooling of both tensors, "
+                                                            "y = mean(x_s) @ W, dW and d mean as fp32 CUDA-core products, row kernel, "
+                                                            "store-only broadcast; gradients w.r.t. the features and W"}
+            try:
+                msg = timeit_graph(nce_proj)
+                side["info_nce_64x729x1152_proj896"].update({"graph_replay_us": msg * 1e3,
+                                                             "graph_replay_frac": proj_bytes / (msg / 1e3) / 1e9 / peak_gbs})
+            except Exception as exc:  # noqa: BLE001
+                side["info_nce_64x729x1152_proj896"]["graph_replay_error"] = f"{type(exc).__name__}: {exc}"
+            xs.grad = None
             del wp, xt896
         except Exception as exc:  # noqa: BLE001
             side["info_nce_64x729x1152_proj896"] = {"error": f"{type(exc).__name__}: {exc}"}

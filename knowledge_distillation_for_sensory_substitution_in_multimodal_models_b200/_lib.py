@@ -109,9 +109,19 @@ def check(rc: int) -> None:
         raise KDError(f"libkd_b200 error {rc}: {msg}")
 
 
+_size_cache: dict = {}
+
+
 def size_query(fn_name: str, *args) -> int:
+    """Workspace-size queries are pure functions of their integer arguments: answered from a cache after the first call."""
+    key = (fn_name, args)
+    hit = _size_cache.get(key)
+    if hit is not None:
+        return hit
     out = _sz(0)
     check(getattr(load(), fn_name)(*args, C.byref(out)))
+    if len(_size_cache) < 4096:
+        _size_cache[key] = out.value
     return out.value
 
 

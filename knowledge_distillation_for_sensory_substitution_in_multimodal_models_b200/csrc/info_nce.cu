@@ -105,7 +105,7 @@ pool_finish_kernel(const float* __restrict__ partials, float* __restrict__ us, f
 }
 
 // ---- one similarity row per CTA: logits, log-softmax, gradient w.r.t. the pooled student vector -----
-__global__ void __launch_bounds__(kRowThreads)
+__global__ void __launch_bounds__(kRowThreads, 1)
 similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut, const float* __restrict__ norm_s,
                       float* __restrict__ dmean, float* __restrict__ rowloss, int M, int D, float inv_temp,
                       float inv_tokens /* 1/P */, const float* upstream, bool want_grad,
@@ -147,8 +147,8 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
         if (vec4) {
             const float4* t4 = reinterpret_cast<const float4*>(t);
             const float4* s4 = reinterpret_cast<const float4*>(su);
-#pragma unroll 4
-            for (int d = l; d < D / 4; d += 32) {
+#pragma unroll 12
+            for (int d = l; d < D / 4; d += 32) {      // (12 loads in flight per lane: the whole row at D = 1152)
                 const float4 a = s4[d], b = __ldg(t4 + d);
                 acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
             }
@@ -193,12 +193,30 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
     // du[d] = sum_j G[j] * ut[j,d]  (coalesced over d; ut is L2 resident)
     const float nrm = raw_parts > 0 ? nrm_raw : norm_s[i];
     float dots = 0.f;
-    for (int d = threadIdx.x; d < D; d += kRowThreads) {
-        float acc = 0.f;
+    if (D % 2 == 0 && D <= 2 * kRowThreads) {
+        // one pass: a thread owns two adjacent columns and keeps 16 rows of u_t in flight (D = 1152 on 1024 threads used to take
+        // two passes of eight 8-deep batches: this column sum, not the dot products, was most of the kernel's 20 us)
+        const int d = 2 * threadIdx.x;
+        if (d < D) {
+            float2 acc = make_float2(0.f, 0.f);
+            const float2* t2 = reinterpret_cast<const float2*>(ut + d);
+#pragma unroll 16
+            for (int j = 0; j < M; ++j) {
+                const float2 v = __ldg(t2 + (int64_t)j * (D / 2));
+                acc.x = fmaf(sl[j], v.x, acc.x);
+                acc.y = fmaf(sl[j], v.y, acc.y);
+            }
+            dots = fmaf(acc.x, su[d], acc.y * su[d + 1]);
+            *reinterpret_cast<float2*>(dmean + (int64_t)i * D + d) = acc;
+        }
+    } else {
+        for (int d = threadIdx.x; d < D; d += kRowThreads) {
+            float acc = 0.f;
 #pragma unroll 8
-        for (int j = 0; j < M; ++j) acc = fmaf(sl[j], __ldg(ut + (int64_t)j * D + d), acc);
-        dots = fmaf(acc, su[d], dots);
-        dmean[(int64_t)i * D + d] = acc;
+            for (int j = 0; j < M; ++j) acc = fmaf(sl[j], __ldg(ut + (int64_t)j * D + d), acc);
+            dots = fmaf(acc, su[d], dots);
+            dmean[(int64_t)i * D + d] = acc;
+        }
     }
     dots = warp_sum(dots);
     if (l == 0) red[w] = dots;
@@ -454,43 +472,87 @@ pool_ranges_kernel(const PoolPlan plan, float* __restrict__ partials) {
 }
 
 // One CTA per (tensor, image): add the image's pieces in CTA order, take the mean and (bit k of normalize_mask) L2-normalise
-// tensor k's rows (F.normalize eps); the student's norm goes to norm0 when that is given.
-__global__ void __launch_bounds__(256)
+// tensor k's rows (F.normalize eps); the student's norm goes to norm0 when that is given.  A thread owns 4 consecutive
+// features and fetches its float4 of every piece (at most 6: G <= 4 M) before adding them: one round trip to L2, not one per piece.
+constexpr int kFinishPieces = 8;
+__global__ void __launch_bounds__(1024)
 pool_ranges_finish_kernel(const PoolPlan plan, const float* __restrict__ partials, float* __restrict__ out0, float* __restrict__ out1,
                           float* __restrict__ norm0, unsigned normalize_mask) {
-    extern __shared__ float sm[];        // [D] pooled vector
-    __shared__ float red[8];
+    __shared__ float red[32];
+    __shared__ long long offs[kFinishPieces];
+    __shared__ int s_first, s_count;
     const int k = (plan.n > 1 && (int)blockIdx.x >= plan.t[0].M) ? 1 : 0;
     const PoolTensor t = k ? plan.t[1] : plan.t[0];
     const int m = (int)blockIdx.x - (k ? plan.t[0].M : 0);
     const int D = t.D, P = t.P, G = t.G;
     const int64_t R = (int64_t)t.M * P;
     const int64_t lo = (int64_t)m * P, hi = lo + P;
-    int b = (int)(lo * G / R);
-    b = b > 0 ? b - 1 : 0;
-    while (R * (b + 1) / G <= lo) ++b;                       // first CTA whose range reaches into the image
-    for (int d = threadIdx.x; d < D; d += 256) sm[d] = 0.f;
-    for (; b < G && R * b / G < hi; ++b) {
-        const int seg = ((R * b / G) / P == m) ? 0 : 1;      // the image is the first / second one of that CTA's range
-        const float* src = partials + ((int64_t)(t.cta0 + b) * 2 + seg) * plan.dmax;
-        for (int d = threadIdx.x; d < D; d += 256) sm[d] += src[d];      // a thread owns its d's: no barrier needed
+    const bool vec4 = (D % 4 == 0) && (plan.dmax % 4 == 0);
+    const int ncol = vec4 ? D / 4 : D;
+    if (threadIdx.x == 0) {
+        int b = (int)(lo * G / R);
+        b = b > 0 ? b - 1 : 0;
+        while (R * (b + 1) / G <= lo) ++b;                   // first CTA whose range reaches into the image
+        int n = 0;
+        while (b + n < G && R * (b + n) / G < hi) ++n;
+        s_first = b;
+        s_count = n;
+    }
+    __syncthreads();
+    const int first = s_first, count = s_count;
+    float4 acc[4];       // up to 4 column slots per thread (D <= 16 384 with 1024 threads)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = 0; c0 < count; c0 += kFinishPieces) {
+        const int nb = min(kFinishPieces, count - c0);
+        __syncthreads();
+        if ((int)threadIdx.x < nb) {
+            const int b = first + c0 + threadIdx.x;
+            const int seg = ((R * b / G) / P == m) ? 0 : 1;  // the image is the first / second one of that CTA's range
+            offs[threadIdx.x] = ((long long)(t.cta0 + b) * 2 + seg) * plan.dmax;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = threadIdx.x + q * blockDim.x;
+            if (c >= ncol) break;
+            float4 v[kFinishPieces];
+#pragma unroll
+            for (int bi = 0; bi < kFinishPieces; ++bi) {
+                v[bi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bi < nb) {
+                    if (vec4) v[bi] = *reinterpret_cast<const float4*>(partials + offs[bi] + 4 * c);
+                    else v[bi].x = partials[offs[bi] + c];
+                }
+            }
+#pragma unroll
+            for (int bi = 0; bi < kFinishPieces; ++bi) {      // fixed order: deterministic
+                acc[q].x += v[bi].x; acc[q].y += v[bi].y; acc[q].z += v[bi].z; acc[q].w += v[bi].w;
+            }
+        }
     }
     const float invP = 1.f / (float)P;
     float ss = 0.f;
-    for (int d = threadIdx.x; d < D; d += 256) {
-        const float a = sm[d] * invP;
-        ss = fmaf(a, a, ss);
-        sm[d] = a;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        acc[q].x *= invP; acc[q].y *= invP; acc[q].z *= invP; acc[q].w *= invP;
+        ss += acc[q].x * acc[q].x + acc[q].y * acc[q].y + acc[q].z * acc[q].z + acc[q].w * acc[q].w;      // unused slots are 0
     }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
     float tot = 0.f;
-    for (int i = 0; i < 8; ++i) tot += red[i];
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
     const float nrm = sqrtf(tot);
     const float inv = ((normalize_mask >> k) & 1u) ? 1.f / fmaxf(nrm, kNormEps) : 1.f;
     float* u = (k ? out1 : out0) + (int64_t)m * D;
-    for (int d = threadIdx.x; d < D; d += 256) u[d] = sm[d] * inv;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = threadIdx.x + q * blockDim.x;
+        if (c >= ncol) break;
+        if (vec4) *reinterpret_cast<float4*>(u + 4 * c) = make_float4(acc[q].x * inv, acc[q].y * inv, acc[q].z * inv, acc[q].w * inv);
+        else u[c] = acc[q].x * inv;
+    }
     if (k == 0 && threadIdx.x == 0 && norm0) norm0[m] = nrm;
 }
 
@@ -557,9 +619,15 @@ int launch_pool_ranges(PoolPlan& pl, float* partials, float* out0, float* out1, 
         kfn<<<ctas, kPoolThreads, smem, st>>>(pl, partials);
     }
     KD_CHECK_LAUNCH("pool_ranges_kernel");
-    const size_t fsmem = sizeof(float) * (size_t)pl.dmax;
-    if (fsmem > 48 * 1024) cudaFuncSetAttribute(pool_ranges_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-    pool_ranges_finish_kernel<<<images, 256, fsmem, st>>>(pl, partials, out0, out1, norm0, normalize_mask);
+    int fcols = 0;        // column slots (float4 or scalar) of the widest tensor: one per thread, up to 4 when a CTA cannot hold them
+    for (int k = 0; k < pl.n; ++k) {
+        const int c = (pl.t[k].D % 4 == 0 && pl.dmax % 4 == 0) ? pl.t[k].D / 4 : pl.t[k].D;
+        fcols = c > fcols ? c : fcols;
+    }
+    KD_CHECK_ARG(fcols <= 4096, "pooling: feature dimension %d too large for the finishing kernel", pl.dmax);
+    int fthreads = (fcols + 31) / 32 * 32;
+    if (fthreads > 1024) fthreads = 1024;
+    pool_ranges_finish_kernel<<<images, fthreads, 0, st>>>(pl, partials, out0, out1, norm0, normalize_mask);
     KD_CHECK_LAUNCH("pool_ranges_finish_kernel");
     return KD_OK;
 }

@@ -36,6 +36,29 @@ def _require_cuda(*tensors: torch.Tensor) -> torch.device:
     return dev
 
 
+class _device_guard:
+    """``torch.cuda.device(dev)`` that costs nothing when ``dev`` already is the current device (the usual case: one process
+    per GPU) — the stock context manager is ~10 us of the ~140 us a small op spends on the host."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev: torch.device):
+        self.idx = dev.index
+
+    def __enter__(self):
+        self.prev = -1
+        if self.idx is not None:
+            cur = torch.cuda.current_device()
+            if cur != self.idx:
+                torch.cuda.set_device(self.idx)
+                self.prev = cur
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def _dtype_code(t: torch.Tensor) -> int:
     try:
         return _DTYPES[t.dtype]
@@ -110,7 +133,7 @@ class _LogitKD(torch.autograd.Function):
         if not need_grad:
             flags |= _lib.FLAG_NO_GRAD
         lib = _lib.load()
-        with torch.cuda.device(dev):
+        with _device_guard(dev):
             ws_bytes = _lib.size_query("kd_logit_kd_workspace_bytes", n_rows, V)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -147,7 +170,7 @@ class _LogitKD(torch.autograd.Function):
         t2, s2 = ctx.rows
         n_rows, V, dt, T, eps, variant, inv_norm = ctx.call
         ws = ctx.workspace
-        with torch.cuda.device(ctx.dev):
+        with _device_guard(ctx.dev):
             grad = ctx.grad if first else torch.empty((n_rows, V), dtype=s2.dtype, device=ctx.dev)
             ctx.grad = None
             _lib.check(_lib.load().kd_logit_kd_regrad(t2.data_ptr(), t2.stride(0), s2.data_ptr(), s2.stride(0),
@@ -193,7 +216,7 @@ class _LocaKLWithCE(torch.autograd.Function):
         flags = 0 if need_grad else _lib.FLAG_NO_GRAD
         inv_norm = _inv_norm("mean", n_rows, V, 1, n_total)
         lib = _lib.load()
-        with torch.cuda.device(dev):
+        with _device_guard(dev):
             ws_bytes = _lib.size_query("kd_logit_kd_workspace_bytes", n_rows, V)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -221,7 +244,7 @@ class _LocaKLWithCE(torch.autograd.Function):
         t2, s2, cel, inv_count = ctx.rows
         n_rows, V, dt, T, eps, ce_weight, inv_norm = ctx.call
         ws = ctx.workspace
-        with torch.cuda.device(ctx.dev):
+        with _device_guard(ctx.dev):
             grad = ctx.grad if first else torch.empty((n_rows, V), dtype=s2.dtype, device=ctx.dev)
             ctx.grad = None
             _lib.check(_lib.load().kd_logit_kd_ce_regrad(t2.data_ptr(), t2.stride(0), s2.data_ptr(), s2.stride(0), cel.data_ptr(),
@@ -337,7 +360,7 @@ class _PoolTokens(torch.autograd.Function):
             raise ValueError("pool_tokens: [M, tokens, D] features expected")
         xd = x.detach().contiguous()
         M, P, D = xd.shape
-        with torch.cuda.device(dev):
+        with _device_guard(dev):
             ws_bytes = _lib.size_query("kd_feature_pool_workspace_bytes", M, P, D)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             out = torch.empty((M, D), dtype=torch.float32, device=dev)
@@ -350,7 +373,7 @@ class _PoolTokens(torch.autograd.Function):
     def backward(ctx, g):
         M, P, D = ctx.shape3
         gm = (g.to(torch.float32) * (1.0 / P)).contiguous()
-        with torch.cuda.device(ctx.dev):
+        with _device_guard(ctx.dev):
             dx = torch.empty((M, P, D), dtype=ctx.dtype, device=ctx.dev)
             _lib.check(_lib.load().kd_feature_pool_bwd(gm.data_ptr(), dx.data_ptr(), M, P, D, _DTYPES[ctx.dtype], None, _stream_ptr(ctx.dev)))
         return dx
@@ -378,7 +401,7 @@ class _InfoNCE(torch.autograd.Function):
         xs, xt = student.detach().contiguous(), teacher.detach().contiguous()
         need_grad = student.requires_grad
         lib = _lib.load()
-        with torch.cuda.device(dev):
+        with _device_guard(dev):
             ws_bytes = _lib.size_query("kd_info_nce_workspace_bytes", M, P, D)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -402,7 +425,7 @@ class _InfoNCE(torch.autograd.Function):
         _, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
         M, P, D = ctx.shape3
         ws = ctx.workspace
-        with torch.cuda.device(ctx.dev):
+        with _device_guard(ctx.dev):
             grad = ctx.grad if first else torch.empty(ctx.gshape, dtype=ctx.gdtype, device=ctx.dev)
             ctx.grad = None
             _lib.check(_lib.load().kd_info_nce_regrad(ws.data_ptr(), ws.numel(), grad.data_ptr(), M, P, D,
@@ -432,7 +455,7 @@ class _InfoNCEProjected(torch.autograd.Function):
             raise ValueError(f"proj must be [{Ds}, {Dt}] (student width x teacher width), got {tuple(w.shape)}")
         need_x, need_w = student.requires_grad, proj.requires_grad
         lib = _lib.load()
-        with torch.cuda.device(dev):
+        with _device_guard(dev):
             ws_bytes = _lib.size_query("kd_info_nce_proj_workspace_bytes", M, Ds, Dt)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -458,7 +481,7 @@ class _InfoNCEProjected(torch.autograd.Function):
         M, Ps, Ds, Dt = ctx.dims
         xshape, xdtype, wdtype = ctx.meta
         ws = ctx.workspace
-        with torch.cuda.device(ctx.dev):
+        with _device_guard(ctx.dev):
             if first:
                 gx, gw = ctx.grads
             else:
@@ -512,7 +535,7 @@ class _FeatureMSE(torch.autograd.Function):
         a, b = inp.detach().contiguous(), target.detach().contiguous()
         need_grad = inp.requires_grad
         lib = _lib.load()
-        with torch.cuda.device(dev):
+        with _device_guard(dev):
             ws_bytes = _lib.size_query("kd_feature_mse_workspace_bytes", a.numel())
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -532,7 +555,7 @@ class _FeatureMSE(torch.autograd.Function):
         first = ctx.grad is not None           # see _LogitKD.backward: a repeated backward re-emits into a fresh buffer
         go, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
         a, b = ctx.inputs
-        with torch.cuda.device(ctx.dev):
+        with _device_guard(ctx.dev):
             grad = ctx.grad if first else torch.empty_like(a)
             ctx.grad = None
             _lib.check(_lib.load().kd_feature_mse_regrad(a.data_ptr(), b.data_ptr(), grad.data_ptr(), a.numel(),
@@ -561,7 +584,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False, b_mn_major:
         out = torch.empty((M, N), dtype=out_dtype, device=dev)
     elif out.shape != (M, N) or out.dtype != out_dtype or out.stride(1) != 1:
         raise ValueError("gemm: `out` must be a row-major [M, N] tensor of the output dtype")
-    with torch.cuda.device(dev):
+    with _device_guard(dev):
         _lib.check(_lib.load().kd_gemm(a.data_ptr(), a.stride(0), int(a_mn_major), b.data_ptr(), b.stride(0), int(b_mn_major),
                                        out.data_ptr(), out.stride(0), int(out_dtype == torch.float32), M, N, K, _dtype_code(a),
                                        _stream_ptr(dev)))
@@ -584,7 +607,7 @@ class _ProjectedMSE(torch.autograd.Function):
         if w.shape[0] != K or tgt.shape != (M, N) or not (x.dtype == w.dtype == tgt.dtype):
             raise ValueError("feature_mse(proj=...): input [.., K], proj [K, N], target [.., N] of one 16-bit dtype expected")
         lib = _lib.load()
-        with torch.cuda.device(dev):
+        with _device_guard(dev):
             ws_bytes = _lib.size_query("kd_proj_mse_workspace_bytes", M, N)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -605,7 +628,7 @@ class _ProjectedMSE(torch.autograd.Function):
         x, w, g = ctx.saved
         ctx.saved = None
         _, ratio = _backward_scalars(grad_output, ctx.upstream, ctx.dev)
-        with torch.cuda.device(ctx.dev):         # d loss / d projected *= grad_output / upstream, skipped on the device when that is 1
+        with _device_guard(ctx.dev):         # d loss / d projected *= grad_output / upstream, skipped on the device when that is 1
             _lib.check(_lib.load().kd_scale_rows(g.data_ptr(), g.stride(0), g.shape[0], g.shape[1], _dtype_code(g), ratio.data_ptr(),
                                                  _stream_ptr(ctx.dev)))
         d_in = gemm(g, w).view(ctx.in_shape) if ctx.needs[0] else None                       # [M, N] . [K, N]^T
