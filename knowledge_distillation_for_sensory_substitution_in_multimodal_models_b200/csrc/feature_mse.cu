@@ -8,6 +8,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxBlocks = 148 * 8;
+constexpr int kBatch = 4;        // 16-byte vector pairs in flight per thread of the forward kernel
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -23,18 +24,32 @@ mse_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ g, 
     const uint4* bv = reinterpret_cast<const uint4*>(b);
     uint4* gv = reinterpret_cast<uint4*>(g);
     int since = 0;
-    for (int64_t v = blockIdx.x * (int64_t)kThreads + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * kThreads) {
-        float x[P], y[P], o[P];
-        Elem<T>::unpack(ldg_stream(av + v), x);
-        Elem<T>::unpack(ldg_stream(bv + v), y);
+    // kBatch vector pairs per thread are fetched before any is consumed (the volatile streaming store would otherwise fence
+    // every iteration's loads behind the previous iteration's store: two loads in flight per thread)
+    for (int64_t v0 = blockIdx.x * (int64_t)(kThreads * kBatch) + threadIdx.x; v0 < nvec; v0 += (int64_t)gridDim.x * kThreads * kBatch) {
+        uint4 xa[kBatch], xb[kBatch];
 #pragma unroll
-        for (int i = 0; i < P; ++i) {
-            const float d = x[i] - y[i];
-            acc = fmaf(d, d, acc);
-            o[i] = gs * d;
+        for (int u = 0; u < kBatch; ++u) {
+            const int64_t v = v0 + (int64_t)u * kThreads;
+            xa[u] = make_uint4(0u, 0u, 0u, 0u);
+            xb[u] = xa[u];
+            if (v < nvec) { xa[u] = ldg_stream(av + v); xb[u] = ldg_stream(bv + v); }
         }
-        if (want_grad) stg_stream(gv + v, Elem<T>::pack(o));
-        if (++since == 64) { dacc += acc; acc = 0.f; since = 0; }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int64_t v = v0 + (int64_t)u * kThreads;
+            float x[P], y[P], o[P];
+            Elem<T>::unpack(xa[u], x);
+            Elem<T>::unpack(xb[u], y);
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const float d = x[i] - y[i];            // (out-of-range slots hold 0 - 0)
+                acc = fmaf(d, d, acc);
+                o[i] = gs * d;
+            }
+            if (want_grad && v < nvec) stg_stream(gv + v, Elem<T>::pack(o));
+        }
+        if (++since == 16) { dacc += acc; acc = 0.f; since = 0; }
     }
     for (int64_t c = nvec * P + blockIdx.x * (int64_t)kThreads + threadIdx.x; c < numel; c += (int64_t)gridDim.x * kThreads) {
         const float d = Elem<T>::to_float(a[c]) - Elem<T>::to_float(b[c]);
@@ -100,7 +115,7 @@ int launch(const void* a, const void* b, void* g, float* loss, double* partials,
     const bool want_grad = !(flags & KD_FLAG_NO_GRAD);
     const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
                        (want_grad ? reinterpret_cast<uintptr_t>(g) : 0)) & 15u) == 0;
-    int64_t blocks = (numel / P + kThreads - 1) / kThreads;
+    int64_t blocks = (numel / P + kThreads * kBatch - 1) / (kThreads * kBatch);
     if (blocks < 1) blocks = 1;
     if (blocks > kMaxBlocks) blocks = kMaxBlocks;
     mse_kernel<T><<<(int)blocks, kThreads, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b), static_cast<T*>(g),

@@ -369,6 +369,13 @@ class DistCollectives:
             dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
         return x
 
+    def sum_async(self, x: torch.Tensor):
+        """In-place sum started on the collective's own stream; ``.wait()`` on the returned handle (None when there is nothing
+        to exchange) makes the current stream wait for it — kernels issued in between overlap the exchange."""
+        if self.active:
+            return dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return None
+
 
 def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, T, mode="reference", alpha=0.8, eps=1e-8,
                            n_rows_norm=None, reduction="mean", upstream=None, group=None, phases=None, collectives=None,
@@ -400,7 +407,7 @@ def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, 
     else:
         raise ValueError(f"unknown reduction {reduction!r}")
 
-    if student_partials is not None:                                        # student (max, sum-exp) left by the lm_head GEMM
+    if student_partials is not None:                                      # student (max, sum-exp) left by the lm_head GEMM
         stats = phases.stats(t2, s2, lab, col0, T, student_partials=student_partials)
     else:
         stats = phases.stats(t2, s2, lab, col0, T)
@@ -466,6 +473,8 @@ class _LmHeadVocabShardedKD(torch.autograd.Function):
         ctx.gemm = "library"
         if gemm == "tcgen05" and phases is None and _tensor_core_head_applies(hidden, weight_shard):
             ctx.gemm = "tcgen05"
+            # (measured: running the teacher's half of the statistics beside this GEMM on a second stream gains nothing —
+            # 5.85 against 5.80 ms for head + KD forward; the power-bound GEMM slows by what the overlap saves)
             logits, partials = lm_head_fwd(hidden.detach(), weight_shard.detach(), T=T)
         elif gemm == "tcgen05" and phases is None and hidden.is_cuda and hidden.dtype != torch.float32:
             raise ValueError("lm_head_kd_vocab_sharded: hidden size and V_local must be multiples of 8 for the tensor-core head "
@@ -499,9 +508,16 @@ class _LmHeadVocabShardedKD(torch.autograd.Function):
         if ctx.gemm == "tcgen05":
             # both backward products on the tcgen05 kernel, operands read in place through MN-major descriptors (kd_gemm):
             # the partial dH leaves the kernel in fp32 and is summed over the vocabulary shards in fp32, rounded ONCE
+            # The all-reduce of the partial dH (117 MB at 65 536 x 896) travels while the dW product runs.
             d_hidden = tc_gemm(g, weight_shard.detach(), b_mn_major=True, out_dtype=torch.float32)       # [n, V_l] . [V_l, H]
-            d_hidden = ctx.collectives.sum_(d_hidden).to(hidden.dtype)
+            start = getattr(ctx.collectives, "sum_async", None)
+            work = start(d_hidden) if start is not None else None
+            if start is None:
+                d_hidden = ctx.collectives.sum_(d_hidden)
             d_weight = tc_gemm(g, hidden.detach(), a_mn_major=True, b_mn_major=True)                     # [n, V_l]^T . [n, H]
+            if work is not None:
+                work.wait()
+            d_hidden = d_hidden.to(hidden.dtype)
         else:
             try:                                    # library GEMM with an fp32 result
                 d_hidden = torch.mm(g, weight_shard.detach(), out_dtype=torch.float32)
