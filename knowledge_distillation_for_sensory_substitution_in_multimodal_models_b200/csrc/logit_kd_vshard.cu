@@ -212,7 +212,27 @@ struct ShardOverride {
         if constexpr (VARIANT == KD_LOCA_PER_ROW) return (c == k_local) ? v2 : ((c == lab_local) ? v1 : NaN);
         return NaN;
     }
+    // the overrides of the P cells from local column c (c % P == 0): two 128-bit loads of the table slice when it is 16-byte
+    // aligned (one scalar load per CELL made the LSU, not HBM, the bound of the accumulate / emit sweeps)
+    template <int P>
+    __device__ __forceinline__ void of_vec(int c, float (&o)[P]) const {
+        if constexpr (VARIANT == KD_LOCA_REFERENCE) {
+            if ((reinterpret_cast<uintptr_t>(table_local) & 15u) == 0) {
+#pragma unroll
+                for (int i = 0; i < P; i += 4) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(table_local + c + i));
+                    o[i] = t4.x; o[i + 1] = t4.y; o[i + 2] = t4.z; o[i + 3] = t4.w;
+                }
+                return;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) o[i] = of(c + i);
+    }
 };
+// vector pairs fetched per lane before any is consumed (the streaming store is a volatile asm with a memory clobber: loads do not
+// move above it, so an unrolled load-compute-store loop keeps ONE pair in flight)
+template <typename T> struct VsBatch { static constexpr int kB = sizeof(T) == 2 ? 4 : 2; };
 
 template <int VARIANT>
 __device__ __forceinline__ ShardOverride<VARIANT> make_override(const float* table, const kd_token_record* rec, int64_t r, int col0) {
@@ -255,14 +275,32 @@ vshard_accum_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __rest
             constexpr int P = Elem<T>::kPack;
             const uint4* tv = reinterpret_cast<const uint4*>(trow);
             const uint4* sv = reinterpret_cast<const uint4*>(srow);
-#pragma unroll 4
-            for (int v = gl; v < V_local / P; v += G) {
-                float xt[P], xs[P];
-                Elem<T>::unpack(ldg_stream(tv + v), xt);
-                Elem<T>::unpack(ldg_stream(sv + v), xs);
+            constexpr int B = VsBatch<T>::kB;
+            const int nv = V_local / P;
+            for (int v0 = gl; v0 < nv; v0 += G * B) {
+                uint4 rt[B], rs[B];
+                float ovv[B][P];
 #pragma unroll
-                for (int i = 0; i < P; ++i)
-                    PointTerm<VARIANT>::accum(xt[i], xs[i], LOCA ? ov.of(v * P + i) : NaN, k2, l2.x, l2.y, thr2, row, Q);
+                for (int u = 0; u < B; ++u) {
+                    const int v = v0 + u * G;
+                    if (v < nv) {
+                        rt[u] = ldg_stream(tv + v);
+                        rs[u] = ldg_stream(sv + v);
+                        if constexpr (LOCA) ov.template of_vec<P>(v * P, ovv[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < B; ++u) {
+                    const int v = v0 + u * G;
+                    if (v < nv) {
+                        float xt[P], xs[P];
+                        Elem<T>::unpack(rt[u], xt);
+                        Elem<T>::unpack(rs[u], xs);
+#pragma unroll
+                        for (int i = 0; i < P; ++i)
+                            PointTerm<VARIANT>::accum(xt[i], xs[i], LOCA ? ovv[u][i] : NaN, k2, l2.x, l2.y, thr2, row, Q);
+                    }
+                }
             }
         } else {
             for (int c = gl; c < V_local; c += G)
@@ -310,15 +348,33 @@ vshard_emit_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __restr
             const uint4* tv = reinterpret_cast<const uint4*>(trow);
             const uint4* sv = reinterpret_cast<const uint4*>(srow);
             uint4* gv = reinterpret_cast<uint4*>(grow);
-#pragma unroll 2
-            for (int v = blockIdx.x * kVsThreads + threadIdx.x; v < V_local / P; v += gridDim.x * kVsThreads) {
-                float xt[P], xs[P], o[P];
-                Elem<T>::unpack(ldg_stream(tv + v), xt);
-                Elem<T>::unpack(ldg_stream(sv + v), xs);
+            constexpr int B = VsBatch<T>::kB;
+            const int nv = V_local / P, stride = gridDim.x * kVsThreads;
+            for (int v0 = blockIdx.x * kVsThreads + threadIdx.x; v0 < nv; v0 += stride * B) {
+                uint4 rt[B], rs[B];
+                float ovv[B][P];
 #pragma unroll
-                for (int i = 0; i < P; ++i)
-                    o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? ov.of(v * P + i) : NaN, k2, l2.x, l2.y, thr2, g, gQ);
-                stg_stream(gv + v, Elem<T>::pack(o));
+                for (int u = 0; u < B; ++u) {
+                    const int v = v0 + u * stride;
+                    if (v < nv) {
+                        rt[u] = ldg_stream(tv + v);
+                        rs[u] = ldg_stream(sv + v);
+                        if constexpr (LOCA) ov.template of_vec<P>(v * P, ovv[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < B; ++u) {
+                    const int v = v0 + u * stride;
+                    if (v < nv) {
+                        float xt[P], xs[P], o[P];
+                        Elem<T>::unpack(rt[u], xt);
+                        Elem<T>::unpack(rs[u], xs);
+#pragma unroll
+                        for (int i = 0; i < P; ++i)
+                            o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? ovv[u][i] : NaN, k2, l2.x, l2.y, thr2, g, gQ);
+                        stg_stream(gv + v, Elem<T>::pack(o));
+                    }
+                }
             }
         } else {
             for (int c = blockIdx.x * kVsThreads + threadIdx.x; c < V_local; c += gridDim.x * kVsThreads)
@@ -352,15 +408,33 @@ vshard_emit_rows_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __
             const uint4* tv = reinterpret_cast<const uint4*>(trow);
             const uint4* sv = reinterpret_cast<const uint4*>(srow);
             uint4* gv = reinterpret_cast<uint4*>(grow);
-#pragma unroll 4
-            for (int v = gl; v < V_local / P; v += 32) {
-                float xt[P], xs[P], o[P];
-                Elem<T>::unpack(ldg_stream(tv + v), xt);
-                Elem<T>::unpack(ldg_stream(sv + v), xs);
+            constexpr int B = VsBatch<T>::kB;
+            const int nv = V_local / P;
+            for (int v0 = gl; v0 < nv; v0 += 32 * B) {
+                uint4 rt[B], rs[B];
+                float ovv[B][P];
 #pragma unroll
-                for (int i = 0; i < P; ++i)
-                    o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? ov.of(v * P + i) : NaN, k2, l2.x, l2.y, thr2, g, gQ);
-                stg_stream(gv + v, Elem<T>::pack(o));
+                for (int u = 0; u < B; ++u) {
+                    const int v = v0 + u * 32;
+                    if (v < nv) {
+                        rt[u] = ldg_stream(tv + v);
+                        rs[u] = ldg_stream(sv + v);
+                        if constexpr (LOCA) ov.template of_vec<P>(v * P, ovv[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < B; ++u) {
+                    const int v = v0 + u * 32;
+                    if (v < nv) {
+                        float xt[P], xs[P], o[P];
+                        Elem<T>::unpack(rt[u], xt);
+                        Elem<T>::unpack(rs[u], xs);
+#pragma unroll
+                        for (int i = 0; i < P; ++i)
+                            o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? ovv[u][i] : NaN, k2, l2.x, l2.y, thr2, g, gQ);
+                        stg_stream(gv + v, Elem<T>::pack(o));
+                    }
+                }
             }
         } else {
             for (int c = gl; c < V_local; c += 32)
