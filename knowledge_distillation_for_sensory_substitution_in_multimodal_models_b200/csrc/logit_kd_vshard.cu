@@ -83,6 +83,114 @@ __device__ __forceinline__ void shard_row_stats(const T* __restrict__ row, int n
     }
 }
 
+// 16-bit logits, 16-byte aligned rows: the scheme of phase A's row_stats_packed (logit_kd.cu) for a lane of a warp-per-row / block-
+// per-row walk — packed 16-bit maxima, fp32x2 arithmetic, a LAZY rescale (only when a cell exceeds the running reference by more
+// than `slack`, so 2^((x - ref) k2) stays finite), eight loads in flight per lane, and runner-up candidates behind a threshold
+// seeded from the first batch (the 2nd largest lane maximum of the warp: two distinct cells reach it, so it bounds the row's
+// runner-up from below).  The generic walk above costs ~29 issue slots per cell (measured: issue-bound at 88 %); this one ~6.
+template <typename T, bool WANT_TOP2>
+__device__ __forceinline__ void shard_row_stats_packed(const T* __restrict__ row, int n, float k2, MaxSum& ms, Top2& top, int col0,
+                                                       int lane, int stride) {
+    ms.init();
+    if (WANT_TOP2) top.init();
+    const int nv = n / 8;
+    const uint4* rv = reinterpret_cast<const uint4*>(row);
+    const u64 k2p = pk(k2, k2);
+    const float slack = 64.f / k2;
+    float ref = -INFINITY, lane_max = -INFINITY, thr_top = -INFINITY;
+    u64 mkp = pk(0.f, 0.f), acc0 = pk(0.f, 0.f), acc1 = pk(0.f, 0.f);
+    auto vec_max = [&](const uint4& raw) -> float {
+        const uint32_t m2 = Pair<T>::vmax(Pair<T>::vmax(raw.x, raw.y), Pair<T>::vmax(raw.z, raw.w));
+        float m_lo, m_hi;
+        upk(Pair<T>::widen(m2), m_lo, m_hi);
+        return fmaxf(m_lo, m_hi);
+    };
+    // The hot path is straight-line code: a vector that may hold a best / runner-up cell only sets its bit in `cand`; the
+    // (rare, divergent) per-cell insertion runs once per batch from ONE copy of its code, re-reading the vector (an L1 / L2 hit).
+    // Inlined into every unrolled copy of the sweep it pushed the loop out of the instruction cache (ncu: "no instruction" 15.7
+    // stall cycles per issue, the kernel 1.7x SLOWER than the generic walk).
+    auto consume = [&](const uint4& raw, unsigned bit, unsigned& cand) {
+        const float vm = vec_max(raw);
+        lane_max = fmaxf(lane_max, vm);
+        if (vm > ref + slack || ref == -INFINITY) {     // rare: first vector, or a cell far above the reference
+            const float sc = (ref == -INFINITY) ? 0.f : ex2((ref - vm) * k2);
+            acc0 = mul2(acc0, pk(sc, sc));
+            acc1 = mul2(acc1, pk(sc, sc));
+            ref = vm;
+            mkp = pk(-vm * k2, -vm * k2);
+        }
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float e0, e1;
+            upk(fma2(Pair<T>::widen(w[i]), k2p, mkp), e0, e1);
+            if (i & 1) acc1 = add2(acc1, pk(ex2(e0), ex2(e1)));
+            else acc0 = add2(acc0, pk(ex2(e0), ex2(e1)));
+        }
+        if (WANT_TOP2 && vm >= thr_top) cand |= bit;
+    };
+    constexpr int U = 4;
+    const int wl = lane & 31;
+    const int v_first = lane - wl;                       // the warp's first vector of a batch: warp-uniform trip count
+    bool seeded = !WANT_TOP2;
+    for (int vb = v_first; vb < nv; vb += U * stride) {
+        const int v = vb + wl;
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            raw[u] = make_uint4(Pair<T>::kNegInf2, Pair<T>::kNegInf2, Pair<T>::kNegInf2, Pair<T>::kNegInf2);
+            if (v + u * stride < nv) raw[u] = ldg_stream(rv + v + u * stride);
+        }
+        if (!seeded) {      // (warp-uniform) 2nd largest lane maximum of the first batch
+            float bm = vec_max(raw[0]);
+#pragma unroll
+            for (int u = 1; u < U; ++u) bm = fmaxf(bm, vec_max(raw[u]));
+            const float wm = warp_max(bm);
+            const unsigned holders = __ballot_sync(0xffffffffu, bm == wm);
+            thr_top = warp_max((wl == __ffs(holders) - 1) ? -INFINITY : bm);
+            seeded = true;
+        }
+        unsigned cand = 0u;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (v + u * stride < nv) consume(raw[u], 1u << u, cand);
+        if (WANT_TOP2) {
+            while (cand) {
+                const int u = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const int vv = v + u * stride;
+                const uint4 r = __ldg(rv + vv);
+                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float x0, x1;
+                    upk(Pair<T>::widen(w[i]), x0, x1);
+                    top.push(x0, col0 + vv * 8 + 2 * i);
+                    top.push(x1, col0 + vv * 8 + 2 * i + 1);
+                }
+                thr_top = fmaxf(thr_top, top.a2);
+            }
+        }
+    }
+    float a0, a1;
+    upk(add2(acc0, acc1), a0, a1);
+    ms.m = lane_max;                                      // the partial relative to the lane's true maximum (<= ref + slack)
+    ms.s = (lane_max == -INFINITY) ? 0.f : (a0 + a1) * ex2((ref - lane_max) * k2);
+}
+
+// dispatch: the packed walk for aligned 16-bit rows, the generic one otherwise
+template <typename T, bool WANT_TOP2>
+__device__ __forceinline__ void shard_row_stats_any(const T* __restrict__ row, int n, float k2, MaxSum& ms, Top2& top, int col0, int lane,
+                                                    int stride) {
+    if constexpr (sizeof(T) == 2) {
+        if (vec_ok(row, n)) {        // (uniform over the threads that share the row)
+            shard_row_stats_packed<T, WANT_TOP2>(row, n, k2, ms, top, col0, lane, stride);
+            return;
+        }
+    }
+    shard_row_stats<T>(row, n, k2, ms, WANT_TOP2 ? &top : nullptr, col0, lane, stride);
+}
+
 __device__ __forceinline__ MaxSum block_merge_ms(MaxSum v, float k2, float* sm) {
     warp_merge(v, k2);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -125,8 +233,11 @@ vshard_stats_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __rest
         MaxSum mt, msd;
         Top2 top;
         msd.init();
-        shard_row_stats<T>(teacher + r * ld_t, V_local, k2, mt, &top, col0, gl, G);
-        if (student) shard_row_stats<T>(student + r * ld_s, V_local, k2, msd, nullptr, col0, gl, G);
+        shard_row_stats_any<T, true>(teacher + r * ld_t, V_local, k2, mt, top, col0, gl, G);
+        if (student) {
+            Top2 unused;
+            shard_row_stats_any<T, false>(student + r * ld_s, V_local, k2, msd, unused, col0, gl, G);
+        }
         if constexpr (G == 32) {
             warp_merge(mt, k2);
             if (student) warp_merge(msd, k2);
