@@ -565,16 +565,61 @@ regrad_kernel(const EmitParams p, const float* skip_if_one) {
             const uint4* tv = reinterpret_cast<const uint4*>(trow);
             const uint4* sv = reinterpret_cast<const uint4*>(srow);
             uint4* gv = reinterpret_cast<uint4*>(grow);
-#pragma unroll 2
-            for (int v = t0; v < nvec; v += stride) {
-                float xt[P], xs[P], o[P];
-                Elem<T>::unpack(ldg_stream(tv + v), xt);
-                Elem<T>::unpack(ldg_stream(sv + v), xs);
+            // B vector pairs (and their slice of the override table, as 128-bit loads) are fetched before any is consumed: the
+            // streaming store is a volatile asm with a memory clobber, so a load-compute-store loop keeps ONE pair in flight
+            constexpr int B = sizeof(T) == 2 ? 4 : 2;
+            constexpr bool TABLE = (VARIANT == KD_LOCA_REFERENCE);
+            const bool tab_vec = TABLE && (reinterpret_cast<uintptr_t>(p.table) & 15u) == 0;
+            for (int v0 = t0; v0 < nvec; v0 += stride * B) {
+                uint4 rt[B], rs[B];
+                [[maybe_unused]] float ovv[B][P];
 #pragma unroll
-                for (int i = 0; i < P; ++i)
-                    o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? override_of(v * P + i) : NaN, p.k2, lse2_t, lse2_s, p.thr2, g, gQ) +
-                           ce_term(xs[i], v * P + i);
-                stg_stream(gv + v, Elem<T>::pack(o));
+                for (int u = 0; u < B; ++u) {
+                    const int v = v0 + u * stride;
+                    if (v < nvec) {
+                        rt[u] = ldg_stream(tv + v);
+                        rs[u] = ldg_stream(sv + v);
+                        if constexpr (TABLE) {
+                            if (tab_vec) {
+#pragma unroll
+                                for (int i = 0; i < P; i += 4) {
+                                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.table + v * P + i));
+                                    ovv[u][i] = t4.x; ovv[u][i + 1] = t4.y; ovv[u][i + 2] = t4.z; ovv[u][i + 3] = t4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < P; ++i) ovv[u][i] = override_of(v * P + i);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < B; ++u) {
+                    const int v = v0 + u * stride;
+                    if (v < nvec) {
+                        float xt[P], xs[P], o[P];
+                        Elem<T>::unpack(rt[u], xt);
+                        Elem<T>::unpack(rs[u], xs);
+#pragma unroll
+                        for (int i = 0; i < P; ++i)      // per-row LoCa: every cell as q = tp here, the row's own two cells below
+                            o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], TABLE ? ovv[u][i] : NaN, p.k2, lse2_t, lse2_s, p.thr2, g, gQ) +
+                                   ce_term(xs[i], v * P + i);
+                        stg_stream(gv + v, Elem<T>::pack(o));
+                    }
+                }
+            }
+            if constexpr (VARIANT == KD_LOCA_PER_ROW) {
+                // the row's own override cells (label -> v1, then runner-up -> v2, P1:184-185 per row): the thread that stored the
+                // vector rewrites the element (same thread, program order)
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {
+                    const int c = which ? ov_k : ov_label;
+                    if (c < 0 || c >= nvec * P || (which == 0 && ov_k == ov_label)) continue;
+                    const int v = c / P;
+                    if (v >= t0 && (v - t0) % stride == 0)
+                        grow[c] = Elem<T>::from_float(PointTerm<VARIANT>::grad(Elem<T>::to_float(trow[c]), Elem<T>::to_float(srow[c]),
+                                                                               which ? v2 : v1, p.k2, lse2_t, lse2_s, p.thr2, g, gQ));
+                }
             }
         }
         for (int c = nvec * P + t0; c < V; c += stride)
@@ -857,7 +902,9 @@ template <int VARIANT, typename T>
 int launch_regrad_t(const EmitParams& p, const float* skip, cudaStream_t st) {
     const bool vec = rows_vectorizable<T>(p.teacher, p.ld_t) && rows_vectorizable<T>(p.student, p.ld_s) &&
                      rows_vectorizable<T>(p.grad, p.ld_g);
-    int64_t gx = (p.V / Elem<T>::kPack + 255) / 256;
+    // a thread takes one batch of kRegradBatch vectors of a row (the kernel fetches them all before consuming any)
+    constexpr int kRegradBatch = sizeof(T) == 2 ? 4 : 2;
+    int64_t gx = (p.V / Elem<T>::kPack + 256 * kRegradBatch - 1) / (256 * kRegradBatch);
     gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
     int64_t gy = (int64_t)sm_count() * 16 / gx;
     gy = gy < 1 ? 1 : (gy > p.n_rows ? p.n_rows : gy);
