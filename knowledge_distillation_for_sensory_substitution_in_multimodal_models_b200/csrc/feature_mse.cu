@@ -76,13 +76,28 @@ mse_regrad_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restric
     constexpr int P = Elem<T>::kPack;
     const float gs = gscale * (upstream ? *upstream : 1.f);
     const int64_t nvec = vec ? numel / P : 0;
-    for (int64_t v = blockIdx.x * (int64_t)kThreads + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * kThreads) {
-        float x[P], y[P], o[P];
-        Elem<T>::unpack(ldg_stream(reinterpret_cast<const uint4*>(a) + v), x);
-        Elem<T>::unpack(ldg_stream(reinterpret_cast<const uint4*>(b) + v), y);
+    const uint4* av = reinterpret_cast<const uint4*>(a);
+    const uint4* bv = reinterpret_cast<const uint4*>(b);
+    uint4* gv = reinterpret_cast<uint4*>(g);
+    for (int64_t v0 = blockIdx.x * (int64_t)(kThreads * kBatch) + threadIdx.x; v0 < nvec; v0 += (int64_t)gridDim.x * kThreads * kBatch) {
+        uint4 xa[kBatch], xb[kBatch];
 #pragma unroll
-        for (int i = 0; i < P; ++i) o[i] = gs * (x[i] - y[i]);
-        stg_stream(reinterpret_cast<uint4*>(g) + v, Elem<T>::pack(o));
+        for (int u = 0; u < kBatch; ++u) {
+            const int64_t v = v0 + (int64_t)u * kThreads;
+            if (v < nvec) { xa[u] = ldg_stream(av + v); xb[u] = ldg_stream(bv + v); }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int64_t v = v0 + (int64_t)u * kThreads;
+            if (v < nvec) {
+                float x[P], y[P], o[P];
+                Elem<T>::unpack(xa[u], x);
+                Elem<T>::unpack(xb[u], y);
+#pragma unroll
+                for (int i = 0; i < P; ++i) o[i] = gs * (x[i] - y[i]);
+                stg_stream(gv + v, Elem<T>::pack(o));
+            }
+        }
     }
     for (int64_t c = nvec * P + blockIdx.x * (int64_t)kThreads + threadIdx.x; c < numel; c += (int64_t)gridDim.x * kThreads)
         g[c] = Elem<T>::from_float(gs * (Elem<T>::to_float(a[c]) - Elem<T>::to_float(b[c])));
@@ -92,7 +107,7 @@ template <typename T>
 int launch_regrad(const void* a, const void* b, void* g, int64_t numel, const float* upstream, const float* skip, cudaStream_t st) {
     constexpr int P = Elem<T>::kPack;
     const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(g)) & 15u) == 0;
-    int64_t blocks = (numel / P + kThreads - 1) / kThreads;
+    int64_t blocks = (numel / P + kThreads * kBatch - 1) / (kThreads * kBatch);
     blocks = blocks < 1 ? 1 : (blocks > kMaxBlocks ? kMaxBlocks : blocks);
     mse_regrad_kernel<T><<<(int)blocks, kThreads, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b), static_cast<T*>(g), numel,
                                                            static_cast<float>(2.0 / (double)numel), upstream, skip, vec);

@@ -940,6 +940,7 @@ int run_proj(const void* xs, int Ps, const void* xt, int Pt, const TW* W, void* 
         const bool vec_out = (Ds % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
         int bx = vec_out ? (Ps + 15) / 16 : (int)(((int64_t)Ps * Ds + 255) / 256);
         bx = bx > 32 ? 32 : (bx < 1 ? 1 : bx);
+        if (sd > 1 && bx > 8) bx = 8;       // every CTA adds the sd partials of its row first: fewer, longer CTAs (32 -> 18 us)
         broadcast_rows_kernel<T><<<dim3(M, bx), 256, 0, st>>>(dpspart, static_cast<T*>(dx), Ps, Ds, vec_out, nullptr, nullptr, sd,
                                                               (int64_t)M * Ds, 1.f / (float)Ps);
         KD_CHECK_LAUNCH("broadcast_rows_kernel");
@@ -957,6 +958,7 @@ int run_proj_regrad(const char* ws, const NceProjWorkspace& w, void* dx, TW* dW,
         const bool vec_out = (Ds % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
         int bx = vec_out ? (Ps + 15) / 16 : (int)(((int64_t)Ps * Ds + 255) / 256);
         bx = bx > 32 ? 32 : (bx < 1 ? 1 : bx);
+        if (sd > 1 && bx > 8) bx = 8;
         broadcast_rows_kernel<T><<<dim3(M, bx), 256, 0, st>>>(dpspart, static_cast<T*>(dx), Ps, Ds, vec_out, ratio, skip, sd,
                                                               (int64_t)M * Ds, 1.f / (float)Ps);
         KD_CHECK_LAUNCH("broadcast_rows_kernel");

@@ -63,5 +63,8 @@ def measure(name, f, k=50):
     print(f"{name:8s} eager {eager:7.1f} us/step   host issue {host:7.1f} us/step   graph replay {a.elapsed_time(b) / k * 1e3:7.1f} us/step")
 
 
-measure("plain", plain)
-measure("proj896", proj)
+which = sys.argv[1] if len(sys.argv) > 1 else "both"
+if which in ("both", "plain"):
+    measure("plain", plain)
+if which in ("both", "proj"):
+    measure("proj896", proj)
