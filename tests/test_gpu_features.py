@@ -23,7 +23,8 @@ def test_info_nce_goldens(name, dtype):
     assert grad_close(xs.grad.float().cpu(), g["grad"]) if dtype == torch.bfloat16 else rel_err(xs.grad.float().cpu(), g["grad"]) <= 1e-4
 
 
-@pytest.mark.parametrize("M,P,D", [(64, 729, 1152), (16, 10, 1152), (8, 1, 896), (5, 3, 100)])
+@pytest.mark.parametrize("M,P,D", [(64, 729, 1152), (16, 10, 1152), (8, 1, 896), (5, 3, 100), (3, 1000, 4104), (2, 5000, 16), (1, 1, 8),
+                                   (300, 7, 64)])
 def test_info_nce_against_oracle(M, P, D):
     xs, xt = synthetic.vision_feature_batch(M, P, D, seed=M)
     if M == 16:     # unrelated teacher: every softmax entry matters
@@ -101,6 +102,23 @@ def test_info_nce_grad_output_scaling():
     xd = xs.cuda().requires_grad_(True)
     (kd.info_nce(xd, xt.cuda()) * 0.5).backward()         # weight 0.5 of phase 1 (P1:68, P1:351)
     assert grad_close(xd.grad.float().cpu(), ref.grad * 0.5)
+
+
+@pytest.mark.parametrize("M,P,D,dtype", [(64, 729, 1152, torch.bfloat16), (7, 33, 100, torch.bfloat16), (1, 5, 8, torch.float16),
+                                         (130, 3, 72, torch.float32), (2, 3000, 264, torch.bfloat16)])
+def test_pool_tokens_is_the_fp32_mean_over_tokens(M, P, D, dtype):
+    """`kd_feature_pool_fwd` / `_bwd`: the `.mean(dim=1)` of P1:243-246 in fp32 and its store-only broadcast backward."""
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200.functional import pool_tokens
+    g = torch.Generator().manual_seed(M + P)
+    x = torch.randn(M, P, D, generator=g).to(dtype)
+    w = torch.randn(M, D, generator=g)
+    xd = x.cuda().requires_grad_(True)
+    pooled = pool_tokens(xd)
+    assert pooled.dtype == torch.float32
+    assert rel_err(pooled.cpu(), x.double().mean(1)) <= 2e-6
+    (pooled * w.cuda()).sum().backward()
+    want = (w.double() / P).unsqueeze(1).expand(M, P, D)
+    assert rel_err(xd.grad.cpu(), want) <= (1e-6 if dtype == torch.float32 else 3e-3)
 
 
 def _proj_reference(xs, xt, W, temperature=0.07):

@@ -1,7 +1,7 @@
 """Driver for ncu: runs ONE op of the path a few times at its benchmark shape (the ncu command line picks the kernel).
 
 usage: python tools/profile_ops.py <op> [rows]      op in: loca_reference loca_reference_ce loca_per_row loca_reference_T08 kl kl_log_target regrad
-                                                          mse proj_mse info_nce nce_tc gemm_dh gemm_dw lm_head vshard
+                                                          mse proj_mse info_nce info_nce_proj nce_tc gemm_dh gemm_dw lm_head vshard vshard_phases
 """
 import os
 import sys
@@ -72,6 +72,23 @@ elif op == "info_nce":
         xs.grad = None
         loss = kd.info_nce(xs, xt)
         loss.backward()
+elif op == "info_nce_proj":                       # BASELINE configs[2] with its learned 1152 -> 896 projection (one library call)
+    xs, _ = synthetic.vision_feature_batch(64, 729, 1152, device=dev)
+    xs.requires_grad_(True)
+    wp = (torch.randn(1152, 896, device=dev) * 0.03).to(torch.bfloat16).requires_grad_(True)
+    xt = torch.randn(64, 729, 896, device=dev).to(torch.bfloat16)
+    for _ in range(REPS):
+        xs.grad = None
+        wp.grad = None
+        loss = kd.info_nce(xs, xt, proj=wp)
+        loss.backward()
+elif op == "vshard_phases":                       # the streaming KD phases of one configs[4] shard, both tensors from HBM
+    n, vl = 65536, 18992
+    ts = (torch.randn(n, vl, device=dev) * 2.0).to(torch.bfloat16)
+    ss = (torch.randn(n, vl, device=dev) * 2.0).to(torch.bfloat16)
+    lab = torch.randint(0, vl, (n,), device=dev)
+    for _ in range(2):
+        loss, _g = sharded.logit_kd_vocab_sharded(ts, ss, lab, 0, V, 2.0)
 elif op == "nce_tc":                              # token-level contrastive loss: 64 x 729 un-pooled SigLIP tokens as rows
     M = rows if len(sys.argv) > 2 else 46656
     xs, xt = synthetic.vision_feature_batch(M, 1, 1152, seed=7, device=dev)
