@@ -494,15 +494,21 @@ def main() -> None:
     # ---- secondary paths (one GPU, rank 0): per_row LoCa, plain KL, InfoNCE, MSE -----------------------
     if rank == 0 and not args.no_secondary:
         def timeit(fn, k=10, w=3):
+            import gc
             for _ in range(w):
                 fn()
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(k):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
+            gc.collect()
+            gc.disable()                      # (the sub-millisecond ops are host-bound: keep collector pauses out of their loop)
+            try:
+                a.record()
+                for _ in range(k):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+            finally:
+                gc.enable()
             return a.elapsed_time(b) / k
 
         def timeit_graph(fn, k=50):

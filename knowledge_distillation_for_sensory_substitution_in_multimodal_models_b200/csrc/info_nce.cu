@@ -648,8 +648,9 @@ small_gemm_kernel(const TA* __restrict__ A, int64_t lda, const TB* __restrict__ 
     static_assert(A_RM || B_RM, "one operand must be reduction-major");
     if (skip_if_one && *skip_if_one == 1.f) return;      // backward re-emission: grad_output is what forward assumed
     const float oscale = out_scale ? *out_scale : 1.f;
-    __shared__ __align__(16) float As[A_RM ? kSgRc * kSgTile : kSgTile * (kSgRc + 1)];
-    __shared__ __align__(16) float Bs[B_RM ? kSgRc * kSgTile : kSgTile * (kSgRc + 1)];
+    constexpr int kPitch = kSgRc + 4;       // [i][r] operand: rows 36 floats apart — 16-byte aligned float4s of 4 consecutive r, conflict-free fills
+    __shared__ __align__(16) float As[A_RM ? kSgRc * kSgTile : kSgTile * kPitch];
+    __shared__ __align__(16) float Bs[B_RM ? kSgRc * kSgTile : kSgTile * kPitch];
     const int tid = threadIdx.x;
     const int ti = A_RM ? tid % 16 : tid / 16;       // the broadcast operand takes the slow index
     const int tj = A_RM ? tid / 16 : tid % 16;
@@ -669,38 +670,53 @@ small_gemm_kernel(const TA* __restrict__ A, int64_t lda, const TB* __restrict__ 
                 As[r * kSgTile + i] = (rc + r < rend && i0 + i < I) ? Elem<TA>::to_float(A[(int64_t)(rc + r) * lda + i0 + i]) : 0.f;
             } else {
                 const int i = idx / kSgRc, r = idx % kSgRc;
-                As[i * (kSgRc + 1) + r] = (rc + r < rend && i0 + i < I) ? Elem<TA>::to_float(A[(int64_t)(i0 + i) * lda + rc + r]) : 0.f;
+                As[i * kPitch + r] = (rc + r < rend && i0 + i < I) ? Elem<TA>::to_float(A[(int64_t)(i0 + i) * lda + rc + r]) : 0.f;
             }
             if constexpr (B_RM) {
                 const int r = idx / kSgTile, j = idx % kSgTile;
                 Bs[r * kSgTile + j] = (rc + r < rend && j0 + j < J) ? Elem<TB>::to_float(B[(int64_t)(rc + r) * ldb + j0 + j]) : 0.f;
             } else {
                 const int j = idx / kSgRc, r = idx % kSgRc;
-                Bs[j * (kSgRc + 1) + r] = (rc + r < rend && j0 + j < J) ? Elem<TB>::to_float(B[(int64_t)(j0 + j) * ldb + rc + r]) : 0.f;
+                Bs[j * kPitch + r] = (rc + r < rend && j0 + j < J) ? Elem<TB>::to_float(B[(int64_t)(j0 + j) * ldb + rc + r]) : 0.f;
             }
         }
         __syncthreads();
-#pragma unroll 8
-        for (int r = 0; r < kSgRc; ++r) {
-            float a[4], bb[4];
+        // four reduction steps per iteration: eight 128-bit shared loads up front, then 64 independent FMAs
+#pragma unroll 2
+        for (int r = 0; r < kSgRc; r += 4) {
+            float a[4][4], bb[4][4];       // [reduction step][output]
             if constexpr (A_RM) {
-                const float4 v = *reinterpret_cast<const float4*>(&As[r * kSgTile + ti * 4]);
-                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 v = *reinterpret_cast<const float4*>(&As[(r + k) * kSgTile + ti * 4]);
+                    a[k][0] = v.x; a[k][1] = v.y; a[k][2] = v.z; a[k][3] = v.w;
+                }
             } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) a[q] = As[(ti * 4 + q) * (kSgRc + 1) + r];
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = *reinterpret_cast<const float4*>(&As[(ti * 4 + q) * kPitch + r]);
+                    a[0][q] = v.x; a[1][q] = v.y; a[2][q] = v.z; a[3][q] = v.w;
+                }
             }
             if constexpr (B_RM) {
-                const float4 v = *reinterpret_cast<const float4*>(&Bs[r * kSgTile + tj * 4]);
-                bb[0] = v.x; bb[1] = v.y; bb[2] = v.z; bb[3] = v.w;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 v = *reinterpret_cast<const float4*>(&Bs[(r + k) * kSgTile + tj * 4]);
+                    bb[k][0] = v.x; bb[k][1] = v.y; bb[k][2] = v.z; bb[k][3] = v.w;
+                }
             } else {
 #pragma unroll
-                for (int p = 0; p < 4; ++p) bb[p] = Bs[(tj * 4 + p) * (kSgRc + 1) + r];
+                for (int p = 0; p < 4; ++p) {
+                    const float4 v = *reinterpret_cast<const float4*>(&Bs[(tj * 4 + p) * kPitch + r]);
+                    bb[0][p] = v.x; bb[1][p] = v.y; bb[2][p] = v.z; bb[3][p] = v.w;
+                }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int p = 0; p < 4; ++p) acc[q][p] = fmaf(a[q], bb[p], acc[q][p]);
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) acc[q][p] = fmaf(a[k][q], bb[k][p], acc[q][p]);
         }
         __syncthreads();
     }

@@ -85,7 +85,9 @@ def _stream_ptr(dev: torch.device) -> int:
 
 def _backward_scalars(grad_output, upstream, dev):
     """(grad_output, grad_output / scale folded in at forward time) as device scalars — no host sync."""
-    go = grad_output.detach().to(device=dev, dtype=torch.float32).reshape(()).contiguous()
+    go = grad_output
+    if go.dtype != torch.float32 or go.device != dev or go.dim() != 0 or go.requires_grad:      # (the usual case needs none of it)
+        go = go.detach().to(device=dev, dtype=torch.float32).reshape(()).contiguous()
     ratio = go if upstream is None else (go / upstream).contiguous()
     return go, ratio
 
@@ -398,7 +400,9 @@ class _InfoNCE(torch.autograd.Function):
             M, P, D = student.shape
         else:
             raise ValueError("features must be [M, D] or [M, tokens, D]")
-        xs, xt = student.detach().contiguous(), teacher.detach().contiguous()
+        # (inside Function.forward the inputs carry no graph: no detach needed, and .contiguous() only when it does something)
+        xs = student if student.is_contiguous() else student.contiguous()
+        xt = teacher if teacher.is_contiguous() else teacher.contiguous()
         need_grad = student.requires_grad
         lib = _lib.load()
         with _device_guard(dev):
