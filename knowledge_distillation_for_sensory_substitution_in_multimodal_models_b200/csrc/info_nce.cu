@@ -661,25 +661,41 @@ small_gemm_kernel(const TA* __restrict__ A, int64_t lda, const TB* __restrict__ 
     for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int p = 0; p < 4; ++p) acc[q][p] = 0.f;
-    for (int rc = rbeg; rc < rend; rc += kSgRc) {
+    // the next reduction chunk's operands are fetched into registers while the current one is multiplied (the global round trip
+    // of every chunk used to sit in front of its 32 steps of arithmetic)
+    constexpr int NQ = (kSgRc * kSgTile) / 256;
+    float pa[NQ], pb[NQ];
+    auto fetch = [&](int rc) {
 #pragma unroll
-        for (int q = 0; q < (kSgRc * kSgTile) / 256; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             const int idx = tid + 256 * q;
             if constexpr (A_RM) {
                 const int r = idx / kSgTile, i = idx % kSgTile;
-                As[r * kSgTile + i] = (rc + r < rend && i0 + i < I) ? Elem<TA>::to_float(A[(int64_t)(rc + r) * lda + i0 + i]) : 0.f;
+                pa[q] = (rc + r < rend && i0 + i < I) ? Elem<TA>::to_float(A[(int64_t)(rc + r) * lda + i0 + i]) : 0.f;
             } else {
                 const int i = idx / kSgRc, r = idx % kSgRc;
-                As[i * kPitch + r] = (rc + r < rend && i0 + i < I) ? Elem<TA>::to_float(A[(int64_t)(i0 + i) * lda + rc + r]) : 0.f;
+                pa[q] = (rc + r < rend && i0 + i < I) ? Elem<TA>::to_float(A[(int64_t)(i0 + i) * lda + rc + r]) : 0.f;
             }
             if constexpr (B_RM) {
                 const int r = idx / kSgTile, j = idx % kSgTile;
-                Bs[r * kSgTile + j] = (rc + r < rend && j0 + j < J) ? Elem<TB>::to_float(B[(int64_t)(rc + r) * ldb + j0 + j]) : 0.f;
+                pb[q] = (rc + r < rend && j0 + j < J) ? Elem<TB>::to_float(B[(int64_t)(rc + r) * ldb + j0 + j]) : 0.f;
             } else {
                 const int j = idx / kSgRc, r = idx % kSgRc;
-                Bs[j * kPitch + r] = (rc + r < rend && j0 + j < J) ? Elem<TB>::to_float(B[(int64_t)(j0 + j) * ldb + rc + r]) : 0.f;
+                pb[q] = (rc + r < rend && j0 + j < J) ? Elem<TB>::to_float(B[(int64_t)(j0 + j) * ldb + rc + r]) : 0.f;
             }
         }
+    };
+    if (rbeg < rend) fetch(rbeg);
+    for (int rc = rbeg; rc < rend; rc += kSgRc) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int idx = tid + 256 * q;
+            if constexpr (A_RM) As[(idx / kSgTile) * kSgTile + idx % kSgTile] = pa[q];
+            else As[(idx / kSgRc) * kPitch + idx % kSgRc] = pa[q];
+            if constexpr (B_RM) Bs[(idx / kSgTile) * kSgTile + idx % kSgTile] = pb[q];
+            else Bs[(idx / kSgRc) * kPitch + idx % kSgRc] = pb[q];
+        }
+        if (rc + kSgRc < rend) fetch(rc + kSgRc);
         __syncthreads();
         // four reduction steps per iteration: eight 128-bit shared loads up front, then 64 independent FMAs
 #pragma unroll 2
@@ -721,14 +737,26 @@ small_gemm_kernel(const TA* __restrict__ A, int64_t lda, const TB* __restrict__ 
         __syncthreads();
     }
     TC* out = C + (int64_t)blockIdx.z * split_stride;
+    const bool vec_st = (ldc % 4 == 0) && (split_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(C) & 15u) == 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int i = i0 + ti * 4 + q;
-        if (i >= I) continue;
+        if (i < I) {
+            const int j = j0 + tj * 4;
+            TC* dst = out + (int64_t)i * ldc + j;
+            if (vec_st && j + 3 < J) {      // the thread's four consecutive outputs of the row as one store
+                if constexpr (sizeof(TC) == 4) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(acc[q][0] * oscale, acc[q][1] * oscale, acc[q][2] * oscale, acc[q][3] * oscale);
+                } else {
+                    const uint2 pk2 = make_uint2(Pair<TC>::narrow(acc[q][0] * oscale, acc[q][1] * oscale),
+                                                 Pair<TC>::narrow(acc[q][2] * oscale, acc[q][3] * oscale));
+                    *reinterpret_cast<uint2*>(dst) = pk2;
+                }
+            } else {
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int j = j0 + tj * 4 + p;
-            if (j < J) out[(int64_t)i * ldc + j] = Elem<TC>::from_float(acc[q][p] * oscale);
+                for (int p = 0; p < 4; ++p)
+                    if (j + p < J) dst[p] = Elem<TC>::from_float(acc[q][p] * oscale);
+            }
         }
     }
 }
