@@ -219,6 +219,10 @@ int kd_lm_head_stats_merge(const float* stat_partials, int64_t n_tiles, float* s
  * ---------------------------------------------------------------------------------------------------- */
 int kd_gemm(const void* A, int64_t ld_a, int a_mn_major, const void* B, int64_t ld_b, int b_mn_major, void* C, int64_t ld_c,
             int c_is_f32, int64_t M, int64_t N, int64_t K, int dtype, void* stream);
+/* kd_gemm on at most `max_ctas` CTAs (0 = one per SM): the persistent kernel otherwise holds every SM until it ends, and a
+ * collective started beside it (the all-reduce of the partial d hidden under the d weight product, sharded.py) cannot get one. */
+int kd_gemm_ex(const void* A, int64_t ld_a, int a_mn_major, const void* B, int64_t ld_b, int b_mn_major, void* C, int64_t ld_c,
+            int c_is_f32, int64_t M, int64_t N, int64_t K, int dtype, int max_ctas, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Projected feature MSE (BASELINE configs[3]; mse_loss EV:160-165 applied to `input @ proj`, the intended use at EV:304 / P1:375

@@ -51,6 +51,7 @@ SIGNATURES = {
     "kd_lm_head_fwd": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i, _f, _p]),
     "kd_lm_head_stats_merge": (_i, [_p, _i64, _p, _i64, _f, _p]),
     "kd_gemm": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i64, _i, _i64, _i64, _i64, _i, _p]),
+    "kd_gemm_ex": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i64, _i, _i64, _i64, _i64, _i, _i, _p]),
     "kd_proj_mse_workspace_bytes": (_i, [_i64, _i64, C.POINTER(_sz)]),
     "kd_proj_mse_fwd_bwd": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _sz, _i64, _i64, _i64, _i, _p, _p]),
     "kd_info_nce_workspace_bytes": (_i, [_i64, _i64, _i64, C.POINTER(_sz)]),

@@ -168,6 +168,7 @@ struct GemmExtra {                // what the non-plain epilogues need
     float* sq_partials;           // EPI_MSE: [tiles * 2 CTAs * EPI_HALVES * 4 warps] sums of squared differences
     float* diag;                  // EPI_NCE_STATS: [M] acc[i, i]
     const float* lse2;            // EPI_NCE_GRAD: [M] log2-sum-exp2 of the rows' acc * k2
+    int max_ctas;                 // 0 = one CTA per SM; else at most this many (leaves SMs to a collective running beside the product)
 };
 
 template <typename OutT> struct OutPack;          // accumulator values -> the 16-byte chunks of a 128-byte staging row
@@ -509,7 +510,8 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);      // per device, cheap
     if (e != cudaSuccess) return cuda_fail(e, "kd_gemm_kernel: shared-memory opt-in");
     const int64_t tiles = (int64_t)((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
-    const int64_t pairs = gemm_sm_count() / 2;
+    int64_t pairs = gemm_sm_count() / 2;
+    if (ex.max_ctas > 0 && ex.max_ctas / 2 < pairs) pairs = ex.max_ctas / 2 > 0 ? ex.max_ctas / 2 : 1;
     const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);      // persistent CTA pairs (cluster 2 x 1 x 1)
     kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, b, c, tg, M, N, K, ex);
     KD_CHECK_LAUNCH("kd_gemm_kernel");
@@ -647,12 +649,18 @@ int kd_lm_head_fwd(const void* hidden, int64_t ld_h, const void* weight, int64_t
                     n_rows, V_local, H, dtype, ex, static_cast<cudaStream_t>(stream));
 }
 
-int kd_gemm(const void* A, int64_t ld_a, int a_mn_major, const void* B, int64_t ld_b, int b_mn_major, void* C, int64_t ld_c, int c_is_f32,
-            int64_t M, int64_t N, int64_t K, int dtype, void* stream) {
-    KD_CHECK_ARG(M >= 0 && N >= 0 && K >= 1, "kd_gemm: bad shape");
+int kd_gemm_ex(const void* A, int64_t ld_a, int a_mn_major, const void* B, int64_t ld_b, int b_mn_major, void* C, int64_t ld_c, int c_is_f32,
+               int64_t M, int64_t N, int64_t K, int dtype, int max_ctas, void* stream) {
+    KD_CHECK_ARG(M >= 0 && N >= 0 && K >= 1 && max_ctas >= 0, "kd_gemm: bad shape");
     GemmExtra ex{};
+    ex.max_ctas = max_ctas;
     return run_gemm("kd_gemm", EPI_STORE, A, ld_a, a_mn_major != 0, B, ld_b, b_mn_major != 0, C, ld_c, c_is_f32 != 0, M, N, K, dtype, ex,
                     static_cast<cudaStream_t>(stream));
+}
+
+int kd_gemm(const void* A, int64_t ld_a, int a_mn_major, const void* B, int64_t ld_b, int b_mn_major, void* C, int64_t ld_c, int c_is_f32,
+            int64_t M, int64_t N, int64_t K, int dtype, void* stream) {
+    return kd_gemm_ex(A, ld_a, a_mn_major, B, ld_b, b_mn_major, C, ld_c, c_is_f32, M, N, K, dtype, 0, stream);
 }
 
 int kd_proj_mse_workspace_bytes(int64_t M, int64_t N, size_t* bytes) {

@@ -568,10 +568,12 @@ class _FeatureMSE(torch.autograd.Function):
         return grad, None, None
 
 
-def gemm(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False, b_mn_major: bool = False, out_dtype=None, out=None):
+def gemm(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False, b_mn_major: bool = False, out_dtype=None, out=None,
+         max_ctas: int = 0):
     """``C[M, N] = A[M, K] . B[N, K]^T`` on the tcgen05 kernel (``kd_gemm``).  ``a`` is ``[M, K]`` (or ``[K, M]`` with
     ``a_mn_major``: the operand is stored transposed and read through an MN-major descriptor, nothing is transposed in HBM),
-    ``b`` is ``[N, K]`` (or ``[K, N]`` with ``b_mn_major``).  bf16 / fp16 CUDA operands; ``out_dtype``: theirs or float32."""
+    ``b`` is ``[N, K]`` (or ``[K, N]`` with ``b_mn_major``).  bf16 / fp16 CUDA operands; ``out_dtype``: theirs or float32.
+    ``max_ctas`` > 0 caps the persistent grid (``kd_gemm_ex``) so that a collective running beside the product finds free SMs."""
     dev = _require_cuda(a, b)
     if a.dim() != 2 or b.dim() != 2 or a.dtype != b.dtype:
         raise ValueError("gemm: two 2-D operands of one dtype expected")
@@ -589,9 +591,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False, b_mn_major:
     elif out.shape != (M, N) or out.dtype != out_dtype or out.stride(1) != 1:
         raise ValueError("gemm: `out` must be a row-major [M, N] tensor of the output dtype")
     with _device_guard(dev):
-        _lib.check(_lib.load().kd_gemm(a.data_ptr(), a.stride(0), int(a_mn_major), b.data_ptr(), b.stride(0), int(b_mn_major),
-                                       out.data_ptr(), out.stride(0), int(out_dtype == torch.float32), M, N, K, _dtype_code(a),
-                                       _stream_ptr(dev)))
+        _lib.check(_lib.load().kd_gemm_ex(a.data_ptr(), a.stride(0), int(a_mn_major), b.data_ptr(), b.stride(0), int(b_mn_major),
+                                          out.data_ptr(), out.stride(0), int(out_dtype == torch.float32), M, N, K, _dtype_code(a),
+                                          int(max_ctas), _stream_ptr(dev)))
     return out
 
 

@@ -460,6 +460,25 @@ def lm_head_fwd(hidden, weight, T=None, out=None):
     return logits, partials
 
 
+_MAX_RESERVED_SMS = 16      # SMs the d weight product may leave to the d hidden all-reduce (0: never cap the product)
+
+
+def _dw_cta_cap(dev, m: int, n: int) -> int:
+    """CTAs for the [m, n] d weight product when a collective runs beside it.  The persistent kernel works through its 256 x 256
+    tiles in waves of one tile per CTA pair; 300 tiles (18 992 x 896) take five waves on 74 pairs and on 60 — so 28 of the 148 SMs
+    can go to the all-reduce at no cost to the product.  Measured on 8 GPUs, two boxes (tools/vshard_overlap_check.py): blocking
+    all-reduce 9.58 / 9.32 ms per step, asynchronous with every SM held by the product 9.62 / 9.68 (the collective cannot start:
+    no gain), with 16 SMs free 9.28 / 9.15, with 28 free 9.31, with 32 free and a sixth wave 10.14 — a gain of ~2 %, close to the
+    run-to-run spread (0.15 ms), kept because it never costs a wave."""
+    if _MAX_RESERVED_SMS <= 0:
+        return 0
+    pairs = torch.cuda.get_device_properties(dev).multi_processor_count // 2
+    tiles = ((m + 255) // 256) * ((n + 255) // 256)
+    waves = (tiles + pairs - 1) // pairs
+    keep = max((tiles + waves - 1) // waves, pairs - _MAX_RESERVED_SMS // 2, 1)      # fewest pairs with the same number of waves
+    return 0 if keep >= pairs else 2 * keep
+
+
 def _tensor_core_head_applies(hidden, weight) -> bool:
     return (hidden.is_cuda and hidden.dtype in (torch.bfloat16, torch.float16) and weight.dtype == hidden.dtype
             and hidden.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0)
@@ -514,7 +533,9 @@ class _LmHeadVocabShardedKD(torch.autograd.Function):
             work = start(d_hidden) if start is not None else None
             if start is None:
                 d_hidden = ctx.collectives.sum_(d_hidden)
-            d_weight = tc_gemm(g, hidden.detach(), a_mn_major=True, b_mn_major=True)                     # [n, V_l]^T . [n, H]
+            # ... on a few SMs fewer than the machine has: the persistent kernel would otherwise keep every SM to the end
+            d_weight = tc_gemm(g, hidden.detach(), a_mn_major=True, b_mn_major=True,                     # [n, V_l]^T . [n, H]
+                               max_ctas=_dw_cta_cap(g.device, g.shape[1], hidden.shape[1]) if work is not None else 0)
             if work is not None:
                 work.wait()
             d_hidden = d_hidden.to(hidden.dtype)
