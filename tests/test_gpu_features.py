@@ -201,6 +201,40 @@ def test_projected_info_nce_weights_and_repeated_backward():
     assert grad_close(Wd.grad.float().cpu(), gW)
 
 
+def test_projected_info_nce_error_paths_through_the_c_abi():
+    """Raw ctypes calls of `kd_info_nce_proj_*`: a short workspace, more rows than the CUDA-core form takes, a null pointer and a bad
+    temperature are reported through the return code + kd_last_error(), nothing is launched."""
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import _lib
+    lib = _lib.load()
+    M, P, Ds, Dt = 8, 3, 64, 32
+    xs = torch.randn(M, P, Ds, device="cuda").to(torch.bfloat16)
+    xt = torch.randn(M, P, Dt, device="cuda").to(torch.bfloat16)
+    w = torch.randn(Ds, Dt, device="cuda").to(torch.bfloat16)
+    gx, gw = torch.empty_like(xs), torch.empty_like(w)
+    loss = torch.zeros((), device="cuda")
+    need = _lib.size_query("kd_info_nce_proj_workspace_bytes", M, Ds, Dt)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def call(m=M, ws_bytes=need, temp=0.07, student=xs.data_ptr()):
+        return lib.kd_info_nce_proj_fwd_bwd(student, P, xt.data_ptr(), P, w.data_ptr(), gx.data_ptr(), gw.data_ptr(), loss.data_ptr(),
+                                            ws.data_ptr(), ws_bytes, m, Ds, Dt, _lib.DTYPE_BF16, _lib.DTYPE_BF16, temp, None, 0, st)
+    assert call() == 0
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).item()
+    assert call(ws_bytes=need - 1) == 3 and b"workspace" in lib.kd_last_error()          # KD_ERR_WORKSPACE_TOO_SMALL
+    assert call(m=5000) == 2 and b"kd_gemm" in lib.kd_last_error()                       # KD_ERR_UNSUPPORTED: use the tensor-core route
+    assert call(temp=0.0) == 1                                                            # KD_ERR_INVALID_ARGUMENT
+    assert call(student=None) == 1
+    ratio = torch.ones((), device="cuda")
+    assert lib.kd_info_nce_proj_regrad(ws.data_ptr(), need - 1, gx.data_ptr(), gw.data_ptr(), M, P, Ds, Dt, _lib.DTYPE_BF16,
+                                       _lib.DTYPE_BF16, ratio.data_ptr(), None, st) == 3
+    assert lib.kd_info_nce_proj_regrad(ws.data_ptr(), need, None, None, M, P, Ds, Dt, _lib.DTYPE_BF16, _lib.DTYPE_BF16,
+                                       ratio.data_ptr(), None, st) == 1
+    with pytest.raises(ValueError):
+        kd.info_nce(xs, xt, proj=w.t().contiguous())                                      # [D_t, D_s]: wrong orientation
+
+
 def test_mse_odd_sizes_and_unaligned():
     for n in (1, 7, 1025, 8191):
         a = torch.randn(n + 1, device="cuda", dtype=torch.bfloat16)[1:]     # 2-byte offset: not 16-B aligned

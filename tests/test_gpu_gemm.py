@@ -77,3 +77,17 @@ def test_projected_mse_matches_oracle(M, K, N):
     if xs3 is not None:
         l3 = kd.feature_mse(xs3, t.reshape(5, -1, N).cuda(), proj=w.cuda())
         assert abs(l3.item() - loss.item()) <= 1e-7 * abs(loss.item())
+
+
+def test_gemm_on_a_capped_grid_gives_the_same_product():
+    """`kd_gemm_ex(max_ctas=...)`: the persistent kernel on fewer CTA pairs (what the vocabulary-parallel head's dW product uses
+    while the dH all-reduce runs) walks the same tiles — bit-identical output."""
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(1500, 520, generator=g).to(torch.bfloat16).cuda()
+    b = torch.randn(704, 520, generator=g).to(torch.bfloat16).cuda()
+    full = kd.gemm(a, b)
+    for cap in (2, 6, 120, 10_000):
+        assert torch.equal(kd.gemm(a, b, max_ctas=cap), full)
+    with pytest.raises(_lib.KDError):
+        kd.gemm(a, b, max_ctas=-1)
+
