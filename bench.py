@@ -547,6 +547,21 @@ def main() -> None:
             ms = timeit(f, k=5, w=2)
             side[name] = {"ms": ms, "tokens_per_s": N / (ms / 1e3), "achieved_gbs": byt / (ms / 1e3) / 1e9,
                           "frac": byt / (ms / 1e3) / 1e9 / peak_gbs}
+        # backward re-emission: what `(w * loss).backward()` (grad_output != the scale folded in at forward time; a changing AMP loss
+        # scale, TR2:145) costs on top of the step — one streaming 6V sweep from the saved row statistics
+        try:
+            def weighted():
+                student.grad = None
+                (0.5 * kd.loca_kl(teacher, student, labels, T_KD, alpha=ALPHA, mode=mode)).backward()
+            ms_w = timeit(weighted, k=5, w=2)
+            ms_p = timeit(fb(lambda: kd.loca_kl(teacher, student, labels, T_KD, alpha=ALPHA, mode=mode)), k=5, w=2)
+            re_ms = max(ms_w - ms_p, 1e-6)
+            side["backward_re_emission"] = {"step_ms": ms_p, "step_with_re_emission_ms": ms_w, "re_emission_ms": re_ms,
+                                            "achieved_gbs": 6 * V * N / (re_ms / 1e3) / 1e9, "frac": 6 * V * N / (re_ms / 1e3) / 1e9 / peak_gbs,
+                                            "algorithmic_bytes_per_token": 6 * V,
+                                            "note": "difference of two step times (includes the two scalar multiplies of autograd)"}
+        except Exception as exc:  # noqa: BLE001
+            side["backward_re_emission"] = {"error": f"{type(exc).__name__}: {exc}"}
         # the reference's own temperatures (P1:71 T = 0.8, LG:75 T = 1) on peaked logits (label = teacher's best class on ~70 % of
         # the rows, student 4x sharper): every row takes the sp >= eps clamp path (pass B' + second reduction), the slow case
         tpk, spk, lpk = synthetic.logit_batch(N, V, seed=4321, device=dev, peaked=True)
@@ -741,6 +756,31 @@ def main() -> None:
         except Exception as exc:  # noqa: BLE001 - a side measurement must not take the headline down
             side["lm_head_gemm"] = {"error": f"{type(exc).__name__}: {exc}"}
         torch.cuda.empty_cache()
+
+        # one vocabulary shard of BASELINE configs[4] on THIS GPU (65 536 tokens x 18 992 of the 151 936 columns = what each of 8 GPUs
+        # computes; no exchange partner, so the collectives are no-ops): head GEMM + vocabulary-sharded LoCa KD, forward + backward
+        if world == 1:
+            try:
+                n_s, v_s = 65536, V // 8
+                hd = torch.randn(n_s, 896, device=dev, dtype=torch.bfloat16)
+                ws_ = (torch.randn(v_s, 896, device=dev) * 0.02).to(torch.bfloat16)
+                ts_ = (torch.randn(n_s, v_s, device=dev) * 2.0).to(torch.bfloat16)
+                lb_ = torch.randint(0, v_s, (n_s,), device=dev)
+
+                def shard_step():
+                    h_, w_ = hd.detach().requires_grad_(True), ws_.detach().requires_grad_(True)
+                    sharded.lm_head_kd_vocab_sharded(h_, w_, ts_, lb_, 0, V, T_KD).backward()
+                ms = timeit(shard_step, k=5, w=2)
+                fl = 3 * 2.0 * n_s * v_s * 896
+                side["lm_head_kd_one_shard_65536x18992"] = {
+                    "ms": ms, "tokens_per_s": n_s / (ms / 1e3), "tflops": fl / (ms / 1e3) / 1e12, "bound": "tensor",
+                    "peak_tflops": tf_peak, "frac": fl / (ms / 1e3) / 1e12 / tf_peak,
+                    "note": "one of the 8 shards of configs[4] on one GPU: tcgen05 head with fused statistics, streamed KD phases "
+                            "(stats / accum / emit), dH and dW on the same GEMM; the 8-GPU step adds ~0.7 ms of exchanges"}
+                del hd, ws_, ts_, lb_
+            except Exception as exc:  # noqa: BLE001
+                side["lm_head_kd_one_shard"] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
 
     # ---- BASELINE configs[4] at N >= 2 (all ranks take part) ----------------------------------------------
     vshard = None
