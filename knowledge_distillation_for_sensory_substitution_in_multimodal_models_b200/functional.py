@@ -79,7 +79,14 @@ def _rows(x: torch.Tensor) -> torch.Tensor:
     return x.reshape(-1, v).contiguous()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)      # what torch's own generated code uses: ~0.3 us
+
+
 def _stream_ptr(dev: torch.device) -> int:
+    """The current CUDA stream of ``dev`` as an integer handle (``torch.cuda.current_stream(dev).cuda_stream`` builds a Stream
+    object per call: ~4 us, twice per step of a small op)."""
+    if _raw_stream is not None and dev.index is not None:
+        return _raw_stream(dev.index)
     return torch.cuda.current_stream(dev).cuda_stream
 
 
