@@ -110,7 +110,9 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
                       float* __restrict__ dmean, float* __restrict__ rowloss, int M, int D, float inv_temp,
                       float inv_tokens /* 1/P */, const float* upstream, bool want_grad,
                       int raw_parts = 0 /* > 0: `us` holds that many [M, D] partials of the UN-normalised student rows */,
-                      float* __restrict__ dmeanT = nullptr /* optional [D, M] copy of the gradient rows */) {
+                      float* __restrict__ dmeanT = nullptr /* optional [D, M] copy of the gradient rows */,
+                      unsigned* __restrict__ done_counter = nullptr /* zeroed by the pooling's finishing kernel ... */,
+                      float* __restrict__ loss_out = nullptr /* ... the LAST CTA to get here writes mean(rowloss) */) {
     extern __shared__ float sm[];   // [D] u_s row | [M] logits / G row
     float* su = sm;
     float* sl = sm + D;
@@ -183,6 +185,23 @@ similarity_row_kernel(const float* __restrict__ us, const float* __restrict__ ut
     // loss_i = lse - L_ii = log(denom) - (L_ii - mx);  when the diagonal is the max (ed == 1) use log1p(r)
     const float loss_i = (lii == mx) ? log1pf(r) : (logf(denom) - (lii - mx));
     if (threadIdx.x == 0) rowloss[i] = loss_i;
+    if (done_counter && w == 0) {
+        // the last CTA adds the rows' terms (fixed lane assignment + fixed shuffle tree: deterministic) — saves the finalize launch
+        unsigned prev = 0;
+        if (l == 0) {
+            __threadfence();
+            prev = atomicAdd(done_counter, 1u);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev == (unsigned)M - 1u) {
+            __threadfence();
+            double a = 0.0;
+            for (int j = l; j < M; j += 32) a += (double)__ldcg(rowloss + j);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (l == 0) *loss_out = static_cast<float>(a / (double)M);
+        }
+    }
     if (!want_grad) return;
     __syncthreads();
     // G row: (softmax - onehot)/M, folded with 1/temp; diagonal = -(sum of the others)/denom
@@ -477,9 +496,10 @@ pool_ranges_kernel(const PoolPlan plan, float* __restrict__ partials) {
 constexpr int kFinishPieces = 8;
 __global__ void __launch_bounds__(1024)
 pool_ranges_finish_kernel(const PoolPlan plan, const float* __restrict__ partials, float* __restrict__ out0, float* __restrict__ out1,
-                          float* __restrict__ norm0, unsigned normalize_mask) {
+                          float* __restrict__ norm0, unsigned normalize_mask, unsigned* __restrict__ zero_word) {
     __shared__ float red[32];
     __shared__ long long offs[kFinishPieces];
+    if (zero_word && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0u;      // the row kernel's "CTAs done" counter
     __shared__ int s_first, s_count;
     const int k = (plan.n > 1 && (int)blockIdx.x >= plan.t[0].M) ? 1 : 0;
     const PoolTensor t = k ? plan.t[1] : plan.t[0];
@@ -593,7 +613,8 @@ size_t pool_ranges_partial_bound(int64_t M0, int64_t D0, int64_t M1, int64_t D1)
 }
 
 template <typename T>
-int launch_pool_ranges(PoolPlan& pl, float* partials, float* out0, float* out1, float* norm0, unsigned normalize_mask, cudaStream_t st) {
+int launch_pool_ranges(PoolPlan& pl, float* partials, float* out0, float* out1, float* norm0, unsigned normalize_mask, cudaStream_t st,
+                       unsigned* zero_word = nullptr) {
     constexpr int E = Elem<T>::kPack;
     bool vec = true;
     for (int k = 0; k < pl.n; ++k) vec = vec && (pl.t[k].D % E == 0) && (reinterpret_cast<uintptr_t>(pl.t[k].x) & 15u) == 0;
@@ -627,7 +648,7 @@ int launch_pool_ranges(PoolPlan& pl, float* partials, float* out0, float* out1, 
     KD_CHECK_ARG(fcols <= 4096, "pooling: feature dimension %d too large for the finishing kernel", pl.dmax);
     int fthreads = (fcols + 31) / 32 * 32;
     if (fthreads > 1024) fthreads = 1024;
-    pool_ranges_finish_kernel<<<images, fthreads, 0, st>>>(pl, partials, out0, out1, norm0, normalize_mask);
+    pool_ranges_finish_kernel<<<images, fthreads, 0, st>>>(pl, partials, out0, out1, norm0, normalize_mask, zero_word);
     KD_CHECK_LAUNCH("pool_ranges_finish_kernel");
     return KD_OK;
 }
@@ -784,7 +805,7 @@ int small_gemm_splits(int I, int J, int Rr) {
 }
 
 constexpr int kMaxPoolSplit = 8;
-struct NceWorkspace { size_t us, ut, norm_s, dmean, rowloss, partials, total; };
+struct NceWorkspace { size_t us, ut, norm_s, dmean, rowloss, counter, partials, total; };
 NceWorkspace nce_layout(int64_t M, int64_t D) {
     NceWorkspace w{};
     size_t off = 0;
@@ -794,6 +815,7 @@ NceWorkspace nce_layout(int64_t M, int64_t D) {
     w.norm_s = take(sizeof(float) * M);
     w.dmean = take(sizeof(float) * M * D);
     w.rowloss = take(sizeof(float) * M);
+    w.counter = take(sizeof(unsigned));
     w.partials = take(sizeof(float) * kMaxPoolSplit * 2 * M * D);
     w.total = off;
     return w;
@@ -843,7 +865,9 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
         pl.n = 2;
         pl.t[0] = PoolTensor{xs, M, P, D, 0, 0};
         pl.t[1] = PoolTensor{xt, M, P, D, 0, 0};
-        if (int rc = launch_pool_ranges<T>(pl, reinterpret_cast<float*>(ws + w.partials), us, ut, norm_s, 3u, st)) return rc;
+        if (int rc = launch_pool_ranges<T>(pl, reinterpret_cast<float*>(ws + w.partials), us, ut, norm_s, 3u, st,
+                                           reinterpret_cast<unsigned*>(ws + w.counter)))
+            return rc;
     } else {
         float* partials = reinterpret_cast<float*>(ws + w.partials);
         const int ncol = vec_in ? D / E : D;
@@ -893,12 +917,16 @@ int run(const void* xs, const void* xt, void* dx, float* loss, char* ws, const N
         const size_t smem = sizeof(float) * ((size_t)D + M);
         KD_CHECK_ARG(smem <= 220 * 1024, "info_nce: M + D = %d floats exceed the row kernel's shared memory; the tensor-core form needs M and D to be multiples of 8", M + D);
         if (smem > 48 * 1024) cudaFuncSetAttribute(similarity_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // (the pooling's finishing kernel zeroed the counter: the last row CTA writes the loss)
         similarity_row_kernel<<<M, kRowThreads, smem, st>>>(us, ut, norm_s, dmean, rowloss, M, D, 1.f / temperature,
-                                                            1.f / (float)P, upstream, want_grad);
+                                                            1.f / (float)P, upstream, want_grad, 0, nullptr,
+                                                            reinterpret_cast<unsigned*>(ws + w.counter), loss);
         KD_CHECK_LAUNCH("similarity_row_kernel");
     }
-    nce_finalize_kernel<<<1, M >= 1024 ? 1024 : 32, 0, st>>>(rowloss, M, loss);
-    KD_CHECK_LAUNCH("nce_finalize_kernel");
+    if (tc) {
+        nce_finalize_kernel<<<1, M >= 1024 ? 1024 : 32, 0, st>>>(rowloss, M, loss);
+        KD_CHECK_LAUNCH("nce_finalize_kernel");
+    }
     if (want_grad) {
         const bool vec_out = (D % E == 0) && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
         int bx = vec_out ? (P + 15) / 16 : (int)(((int64_t)P * D + 255) / 256);      // >= 16 tokens per CTA and row
@@ -927,7 +955,7 @@ int run_regrad(const float* dmean, void* dx, int M, int P, int D, const float* r
 //   loss = contrastive_loss(y, mean_p x_t)  (P1:393-416 on the projected student vectors — pooling is linear, so projecting the
 //   pooled vectors equals pooling the projected tokens);  dy from the row kernel,  dW = ps^T . dy,  d ps = dy . W^T,
 //   dx_s[m, p, :] = d ps[m, :] / P.  Eight launches, every product in fp32 on the CUDA cores.
-struct NceProjWorkspace { size_t ps, ut, ypart, dy, dyT, rowloss, dpspart, pool, total; };
+struct NceProjWorkspace { size_t ps, ut, ypart, dy, dyT, rowloss, counter, dpspart, pool, total; };
 constexpr int kProjMaxSplit = 16;
 NceProjWorkspace nce_proj_layout(int64_t M, int64_t Ds, int64_t Dt) {
     NceProjWorkspace w{};
@@ -938,6 +966,7 @@ NceProjWorkspace nce_proj_layout(int64_t M, int64_t Ds, int64_t Dt) {
     w.dy = take(sizeof(float) * M * Dt);
     w.dyT = take(sizeof(float) * M * Dt);
     w.rowloss = take(sizeof(float) * M);
+    w.counter = take(sizeof(unsigned));
     w.dpspart = take(sizeof(float) * kProjMaxSplit * M * Ds);
     w.ypart = take(sizeof(float) * kProjMaxSplit * M * Dt);
     w.pool = take(sizeof(float) * pool_ranges_partial_bound(M, Ds, M, Dt));
@@ -963,7 +992,9 @@ int run_proj(const void* xs, int Ps, const void* xt, int Pt, const TW* W, void* 
     pl.t[0] = PoolTensor{xs, M, Ps, Ds, 0, 0};
     pl.t[1] = PoolTensor{xt, M, Pt, Dt, 0, 0};
     // student: the plain mean (the projection comes first); teacher: mean + F.normalize
-    if (int rc = launch_pool_ranges<T>(pl, reinterpret_cast<float*>(ws + w.pool), ps, ut, nullptr, 2u, st)) return rc;
+    if (int rc = launch_pool_ranges<T>(pl, reinterpret_cast<float*>(ws + w.pool), ps, ut, nullptr, 2u, st,
+                                       reinterpret_cast<unsigned*>(ws + w.counter)))
+        return rc;
     const int sy = small_gemm_splits(M, Dt, Ds);
     if (int rc = launch_small_gemm<float, TW, false, true, float>(ps, Ds, W, Dt, ypart, Dt, M, Dt, Ds, sy, st)) return rc;
     const bool want_grad = want_dx || want_dw;
@@ -971,10 +1002,8 @@ int run_proj(const void* xs, int Ps, const void* xt, int Pt, const TW* W, void* 
     KD_CHECK_ARG(smem <= 220 * 1024, "info_nce (projected): M + D_t = %d floats exceed the row kernel's shared memory", M + Dt);
     if (smem > 48 * 1024) cudaFuncSetAttribute(similarity_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     similarity_row_kernel<<<M, kRowThreads, smem, st>>>(ypart, ut, nullptr, dy, rowloss, M, Dt, 1.f / temperature, 1.f, upstream, want_grad,
-                                                        sy, dyT);
+                                                        sy, dyT, reinterpret_cast<unsigned*>(ws + w.counter), loss);
     KD_CHECK_LAUNCH("similarity_row_kernel");
-    nce_finalize_kernel<<<1, M >= 1024 ? 1024 : 32, 0, st>>>(rowloss, M, loss);
-    KD_CHECK_LAUNCH("nce_finalize_kernel");
     if (want_dw) {       // dW[k, n] = sum_m ps[m, k] dy[m, n]: both operands reduction-major as stored
         if (int rc = launch_small_gemm<float, float, true, true, TW>(ps, Ds, dy, Dt, dW, Dt, Ds, Dt, M, 1, st)) return rc;
     }
