@@ -507,7 +507,9 @@ pool_ranges_finish_kernel(const PoolPlan plan, const float* __restrict__ partial
     const int D = t.D, P = t.P, G = t.G;
     const int64_t R = (int64_t)t.M * P;
     const int64_t lo = (int64_t)m * P, hi = lo + P;
-    const bool vec4 = (D % 4 == 0) && (plan.dmax % 4 == 0);
+    float* const u_out = (k ? out1 : out0) + (int64_t)m * D;
+    const bool vec4 = (D % 4 == 0) && (plan.dmax % 4 == 0) && (reinterpret_cast<uintptr_t>(u_out) & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(partials) & 15u) == 0;
     const int ncol = vec4 ? D / 4 : D;
     if (threadIdx.x == 0) {
         int b = (int)(lo * G / R);
@@ -565,7 +567,7 @@ pool_ranges_finish_kernel(const PoolPlan plan, const float* __restrict__ partial
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
     const float nrm = sqrtf(tot);
     const float inv = ((normalize_mask >> k) & 1u) ? 1.f / fmaxf(nrm, kNormEps) : 1.f;
-    float* u = (k ? out1 : out0) + (int64_t)m * D;
+    float* u = u_out;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int c = threadIdx.x + q * blockDim.x;
@@ -642,7 +644,10 @@ int launch_pool_ranges(PoolPlan& pl, float* partials, float* out0, float* out1, 
     KD_CHECK_LAUNCH("pool_ranges_kernel");
     int fcols = 0;        // column slots (float4 or scalar) of the widest tensor: one per thread, up to 4 when a CTA cannot hold them
     for (int k = 0; k < pl.n; ++k) {
-        const int c = (pl.t[k].D % 4 == 0 && pl.dmax % 4 == 0) ? pl.t[k].D / 4 : pl.t[k].D;
+        const float* o = k ? out1 : out0;
+        const bool v4 = pl.t[k].D % 4 == 0 && pl.dmax % 4 == 0 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0 &&
+                        (reinterpret_cast<uintptr_t>(partials) & 15u) == 0;
+        const int c = v4 ? pl.t[k].D / 4 : pl.t[k].D;
         fcols = c > fcols ? c : fcols;
     }
     KD_CHECK_ARG(fcols <= 4096, "pooling: feature dimension %d too large for the finishing kernel", pl.dmax);

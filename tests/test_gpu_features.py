@@ -121,6 +121,23 @@ def test_pool_tokens_is_the_fp32_mean_over_tokens(M, P, D, dtype):
     assert rel_err(xd.grad.cpu(), want) <= (1e-6 if dtype == torch.float32 else 3e-3)
 
 
+def test_pool_into_an_unaligned_output_through_the_c_abi():
+    """A C caller may hand `kd_feature_pool_fwd` an output that is only 4-byte aligned: the finishing kernel then stores scalars."""
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import _lib
+    lib = _lib.load()
+    M, P, D = 5, 11, 64
+    x = torch.randn(M, P, D, device="cuda").to(torch.bfloat16)
+    buf = torch.zeros(M * D + 1, device="cuda")
+    out = buf[1:]                                                   # 4 bytes past a 16-byte boundary
+    need = _lib.size_query("kd_feature_pool_workspace_bytes", M, P, D)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    assert out.data_ptr() % 16 == 4
+    assert lib.kd_feature_pool_fwd(x.data_ptr(), out.data_ptr(), ws.data_ptr(), need, M, P, D, _lib.DTYPE_BF16,
+                                   torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    assert rel_err(out.view(M, D).cpu(), x.double().mean(1).cpu()) <= 2e-6
+
+
 def _proj_reference(xs, xt, W, temperature=0.07):
     """contrastive_loss(x_s @ W, x_t) after the pooling of P1:243-248, in fp64 with autograd gradients."""
     x64, W64 = xs.double().requires_grad_(True), W.double().requires_grad_(True)
