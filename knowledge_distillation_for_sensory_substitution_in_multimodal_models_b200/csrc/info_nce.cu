@@ -5,8 +5,10 @@
 //   L = u_s u_t^T / temp ; loss = mean_m( logsumexp_j L[m,j] - L[m,m] )
 //   G = (softmax(L) - I)/M ; du = G u_t / temp ; dmean = (du - (du.u_s) u_s)/|mean| ; dx[m,p,:] = dmean[m,:]/P
 //
-// Three launches: pool+normalise (HBM-bound, the only pass that touches the [M,P,D] tensors), one CTA per
-// similarity row for logits -> log-softmax -> gradient row, and the broadcast write of dx.
+// Four launches: balanced pooling of both tensors (HBM-bound, the only pass that reads the [M,P,D] tensors) + its finishing
+// kernel (mean, F.normalize), one CTA per similarity row for logits -> log-softmax -> gradient row (the last CTA also writes the
+// loss), and the store-only broadcast of dx.  With a learned projection of the student features (BASELINE configs[2]): three
+// few-row fp32 products around the row kernel (kd_info_nce_proj_fwd_bwd, below).
 //
 // Token-level M (>= 1024 rows, M and D multiples of 8): the similarity matrix runs on the TENSOR CORES and never reaches HBM —
 // kd_gemm.cu's tcgen05 kernel with (1) an epilogue that folds the rows' online (max, sum-exp) and picks up the diagonal,

@@ -431,10 +431,11 @@ def logit_kd_vocab_sharded(teacher_shard, student_shard, labels, col0, V_total, 
 # ---------------------------------------------------------------------------------------------------------------------
 # Vocabulary-parallel student lm_head feeding the vocabulary-sharded KD loss (BASELINE.json configs[4]):
 # logits_shard = hidden @ weight_shard^T is produced per rank by the hand-written tcgen05 kernel (kd_lm_head_fwd,
-# csrc/lm_head_gemm.cu), whose epilogue also leaves the student's per-tile (max, sum-exp) so that the stats phase streams the
-# teacher only; the loss and d loss / d logits_shard come from logit_kd_vocab_sharded, and the two weight-side GEMMs of the
-# backward (library GEMMs) close the loop — dH needs the sum over the vocabulary shards: one all-reduce of [n_rows, hidden].
-# Keeping the logits out of HBM altogether (recomputing them in the backward) is the step after this one.
+# csrc/kd_gemm.cu), whose epilogue also leaves the student's per-tile (max, sum-exp) so that the stats phase streams the
+# teacher only; the loss and d loss / d logits_shard come from logit_kd_vocab_sharded, and the two weight-side products of the
+# backward (the same tcgen05 kernel, MN-major operands) close the loop — dH needs the sum over the vocabulary shards: one all-reduce
+# of the fp32 partial [n_rows, hidden], started under the dW product.  Keeping the logits out of HBM altogether does not pay at
+# this shape: the recomputed product costs what the logit traffic it removes does.
 # ---------------------------------------------------------------------------------------------------------------------
 def lm_head_fwd(hidden, weight, T=None, out=None):
     """``hidden`` [n_rows, H] x ``weight`` [V_local, H] -> (``logits`` [n_rows, V_local], ``partials`` or None) through
