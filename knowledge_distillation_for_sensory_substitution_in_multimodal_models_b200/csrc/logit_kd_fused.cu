@@ -59,6 +59,19 @@ constexpr float kPolyFloor = -120.f;
 #ifndef KD_ECACHE
 #define KD_ECACHE 1
 #endif
+#ifndef KD_P0_UNROLL
+#define KD_P0_UNROLL 4         // pass 0 (packed maxima)
+#endif
+#ifndef KD_BP_UNROLL
+#define KD_BP_UNROLL 3         // pass B' (clamped rows): 3 against 2 = 4.77 -> 4.62 ms at T = 0.8 on peaked logits (1: 4.71)
+#endif
+#ifndef KD_C_NV
+#define KD_C_NV 4             // vectors per tensor-memory wait in the cached gradient sweep
+#endif
+#ifndef KD_AB_UNROLL
+#define KD_AB_UNROLL 3        // iterations of the statistics + accumulation sweep unrolled together: a 9-CTA cluster gives a warp 9 of them.
+#endif                        // Measured, two boxes (tools/build_variant.sh): 3 against 2: as-written 3.72 -> 3.66 / 3.71 -> 3.67 ms, plain KL 2.86 -> 2.78 /
+                              // 3.03 -> 2.93, clamped rows 4.80 -> 4.75; 4 and 9 no better; per-row LoCa within noise either way (kept at 2)
 constexpr int kTmE = 80;
 constexpr float kEScaleLog2 = 15.f;    // the polynomial path needs its argument >= -126
 
@@ -143,6 +156,8 @@ row_emit_fused_kernel(const FusedParams cp) {
     constexpr bool PER_ROW = (VARIANT == KD_LOCA_PER_ROW);          // the row's own label / runner-up cells only
     constexpr bool KLLT = (VARIANT == KD_KL_LOG_TARGET);            // w = e^{tp}: power sums of the teacher exponentials
     constexpr bool CLAMP = TAB || PER_ROW;                          // sp >= eps clamp: student minimum, masked pass B'
+    constexpr int kP0Unroll = KD_P0_UNROLL, kBpUnroll = KD_BP_UNROLL;
+    constexpr int kAbUnroll = PER_ROW ? 2 : KD_AB_UNROLL;           // (a macro is not expanded inside #pragma unroll; a constant expression is)
     constexpr int WPP = kWarps / NPIPE;
     constexpr int NSLOT = CS * WPP;
     constexpr int SLOTB = FusedPlan<VARIANT, CS, NPIPE, CE>::SLOTB;
@@ -328,7 +343,7 @@ row_emit_fused_kernel(const FusedParams cp) {
         [[maybe_unused]] float xs_ce = 0.f; // fused CE: the student logit at the row's next-token id (same ownership rule)
         {
             uint32_t smax2 = Pair<T>::kNegInf2, smin2 = Pair<T>::kPosInf2, tmax2 = Pair<T>::kNegInf2;
-#pragma unroll 4
+#pragma unroll kP0Unroll
             for (int v = lane; v < w_n; v += 32) {
                 const uint4 rs = load_s(v);
                 smax2 = Pair<T>::vmax(smax2, Pair<T>::vmax(Pair<T>::vmax(rs.x, rs.y), Pair<T>::vmax(rs.z, rs.w)));
@@ -480,13 +495,13 @@ row_emit_fused_kernel(const FusedParams cp) {
             auto run_ab = [&](auto ce_tag) {
                 // the other pipeline may start its pass AB once this warp has `tok_after` iterations left (0 = strict alternation)
                 const int j_split = max(0, n_full - cp.tok_after);
-#pragma unroll 2
+#pragma unroll kAbUnroll
                 for (int j = 0; j < j_split; ++j) ab_body(j, true, std::false_type{}, std::false_type{}, ce_tag);
                 if (NPIPE == 2 && cp.tok_after > 0) {
                     if (lane == 0) mbar_arrive_cta(tok_other);
                     token_given = true;
                 }
-#pragma unroll 2
+#pragma unroll kAbUnroll
                 for (int j = j_split; j < n_full; ++j) ab_body(j, true, std::false_type{}, std::false_type{}, ce_tag);
                 if (n_tail) ab_body(n_full, lane < n_tail, std::true_type{}, std::false_type{}, ce_tag);
             };
@@ -998,7 +1013,7 @@ row_emit_fused_kernel(const FusedParams cp) {
                     if constexpr (decltype(tail_tag)::value) __syncwarp();
                     if constexpr (WRITE_BACK) tmem_st8(tq + 8 * j, qb);
                 };
-#pragma unroll 2
+#pragma unroll kBpUnroll
                 for (int j = 0; j < n_full; ++j) bp_body(j, true, std::false_type{});
                 if (n_tail) bp_body(n_full, lane < n_tail, std::true_type{});
                 if constexpr (WRITE_BACK) {
@@ -1157,12 +1172,12 @@ row_emit_fused_kernel(const FusedParams cp) {
                     }
                     if constexpr (decltype(tail_tag)::value) __syncwarp();
                 };
-                using V4 = std::integral_constant<int, 4>;
+                using VM = std::integral_constant<int, KD_C_NV>;
                 using V2 = std::integral_constant<int, 2>;
                 using V1 = std::integral_constant<int, 1>;
                 int j = 0;
-                for (; j + 3 < n_full; j += 4) c_step(j, V4{}, true, std::false_type{});
-                if (j + 1 < n_full) { c_step(j, V2{}, true, std::false_type{}); j += 2; }
+                for (; j + KD_C_NV - 1 < n_full; j += KD_C_NV) c_step(j, VM{}, true, std::false_type{});
+                for (; j + 1 < n_full; j += 2) c_step(j, V2{}, true, std::false_type{});
                 if (j < n_full) c_step(j, V1{}, true, std::false_type{});
                 if (n_tail) c_step(n_full, V1{}, lane < n_tail, std::true_type{});
             };
