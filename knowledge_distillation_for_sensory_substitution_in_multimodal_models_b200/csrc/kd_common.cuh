@@ -132,6 +132,10 @@ __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {  // write-
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void stg_stream_cs(void* p, const uint4& v) {   // write-once data, cache-streaming (evict-first in L2)
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // reductions

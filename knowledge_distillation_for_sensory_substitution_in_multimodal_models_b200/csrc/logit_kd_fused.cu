@@ -59,6 +59,15 @@ constexpr float kPolyFloor = -120.f;
 #ifndef KD_ECACHE
 #define KD_ECACHE 1
 #endif
+// Prefetching the next row's slices into L2 at the start of a row (cp.async.bulk.prefetch.L2) is measured HARMFUL now that the
+// refills are issued early — the TMA refill right after the sweep already hides the latency.  Three A/B pairs on one box: as-written
+// 3.645 -> 3.564 ms, per-row 3.74 -> 3.56, clamped rows 4.63 -> 4.50, log_target 3.63 -> 3.53, plain KL unchanged.  Kept as a knob.
+#ifndef KD_WARM_L2
+#define KD_WARM_L2 0
+#endif
+#ifndef KD_STREAM_HINTS
+#define KD_STREAM_HINTS 0
+#endif
 #ifndef KD_P0_UNROLL
 #define KD_P0_UNROLL 4         // pass 0 (packed maxima)
 #endif
@@ -156,6 +165,11 @@ row_emit_fused_kernel(const FusedParams cp) {
     constexpr bool PER_ROW = (VARIANT == KD_LOCA_PER_ROW);          // the row's own label / runner-up cells only
     constexpr bool KLLT = (VARIANT == KD_KL_LOG_TARGET);            // w = e^{tp}: power sums of the teacher exponentials
     constexpr bool CLAMP = TAB || PER_ROW;                          // sp >= eps clamp: student minimum, masked pass B'
+    // Experiment knob (off): evict-first row loads + cache-streaming gradient stores for the single-launch variants.  Two A/B pairs on
+    // one box: no difference (plain KL 2.81-2.84 against 2.80, per-row 3.47 against 3.45 ms); a first reading of -3 % was the
+    // compiler laying the kernel out differently, not the hints — differences of a few percent between builds of this kernel are noise
+    // of that kind unless they repeat across unrelated edits.
+    constexpr bool STREAM_HINTS = (KD_STREAM_HINTS != 0) && !TAB;
     constexpr int kP0Unroll = KD_P0_UNROLL, kBpUnroll = KD_BP_UNROLL;
     constexpr int kAbUnroll = PER_ROW ? 2 : KD_AB_UNROLL;           // (a macro is not expanded inside #pragma unroll; a constant expression is)
     constexpr int WPP = kWarps / NPIPE;
@@ -258,21 +272,23 @@ row_emit_fused_kernel(const FusedParams cp) {
             const uint32_t bytes = (uint32_t)w_n * 16u;
             fence_proxy_async();
             mbar_expect_tx(bar_full, 2u * bytes);
-            tma_load_1d(s_t, tbase + row * p.ld_t + (int64_t)g_v0 * 8, bytes, bar_full);
+            if constexpr (STREAM_HINTS) tma_load_1d_evict_first(s_t, tbase + row * p.ld_t + (int64_t)g_v0 * 8, bytes, bar_full);
+            else tma_load_1d(s_t, tbase + row * p.ld_t + (int64_t)g_v0 * 8, bytes, bar_full);
         }
     };
     auto issue_student = [&](int64_t row) {
         if (lane == 0 && w_n > 0) {
             const uint32_t bytes = (uint32_t)w_n * 16u;
             fence_proxy_async();
-            tma_load_1d(s_s, sbase + row * p.ld_s + (int64_t)g_v0 * 8, bytes, bar_full);
+            if constexpr (STREAM_HINTS) tma_load_1d_evict_first(s_s, sbase + row * p.ld_s + (int64_t)g_v0 * 8, bytes, bar_full);
+            else tma_load_1d(s_s, sbase + row * p.ld_s + (int64_t)g_v0 * 8, bytes, bar_full);
         }
     };
     auto issue_load = [&](int64_t row) {
         issue_teacher(row);
         issue_student(row);
     };
-    auto warm_l2 = [&](int64_t row) {           // bring the warp's slice of `row` into L2 ahead of its use
+    [[maybe_unused]] auto warm_l2 = [&](int64_t row) {           // bring the warp's slice of `row` into L2 ahead of its use (KD_WARM_L2)
         if (lane == 0 && w_n > 0 && row < p.n_rows) {
             prefetch_l2(tbase + row * p.ld_t + (int64_t)g_v0 * 8, (uint32_t)w_n * 16u);
             prefetch_l2(sbase + row * p.ld_s + (int64_t)g_v0 * 8, (uint32_t)w_n * 16u);
@@ -328,7 +344,9 @@ row_emit_fused_kernel(const FusedParams cp) {
             ce_c = (ce_on && !ce_bad) ? (int)cel64 : -1;
             if (next_r < p.n_rows) cel64 = p.ce_labels[next_r];
         }
+#if KD_WARM_L2
         warm_l2(next_r);
+#endif
         const uint32_t epoch = (uint32_t)r;
         auto load_s = [&](int v) -> uint4 { return lds128_ep(s_s + v * 16, epoch); };
         auto load_t = [&](int v) -> uint4 { return lds128_ep(s_t + v * 16, epoch); };
@@ -1121,7 +1139,8 @@ row_emit_fused_kernel(const FusedParams cp) {
                             upk(o2, n_lo, n_hi);
                             out[i] = Pair<T>::narrow(n_lo, n_hi);
                         }
-                        stg_stream(grow + (int64_t)v * 8, make_uint4(out[0], out[1], out[2], out[3]));
+                        if constexpr (STREAM_HINTS) stg_stream_cs(grow + (int64_t)v * 8, make_uint4(out[0], out[1], out[2], out[3]));
+                        else stg_stream(grow + (int64_t)v * 8, make_uint4(out[0], out[1], out[2], out[3]));
                     }
                     if constexpr (decltype(tail_tag)::value) __syncwarp();
                 };
@@ -1167,7 +1186,8 @@ row_emit_fused_kernel(const FusedParams cp) {
                                 upk(o2, n_lo, n_hi);
                                 out[i] = Pair<T>::narrow(n_lo, n_hi);
                             }
-                            stg_stream(grow + (int64_t)(lane + 32 * (j + u)) * 8, make_uint4(out[0], out[1], out[2], out[3]));
+                            if constexpr (STREAM_HINTS) stg_stream_cs(grow + (int64_t)(lane + 32 * (j + u)) * 8, make_uint4(out[0], out[1], out[2], out[3]));
+                            else stg_stream(grow + (int64_t)(lane + 32 * (j + u)) * 8, make_uint4(out[0], out[1], out[2], out[3]));
                         }
                     }
                     if constexpr (decltype(tail_tag)::value) __syncwarp();
