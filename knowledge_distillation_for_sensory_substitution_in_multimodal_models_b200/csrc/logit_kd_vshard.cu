@@ -19,6 +19,18 @@
 
 #include "logit_kd.cuh"
 
+// tuning knobs (tools/build_variant.sh --src logit_kd_vshard.cu): vector pairs per lane fetched before any is consumed in the accumulate /
+// emit sweeps, and loads per lane and batch in the statistics walk (8 against 4: 1.046 -> 1.009 ms for both tensors of a configs[4] shard)
+#ifndef KD_VS_ACCUM_BATCH
+#define KD_VS_ACCUM_BATCH 2      // accumulate sweep: 2 against 4 = 0.931 -> 0.838 ms (fewer registers, more resident warps)
+#endif
+#ifndef KD_VS_EMIT_BATCH
+#define KD_VS_EMIT_BATCH 5       // emit sweep: 2 / 3 / 4 / 5 / 6 = 1.315 / 1.310 / 1.213 / 1.150 / 1.496 ms (floor 1.140)
+#endif
+#ifndef KD_VS_STATS_U
+#define KD_VS_STATS_U 8
+#endif
+
 namespace kd {
 
 namespace {
@@ -129,7 +141,7 @@ __device__ __forceinline__ void shard_row_stats_packed(const T* __restrict__ row
         }
         if (WANT_TOP2 && vm >= thr_top) cand |= bit;
     };
-    constexpr int U = 4;
+    constexpr int U = KD_VS_STATS_U;
     const int wl = lane & 31;
     const int v_first = lane - wl;                       // the warp's first vector of a batch: warp-uniform trip count
     bool seeded = !WANT_TOP2;
@@ -343,7 +355,10 @@ struct ShardOverride {
 };
 // vector pairs fetched per lane before any is consumed (the streaming store is a volatile asm with a memory clobber: loads do not
 // move above it, so an unrolled load-compute-store loop keeps ONE pair in flight)
-template <typename T> struct VsBatch { static constexpr int kB = sizeof(T) == 2 ? 4 : 2; };
+template <typename T> struct VsBatch {
+    static constexpr int kAccum = sizeof(T) == 2 ? KD_VS_ACCUM_BATCH : (KD_VS_ACCUM_BATCH + 1) / 2;
+    static constexpr int kEmit = sizeof(T) == 2 ? KD_VS_EMIT_BATCH : (KD_VS_EMIT_BATCH + 1) / 2;
+};
 
 template <int VARIANT>
 __device__ __forceinline__ ShardOverride<VARIANT> make_override(const float* table, const kd_token_record* rec, int64_t r, int col0) {
@@ -386,7 +401,7 @@ vshard_accum_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __rest
             constexpr int P = Elem<T>::kPack;
             const uint4* tv = reinterpret_cast<const uint4*>(trow);
             const uint4* sv = reinterpret_cast<const uint4*>(srow);
-            constexpr int B = VsBatch<T>::kB;
+            constexpr int B = VsBatch<T>::kAccum;
             const int nv = V_local / P;
             for (int v0 = gl; v0 < nv; v0 += G * B) {
                 uint4 rt[B], rs[B];
@@ -459,7 +474,7 @@ vshard_emit_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __restr
             const uint4* tv = reinterpret_cast<const uint4*>(trow);
             const uint4* sv = reinterpret_cast<const uint4*>(srow);
             uint4* gv = reinterpret_cast<uint4*>(grow);
-            constexpr int B = VsBatch<T>::kB;
+            constexpr int B = VsBatch<T>::kEmit;
             const int nv = V_local / P, stride = gridDim.x * kVsThreads;
             for (int v0 = blockIdx.x * kVsThreads + threadIdx.x; v0 < nv; v0 += stride * B) {
                 uint4 rt[B], rs[B];
@@ -519,7 +534,7 @@ vshard_emit_rows_kernel(const T* __restrict__ teacher, int64_t ld_t, const T* __
             const uint4* tv = reinterpret_cast<const uint4*>(trow);
             const uint4* sv = reinterpret_cast<const uint4*>(srow);
             uint4* gv = reinterpret_cast<uint4*>(grow);
-            constexpr int B = VsBatch<T>::kB;
+            constexpr int B = VsBatch<T>::kEmit;
             const int nv = V_local / P;
             for (int v0 = gl; v0 < nv; v0 += 32 * B) {
                 uint4 rt[B], rs[B];
