@@ -8,7 +8,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxBlocks = 148 * 8;
-constexpr int kBatch = 4;        // 16-byte vector pairs in flight per thread of the forward kernel
+#ifndef KD_MSE_BATCH
+#define KD_MSE_BATCH 4
+#endif
+constexpr int kBatch = KD_MSE_BATCH;        // 16-byte vector pairs in flight per thread
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)

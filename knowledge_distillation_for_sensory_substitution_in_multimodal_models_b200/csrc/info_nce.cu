@@ -421,7 +421,10 @@ nce_tc_finish_kernel(const float* __restrict__ dU, const float* __restrict__ us,
 // pool_ranges_finish_kernel adds an image's pieces in CTA order (deterministic).  The loads go out in explicit batches of
 // kPoolBatch 16-byte vectors per thread before any is consumed: an unrolled loop with an exit test per iteration compiles to
 // one load in flight per thread (SASS of pool_partial_kernel), 27 KB per SM — half of what the HBM latency asks for.
-constexpr int kPoolBatch = 8;
+#ifndef KD_POOL_BATCH
+#define KD_POOL_BATCH 8
+#endif
+constexpr int kPoolBatch = KD_POOL_BATCH;
 struct PoolTensor { const void* x; int M, P, D, G, cta0; };
 struct PoolPlan { PoolTensor t[2]; int n, dmax; };
 

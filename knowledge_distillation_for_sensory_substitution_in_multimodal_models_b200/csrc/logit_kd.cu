@@ -11,6 +11,10 @@
 #include "cluster_prims.cuh"
 #include "logit_kd.cuh"
 
+#ifndef KD_REGRAD_BATCH
+#define KD_REGRAD_BATCH 4      // vector pairs per thread and row chunk of the backward re-emission (tools/build_variant.sh --src logit_kd.cu)
+#endif
+
 namespace kd {
 
 namespace {
@@ -567,7 +571,7 @@ regrad_kernel(const EmitParams p, const float* skip_if_one) {
             uint4* gv = reinterpret_cast<uint4*>(grow);
             // B vector pairs (and their slice of the override table, as 128-bit loads) are fetched before any is consumed: the
             // streaming store is a volatile asm with a memory clobber, so a load-compute-store loop keeps ONE pair in flight
-            constexpr int B = sizeof(T) == 2 ? 4 : 2;
+            constexpr int B = sizeof(T) == 2 ? KD_REGRAD_BATCH : (KD_REGRAD_BATCH + 1) / 2;
             constexpr bool TABLE = (VARIANT == KD_LOCA_REFERENCE);
             const bool tab_vec = TABLE && (reinterpret_cast<uintptr_t>(p.table) & 15u) == 0;
             for (int v0 = t0; v0 < nvec; v0 += stride * B) {
@@ -903,7 +907,7 @@ int launch_regrad_t(const EmitParams& p, const float* skip, cudaStream_t st) {
     const bool vec = rows_vectorizable<T>(p.teacher, p.ld_t) && rows_vectorizable<T>(p.student, p.ld_s) &&
                      rows_vectorizable<T>(p.grad, p.ld_g);
     // a thread takes one batch of kRegradBatch vectors of a row (the kernel fetches them all before consuming any)
-    constexpr int kRegradBatch = sizeof(T) == 2 ? 4 : 2;
+    constexpr int kRegradBatch = sizeof(T) == 2 ? KD_REGRAD_BATCH : (KD_REGRAD_BATCH + 1) / 2;
     int64_t gx = (p.V / Elem<T>::kPack + 256 * kRegradBatch - 1) / (256 * kRegradBatch);
     gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
     int64_t gy = (int64_t)sm_count() * 16 / gx;
