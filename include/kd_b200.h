@@ -13,7 +13,8 @@
  *   - the library never allocates or frees device memory and never synchronises the device;
  *   - process-wide state is limited to: the thread-local error string, per-device launch configuration cached on first use
  *     (occupancy of the cluster kernels, opt-in shared-memory size), tuning switches read ONCE from the environment
- *     (KD_FUSED, KD_CLUSTER_SIZE, KD_SPARE_SMS, KD_HELPER_RESERVE — A/B experiments, never needed in production) and one
+ *     (KD_FUSED, KD_CLUSTER_SIZE, KD_CLUSTER_CONFIG, KD_SPARE_SMS, KD_HELPER_RESERVE — A/B experiments and the test suite's
+ *     way to reach the non-default kernels, never needed in production) and one
  *     internal non-blocking helper stream + event pair per device, used only where clusters of 8 would leave >= 20 SMs idle;
  *     nothing of it changes results;
  *   - every call takes the CUDA stream (a cudaStream_t passed as void*) and is graph-capture safe;
