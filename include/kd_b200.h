@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define KD_B200_ABI_VERSION 4
+#define KD_B200_ABI_VERSION 5
 
 /* element types of logits / features (gradients are written in the same type as the student tensor) */
 enum { KD_DTYPE_BF16 = 0, KD_DTYPE_F16 = 1, KD_DTYPE_F32 = 2 };
@@ -95,6 +95,7 @@ int kd_logit_kd_fwd_bwd(const void* teacher, int64_t ld_t, const void* student, 
  *   (caller all-gathers the records of every rank in global token order)
  *   B. kd_loca_build_table   : all records -> the V-entry override table (last token wins; k pass after labels)
  *   C. kd_loca_emit          : local rows + table -> loss partial (already scaled) + gradient
+ *      (kd_loca_emit_ce      : the same + the student's cross-entropy on those rows)
  */
 typedef struct {
     int32_t label;
@@ -124,6 +125,18 @@ int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t
                  float T, float eps, double inv_norm, const float* upstream,
                  const uint32_t* status /* phase A's status word (may be NULL): a bad label NaN-poisons the loss like P1:166 raises */,
                  unsigned flags, void* stream);
+
+/* kd_loca_emit with the student's cross-entropy of the LOCAL rows fused in (token-sharded form of kd_logit_kd_ce_fwd_bwd below, which
+ * documents the CE semantics): loss_out = KD partial + ce_weight * CE partial, ce_loss_out (may be NULL) = CE partial =
+ * sum over the local valid rows of (lse(xs) - xs[c]) * (*ce_inv_count).  The caller chooses the divisor: 1 / (valid targets of ALL
+ * ranks) makes the sum of the ranks' partials the cross-entropy of the concatenated batch.  ceaux = float2[n_rows] scratch;
+ * status = phase A's status word, REQUIRED here (a ce_label outside [0, V) other than -100 sets KD_STATUS_BAD_LABEL in it).
+ * Same shape limits as kd_logit_kd_ce_fwd_bwd (KD_ERR_UNSUPPORTED otherwise). */
+int kd_loca_emit_ce(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const float* lse2_t,
+                    const float* table, const double* table_consts, const int64_t* ce_labels, const float* ce_inv_count,
+                    float ce_weight, void* grad_student, int64_t ld_g, float* loss_out, float* ce_loss_out,
+                    void* rowaux /* float4[n_rows + 1] */, void* ceaux /* float2[n_rows] */, int64_t n_rows, int64_t V, int dtype,
+                    float T, float eps, double inv_norm, const float* upstream, uint32_t* status, unsigned flags, void* stream);
 
 /* Re-emission of the gradient for autograd's backward when the incoming grad_output differs from the scale that
  * was folded into the forward launch: grad = (*upstream) * T * inv_norm * (sp * Q_r - w) recomputed from the row

@@ -15,7 +15,7 @@ _lock = threading.Lock()
 _lib: C.CDLL | None = None
 
 # mirrors of the header enums
-ABI_VERSION = 4
+ABI_VERSION = 5
 DTYPE_BF16, DTYPE_F16, DTYPE_F32 = 0, 1, 2
 LOCA_REFERENCE, LOCA_PER_ROW, KL_PLAIN, KL_LOG_TARGET = 0, 1, 2, 3
 FLAG_NO_GRAD, FLAG_FORCE_STREAMING = 1, 2
@@ -39,6 +39,8 @@ SIGNATURES = {
     "kd_loca_table_workspace_bytes": (_i, [_i64, C.POINTER(_sz)]),
     "kd_loca_build_table": (_i, [_p, _i64, _i64, _p, _p, _p, _sz, _p]),
     "kd_loca_emit": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i, _f, _f, _d, _p, _p, _u, _p]),
+    "kd_loca_emit_ce": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _f, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _d, _p,
+                             _p, _u, _p]),
     "kd_logit_kd_regrad": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _sz, _i64, _i64, _i, _f, _f, _i, _d, _p, _p, _p]),
     "kd_logit_kd_ce_fwd_bwd": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _f, _p, _i64, _p, _p, _p, _sz, _i64, _i64, _i, _f, _f, _f, _d, _p, _u, _p]),
     "kd_logit_kd_ce_regrad": (_i, [_p, _i64, _p, _i64, _p, _p, _f, _p, _i64, _p, _sz, _i64, _i64, _i, _f, _f, _d, _p, _p, _p]),

@@ -1073,6 +1073,35 @@ int kd_loca_emit(const void* teacher, int64_t ld_t, const void* student, int64_t
     return KD_OK;
 }
 
+// kd_loca_emit + the student's cross-entropy of the LOCAL rows (the token-sharded form of kd_logit_kd_ce_fwd_bwd)
+int kd_loca_emit_ce(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const float* lse2_t,
+                    const float* table, const double* table_consts, const int64_t* ce_labels, const float* ce_inv_count,
+                    float ce_weight, void* grad_student, int64_t ld_g, float* loss_out, float* ce_loss_out, void* rowaux,
+                    void* ceaux, int64_t n_rows, int64_t V, int dtype, float T, float eps, double inv_norm,
+                    const float* upstream, uint32_t* status, unsigned flags, void* stream) {
+    if (int rc = check_common(n_rows, V, dtype, T)) return rc;
+    KD_CHECK_ARG(teacher && student && lse2_t && table && table_consts && loss_out && rowaux, "kd_loca_emit_ce: null pointer");
+    KD_CHECK_ARG(ce_labels && ce_inv_count && ceaux && status, "kd_loca_emit_ce: null pointer (ce_labels / ce_inv_count / ceaux / status)");
+    KD_CHECK_ARG((flags & KD_FLAG_NO_GRAD) || grad_student, "kd_loca_emit_ce: grad_student is null");
+    KD_CHECK_ARG(ld_t >= V && ld_s >= V && ((flags & KD_FLAG_NO_GRAD) || ld_g >= V), "leading dimension < V");
+    KD_CHECK_ARG(eps > 0.f, "eps must be positive");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    EmitParams p{};
+    p.teacher = teacher; p.ld_t = ld_t; p.student = student; p.ld_s = ld_s;
+    p.lse2_t_in = lse2_t; p.table = table; p.grad = grad_student; p.ld_g = ld_g;
+    p.rowaux = static_cast<float4*>(rowaux); p.upstream = upstream; p.n_rows = n_rows; p.V = (int)V;
+    p.k2 = kLog2e / T; p.thr2 = log2f(eps); p.gscale = static_cast<float>(T * inv_norm); p.flags = flags;
+    p.status = status;
+    p.ce_labels = ce_labels; p.ce_inv_count = ce_inv_count; p.ce_weight = ce_weight; p.ceaux = static_cast<float2*>(ceaux);
+    if (n_rows > 0) {
+        if (int rc = launch_emit(p, KD_LOCA_REFERENCE, dtype, st, nullptr)) return rc;
+    }
+    loss_finalize_kernel<<<1, kFinalThreads, 0, st>>>(p.rowaux, n_rows, (double)kLn2, (double)T * T * inv_norm, table_consts,
+                                                      status, loss_out, p.ceaux, ce_inv_count, ce_weight, ce_loss_out);
+    KD_CHECK_LAUNCH("loss_finalize_kernel");
+    return KD_OK;
+}
+
 static int logit_kd_fwd_bwd_impl(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const int64_t* labels,
                                  void* grad_student, int64_t ld_g, float* loss_out, void* workspace, size_t workspace_bytes,
                                  int64_t n_rows, int64_t V, int dtype, float T, float alpha, float eps, int variant,

@@ -49,11 +49,20 @@ class KDLossMethods:
         """``loca + ce_weight * CE`` where CE is what ``student_outputs.loss`` would have been — call the student with
         ``labels=None`` so it is not computed twice.  ``ce_labels`` defaults to the next-token shift of ``labels``; the CE alone
         is left in ``self.last_student_loss`` (detached) for logging / the phase-3 mix."""
-        if getattr(self, "kd_group", None) is not None or getattr(self, "loca_mode", "reference") != "reference":
-            raise NotImplementedError("the fused cross-entropy rides the single-process as-written LoCa kernel; "
-                                      "pass student_loss for per_row / token-sharded calls")
+        if getattr(self, "loca_mode", "reference") != "reference":
+            raise NotImplementedError("the fused cross-entropy rides the as-written LoCa kernel; pass student_loss for per_row calls")
         if ce_labels is None:
             ce_labels = F_kd.shift_labels(labels)
+        group = getattr(self, "kd_group", None)
+        if group is not None:
+            # token shards: KD and CE are those of the concatenated batch (the CE's divisor is summed over the ranks on the device)
+            from . import sharded
+            total, ce = sharded.loca_kl_ce_token_sharded_autograd(teacher_logits, student_logits, labels, ce_labels, self.T,
+                                                                  alpha=alpha, ce_weight=ce_weight, group=group, upstream=upstream,
+                                                                  exchange=getattr(self, "kd_exchange", "nccl"),
+                                                                  phases=getattr(self, "kd_phases", None))
+            self.last_student_loss = ce
+            return total
         total, ce = F_kd.loca_kl_ce(teacher_logits, student_logits, labels, ce_labels, self.T, alpha=alpha, ce_weight=ce_weight,
                                     upstream=upstream)
         self.last_student_loss = ce

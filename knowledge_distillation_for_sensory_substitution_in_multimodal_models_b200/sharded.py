@@ -79,6 +79,29 @@ class CudaPhases:
         return loss, grad
 
 
+    def emit_ce(self, teacher, student, lse2_t, table, consts, ce_labels, inv_count, ce_weight, T, eps, inv_norm, upstream,
+                want_grad=True, status=None):
+        """Phase C with the student's cross-entropy of the local rows fused in (``kd_loca_emit_ce``): ``(loss, ce, grad)``."""
+        dev = student.device
+        n, V = student.shape
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ce = torch.empty((), dtype=torch.float32, device=dev)
+        rowaux = torch.empty((n + 1, 4), dtype=torch.float32, device=dev)
+        ceaux = torch.empty((max(n, 1), 2), dtype=torch.float32, device=dev)
+        grad = torch.empty((n, V), dtype=student.dtype, device=dev) if want_grad else None
+        up_t, up_ptr = _upstream_ptr(upstream, dev)
+        if status is None:
+            status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().kd_loca_emit_ce(teacher.data_ptr(), teacher.stride(0), student.data_ptr(), student.stride(0),
+                                                   lse2_t.data_ptr(), table.data_ptr(), consts.data_ptr(), ce_labels.data_ptr(),
+                                                   inv_count.data_ptr(), float(ce_weight), grad.data_ptr() if want_grad else None, V,
+                                                   loss.data_ptr(), ce.data_ptr(), rowaux.data_ptr(), ceaux.data_ptr(), n, V,
+                                                   _dtype_code(student), float(T), float(eps), float(inv_norm), up_ptr,
+                                                   status.data_ptr(), 0 if want_grad else _lib.FLAG_NO_GRAD, _stream_ptr(dev)))
+        return loss, ce, grad
+
+
 def shard_rows(n_total: int, world_size: int, rank: int) -> tuple[int, int]:
     """Contiguous, balanced token partition: ranks [0, n_total % world) get one extra row."""
     base, extra = divmod(n_total, world_size)
@@ -173,7 +196,8 @@ def _sum_status(status, group, multi):
 
 
 def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, group=None, upstream=None,
-                          phases=None, reduce_loss=True, want_grad=True, n_total=None, exchange="nccl", counts=None):
+                          phases=None, reduce_loss=True, want_grad=True, n_total=None, exchange="nccl", counts=None,
+                          ce_labels=None, ce_weight=1.0, ce_valid_count=None):
     """As-written LoCa over tokens sharded across the ranks of ``group``.
 
     ``teacher``/``student``/``labels`` hold this rank's rows.  Returns ``(loss, grad_local)`` where
@@ -184,6 +208,12 @@ def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, grou
     oracle-backed stand-in; the product default is :class:`CudaPhases`).  ``exchange="peer"`` replaces the NCCL
     all-gather of the records by peer stores issued from the phase-A kernel itself (:class:`PeerRecordExchange`).
     A label outside ``[0, V)`` on ANY rank NaN-poisons the loss on every rank (the reference raises at P1:166).
+
+    ``ce_labels`` (this rank's next-token targets, ``-100`` = ignored; :func:`functional.shift_labels`) adds the student's
+    cross-entropy from the same pass over the local rows (``kd_loca_emit_ce``) and changes the return value
+    to ``(loss, ce, grad_local)`` with ``loss = KD + ce_weight * CE``.  The CE is the mean over the valid targets of ALL ranks —
+    the concatenated batch, like the KD term — unless ``ce_valid_count`` (a number or device scalar) gives another divisor: the
+    count is summed across the ranks on the device, nothing is read back.
     """
     if phases is None:
         phases = CudaPhases()
@@ -209,6 +239,24 @@ def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, grou
         n_total = rec_all.shape[0]
     table, consts = phases.build_table(rec_all, V)
     inv_norm = 1.0 / (float(n_total) * float(V))
+    if ce_labels is not None:
+        cel = ce_labels.reshape(-1).to(torch.int64).contiguous()
+        if cel.numel() != t2.shape[0]:
+            raise ValueError(f"ce_labels has {cel.numel()} entries for {t2.shape[0]} local tokens")
+        if ce_valid_count is None:
+            count = (cel != -100).sum().to(torch.float32).reshape(1)
+            if multi:
+                dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        else:
+            count = torch.as_tensor(ce_valid_count, device=cel.device).to(torch.float32).reshape(1)
+        inv_count = (1.0 / count).contiguous()              # 0 valid targets -> inf -> NaN, like F.cross_entropy
+        loss, ce, grad = phases.emit_ce(t2, s2, lse2_t, table, consts, cel, inv_count, ce_weight, T, eps, inv_norm, upstream,
+                                        want_grad=want_grad, status=status)
+        if reduce_loss and multi:
+            both = torch.stack([loss, ce])
+            dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
+            loss, ce = both[0].clone(), both[1].clone()      # separate tensors: the autograd front marks the CE non-differentiable
+        return loss, ce, grad
     loss, grad = phases.emit(t2, s2, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad=want_grad, status=status)
     if reduce_loss and multi:
         loss = loss.clone()
@@ -222,18 +270,24 @@ class _TokenShardedLoCa(torch.autograd.Function):
     ``grad_output / upstream`` on the device — a no-op kernel exit when that is 1, the usual ``loss.backward()``."""
 
     @staticmethod
-    def forward(ctx, teacher, student, labels, T, alpha, eps, group, upstream, phases, exchange, counts):
+    def forward(ctx, teacher, student, labels, T, alpha, eps, group, upstream, phases, exchange, counts,
+                ce_labels=None, ce_weight=1.0, ce_valid_count=None):
         need_grad = student.requires_grad
-        loss, grad = loca_kl_token_sharded(teacher.detach(), student.detach(), labels, T, alpha, eps, group=group, upstream=upstream,
-                                           phases=phases, want_grad=need_grad, exchange=exchange, counts=counts)
+        res = loca_kl_token_sharded(teacher.detach(), student.detach(), labels, T, alpha, eps, group=group, upstream=upstream,
+                                    phases=phases, want_grad=need_grad, exchange=exchange, counts=counts,
+                                    ce_labels=ce_labels, ce_weight=ce_weight, ce_valid_count=ce_valid_count)
+        loss, grad = res[0], res[-1]
         ctx.grad, ctx.shape, ctx.need_grad = grad, student.shape, need_grad
         ctx.upstream = None if upstream is None else torch.as_tensor(upstream, dtype=torch.float32, device=student.device).reshape(())
-        return loss
+        if ce_labels is None:
+            return loss
+        ctx.mark_non_differentiable(res[1])
+        return loss, res[1]
 
     @staticmethod
-    def backward(ctx, grad_output):
+    def backward(ctx, grad_output, _grad_ce=None):
         if not ctx.need_grad:
-            return (None,) * 11
+            return (None,) * 14
         if ctx.grad is None:
             raise RuntimeError("loca_kl_token_sharded_autograd: backward through the same graph twice (the gradient is rescaled in place)")
         g, ctx.grad = ctx.grad, None
@@ -245,14 +299,23 @@ class _TokenShardedLoCa(torch.autograd.Function):
                                                      _stream_ptr(g.device)))
         else:                                     # host-side test doubles only (the product path is CUDA)
             g = (g * ratio.to(g.dtype)).to(g.dtype)
-        return (None, g.reshape(ctx.shape)) + (None,) * 9
+        return (None, g.reshape(ctx.shape)) + (None,) * 12
+
+
+def loca_kl_ce_token_sharded_autograd(teacher, student, labels, ce_labels, T, alpha=0.8, eps=1e-8, ce_weight=1.0, group=None,
+                                      upstream=None, phases=None, exchange="nccl", counts=None, ce_valid_count=None):
+    """``(KD + ce_weight * CE, CE)`` of the concatenated batch over token shards, both from one pass over this rank's logits; the
+    gradient w.r.t. the local student rows flows through the first result (the CE alone is detached, for logging)."""
+    return _TokenShardedLoCa.apply(teacher, student, labels, float(T), float(alpha), float(eps), group, upstream, phases, exchange,
+                                   counts, ce_labels, float(ce_weight), ce_valid_count)
 
 
 def loca_kl_token_sharded_autograd(teacher, student, labels, T, alpha=0.8, eps=1e-8, group=None, upstream=None, phases=None,
                                    exchange="nccl", counts=None):
     """As-written LoCa over token shards as a differentiable loss: the GLOBAL loss value on every rank, the gradient w.r.t. this
     rank's student rows through autograd.  Same arguments as :func:`loca_kl_token_sharded`."""
-    return _TokenShardedLoCa.apply(teacher, student, labels, float(T), float(alpha), float(eps), group, upstream, phases, exchange, counts)
+    return _TokenShardedLoCa.apply(teacher, student, labels, float(T), float(alpha), float(eps), group, upstream, phases, exchange, counts,
+                                   None, 1.0, None)
 
 
 def per_row_token_sharded(fn, teacher, student, *args, group=None, reduce_loss=True, n_total=None, **kw):

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in kd_b200.h but not exported by libkd_b200.so"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype in _lib.SIGNATURES"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.kd_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.kd_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_size_queries_and_argument_validation_need_no_gpu():

@@ -103,3 +103,52 @@ def test_patched_reference_method_fuses_the_ce_when_student_loss_is_none():
     assert abs(total.item() - (kl.loss + ce.loss).item()) <= 1e-5 * abs((kl.loss + ce.loss).item())
     assert abs(obj.last_student_loss.item() - hf.item()) <= 1e-5 * abs(hf.item())
     assert grad_close(sd.grad.float().cpu(), (kl.grad.reshape(B, S, V) + ce.grad).cpu())
+
+
+def test_token_sharded_emit_with_fused_ce_matches_the_single_call():
+    """kd_loca_teacher_stats -> kd_loca_build_table -> kd_loca_emit_ce (the token-sharded building blocks with the fused CE):
+    one shard == kd_logit_kd_ce_fwd_bwd bit for bit; two simulated shards (records concatenated in global token order, the CE's
+    divisor = valid targets of both) sum to the full batch's losses and reproduce its gradient rows."""
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import sharded
+    n, V, T, w = 37, synthetic.VOCAB, 2.0, 1.25
+    t, s, lab, cel = _batch(n, V, seed=41, peaked=False, ignore_frac=0.4)
+    ref_loss, ref_ce, ref_grad = _oracle(t, s, lab, cel, T, w)
+    sd = s.clone().requires_grad_(True)
+    one_loss, one_ce = kd.loca_kl_ce(t, sd, lab, cel, T, ce_weight=w)
+    one_loss.backward()
+    loss, ce, grad = sharded.loca_kl_token_sharded(t, s, lab, T, ce_labels=cel, ce_weight=w)
+    assert loss.item() == one_loss.item() and ce.item() == one_ce.item()
+    assert torch.equal(grad, sd.grad)
+    # two shards, ragged on purpose
+    ph = sharded.CudaPhases()
+    cut = 14
+    parts = [(t[:cut], s[:cut], lab[:cut], cel[:cut]), (t[cut:], s[cut:], lab[cut:], cel[cut:])]
+    stats = [ph.teacher_stats(tt, ll, T, 0.8, V) for tt, _, ll, _ in parts]
+    table, consts = ph.build_table(torch.cat([st[0] for st in stats]), V)
+    inv_count = (1.0 / (cel != -100).sum().float()).reshape(1)
+    tot, tot_ce, grads = 0.0, 0.0, []
+    for (tt, ss, _, cc), (_, lse2, status) in zip(parts, stats):
+        l, c, g = ph.emit_ce(tt, ss, lse2, table, consts, cc, inv_count, w, T, 1e-8, 1.0 / (n * V), None, status=status)
+        tot, tot_ce = tot + l.item(), tot_ce + c.item()
+        grads.append(g)
+    assert abs(tot - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert abs(tot_ce - ref_ce.item()) <= 1e-5 * abs(ref_ce.item())
+    assert grad_close(torch.cat(grads).float().cpu(), ref_grad.cpu())
+    # through autograd with another grad_output (the local gradient is rescaled on the device)
+    s2 = s.clone().requires_grad_(True)
+    l2, _ = sharded.loca_kl_ce_token_sharded_autograd(t, s2, lab, cel, T, ce_weight=w)
+    (0.5 * l2).backward()
+    assert grad_close(s2.grad.float().cpu(), 0.5 * ref_grad.cpu(), tol=3e-3)      # rounded twice (bf16 gradient scaled in place)
+
+
+def test_token_sharded_fused_ce_bad_target_and_unsupported_shape():
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import sharded
+    t, s, lab, cel = _batch(12, synthetic.VOCAB, seed=43, peaked=False, ignore_frac=0.3)
+    bad = cel.clone()
+    bad[5] = synthetic.VOCAB + 1
+    loss, ce, _ = sharded.loca_kl_token_sharded(t, s, lab, 2.0, ce_labels=bad)
+    assert torch.isnan(loss).item() and torch.isnan(ce).item()
+    with pytest.raises(_lib.KDError):                          # fp32 logits: no fused kernel, the caller adds its own CE
+        sharded.loca_kl_token_sharded(t.float(), s.float(), lab, 2.0, ce_labels=cel)
+    with pytest.raises(ValueError):
+        sharded.loca_kl_token_sharded(t, s, lab, 2.0, ce_labels=cel[:-1])

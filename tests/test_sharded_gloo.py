@@ -47,6 +47,18 @@ class OraclePhases:
         return loss, res.grad
 
 
+    def emit_ce(self, teacher, student, lse2_t, table, consts, ce_labels, inv_count, ce_weight, T, eps, inv_norm, upstream,
+                want_grad=True, status=None):
+        """kd_loca_emit_ce: the KD partial of emit() + sum over the local valid rows of (lse - s[c]) * inv_count."""
+        loss, grad = self.emit(teacher, student, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad, status=status)
+        with torch.enable_grad():                                    # also called from inside an autograd.Function.forward
+            sd = student.detach().double().requires_grad_(True)
+            ce = torch.nn.functional.cross_entropy(sd, ce_labels, ignore_index=-100, reduction="sum") * inv_count.double().reshape(())
+            (gce,) = torch.autograd.grad(ce, sd)
+        ce = ce.detach().float()
+        return loss + ce_weight * ce, ce, grad + ce_weight * gce
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -130,6 +142,62 @@ def _worker_autograd(rank, world, port, out):
         out[rank] = (ok_loss, ok_grad, abs(ce.grad.item() - 0.8) <= 1e-12)
     finally:
         dist.destroy_process_group()
+
+
+def _worker_fused_ce(rank, world, port, out):
+    """Token shards + the fused cross-entropy: KD and CE are those of the CONCATENATED batch (the CE's divisor is the valid-target
+    count of all ranks, summed on the device), the gradient is the local rows'; then the same through the patched method."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import types
+        from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import patch_reference
+        n_total, cut, w = 13, 5, 1.25
+        t, s, lab = synthetic.logit_batch(n_total, V, seed=12)
+        g = torch.Generator().manual_seed(4)
+        cel = torch.randint(0, V, (n_total,), generator=g)
+        cel[[0, 3, 7, 12]] = -100                                    # uneven numbers of ignored targets on the two ranks
+        lo, hi = (0, cut) if rank == 0 else (cut, n_total)
+        full = O.loca_kl(t, s, lab, T, ALPHA)
+        ce_full = O.student_cross_entropy(s, cel)
+        ref_loss = full.loss + w * ce_full.loss
+        ref_grad = (full.grad + w * ce_full.grad)[lo:hi]
+        loss, ce, grad = sharded.loca_kl_token_sharded(t[lo:hi], s[lo:hi], lab[lo:hi], T, ALPHA, phases=OraclePhases(),
+                                                       ce_labels=cel[lo:hi], ce_weight=w)
+        ok = [abs(loss.item() - ref_loss.item()) <= 1e-6 * abs(ref_loss.item()),
+              abs(ce.item() - ce_full.loss.item()) <= 1e-6 * abs(ce_full.loss.item()),
+              ((grad - ref_grad).norm() / ref_grad.norm()).item() <= 1e-6]
+        # the patched reference method: student_loss=None asks for the fused form; labels [B, S], CE targets = their next-token shift
+        B, S = 2, 4
+        t, s, lab = synthetic.logit_batch(world * B * S, V, seed=13)
+        lab3 = lab.view(world * B, S)
+        cel3 = torch.cat([lab3[:, 1:], torch.full((world * B, 1), -100)], dim=1)
+        full = O.loca_kl(t, s, lab, T, ALPHA)
+        ce_full = O.student_cross_entropy(s, cel3.reshape(-1))
+        lo, hi = rank * B * S, (rank + 1) * B * S
+        mod = types.SimpleNamespace(T=T, compute_loca_loss=None)
+        patch_reference(mod, group=dist.group.WORLD)
+        mod.kd_phases = OraclePhases()
+        sl = s[lo:hi].double().view(B, S, V).requires_grad_(True)
+        total = mod.compute_loca_loss(t[lo:hi].double().view(B, S, V), sl, None, lab3[rank * B:(rank + 1) * B], ALPHA)
+        (0.5 * total).backward()
+        ref = full.loss + ce_full.loss
+        ref_grad = 0.5 * (full.grad + ce_full.grad)[lo:hi]
+        ok += [abs(total.item() - ref.item()) <= 1e-6 * abs(ref.item()),
+               abs(mod.last_student_loss.item() - ce_full.loss.item()) <= 1e-6 * abs(ce_full.loss.item()),
+               ((sl.grad.reshape(-1, V) - ref_grad).norm() / ref_grad.norm()).item() <= 1e-6]
+        out[rank] = tuple(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_token_sharded_fused_cross_entropy_world_size_2():
+    world, port = 2, _free_port()
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_fused_ce, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: (True,) * 6, 1: (True,) * 6}
 
 
 @pytest.mark.timeout(180)
