@@ -793,6 +793,52 @@ def main() -> None:
         if rank == 0:
             side["lm_head_kd_vshard"] = vshard
 
+    # ---- the token-sharded step with the student's cross-entropy fused in (kd_loca_emit_ce; all ranks take part) -------------
+    if world > 1 and mode == "reference" and not args.no_secondary:
+        try:
+            gce = torch.Generator(device="cpu").manual_seed(77 + rank)
+            cel = torch.randint(0, V, (N,), generator=gce)
+            cel[torch.rand(N, generator=gce) < 0.5] = -100
+            cel = cel.to(dev)
+
+            def ce_step():
+                return sharded.loca_kl_token_sharded(teacher, student.detach(), labels, T_KD, ALPHA, phases=phases, exchange=exchange,
+                                                     counts=counts, ce_labels=cel)
+            for _ in range(3):
+                l_ce, c_ce, _g = ce_step()
+            sync_all()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(10):
+                l_ce, c_ce, _g = ce_step()
+            c1.record()
+            sync_all()
+            ms_ce = torch.tensor([c0.elapsed_time(c1) / 10], device=dev)
+            dist.all_reduce(ms_ce, op=dist.ReduceOp.MAX)
+            # parity: the KD part against the plain step's loss, the CE against the library cross-entropy of the concatenated batch
+            part = torch.zeros(2, dtype=torch.float64, device=dev)
+            for r0 in range(0, N, 2048):
+                part[0] += torch.nn.functional.cross_entropy(student.detach()[r0:r0 + 2048].float(), cel[r0:r0 + 2048], ignore_index=-100,
+                                                             reduction="sum").double()
+            part[1] = (cel != -100).sum()
+            dist.all_reduce(part, op=dist.ReduceOp.SUM)
+            ce_ref = (part[0] / part[1]).item()
+            del _g
+            torch.cuda.empty_cache()
+            if rank == 0:
+                kd_part = l_ce.item() - c_ce.item()
+                side["loca_reference_plus_fused_ce_token_sharded"] = {
+                    "ms": ms_ce.item(), "tokens_per_s": n_total / (ms_ce.item() / 1e3), "valid_target_fraction": 0.5,
+                    "ce": c_ce.item(), "library_cross_entropy_of_the_concatenated_batch": ce_ref,
+                    "ce_rel_err": abs(c_ce.item() - ce_ref) / abs(ce_ref),
+                    "kd_part_rel_err_vs_plain_step": abs(kd_part - loss_value) / abs(loss_value),
+                    "ok": abs(c_ce.item() - ce_ref) <= 1e-5 * abs(ce_ref) and abs(kd_part - loss_value) <= 1e-4 * abs(loss_value),
+                    "note": "KD + CE of the concatenated batch from one pass over each rank's logits; the CE's divisor is summed over "
+                            "the ranks on the device; kd_part = loss - ce in fp32 (the CE is ~15x the KD term, hence the 1e-4 gate)"}
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                side["loca_reference_plus_fused_ce_token_sharded"] = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- end-to-end through the public API with HOST buffers ----------------------------------------------
     e2e = None
     if not args.no_e2e:
