@@ -148,6 +148,15 @@ int kd_logit_kd_regrad(const void* teacher, int64_t ld_t, const void* student, i
                        int dtype, float T, float eps, int variant, double inv_norm, const float* upstream,
                        const float* skip_if_one, void* stream);
 
+/* kd_logit_kd_regrad for the phase-split path: re-emits the gradient of the local rows from what kd_loca_emit / kd_loca_emit_ce left in
+ * `rowaux` (and `ceaux`) and the override `table`, with *upstream as the new scale — ONE rounding to the output type, where scaling the
+ * already rounded gradient (kd_scale_rows) would round twice.  ce_labels == NULL: no cross-entropy terms (a kd_loca_emit forward);
+ * otherwise the same ce_labels / ce_inv_count / ce_weight / ceaux as the forward.  Returns at once when *skip_if_one == 1.0f. */
+int kd_loca_regrad(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const float* table, const void* rowaux,
+                   const int64_t* ce_labels, const float* ce_inv_count, float ce_weight, const void* ceaux, void* grad_student,
+                   int64_t ld_g, int64_t n_rows, int64_t V, int dtype, float T, float eps, double inv_norm, const float* upstream,
+                   const float* skip_if_one, void* stream);
+
 /* As-written LoCa KL + the student's cross-entropy in ONE pass over the logits — SURVEY.md §8(f) rank 1.  The reference adds
  * `student_outputs.loss` (P1:194; again at P1:260 in phase 3), which the HF student computes at P1:238-240 from the SAME student
  * logits: shifted labels, ignore_index -100 (the datamodule pads with it, dataset/.../CustomSUNRGBDOneVisionDataModule.py:145-146),

@@ -41,6 +41,7 @@ SIGNATURES = {
     "kd_loca_emit": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i, _f, _f, _d, _p, _p, _u, _p]),
     "kd_loca_emit_ce": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _f, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _d, _p,
                              _p, _u, _p]),
+    "kd_loca_regrad": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _f, _p, _p, _i64, _i64, _i64, _i, _f, _f, _d, _p, _p, _p]),
     "kd_logit_kd_regrad": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _sz, _i64, _i64, _i, _f, _f, _i, _d, _p, _p, _p]),
     "kd_logit_kd_ce_fwd_bwd": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _f, _p, _i64, _p, _p, _p, _sz, _i64, _i64, _i, _f, _f, _f, _d, _p, _u, _p]),
     "kd_logit_kd_ce_regrad": (_i, [_p, _i64, _p, _i64, _p, _p, _f, _p, _i64, _p, _sz, _i64, _i64, _i, _f, _f, _d, _p, _p, _p]),

@@ -1220,6 +1220,34 @@ static int logit_kd_regrad_impl(const void* teacher, int64_t ld_t, const void* s
     }
 }
 
+// re-emission for the phase-split path: the same sweep as kd_logit_kd_regrad, fed by the buffers kd_loca_emit(_ce) left
+int kd_loca_regrad(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, const float* table, const void* rowaux,
+                   const int64_t* ce_labels, const float* ce_inv_count, float ce_weight, const void* ceaux, void* grad_student,
+                   int64_t ld_g, int64_t n_rows, int64_t V, int dtype, float T, float eps, double inv_norm, const float* upstream,
+                   const float* skip_if_one, void* stream) {
+    if (int rc = check_common(n_rows, V, dtype, T)) return rc;
+    KD_CHECK_ARG(teacher && student && table && rowaux && grad_student, "kd_loca_regrad: null pointer");
+    KD_CHECK_ARG(!ce_labels || (ce_inv_count && ceaux), "kd_loca_regrad: ce_labels without ce_inv_count / ceaux");
+    KD_CHECK_ARG(ld_t >= V && ld_s >= V && ld_g >= V, "leading dimension < V");
+    KD_CHECK_ARG(eps > 0.f, "eps must be positive");
+    if (n_rows == 0) return KD_OK;
+    EmitParams p{};
+    p.teacher = teacher; p.ld_t = ld_t; p.student = student; p.ld_s = ld_s; p.grad = grad_student; p.ld_g = ld_g;
+    p.rowaux = static_cast<float4*>(const_cast<void*>(rowaux));
+    p.table = table; p.upstream = upstream; p.n_rows = n_rows; p.V = (int)V; p.k2 = kLog2e / T;
+    p.thr2 = log2f(eps); p.gscale = static_cast<float>(T * inv_norm);
+    if (ce_labels) {
+        p.ce_labels = ce_labels; p.ce_inv_count = ce_inv_count; p.ce_weight = ce_weight;
+        p.ceaux = static_cast<float2*>(const_cast<void*>(ceaux));
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case KD_DTYPE_BF16: return launch_regrad_v<__nv_bfloat16>(p, KD_LOCA_REFERENCE, skip_if_one, st);
+        case KD_DTYPE_F16: return launch_regrad_v<__half>(p, KD_LOCA_REFERENCE, skip_if_one, st);
+        default: return launch_regrad_v<float>(p, KD_LOCA_REFERENCE, skip_if_one, st);
+    }
+}
+
 int kd_logit_kd_regrad(const void* teacher, int64_t ld_t, const void* student, int64_t ld_s, void* grad_student,
                        int64_t ld_g, const void* workspace, size_t workspace_bytes, int64_t n_rows, int64_t V, int dtype,
                        float T, float eps, int variant, double inv_norm, const float* upstream, const float* skip_if_one,

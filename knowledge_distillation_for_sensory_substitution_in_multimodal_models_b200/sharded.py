@@ -61,7 +61,8 @@ class CudaPhases:
         return table, consts
 
     def emit(self, teacher, student, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad=True,
-             force_streaming=False, status=None):
+             force_streaming=False, status=None, saved=None):
+        """``saved`` (a dict) receives the buffers a later re-emission needs (:meth:`regrad`)."""
         dev = student.device
         n, V = student.shape
         loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -76,11 +77,28 @@ class CudaPhases:
                                                 rowaux.data_ptr(), n, V, _dtype_code(student), float(T), float(eps),
                                                 float(inv_norm), up_ptr, status.data_ptr() if status is not None else None,
                                                 flags, _stream_ptr(dev)))
+        if saved is not None:
+            saved.update(teacher=teacher, student=student, table=table, rowaux=rowaux, T=float(T), eps=float(eps), inv_norm=float(inv_norm))
         return loss, grad
 
+    def regrad(self, saved, grad, upstream, skip_if_one=None):
+        """Re-emit the local gradient from a forward's ``saved`` buffers with ``upstream`` (device scalar) as its scale: one rounding
+        to the output type (``kd_loca_regrad``); a no-op launch when ``*skip_if_one == 1``."""
+        t, s = saved["teacher"], saved["student"]
+        dev = s.device
+        n, V = s.shape
+        cel, ceaux, inv_count = saved.get("ce_labels"), saved.get("ceaux"), saved.get("inv_count")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().kd_loca_regrad(t.data_ptr(), t.stride(0), s.data_ptr(), s.stride(0), saved["table"].data_ptr(),
+                                                  saved["rowaux"].data_ptr(), cel.data_ptr() if cel is not None else None,
+                                                  inv_count.data_ptr() if cel is not None else None, float(saved.get("ce_weight", 0.0)),
+                                                  ceaux.data_ptr() if cel is not None else None, grad.data_ptr(), grad.stride(0), n, V,
+                                                  _dtype_code(s), saved["T"], saved["eps"], saved["inv_norm"], upstream.data_ptr(),
+                                                  skip_if_one.data_ptr() if skip_if_one is not None else None, _stream_ptr(dev)))
+        return grad
 
     def emit_ce(self, teacher, student, lse2_t, table, consts, ce_labels, inv_count, ce_weight, T, eps, inv_norm, upstream,
-                want_grad=True, status=None):
+                want_grad=True, status=None, saved=None):
         """Phase C with the student's cross-entropy of the local rows fused in (``kd_loca_emit_ce``): ``(loss, ce, grad)``."""
         dev = student.device
         n, V = student.shape
@@ -99,6 +117,9 @@ class CudaPhases:
                                                    loss.data_ptr(), ce.data_ptr(), rowaux.data_ptr(), ceaux.data_ptr(), n, V,
                                                    _dtype_code(student), float(T), float(eps), float(inv_norm), up_ptr,
                                                    status.data_ptr(), 0 if want_grad else _lib.FLAG_NO_GRAD, _stream_ptr(dev)))
+        if saved is not None:
+            saved.update(teacher=teacher, student=student, table=table, rowaux=rowaux, T=float(T), eps=float(eps), inv_norm=float(inv_norm),
+                         ce_labels=ce_labels, inv_count=inv_count, ce_weight=float(ce_weight), ceaux=ceaux)
         return loss, ce, grad
 
 
@@ -197,7 +218,7 @@ def _sum_status(status, group, multi):
 
 def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, group=None, upstream=None,
                           phases=None, reduce_loss=True, want_grad=True, n_total=None, exchange="nccl", counts=None,
-                          ce_labels=None, ce_weight=1.0, ce_valid_count=None):
+                          ce_labels=None, ce_weight=1.0, ce_valid_count=None, saved=None):
     """As-written LoCa over tokens sharded across the ranks of ``group``.
 
     ``teacher``/``student``/``labels`` hold this rank's rows.  Returns ``(loss, grad_local)`` where
@@ -250,14 +271,16 @@ def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, grou
         else:
             count = torch.as_tensor(ce_valid_count, device=cel.device).to(torch.float32).reshape(1)
         inv_count = (1.0 / count).contiguous()              # 0 valid targets -> inf -> NaN, like F.cross_entropy
+        kw = {} if saved is None else {"saved": saved}       # buffers for a re-emission in backward (CudaPhases.regrad)
         loss, ce, grad = phases.emit_ce(t2, s2, lse2_t, table, consts, cel, inv_count, ce_weight, T, eps, inv_norm, upstream,
-                                        want_grad=want_grad, status=status)
+                                        want_grad=want_grad, status=status, **kw)
         if reduce_loss and multi:
             both = torch.stack([loss, ce])
             dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
             loss, ce = both[0].clone(), both[1].clone()      # separate tensors: the autograd front marks the CE non-differentiable
         return loss, ce, grad
-    loss, grad = phases.emit(t2, s2, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad=want_grad, status=status)
+    kw = {} if saved is None else {"saved": saved}
+    loss, grad = phases.emit(t2, s2, lse2_t, table, consts, T, eps, inv_norm, upstream, want_grad=want_grad, status=status, **kw)
     if reduce_loss and multi:
         loss = loss.clone()
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
@@ -266,18 +289,24 @@ def loca_kl_token_sharded(teacher, student, labels, T, alpha=0.8, eps=1e-8, grou
 
 class _TokenShardedLoCa(torch.autograd.Function):
     """Differentiable front of :func:`loca_kl_token_sharded` (what ``patch_reference(..., group=...)`` binds): the gradient of
-    the local rows is produced in the forward launch with ``upstream`` folded in; ``backward`` multiplies it in place by
-    ``grad_output / upstream`` on the device — a no-op kernel exit when that is 1, the usual ``loss.backward()``."""
+    the local rows is produced in the forward launch with ``upstream`` folded in; ``backward`` launches the re-emission kernel
+    (``kd_loca_regrad``) with ``grad_output`` as the scale — it exits at once when ``grad_output / upstream`` is 1, the usual
+    ``loss.backward()``, and otherwise recomputes the gradient from the saved row statistics so that it is rounded ONCE (P1:260
+    multiplies the loss by gamma: rescaling the rounded bf16 gradient would miss the 2e-3 gate).  A second backward through the same
+    node re-emits into a fresh buffer."""
 
     @staticmethod
     def forward(ctx, teacher, student, labels, T, alpha, eps, group, upstream, phases, exchange, counts,
                 ce_labels=None, ce_weight=1.0, ce_valid_count=None):
         need_grad = student.requires_grad
+        ph = phases if phases is not None else CudaPhases()
+        saved = {} if (need_grad and hasattr(ph, "regrad")) else None
         res = loca_kl_token_sharded(teacher.detach(), student.detach(), labels, T, alpha, eps, group=group, upstream=upstream,
                                     phases=phases, want_grad=need_grad, exchange=exchange, counts=counts,
-                                    ce_labels=ce_labels, ce_weight=ce_weight, ce_valid_count=ce_valid_count)
+                                    ce_labels=ce_labels, ce_weight=ce_weight, ce_valid_count=ce_valid_count, saved=saved)
         loss, grad = res[0], res[-1]
         ctx.grad, ctx.shape, ctx.need_grad = grad, student.shape, need_grad
+        ctx.saved, ctx.phases = saved, ph
         ctx.upstream = None if upstream is None else torch.as_tensor(upstream, dtype=torch.float32, device=student.device).reshape(())
         if ce_labels is None:
             return loss
@@ -288,6 +317,15 @@ class _TokenShardedLoCa(torch.autograd.Function):
     def backward(ctx, grad_output, _grad_ce=None):
         if not ctx.need_grad:
             return (None,) * 14
+        if ctx.saved:                             # CUDA phases: re-emission from the saved row statistics, one rounding
+            s2 = ctx.saved["student"]
+            first = ctx.grad is not None
+            go = grad_output.detach().to(device=s2.device, dtype=torch.float32).reshape(1).contiguous()
+            ratio = (go if ctx.upstream is None else go / ctx.upstream).contiguous()
+            g = ctx.grad if first else torch.empty(s2.shape, dtype=s2.dtype, device=s2.device)
+            ctx.grad = None
+            ctx.phases.regrad(ctx.saved, g, go, skip_if_one=ratio if first else None)
+            return (None, g.reshape(ctx.shape)) + (None,) * 12
         if ctx.grad is None:
             raise RuntimeError("loca_kl_token_sharded_autograd: backward through the same graph twice (the gradient is rescaled in place)")
         g, ctx.grad = ctx.grad, None
