@@ -11,8 +11,15 @@
 #include "cluster_prims.cuh"
 #include "logit_kd.cuh"
 
+// vector pairs per thread and row chunk of the backward re-emission, 16-bit logits (tools/build_variant.sh --src logit_kd.cu,
+// tools/knob_sweep.py at 16 384 x 151 936).  The as-written variant also fetches its slice of the override table per pair and
+// is best with 2 (1 -> 3.17 ms, 2 -> 2.36, 3 -> 2.54, 4 -> 2.53, 8 -> 3.43); the table-free variants with 4 (per-row 2.47 against
+// 2.57 ms with 2, plain KL 2.38 against 2.43).
+#ifndef KD_REGRAD_BATCH_TABLE
+#define KD_REGRAD_BATCH_TABLE 2
+#endif
 #ifndef KD_REGRAD_BATCH
-#define KD_REGRAD_BATCH 4      // vector pairs per thread and row chunk of the backward re-emission (tools/build_variant.sh --src logit_kd.cu)
+#define KD_REGRAD_BATCH 4
 #endif
 
 namespace kd {
@@ -571,7 +578,7 @@ regrad_kernel(const EmitParams p, const float* skip_if_one) {
             uint4* gv = reinterpret_cast<uint4*>(grow);
             // B vector pairs (and their slice of the override table, as 128-bit loads) are fetched before any is consumed: the
             // streaming store is a volatile asm with a memory clobber, so a load-compute-store loop keeps ONE pair in flight
-            constexpr int B = sizeof(T) == 2 ? KD_REGRAD_BATCH : (KD_REGRAD_BATCH + 1) / 2;
+            constexpr int B = sizeof(T) == 2 ? (VARIANT == KD_LOCA_REFERENCE ? KD_REGRAD_BATCH_TABLE : KD_REGRAD_BATCH) : 2;
             constexpr bool TABLE = (VARIANT == KD_LOCA_REFERENCE);
             const bool tab_vec = TABLE && (reinterpret_cast<uintptr_t>(p.table) & 15u) == 0;
             for (int v0 = t0; v0 < nvec; v0 += stride * B) {
@@ -907,7 +914,7 @@ int launch_regrad_t(const EmitParams& p, const float* skip, cudaStream_t st) {
     const bool vec = rows_vectorizable<T>(p.teacher, p.ld_t) && rows_vectorizable<T>(p.student, p.ld_s) &&
                      rows_vectorizable<T>(p.grad, p.ld_g);
     // a thread takes one batch of kRegradBatch vectors of a row (the kernel fetches them all before consuming any)
-    constexpr int kRegradBatch = sizeof(T) == 2 ? KD_REGRAD_BATCH : (KD_REGRAD_BATCH + 1) / 2;
+    constexpr int kRegradBatch = sizeof(T) == 2 ? (VARIANT == KD_LOCA_REFERENCE ? KD_REGRAD_BATCH_TABLE : KD_REGRAD_BATCH) : 2;
     int64_t gx = (p.V / Elem<T>::kPack + 256 * kRegradBatch - 1) / (256 * kRegradBatch);
     gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
     int64_t gy = (int64_t)sm_count() * 16 / gx;
