@@ -63,8 +63,8 @@ class OnlineKnowledgeDistillationModule(_Base, KDLossMethods):
         self.loca_mode, self.sanitize_labels = loca_mode, sanitize_labels
         self.kd_group, self.kd_exchange = group, exchange
         # fuse_ce: the student is called WITHOUT labels and its cross-entropy comes out of the logit-KD kernel's pass over the
-        # student logits — single process, as-written LoCa mode, phases 2 / 3
-        self.fuse_ce = bool(fuse_ce) and group is None and loca_mode == "reference"
+        # student logits — as-written LoCa mode, phases 2 / 3; with a group: kd_loca_emit_ce on the token shards
+        self.fuse_ce = bool(fuse_ce) and loca_mode == "reference"
         self.student_representation_output = None
         self.teacher_representation_output = None
         if vision_hook:
@@ -116,11 +116,19 @@ class OnlineKnowledgeDistillationModule(_Base, KDLossMethods):
         """Phases 2 / 3 with the cross-entropy fused: loca + CE (P1:254), or gamma * (loca + CE) + (1 - gamma) * CE
         = gamma * (loca + CE / gamma) (P1:257-260), from one pass over the logits.  The CE is the mean over ALL valid next-token
         targets; rows LoCa cannot use (label outside [0, V), e.g. the -100 of a prompt token) but whose NEXT token is a target
-        are few (one per answer start) and go through a plain cross-entropy on just those rows."""
+        are few (one per answer start) and go through a plain cross-entropy on just those rows.  With ``group=``: KD and CE are
+        those of the batch concatenated over the ranks (the valid-target count is summed on the device); the value returned is that
+        global loss plus this rank's share of the few left-over rows, the gradient is the local rows'."""
         V = student_logits.shape[-1]
         ce_labels = F_kd.shift_labels(labels).reshape(-1)
         flat = labels.reshape(-1)
         n_valid = (ce_labels != F_kd.CE_IGNORE).sum()
+        group = self.kd_group
+        if group is not None:
+            import torch.distributed as dist
+            n_valid = n_valid.to(torch.float32)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                dist.all_reduce(n_valid, op=dist.ReduceOp.SUM, group=group)
         gamma = self.gamma if self.phase == 3 else 1.0
         s2, t2 = student_logits.reshape(-1, V), teacher_logits.reshape(-1, teacher_logits.shape[-1])
         extra = None
@@ -133,8 +141,14 @@ class OnlineKnowledgeDistillationModule(_Base, KDLossMethods):
                     extra = torch.nn.functional.cross_entropy(s2.index_select(0, rest).float(), ce_labels.index_select(0, rest),
                                                               reduction="sum") / n_valid
                 s2, t2, flat, ce_labels = s2.index_select(0, idx), t2.index_select(0, idx), flat.index_select(0, idx), ce_labels.index_select(0, idx)
-        total, ce = F_kd.loca_kl_ce(t2, s2, flat, ce_labels, self.T, ce_weight=1.0 / gamma, upstream=gamma if gamma != 1.0 else None,
-                                    ce_valid_count=n_valid)
+        up = gamma if gamma != 1.0 else None
+        if group is not None:
+            from . import sharded
+            total, ce = sharded.loca_kl_ce_token_sharded_autograd(t2, s2, flat, ce_labels, self.T, ce_weight=1.0 / gamma, group=group,
+                                                                  upstream=up, exchange=self.kd_exchange, ce_valid_count=n_valid,
+                                                                  phases=getattr(self, "kd_phases", None))
+        else:
+            total, ce = F_kd.loca_kl_ce(t2, s2, flat, ce_labels, self.T, ce_weight=1.0 / gamma, upstream=up, ce_valid_count=n_valid)
         self.last_student_loss = ce if extra is None else ce + extra.detach()
         loss = gamma * total
         return loss if extra is None else loss + extra

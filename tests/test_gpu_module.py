@@ -69,3 +69,31 @@ def test_fused_cross_entropy_equals_the_students_own_loss(phase, pad):
     with torch.no_grad():
         so = TinyCausalLM(2048, 64, seed=1).cuda()(b["depth_input_ids"], b["depth_pixel_values"], labels=b["labels"])
     assert abs(m1.last_student_loss.item() - so.loss.item()) <= 1e-5 * abs(so.loss.item())
+
+
+def test_fused_cross_entropy_on_a_process_group_equals_the_single_process_module():
+    """fuse_ce=True with group=...: phases 2 / 3 go through kd_loca_emit_ce (token shards); on a one-rank group the loss and the
+    parameter gradients are those of the single-process fused module (same kernels, phase-split)."""
+    import socket
+    import torch.distributed as dist
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        for phase in (2, 3):
+            b = _batch(2, pad=True)
+            out = []
+            for group in (None, dist.group.WORLD):
+                student, teacher = TinyCausalLM(2048, 64, seed=1).cuda(), TinyCausalLM(2048, 128, seed=2).cuda()
+                m = OnlineKnowledgeDistillationModule(student, teacher, phase=phase, fuse_ce=True, group=group)
+                assert m.fuse_ce
+                loss = m.training_step(b, 0)
+                loss.backward()
+                out.append((loss.item(), m.last_student_loss.item(),
+                            torch.cat([p.grad.reshape(-1).float() for p in student.parameters() if p.grad is not None])))
+            (l0, c0, g0), (l1, c1, g1) = out
+            assert abs(l1 - l0) <= 1e-6 * abs(l0) and abs(c1 - c0) <= 1e-6 * abs(c0)
+            assert ((g1 - g0).norm() / g0.norm()).item() <= 1e-3
+    finally:
+        dist.destroy_process_group()
