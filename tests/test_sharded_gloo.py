@@ -191,6 +191,49 @@ def _worker_fused_ce(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _worker_module_fused(rank, world, port, out):
+    """The Lightning-shaped module with fuse_ce=True and a group: every rank steps on ITS batch (one with padded labels), the loss
+    is KD + CE of the two batches concatenated — the CE's divisor counts the valid targets of both ranks — times the phase-3 mix."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import train_online_kd
+        from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200.module import (
+            OnlineKnowledgeDistillationModule, TinyCausalLM)
+        from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import functional as F_kd
+        batches = list(train_online_kd.synthetic_batches(2, 2, 16, V, 5, 64, torch.device("cpu"), pad_last=False))
+        gamma, ok = 0.8, []
+        for phase in (2, 3):
+            student, teacher = TinyCausalLM(V, 32, seed=1, dtype=torch.float32), TinyCausalLM(V, 48, seed=2, dtype=torch.float32)
+            m = OnlineKnowledgeDistillationModule(student, teacher, phase=phase, T=T, gamma=gamma, fuse_ce=True, group=dist.group.WORLD)
+            m.kd_phases = OraclePhases()
+            loss = m.training_step(batches[rank], 0)
+            loss.backward()
+            # the concatenated batch, single process, from the same models
+            with torch.no_grad():
+                sl = torch.cat([student(b["depth_input_ids"], b["depth_pixel_values"]).logits.reshape(-1, V) for b in batches])
+                tl = torch.cat([teacher(b["rgb_input_ids"], b["rgb_pixel_values"]).logits.reshape(-1, V) for b in batches])
+            lab = torch.cat([b["labels"].reshape(-1) for b in batches])
+            cel = torch.cat([F_kd.shift_labels(b["labels"]).reshape(-1) for b in batches])
+            kl, ce = O.loca_kl(tl, sl, lab, T, ALPHA), O.student_cross_entropy(sl, cel)
+            want = kl.loss + ce.loss if phase == 2 else gamma * (kl.loss + ce.loss) + (1 - gamma) * ce.loss
+            ok.append(abs(loss.item() - want.item()) <= 1e-5 * abs(want.item()))
+            ok.append(abs(m.last_student_loss.item() - ce.loss.item()) <= 1e-5 * abs(ce.loss.item()))
+            ok.append(all(p.grad is not None and torch.isfinite(p.grad).all().item() for p in student.lm_head.parameters()))
+        out[rank] = tuple(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_module_with_fused_cross_entropy_on_token_shards_world_size_2():
+    world, port = 2, _free_port()
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_module_fused, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: (True,) * 6, 1: (True,) * 6}
+
+
 @pytest.mark.timeout(180)
 def test_token_sharded_fused_cross_entropy_world_size_2():
     world, port = 2, _free_port()
