@@ -698,6 +698,11 @@ def main() -> None:
         ms = timeit(mse)
         side["feature_mse_65536x3584"] = {"ms": ms, "achieved_gbs": 6 * ha.numel() / (ms / 1e3) / 1e9,
                                           "frac": 6 * ha.numel() / (ms / 1e3) / 1e9 / peak_gbs}
+        try:      # the same step without the host between its launches (a 0.22 ms kernel under ~20 us of autograd)
+            msg = timeit_graph(mse)
+            side["feature_mse_65536x3584"].update({"graph_replay_ms": msg, "graph_replay_frac": 6 * ha.numel() / (msg / 1e3) / 1e9 / peak_gbs})
+        except Exception as exc:  # noqa: BLE001
+            side["feature_mse_65536x3584"]["graph_replay_error"] = f"{type(exc).__name__}: {exc}"
         del ha, hb
         torch.cuda.empty_cache()
         tf_peak, tf_src = 1401.6, "fallback"

@@ -165,3 +165,44 @@ def test_token_sharded_fused_ce_bad_target_and_unsupported_shape():
         sharded.loca_kl_token_sharded(t.float(), s.float(), lab, 2.0, ce_labels=cel)
     with pytest.raises(ValueError):
         sharded.loca_kl_token_sharded(t, s, lab, 2.0, ce_labels=cel[:-1])
+
+
+def test_phase_split_ce_entry_points_error_paths_through_the_c_abi():
+    """kd_loca_emit_ce / kd_loca_regrad called raw: null pointers and a short leading dimension are KD_ERR_INVALID_ARGUMENT (1) with a
+    message; fp32 logits are KD_ERR_UNSUPPORTED (2) for the fused cross-entropy — nothing is launched in either case."""
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 import sharded
+    from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200.functional import _stream_ptr
+    lib = _lib.load()
+    n, V, T = 8, 40000, 2.0
+    t, s, lab, cel = _batch(n, V, seed=3, peaked=False, ignore_frac=0.3)
+    ph = sharded.CudaPhases()
+    rec, lse2, status = ph.teacher_stats(t, lab, T, 0.8, V)
+    table, consts = ph.build_table(rec, V)
+    dev = s.device
+    loss, ce = torch.empty((), device=dev), torch.empty((), device=dev)
+    rowaux, ceaux = torch.empty((n + 1, 4), device=dev), torch.empty((n, 2), device=dev)
+    grad = torch.empty_like(s)
+    inv = torch.full((1,), 0.2, device=dev)
+    st = _stream_ptr(dev)
+
+    def emit(ce_labels=cel.data_ptr(), status_ptr=status.data_ptr(), ld_g=V, dtype=0, tt=t, ss=s):
+        return lib.kd_loca_emit_ce(tt.data_ptr(), tt.stride(0), ss.data_ptr(), ss.stride(0), lse2.data_ptr(), table.data_ptr(),
+                                   consts.data_ptr(), ce_labels, inv.data_ptr(), 1.0, grad.data_ptr(), ld_g, loss.data_ptr(), ce.data_ptr(),
+                                   rowaux.data_ptr(), ceaux.data_ptr(), n, V, dtype, T, 1e-8, 1.0 / (n * V), None, status_ptr, 0, st)
+    assert emit() == 0
+    assert emit(ce_labels=None) == 1 and b"kd_loca_emit_ce" in lib.kd_last_error()
+    assert emit(status_ptr=None) == 1
+    assert emit(ld_g=V - 8) == 1 and b"leading dimension" in lib.kd_last_error()
+    assert emit(dtype=2, tt=t.float(), ss=s.float()) == 2 and b"cross-entropy" in lib.kd_last_error()
+    torch.cuda.synchronize()
+    up = torch.full((1,), 0.5, device=dev)
+
+    def regrad(table_ptr=table.data_ptr(), ce_labels=cel.data_ptr(), ceaux_ptr=ceaux.data_ptr()):
+        return lib.kd_loca_regrad(t.data_ptr(), t.stride(0), s.data_ptr(), s.stride(0), table_ptr, rowaux.data_ptr(), ce_labels,
+                                  inv.data_ptr(), 1.0, ceaux_ptr, grad.data_ptr(), V, n, V, 0, T, 1e-8, 1.0 / (n * V), up.data_ptr(), None, st)
+    g_fwd = grad.clone()
+    assert regrad() == 0
+    torch.cuda.synchronize()
+    assert ((grad.float() - 0.5 * g_fwd.float()).norm() / (0.5 * g_fwd.float()).norm()).item() <= 1e-3     # half the forward's gradient
+    assert regrad(table_ptr=None) == 1 and b"kd_loca_regrad" in lib.kd_last_error()
+    assert regrad(ceaux_ptr=None) == 1
