@@ -874,6 +874,13 @@ int launch_emit(const EmitParams& p_in, int variant, int dtype, cudaStream_t st,
     }
     if (p.flags & KD_FLAG_FORCE_STREAMING) return launch_emit_stream_any(p, variant, dtype, st);
 
+    // Per-row LoCa is the one variant where clusters of 8 (120 SMs) + the streaming helper on the other 28 SMs beat clusters of 9
+    // (135 SMs, no helper): its row chain is the longest, so a helper row costs relatively less.  tools/cluster_ab.sh at 16 384 x 151 936:
+    // per-row 3.44 -> 3.22 ms (T = 0.8 on peaked logits 4.33 -> 3.95); plain KL / log_target within 1 %; as-written 3.75 -> 3.87 (stays at 9).
+    struct Prefer8 {
+        explicit Prefer8(bool on) { fused_prefer_cluster8(on); }
+        ~Prefer8() { fused_prefer_cluster8(false); }
+    } prefer8(variant == KD_LOCA_PER_ROW && queue && spare_sm_mode() != 0 && p.n_rows >= 1024);
     int n_clusters = 0, cta_per = 8, pipes = 2, static_rows = 4;
     const int shape_rc = cluster_launch_shape(p, variant, dtype, &n_clusters, &cta_per, &pipes, &static_rows);
     if (shape_rc == KD_ERR_UNSUPPORTED) return launch_emit_stream_any(p, variant, dtype, st);

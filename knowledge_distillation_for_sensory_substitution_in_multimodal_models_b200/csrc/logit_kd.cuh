@@ -118,6 +118,7 @@ int cluster_launch_shape(const EmitParams& p, int variant, int dtype, int* n_clu
 // 0 <= alpha <= 1 and to KD_KL_PLAIN on 16-bit logits; same launch shape as the cluster kernel (clusters of 8, 2 pipelines)
 bool fused_applies(const EmitParams& p, int variant, int dtype);
 int fused_cluster_size();      // CTAs per cluster chosen by the last launch_emit_fused call (8 or 9)
+void fused_prefer_cluster8(bool on);   // this thread's next launch_emit_fused calls take clusters of 8 where both sizes fit (launch_emit's hint)
 int launch_emit_fused(const EmitParams& p, int variant, int dtype, cudaStream_t stream, bool query_only, int* capacity,
                       int* clusters_launched, int* first_free_row, int* rows_in_flight /* per cluster: 1 or 2 pipelines */);
 

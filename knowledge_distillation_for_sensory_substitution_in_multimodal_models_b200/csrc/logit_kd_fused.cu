@@ -1374,8 +1374,10 @@ int launch_fused_c(const EmitParams& e, cudaStream_t st, bool query_only, int* c
     }
 }
 
-// cluster size: whichever of 8 / 9 puts more SMs to work for this shape (KD_CLUSTER_SIZE=8|9 forces one)
+// cluster size: whichever of 8 / 9 puts more SMs to work for this shape (KD_CLUSTER_SIZE=8|9 forces one) — unless launch_emit asks for
+// clusters of 8 because it will run the streaming helper on the SMs they leave free (per-row LoCa, see launch_emit)
 int g_last_cluster_size = 8;
+thread_local bool t_prefer_cluster8 = false;
 template <int VARIANT, typename T, bool CE = false>
 int launch_fused_v(const EmitParams& e, cudaStream_t st, bool query_only, int* capacity, int* launched, int* first_free) {
     static int forced = -1;
@@ -1383,7 +1385,7 @@ int launch_fused_v(const EmitParams& e, cudaStream_t st, bool query_only, int* c
     int cap8 = 0, cap9 = 0;
     const int rc8 = (forced == 9) ? KD_ERR_UNSUPPORTED : launch_fused_c<VARIANT, T, 8, CE>(e, st, true, &cap8, nullptr, nullptr);
     const int rc9 = (forced == 8) ? KD_ERR_UNSUPPORTED : launch_fused_c<VARIANT, T, 9, CE>(e, st, true, &cap9, nullptr, nullptr);
-    const bool use9 = (rc9 == KD_OK) && (rc8 != KD_OK || cap9 * 9 > cap8 * 8);
+    const bool use9 = (rc9 == KD_OK) && (rc8 != KD_OK || (cap9 * 9 > cap8 * 8 && !(t_prefer_cluster8 && forced == 0)));
     if (!use9 && rc8 != KD_OK) return rc8;
     g_last_cluster_size = use9 ? 9 : 8;
     if (use9) return launch_fused_c<VARIANT, T, 9, CE>(e, st, query_only, capacity, launched, first_free);
@@ -1425,6 +1427,7 @@ bool fused_applies(const EmitParams& p, int variant, int dtype) {
 }
 
 int fused_cluster_size() { return g_last_cluster_size; }
+void fused_prefer_cluster8(bool on) { t_prefer_cluster8 = on; }
 
 int launch_emit_fused(const EmitParams& p, int variant, int dtype, cudaStream_t stream, bool query_only, int* capacity,
                       int* clusters_launched, int* first_free_row, int* rows_in_flight) {
