@@ -15,6 +15,11 @@
 // tools/knob_sweep.py at 16 384 x 151 936).  The as-written variant also fetches its slice of the override table per pair and
 // is best with 2 (1 -> 3.17 ms, 2 -> 2.36, 3 -> 2.54, 4 -> 2.53, 8 -> 3.43); the table-free variants with 4 (per-row 2.47 against
 // 2.57 ms with 2, plain KL 2.38 against 2.43).
+#ifndef KD_STREAM_U
+// vector pairs fetched per thread before any is consumed in sweeps B / C of the streaming emit kernel (as the helper beside clusters of
+// 8: per-row 3.275 ms with 2, 3.268 with 3, 3.324 with 4 — flat, the helper's rows are not bound by loads in flight)
+#define KD_STREAM_U 2
+#endif
 #ifndef KD_REGRAD_BATCH_TABLE
 #define KD_REGRAD_BATCH_TABLE 2
 #endif
@@ -455,7 +460,7 @@ row_emit_stream_kernel(const EmitParams p) {
                 for (int i = 0; i < P; ++i)
                     PointTerm<VARIANT>::accum(xt[i], xs[i], LOCA ? override_of(v * P + i) : NaN, k2, lse2_t, lse2_s, thr2, row, Q);
             };
-            constexpr int U = 2;
+            constexpr int U = KD_STREAM_U;
             int v = threadIdx.x;
             for (; v + (U - 1) * NT < nvec; v += U * NT) {
                 uint4 rt[U], rs[U];
@@ -505,7 +510,7 @@ row_emit_stream_kernel(const EmitParams p) {
                     o[i] = PointTerm<VARIANT>::grad(xt[i], xs[i], LOCA ? override_of(v * P + i) : NaN, k2, lse2_t, lse2_s, thr2, g, gQ);
                 stg_stream(gv + v, Elem<T>::pack(o));
             };
-            constexpr int U = 2;
+            constexpr int U = KD_STREAM_U;
             int v = threadIdx.x;
             for (; v + (U - 1) * NT < nvec; v += U * NT) {
                 uint4 rt[U], rs[U];
