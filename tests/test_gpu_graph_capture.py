@@ -9,9 +9,10 @@ from knowledge_distillation_for_sensory_substitution_in_multimodal_models_b200 i
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode", ["reference", "per_row"])
-def test_step_replays_from_a_cuda_graph(mode):
-    t, s, lab = synthetic.logit_batch(96, synthetic.VOCAB, seed=13, device="cuda")
+# 1100 rows of per-row LoCa: clusters of 8 + the streaming helper on a second (internal) stream — a fork / join inside the capture
+@pytest.mark.parametrize("mode,rows", [("reference", 96), ("per_row", 96), ("per_row", 1100)])
+def test_step_replays_from_a_cuda_graph(mode, rows):
+    t, s, lab = synthetic.logit_batch(rows, synthetic.VOCAB, seed=13, device="cuda")
     s.requires_grad_(True)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
